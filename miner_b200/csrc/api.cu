@@ -1,0 +1,230 @@
+// extern "C" entry points of libminer_b200.so (see include/miner_b200.h) and the chunked orchestration of the
+// fused table-based scoring path (Miner.forward, reference src/model/model.py:61-138).
+#include <stdarg.h>
+#include <string.h>
+
+#include "common.cuh"
+#include "tc/tc_gemm.cuh"
+
+namespace miner {
+
+static thread_local char g_err[512] = "";
+
+void set_error(const char* fmt, ...) {
+  va_list ap;
+  va_start(ap, fmt);
+  vsnprintf(g_err, sizeof(g_err), fmt, ap);
+  va_end(ap);
+}
+
+static unsigned long long g_launches = 0;
+void count_launch() { __atomic_add_fetch(&g_launches, 1ull, __ATOMIC_RELAXED); }
+
+int sm_count() {
+  static thread_local int cached_dev = -1, cached = 148;
+  int dev = 0;
+  if (cudaGetDevice(&dev) != cudaSuccess) return cached;
+  if (dev != cached_dev) {
+    int n = 0;
+    if (cudaDeviceGetAttribute(&n, cudaDevAttrMultiProcessorCount, dev) == cudaSuccess && n > 0) cached = n;
+    cached_dev = dev;
+  }
+  return cached;
+}
+
+struct ScoreWs {
+  size_t proj, interests, interests_bf16, target_proj, total;
+};
+
+static ScoreWs score_ws_layout(const miner_score_params* p, int64_t chunk) {
+  ScoreWs w{};
+  size_t off = 0;
+  auto take = [&](size_t bytes) { size_t o = off; off += align_up(bytes, 256); return o; };
+  w.proj = take(sizeof(float) * chunk * p->H * p->Dc);
+  w.interests = take(p->out_interests ? 0 : sizeof(float) * chunk * p->K * p->D);
+  const bool weighted = p->score_type == MINER_SCORE_WEIGHTED;
+  w.interests_bf16 = take((p->math == MINER_MATH_TENSOR && weighted) ? 2 * (size_t)chunk * p->K * p->D : 0);
+  w.target_proj = take(weighted ? sizeof(float) * chunk * p->K * p->D : 0);
+  w.total = off;
+  return w;
+}
+
+static int check_score_params(const miner_score_params* p, int64_t chunk) {
+  MINER_CHECK_ARG(p != nullptr, "score: null params");
+  MINER_CHECK_ARG(p->table && p->his_ids && p->his_mask && p->cand_ids && p->w_proj && p->codes && p->out_scores,
+                  "score: null pointer");
+  MINER_CHECK_ARG(p->B >= 0 && p->H > 0 && p->K > 0 && p->Dc > 0 && p->D > 0 && p->n_rows > 0, "score: bad sizes");
+  MINER_CHECK_ARG(p->cand_offsets || p->C > 0, "score: dense layout needs C > 0");
+  MINER_CHECK_ARG(chunk > 0, "score: chunk_impressions must be positive");
+  MINER_CHECK_ARG(p->table_dtype == MINER_F32 || p->table_dtype == MINER_BF16, "score: table dtype must be fp32 or bf16");
+  MINER_CHECK_ARG(p->id_dtype == MINER_I32 || p->id_dtype == MINER_I64, "score: id dtype must be int32 or int64");
+  if (p->score_type != MINER_SCORE_MAX && p->score_type != MINER_SCORE_MEAN && p->score_type != MINER_SCORE_WEIGHTED) {
+    set_error("Invalid method of aggregating matching score");
+    return MINER_ERR_SCORE_TYPE;
+  }
+  MINER_CHECK_ARG(p->score_type != MINER_SCORE_WEIGHTED || p->w_target, "score: 'weighted' needs w_target");
+  if (p->math == MINER_MATH_TENSOR) {
+    MINER_CHECK_ARG(p->table_dtype == MINER_BF16, "score: the tensor-core family needs a bf16 table");
+    MINER_CHECK_ARG(p->w_proj_bf16 && (p->score_type != MINER_SCORE_WEIGHTED || p->w_target_bf16),
+                    "score: the tensor-core family needs bf16 weight copies");
+    if (!tc_gemm_supported(p->D, p->Dc) || !tc_gemm_supported(p->D, p->D)) {
+      set_error("score: tensor-core family needs D %% 64 == 0 (D=%lld)", (long long)p->D);
+      return MINER_ERR_UNSUPPORTED;
+    }
+  } else {
+    MINER_CHECK_ARG(p->math == MINER_MATH_FP32, "score: unknown math family");
+  }
+  return MINER_OK;
+}
+
+}  // namespace miner
+
+using namespace miner;
+
+extern "C" int miner_abi_version(void) { return MINER_B200_ABI_VERSION; }
+extern "C" const char* miner_last_error(void) { return g_err; }
+
+extern "C" uint64_t miner_launch_count(void) { return __atomic_load_n(&g_launches, __ATOMIC_RELAXED); }
+
+extern "C" int miner_device_info(int* sm, int* major, int* minor) {
+  int dev = 0;
+  MINER_CUDA_OK(cudaGetDevice(&dev));
+  int v = 0;
+  if (sm) { MINER_CUDA_OK(cudaDeviceGetAttribute(&v, cudaDevAttrMultiProcessorCount, dev)); *sm = v; }
+  if (major) { MINER_CUDA_OK(cudaDeviceGetAttribute(&v, cudaDevAttrComputeCapabilityMajor, dev)); *major = v; }
+  if (minor) { MINER_CUDA_OK(cudaDeviceGetAttribute(&v, cudaDevAttrComputeCapabilityMinor, dev)); *minor = v; }
+  return MINER_OK;
+}
+
+extern "C" int miner_gather(const void* table, int64_t n_rows, int64_t dim, int dtype, const void* ids, int64_t n_ids,
+                            int id_dtype, void* out, int32_t* oob_flag, void* stream) {
+  MINER_CHECK_ARG(n_ids >= 0 && dim >= 0 && n_rows >= 0, "gather: negative size");
+  MINER_CHECK_ARG(n_ids == 0 || dim == 0 || (table && ids && out), "gather: null pointer");
+  MINER_CHECK_ARG(dtype == MINER_F32 || dtype == MINER_BF16, "gather: dtype must be fp32 or bf16");
+  MINER_CHECK_ARG(id_dtype == MINER_I32 || id_dtype == MINER_I64, "gather: id dtype must be int32 or int64");
+  return launch_gather(table, n_rows, dim, dtype, ids, n_ids, id_dtype, out, oob_flag, static_cast<cudaStream_t>(stream));
+}
+
+extern "C" int miner_cast_f32_to_bf16(const float* src, void* dst, int64_t n, void* stream) {
+  MINER_CHECK_ARG(n >= 0 && (n == 0 || (src && dst)), "cast: bad arguments");
+  return launch_cast_f32_to_bf16(src, dst, n, static_cast<cudaStream_t>(stream));
+}
+
+extern "C" size_t miner_poly_attn_workspace_bytes(int64_t B, int64_t H, int64_t K, int64_t Dc, int64_t D) {
+  (void)K; (void)D;
+  return align_up(sizeof(float) * (size_t)B * H * Dc, 256);
+}
+
+extern "C" int miner_poly_attn_fwd(const float* emb, const uint8_t* mask, const float* bias_mean, const float* w_proj,
+                                   const float* codes, int64_t B, int64_t H, int64_t K, int64_t Dc, int64_t D,
+                                   float* out_interests, float* out_weights, void* workspace, size_t workspace_bytes,
+                                   void* stream) {
+  MINER_CHECK_ARG(B >= 0 && H > 0 && K > 0 && Dc > 0 && D > 0, "poly_attn: bad sizes");
+  if (B == 0) return MINER_OK;
+  MINER_CHECK_ARG(emb && mask && w_proj && codes && out_interests, "poly_attn: null pointer");
+  if (!workspace || workspace_bytes < miner_poly_attn_workspace_bytes(B, H, K, Dc, D)) {
+    set_error("poly_attn: workspace too small (%zu bytes needed)", miner_poly_attn_workspace_bytes(B, H, K, Dc, D));
+    return MINER_ERR_WORKSPACE;
+  }
+  auto st = static_cast<cudaStream_t>(stream);
+  float* proj = static_cast<float*>(workspace);
+  int rc = launch_sgemm_nt(emb, MINER_F32, nullptr, MINER_I64, 0, w_proj, proj, B * H, Dc, D, EPI_TANH, st);   // model.py:171
+  if (rc) return rc;
+  return launch_poly_softmax_wsum(proj, codes, mask, bias_mean, emb, nullptr, MINER_F32, nullptr, MINER_I64, 0, B, H, K, Dc, D,
+                                  out_interests, out_weights, nullptr, st);
+}
+
+extern "C" size_t miner_target_score_workspace_bytes(int64_t B, int64_t K, int64_t D, int score_type) {
+  return score_type == MINER_SCORE_WEIGHTED ? align_up(sizeof(float) * (size_t)B * K * D, 256) : 0;
+}
+
+extern "C" int miner_target_score_fwd(const float* interests, const float* cand, const float* matching,
+                                      const int64_t* cand_offsets, const float* w_target, int score_type, int64_t B, int64_t C, int64_t K, int64_t D,
+                                      float* out_scores, void* workspace, size_t workspace_bytes, void* stream) {
+  MINER_CHECK_ARG(B >= 0 && K > 0 && D > 0 && (cand_offsets || C > 0), "target_score: bad sizes");
+  if (score_type != MINER_SCORE_MAX && score_type != MINER_SCORE_MEAN && score_type != MINER_SCORE_WEIGHTED) {
+    set_error("Invalid method of aggregating matching score");
+    return MINER_ERR_SCORE_TYPE;
+  }
+  if (B == 0) return MINER_OK;
+  MINER_CHECK_ARG(interests && cand && out_scores, "target_score: null pointer");
+  auto st = static_cast<cudaStream_t>(stream);
+  float* proj = nullptr;
+  if (score_type == MINER_SCORE_WEIGHTED) {
+    MINER_CHECK_ARG(w_target, "target_score: 'weighted' needs w_target");
+    if (!workspace || workspace_bytes < miner_target_score_workspace_bytes(B, K, D, score_type)) {
+      set_error("target_score: workspace too small (%zu bytes needed)", miner_target_score_workspace_bytes(B, K, D, score_type));
+      return MINER_ERR_WORKSPACE;
+    }
+    proj = static_cast<float*>(workspace);
+    int rc = launch_sgemm_nt(interests, MINER_F32, nullptr, MINER_I64, 0, w_target, proj, B * K, D, D, EPI_GELU, st);  // model.py:212
+    if (rc) return rc;
+  }
+  return launch_target_score(interests, proj, matching, cand, nullptr, MINER_F32, nullptr, MINER_I64, 0, cand_offsets, B, C, K, D,
+                             score_type, out_scores, st);
+}
+
+extern "C" size_t miner_score_workspace_bytes(const miner_score_params* p, int64_t chunk) {
+  if (!p || chunk <= 0) return 0;
+  if (p->B > 0 && chunk > p->B) chunk = p->B;
+  return score_ws_layout(p, chunk).total;
+}
+
+extern "C" int miner_score_fwd(const miner_score_params* p, int64_t chunk, void* workspace, size_t workspace_bytes, void* stream) {
+  int rc = check_score_params(p, chunk);
+  if (rc) return rc;
+  if (p->B == 0) return MINER_OK;
+  if (chunk > p->B) chunk = p->B;
+  const ScoreWs w = score_ws_layout(p, chunk);
+  if (!workspace || workspace_bytes < w.total) {
+    set_error("score: workspace too small (%zu bytes needed, %zu given)", w.total, workspace_bytes);
+    return MINER_ERR_WORKSPACE;
+  }
+  auto st = static_cast<cudaStream_t>(stream);
+  char* ws = static_cast<char*>(workspace);
+  const bool weighted = p->score_type == MINER_SCORE_WEIGHTED;
+  const bool tensor = p->math == MINER_MATH_TENSOR;
+  const int64_t id_sz = p->id_dtype == MINER_I64 ? 8 : 4;
+  float* proj = reinterpret_cast<float*>(ws + w.proj);
+  float* tproj = weighted ? reinterpret_cast<float*>(ws + w.target_proj) : nullptr;
+  void* i_bf16 = (tensor && weighted) ? ws + w.interests_bf16 : nullptr;
+
+  for (int64_t b0 = 0; b0 < p->B; b0 += chunk) {
+    const int64_t nb = p->B - b0 < chunk ? p->B - b0 : chunk;
+    const void* his = static_cast<const char*>(p->his_ids) + b0 * p->H * id_sz;
+    const uint8_t* msk = p->his_mask + b0 * p->H;
+    const float* bias = p->bias_mean ? p->bias_mean + b0 * p->H : nullptr;
+    float* interests = p->out_interests ? p->out_interests + b0 * p->K * p->D : reinterpret_cast<float*>(ws + w.interests);
+    const int stages = p->stage_mask ? p->stage_mask : 15;
+    // step 1+2a: proj = tanh(table[his_ids] Wp^T)     (model.py:104-111,171)
+    if (!(stages & 1)) rc = MINER_OK;
+    else if (tensor)
+      rc = launch_tc_gemm(p->table, his, p->id_dtype, p->n_rows, p->w_proj_bf16, proj, nullptr, nb * p->H, p->Dc, p->D, EPI_TANH, st);
+    else
+      rc = launch_sgemm_nt(p->table, p->table_dtype, his, p->id_dtype, p->n_rows, p->w_proj, proj, nb * p->H, p->Dc, p->D, EPI_TANH, st);
+    if (rc) return rc;
+    // step 2b: logits, mask fill, softmax, weighted sum (model.py:174-182)
+    if (stages & 2) rc = launch_poly_softmax_wsum(proj, p->codes, msk, bias, nullptr, p->table, p->table_dtype, his, p->id_dtype, p->n_rows, nb,
+                                  p->H, p->K, p->Dc, p->D, interests, nullptr, i_bf16, st);
+    if (rc) return rc;
+    // step 3a: P = gelu(I Wt^T)                        (model.py:212)
+    if (weighted && (stages & 4)) {
+      if (tensor)
+        rc = launch_tc_gemm(i_bf16, nullptr, p->id_dtype, 0, p->w_target_bf16, tproj, nullptr, nb * p->K, p->D, p->D, EPI_GELU, st);
+      else
+        rc = launch_sgemm_nt(interests, MINER_F32, nullptr, p->id_dtype, 0, p->w_target, tproj, nb * p->K, p->D, p->D, EPI_GELU, st);
+      if (rc) return rc;
+    }
+    // step 3b+4: matching scores, target attention, per-candidate score (model.py:127-136,213-214)
+    if (!(stages & 8)) continue;
+    if (p->cand_offsets)
+      rc = launch_target_score(interests, tproj, nullptr, nullptr, p->table, p->table_dtype, p->cand_ids, p->id_dtype, p->n_rows,
+                               p->cand_offsets + b0, nb, 0, p->K, p->D, p->score_type, p->out_scores, st);
+    else
+      rc = launch_target_score(interests, tproj, nullptr, nullptr, p->table, p->table_dtype,
+                               static_cast<const char*>(p->cand_ids) + b0 * p->C * id_sz, p->id_dtype, p->n_rows, nullptr, nb,
+                               p->C, p->K, p->D, p->score_type, p->out_scores + b0 * p->C, st);
+    if (rc) return rc;
+  }
+  return MINER_OK;
+}

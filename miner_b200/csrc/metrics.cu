@@ -1,0 +1,196 @@
+// (a7..a12) segmented per-impression ranking metrics.
+// Replaces SlowEvaluator / FastEvaluator + BaseEvaluator.compute_scores (reference src/evaluation.py:36-175) and
+// compute_mrr_score / compute_dcg_score / compute_ndcg_score / is_hit (evaluation.py:177-249) plus sklearn's
+// roc_auc_score per impression (group_auc, evaluation.py:56-59).
+//
+// CSR layout: impression b owns candidates offsets[b] .. offsets[b+1].  One warp per impression (grid-stride, the
+// grid a multiple of the SM count).  The warp stages the transformed scores in shared memory, then each lane derives
+// the rank of its candidates by counting -- pure comparisons, so the ranking is bit-exact given the scores:
+//     gt  = #{j : p_j >  p_i}
+//     rank_np = gt + #{j > i : p_j == p_i}   position under np.argsort(p)[::-1] (evaluation.py:188,208) with the tie rule
+//                                            "stable ascending sort, reversed" (oracle/miner_oracle.py)
+//     rank_py = gt + #{j < i : p_j == p_i}   position under python's stable sorted(reverse=True) (evaluation.py:247)
+// group_auc is the tie-aware Mann-Whitney statistic; mrr, ndcg@k (gains 2^y-1, discounts log2(i+2), k=min(n,k)) and
+// hit@k follow.  All metric arithmetic is float64 like the reference's numpy.  Sums over impressions skip NaN
+// (np.nanmean, evaluation.py:59,65,72,80) and are reduced in a fixed order (per-block partials, then one block).
+#include "common.cuh"
+
+namespace miner {
+
+constexpr int MT = 256;            // threads per block (8 warps)
+constexpr int MCAP = 1024;         // candidates per impression staged in shared memory per warp
+constexpr int MAXK = 8;            // cut-offs
+constexpr int MAXM = 2 + 2 * MAXK;
+
+struct MetricKs { int n_k; int k[MAXK]; };
+
+__device__ __forceinline__ float transform_score(float s, int transform, float mx, float sum) {
+  if (transform == 1) return 1.0f / (1.0f + expf(-s));        // torch.sigmoid, evaluation.py:165
+  if (transform == 2) return expf(s - mx) / sum;              // softmax(dim=1), evaluation.py:109
+  return s;
+}
+
+__global__ void __launch_bounds__(MT) rank_metrics_kernel(const float* __restrict__ scores, const int8_t* __restrict__ labels,
+                                                          const int64_t* __restrict__ offsets, int64_t B, int transform,
+                                                          MetricKs ks, double* __restrict__ block_partials,
+                                                          double* __restrict__ per_impression) {
+  __shared__ float p_s[MT / 32][MCAP];
+  __shared__ int8_t y_s[MT / 32][MCAP];
+  __shared__ double red[MT / 32][2 * MAXM];
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int M = 2 + 2 * ks.n_k;
+  float* ps = p_s[warp];
+  int8_t* ys = y_s[warp];
+  double acc_sum[MAXM], acc_cnt[MAXM];
+#pragma unroll
+  for (int m = 0; m < MAXM; ++m) acc_sum[m] = 0.0, acc_cnt[m] = 0.0;
+
+  const int64_t warps_total = static_cast<int64_t>(gridDim.x) * (MT / 32);
+  for (int64_t b = static_cast<int64_t>(blockIdx.x) * (MT / 32) + warp; b < B; b += warps_total) {
+    const int64_t o0 = offsets[b];
+    const int n = static_cast<int>(offsets[b + 1] - o0);
+    const float* sb = scores + o0;
+    const int8_t* yb = labels + o0;
+    const bool staged = n <= MCAP;
+    float mx = 0.f, sum = 1.f;
+    if (transform == 2) {
+      mx = -INFINITY;
+      for (int j = lane; j < n; j += 32) mx = fmaxf(mx, sb[j]);
+      mx = warp_max(mx);
+      sum = 0.f;
+      for (int j = lane; j < n; j += 32) sum += expf(sb[j] - mx);
+      sum = warp_sum(sum);
+    }
+    if (staged) {
+      for (int j = lane; j < n; j += 32) {
+        ps[j] = transform_score(sb[j], transform, mx, sum);
+        ys[j] = yb[j];
+      }
+    }
+    __syncwarp();
+    double auc_wins = 0.0, rr = 0.0, n_pos = 0.0, n_neg = 0.0;
+    double dcg[MAXK], idcg[MAXK], hit[MAXK];
+#pragma unroll
+    for (int q = 0; q < MAXK; ++q) dcg[q] = idcg[q] = hit[q] = 0.0;
+    for (int i = lane; i < n; i += 32) {
+      const float pi = staged ? ps[i] : transform_score(sb[i], transform, mx, sum);
+      const int yi = staged ? ys[i] : yb[i];
+      int gt = 0, eq_before = 0, eq_after = 0, neg_lt = 0, neg_eq = 0, y_gt = 0, y_eq_before = 0;
+      for (int j = 0; j < n; ++j) {
+        const float pj = staged ? ps[j] : transform_score(sb[j], transform, mx, sum);
+        const int yj = staged ? ys[j] : yb[j];
+        gt += pj > pi;
+        const bool eq = pj == pi;
+        eq_before += eq && (j < i);
+        eq_after += eq && (j > i);
+        const bool negj = yj <= 0;
+        neg_lt += negj && (pj < pi);
+        neg_eq += negj && eq;
+        y_gt += yj > yi;
+        y_eq_before += (yj == yi) && (j < i);
+      }
+      const int rank_np = gt + eq_after;
+      const int rank_py = gt + eq_before;
+      const int rank_ideal = y_gt + y_eq_before;
+      const double gain = exp2(static_cast<double>(yi)) - 1.0;          // 2 ** y_true - 1, evaluation.py:210
+      if (yi > 0) {
+        n_pos += 1.0;
+        auc_wins += static_cast<double>(neg_lt) + 0.5 * static_cast<double>(neg_eq);
+      } else {
+        n_neg += 1.0;
+      }
+      rr += static_cast<double>(yi) / static_cast<double>(rank_np + 1);  // evaluation.py:190
+#pragma unroll
+      for (int q = 0; q < MAXK; ++q) {
+        if (q < ks.n_k) {
+          const int kk = ks.k[q] < n ? ks.k[q] : n;                      // k = min(len, k), evaluation.py:207
+          if (rank_np < kk) dcg[q] += gain / log2(static_cast<double>(rank_np + 2));
+          if (rank_ideal < kk) idcg[q] += gain / log2(static_cast<double>(rank_ideal + 2));
+          if (rank_py < ks.k[q] && yi > 0) hit[q] = 1.0;                 // evaluation.py:247-249
+        }
+      }
+    }
+    auc_wins = warp_sum(auc_wins); rr = warp_sum(rr); n_pos = warp_sum(n_pos); n_neg = warp_sum(n_neg);
+    double sum_y = 0.0;
+    for (int i = lane; i < n; i += 32) sum_y += static_cast<double>(staged ? ys[i] : yb[i]);
+    sum_y = warp_sum(sum_y);
+    double vals[MAXM];
+    vals[0] = (n_pos > 0.0 && n_neg > 0.0) ? auc_wins / (n_pos * n_neg) : NAN;   // one class: sklearn raises -> NaN here
+    vals[1] = rr / sum_y;                                                          // 0/0 -> NaN (no positives)
+#pragma unroll
+    for (int q = 0; q < MAXK; ++q) {
+      if (q < ks.n_k) {
+        const double d = warp_sum(dcg[q]), id = warp_sum(idcg[q]);
+        double h = hit[q];
+#pragma unroll
+        for (int o = 16; o > 0; o >>= 1) h = fmax(h, __shfl_xor_sync(0xffffffffu, h, o));
+        vals[2 + q] = d / id;                                                      // evaluation.py:231
+        vals[2 + ks.n_k + q] = h;
+      }
+    }
+    if (lane == 0) {
+      for (int m = 0; m < M; ++m) {
+        if (per_impression) per_impression[b * M + m] = vals[m];
+        if (!isnan(vals[m])) { acc_sum[m] += vals[m]; acc_cnt[m] += 1.0; }
+      }
+    }
+    __syncwarp();
+  }
+  if (lane == 0)
+    for (int m = 0; m < M; ++m) { red[warp][2 * m] = acc_sum[m]; red[warp][2 * m + 1] = acc_cnt[m]; }
+  __syncthreads();
+  if (threadIdx.x < 2 * M) {
+    double s = 0.0;
+    for (int w = 0; w < MT / 32; ++w) s += red[w][threadIdx.x];
+    block_partials[static_cast<int64_t>(blockIdx.x) * 2 * MAXM + threadIdx.x] = s;
+  }
+}
+
+__global__ void rank_metrics_finalize(const double* __restrict__ block_partials, int n_blocks, int M, double* __restrict__ out) {
+  const int t = threadIdx.x;
+  if (t < 2 * M) {
+    double s = 0.0;
+    for (int b = 0; b < n_blocks; ++b) s += block_partials[static_cast<int64_t>(b) * 2 * MAXM + t];
+    out[t] = s;
+  }
+}
+
+static int metrics_grid(int64_t B) {
+  int64_t blocks = (B + MT / 32 - 1) / (MT / 32);
+  const int64_t cap = static_cast<int64_t>(sm_count()) * 4;
+  if (blocks > cap) blocks = cap;
+  if (blocks < 1) blocks = 1;
+  return static_cast<int>(blocks);
+}
+
+}  // namespace miner
+
+extern "C" size_t miner_rank_metrics_workspace_bytes(int64_t B, int n_k) {
+  (void)n_k;
+  return sizeof(double) * 2 * miner::MAXM * static_cast<size_t>(miner::metrics_grid(B));
+}
+
+extern "C" int miner_rank_metrics(const float* scores, const int8_t* labels, const int64_t* offsets, int64_t B, int transform,
+                                  const int* ks, int n_k, double* out_partials, double* out_per_impression, void* workspace,
+                                  size_t workspace_bytes, void* stream) {
+  using namespace miner;
+  MINER_CHECK_ARG(offsets && out_partials, "rank_metrics: null pointer");
+  MINER_CHECK_ARG(B == 0 || (scores && labels), "rank_metrics: null scores/labels");
+  MINER_CHECK_ARG(n_k >= 0 && n_k <= MAXK, "rank_metrics: at most %d cut-offs", MAXK);
+  MINER_CHECK_ARG(transform >= 0 && transform <= 2, "rank_metrics: transform must be 0 (none), 1 (sigmoid) or 2 (softmax)");
+  MINER_CHECK_ARG(n_k == 0 || ks, "rank_metrics: null ks");
+  const int grid = metrics_grid(B);
+  if (workspace_bytes < sizeof(double) * 2 * MAXM * static_cast<size_t>(grid) || !workspace) {
+    set_error("rank_metrics: workspace too small (%zu bytes needed)", sizeof(double) * 2 * MAXM * static_cast<size_t>(grid));
+    return MINER_ERR_WORKSPACE;
+  }
+  MetricKs mk;
+  mk.n_k = n_k;
+  for (int i = 0; i < MAXK; ++i) mk.k[i] = i < n_k ? ks[i] : 0;
+  auto st = static_cast<cudaStream_t>(stream);
+  rank_metrics_kernel<<<grid, MT, 0, st>>>(scores, labels, offsets, B, transform, mk, static_cast<double*>(workspace), out_per_impression);
+  MINER_LAUNCH_OK("rank_metrics");
+  rank_metrics_finalize<<<1, 64, 0, st>>>(static_cast<const double*>(workspace), grid, 2 + 2 * n_k, out_partials);
+  MINER_LAUNCH_OK("rank_metrics_finalize");
+  return MINER_OK;
+}

@@ -1,0 +1,17 @@
+// tcgen05 projection GEMM of the MINER_MATH_TENSOR family (see tc_gemm.cu).
+#pragma once
+#include "../common.cuh"
+
+namespace miner {
+
+// K (reduction) must be a multiple of 64 and N >= 16
+bool tc_gemm_supported(int64_t K, int64_t N);
+
+// C[M,N] (fp32) = epi( A[M,K] * B[N,K]^T ), bf16 operands, fp32 accumulation in TMEM.
+//   A: bf16 row-major; rows taken from `A` directly (a_ids == nullptr) or gathered: row m = A[a_ids[m], :] with the
+//      ids validated against a_rows_in_table (invalid -> zero row).
+//   B: bf16 (N,K) row-major weights (nn.Linear layout).   c_bf16 (nullable): bf16 copy of C.
+int launch_tc_gemm(const void* A, const void* a_ids, int id_dtype, int64_t a_rows_in_table, const void* B, float* C,
+                   void* c_bf16, int64_t M, int64_t N, int64_t K, int epilogue, cudaStream_t stream);
+
+}  // namespace miner

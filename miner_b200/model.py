@@ -1,0 +1,241 @@
+"""Drop-in mirror of the reference's ``src/model/model.py`` API for the scoring path.
+
+Same class names, constructor signatures, forward keywords, parameter names and return tuple as the
+reference (MrRobot2211/miner):
+
+    Miner(news_encoder, use_category_bias, num_context_codes, context_code_dim, score_type, dropout,
+          num_category=None, category_embed_dim=None, category_pad_token_id=None, category_embed=None)   model.py:18-21
+    Miner.forward(title, title_mask, his_title, his_title_mask, his_mask, sapo=None, sapo_mask=None,
+                  his_sapo=None, his_sapo_mask=None, category=None, his_category=None)
+                  -> (multi_user_interest (B,K,D), matching_scores (B,C))                                 model.py:61-64,138
+    PolyAttention(in_embed_dim, num_context_codes, context_code_dim).forward(embeddings, attn_mask, bias=None)  model.py:145,159
+    TargetAwareAttention(embed_dim).forward(query, key, value)                                            model.py:190,200
+    encoder contract: ``embed_dim`` + ``forward(title_encoding, title_attn_mask, sapo_encoding, sapo_attn_mask)``
+                                                                                                          news_encoder.py:60-61,108-110
+
+State-dict keys match the reference (``poly_attn.linear.weight``, ``poly_attn.context_codes``,
+``target_aware_attn.linear.weight``, ``category_embedding.weight``), so reference checkpoints load.
+
+All arithmetic runs in the sm_100a kernels of libminer_b200.so through ``miner_b200.ops``; there is no
+PyTorch fallback -- CPU tensors raise.  The backward of the train variant is SURVEY.md section 8 row f1 and is not
+built yet: a forward under autograd works, calling ``.backward()`` through it raises NotImplementedError.
+"""
+from __future__ import annotations
+
+from typing import Optional, Union
+
+import torch
+import torch.nn as nn
+from torch import Tensor
+
+from . import ops
+from . import _lib as L
+
+
+class _NoBackward(torch.autograd.Function):
+    """Marks kernel outputs as differentiable so that a missing backward fails loudly instead of silently."""
+
+    @staticmethod
+    def forward(ctx, out: Tensor, *params: Tensor):
+        return out.view_as(out)
+
+    @staticmethod
+    def backward(ctx, *grads):
+        raise NotImplementedError('miner_b200: the backward kernels of the train variant (SURVEY.md section 8 f1) are not built yet')
+
+
+def _attach(out: Tensor, *params: Tensor) -> Tensor:
+    live = [p for p in params if isinstance(p, Tensor) and p.requires_grad]
+    if torch.is_grad_enabled() and live:
+        return _NoBackward.apply(out, *live)
+    return out
+
+
+class TableNewsEncoder(nn.Module):
+    """News encoder restated as an embedding table: ``forward`` returns ``table[title_encoding[:, 0]]``.
+
+    Keeps the NewsEncoder call contract (reference news_encoder.py:60-61,108-110) so it drops into ``Miner``.
+    ``table`` is (N, D) float32 or bfloat16 on the GPU; row 0 is the pad news.
+    """
+
+    def __init__(self, table: Tensor):
+        super().__init__()
+        self.register_buffer('table', table.detach().contiguous())
+
+    @property
+    def embed_dim(self) -> int:
+        return self.table.shape[1]
+
+    def forward(self, title_encoding: Tensor, title_attn_mask: Tensor = None, sapo_encoding: Union[Tensor, None] = None,
+                sapo_attn_mask: Union[Tensor, None] = None) -> Tensor:
+        return ops.gather(self.table, title_encoding[:, 0])
+
+
+class _Linear(nn.Module):
+    """``nn.Linear(bias=False)`` parameter holder: keeps the state-dict key ``<name>.weight`` and the default init."""
+
+    def __init__(self, in_features: int, out_features: int):
+        super().__init__()
+        ref = nn.Linear(in_features=in_features, out_features=out_features, bias=False)
+        self.weight = nn.Parameter(ref.weight.detach().clone())
+        self.in_features, self.out_features = in_features, out_features
+
+
+class PolyAttention(nn.Module):
+    r"""Poly attention: ``K`` additive attentions over the click history (reference model.py:141-185)."""
+
+    def __init__(self, in_embed_dim: int, num_context_codes: int, context_code_dim: int):
+        super().__init__()
+        self.linear = _Linear(in_embed_dim, context_code_dim)
+        self.context_codes = nn.Parameter(nn.init.xavier_uniform_(torch.empty(num_context_codes, context_code_dim),
+                                                                  gain=nn.init.calculate_gain('tanh')))
+
+    def forward(self, embeddings: Tensor, attn_mask: Tensor, bias: Tensor = None):
+        r"""
+        Args:
+            embeddings: ``(batch_size, his_length, embed_dim)``
+            attn_mask: ``(batch_size, his_length)`` bool
+            bias: ``(batch_size, his_length, num_candidates)`` or None
+        Returns: ``(batch_size, num_context_codes, embed_dim)``
+        """
+        bias_mean = None if bias is None else bias.mean(dim=2)          # model.py:176 (plumbing on a caller tensor)
+        out = ops.poly_attention(embeddings, attn_mask, self.linear.weight, self.context_codes, bias_mean)
+        return _attach(out, embeddings, self.linear.weight, self.context_codes)
+
+
+class TargetAwareAttention(nn.Module):
+    """Target-aware attention network (reference model.py:188-216)."""
+
+    def __init__(self, embed_dim: int):
+        super().__init__()
+        self.linear = _Linear(embed_dim, embed_dim)
+
+    def forward(self, query: Tensor, key: Tensor, value: Tensor):
+        r"""
+        Args:
+            query: ``(batch_size, num_context_codes, embed_dim)``
+            key: ``(batch_size, num_candidates, embed_dim)``
+            value: ``(batch_size, num_candidates, num_context_codes)``
+        Returns: ``(batch_size, num_candidates)``
+        """
+        B, Cn, _ = key.shape
+        out = ops.target_score(query, key, self.linear.weight, 'weighted', matching=value.reshape(B * Cn, -1))
+        return _attach(out, query, key, value, self.linear.weight)
+
+
+class Miner(nn.Module):
+    r"""MINER scoring path (reference model.py:13-138) on the B200 kernels.
+
+    With a :class:`TableNewsEncoder` the whole forward is the fused table-based path (gather -> poly attention ->
+    target-aware aggregation -> scores; the history tile is never materialised).  With any other encoder module the
+    encoder is called exactly as the reference does and the op-level kernels take its dense outputs.
+    """
+
+    def __init__(self, news_encoder: nn.Module, use_category_bias: bool, num_context_codes: int,
+                 context_code_dim: int, score_type: str, dropout: float, num_category: Union[int, None] = None,
+                 category_embed_dim: Union[int, None] = None, category_pad_token_id: Union[int, None] = None,
+                 category_embed: Union[Tensor, None] = None):
+        super().__init__()
+        self.news_encoder = news_encoder
+        self.news_embed_dim = self.news_encoder.embed_dim
+        self.use_category_bias = use_category_bias
+        if self.use_category_bias:
+            self.category_dropout = nn.Dropout(dropout)
+            if category_embed is not None:
+                self.category_embedding = nn.Embedding.from_pretrained(category_embed, freeze=False,
+                                                                       padding_idx=category_pad_token_id)
+                self.category_embed_dim = category_embed.shape[1]
+            else:
+                assert num_category is not None
+                self.category_embedding = nn.Embedding(num_embeddings=num_category, embedding_dim=category_embed_dim,
+                                                       padding_idx=category_pad_token_id)
+                self.category_embed_dim = category_embed_dim
+        self.poly_attn = PolyAttention(in_embed_dim=self.news_embed_dim, num_context_codes=num_context_codes,
+                                       context_code_dim=context_code_dim)
+        self.score_type = score_type
+        if self.score_type == 'weighted':
+            self.target_aware_attn = TargetAwareAttention(self.news_embed_dim)
+        self.dropout = nn.Dropout(dropout)           # constructed but never applied, as in the reference (model.py:59)
+        self._prepared = None                        # (version key, ops.ScoreWeights)
+
+    # -- parameter staging -------------------------------------------------------------------------------------
+    def _weights(self, with_bf16: bool) -> ops.ScoreWeights:
+        wt = self.target_aware_attn.linear.weight if self.score_type == 'weighted' else None
+        params = (self.poly_attn.linear.weight, self.poly_attn.context_codes, wt)
+        key = tuple((p.data_ptr(), p._version) if p is not None else None for p in params) + (with_bf16,)
+        if self._prepared is None or self._prepared[0] != key:
+            self._prepared = (key, ops.ScoreWeights(params[0], params[1], wt, with_bf16))
+        return self._prepared[1]
+
+    def _bias_mean(self, his_category: Tensor, category: Tensor) -> Tensor:
+        if self.training and self.category_dropout.p > 0:
+            raise NotImplementedError('miner_b200: category dropout in train mode belongs to the train variant (section 8 f1)')
+        mean, _ = ops.category_bias(self.category_embedding.weight, his_category, category)      # model.py:113-120,176
+        return mean
+
+    def forward(self, title: Tensor, title_mask: Tensor, his_title: Tensor, his_title_mask: Tensor,
+                his_mask: Tensor, sapo: Union[Tensor, None] = None, sapo_mask: Union[Tensor, None] = None,
+                his_sapo: Union[Tensor, None] = None, his_sapo_mask: Union[Tensor, None] = None,
+                category: Union[Tensor, None] = None, his_category: Union[Tensor, None] = None):
+        r"""
+        Returns:
+            tuple
+                - multi_user_interest: ``(batch_size, num_context_codes, embed_dim)``
+                - matching_scores: ``(batch_size, num_candidates)``
+        """
+        if self.score_type not in L.SCORE_TYPES:
+            raise ValueError('Invalid method of aggregating matching score')        # model.py:136
+        batch_size, num_candidates = title.shape[0], title.shape[1]
+        his_length = his_title.shape[1]
+        bias_mean = self._bias_mean(his_category, category) if self.use_category_bias else None
+
+        if isinstance(self.news_encoder, TableNewsEncoder):
+            table = self.news_encoder.table
+            math = ops.default_math(table, table.shape[1])
+            w = self._weights(with_bf16=(math == L.MATH_TENSOR))
+            cand_ids = title.reshape(batch_size, num_candidates, -1)[..., 0]
+            his_ids = his_title.reshape(batch_size, his_length, -1)[..., 0]
+            interests, scores = ops.score(table, his_ids, his_mask, cand_ids, w, self.score_type, bias_mean=bias_mean,
+                                          math=math, want_interests=True)
+        else:
+            # encoder called exactly as the reference does (model.py:86-111)
+            title = title.view(batch_size * num_candidates, -1)
+            title_mask = title_mask.view(batch_size * num_candidates, -1)
+            sapo = sapo.view(batch_size * num_candidates, -1)
+            sapo_mask = sapo_mask.view(batch_size * num_candidates, -1)
+            candidate_repr = self.news_encoder(title_encoding=title, title_attn_mask=title_mask, sapo_encoding=sapo,
+                                               sapo_attn_mask=sapo_mask).view(batch_size, num_candidates, -1)
+            his_title = his_title.view(batch_size * his_length, -1)
+            his_title_mask = his_title_mask.view(batch_size * his_length, -1)
+            his_sapo = his_sapo.view(batch_size * his_length, -1)
+            his_sapo_mask = his_sapo_mask.view(batch_size * his_length, -1)
+            history_repr = self.news_encoder(title_encoding=his_title, title_attn_mask=his_title_mask,
+                                             sapo_encoding=his_sapo, sapo_attn_mask=his_sapo_mask).view(batch_size, his_length, -1)
+            interests = ops.poly_attention(history_repr, his_mask, self.poly_attn.linear.weight, self.poly_attn.context_codes,
+                                           bias_mean)
+            wt = self.target_aware_attn.linear.weight if self.score_type == 'weighted' else None
+            scores = ops.target_score(interests, candidate_repr, wt, self.score_type)
+        params = [p for p in self.parameters()]
+        return _attach(interests, *params), _attach(scores, *params)
+
+    # -- grouped (CSR) evaluation entry: extension beyond the reference API ---------------------------------------
+    @torch.no_grad()
+    def score_impressions(self, his_ids: Tensor, his_mask: Tensor, cand_ids: Tensor, cand_offsets: Tensor,
+                          chunk: int = 4096, math: Optional[int] = None) -> Tensor:
+        """Scores of every candidate of every impression, CSR layout (``cand_offsets`` (B+1,) into flat ``cand_ids``).
+
+        Equals the reference's per-candidate eval rows (src/reader.py:376-379: one sample per candidate, interests
+        recomputed per candidate) when category bias is off, but computes the interests once per impression.
+        """
+        if self.use_category_bias:
+            raise NotImplementedError('grouped scoring with category bias: the bias depends on the row layout (model.py:176); '
+                                      'use forward() with the layout you mean')
+        if not isinstance(self.news_encoder, TableNewsEncoder):
+            raise L.MinerError('score_impressions needs a TableNewsEncoder')
+        table = self.news_encoder.table
+        if math is None:
+            math = ops.default_math(table, table.shape[1])
+        w = self._weights(with_bf16=(math == L.MATH_TENSOR))
+        _, scores = ops.score(table, his_ids, his_mask, cand_ids, w, self.score_type, cand_offsets=cand_offsets, math=math,
+                              chunk=chunk)
+        return scores

@@ -1,0 +1,55 @@
+"""Data-parallel sharding of impressions.
+
+Impressions are independent units: an impression's scores depend only on its own ids plus the replicated table and
+weights (reference model.py:61-138 mixes nothing across rows), so the path shards with NO data-path collective.
+Ranks take contiguous impression ranges balanced by cumulative candidate count; the only exchange is one
+all-reduce(SUM) of the [sum, count] metric partials at the end of the evaluation (exact for every np.nanmean
+metric of evaluation.py:59-80).
+"""
+from __future__ import annotations
+
+from typing import Dict, List, Sequence, Tuple
+
+import torch
+import torch.distributed as dist
+
+
+def shard_bounds(offsets: torch.Tensor, world_size: int, his_len: int = 0) -> List[Tuple[int, int]]:
+    """Split impressions ``[0, B)`` into ``world_size`` contiguous ranges of near-equal cost.
+
+    cost(impression) = his_len + n_candidates (rows gathered), taken from the CSR ``offsets`` (B+1,).
+    Returns ``[(start, end), ...]``; ranges are contiguous, cover every impression once and may be empty.
+    """
+    offs = offsets.detach().to('cpu', torch.int64)
+    B = offs.numel() - 1
+    if B <= 0:
+        return [(0, 0)] * world_size
+    cost = (offs[1:] - offs[:-1]) + int(his_len)
+    csum = torch.cumsum(cost, 0)
+    total = int(csum[-1])
+    bounds = [0]
+    for r in range(1, world_size):
+        target = total * r // world_size
+        idx = int(torch.searchsorted(csum, torch.tensor(target, dtype=torch.int64), right=False))
+        bounds.append(min(max(idx, bounds[-1]), B))
+    bounds.append(B)
+    return [(bounds[i], bounds[i + 1]) for i in range(world_size)]
+
+
+def local_shard(offsets: torch.Tensor, rank: int, world_size: int, his_len: int = 0):
+    """``(start, end, local_offsets)`` for this rank; ``local_offsets`` is rebased to start at 0."""
+    s, e = shard_bounds(offsets, world_size, his_len)[rank]
+    loc = offsets[s:e + 1] - offsets[s]
+    return s, e, loc
+
+
+def allreduce_partials(partials: torch.Tensor, group=None) -> torch.Tensor:
+    """Sum the ``[sum, count]`` metric partials over ranks (NCCL on GPUs, gloo in the CPU tests)."""
+    if dist.is_available() and dist.is_initialized() and dist.get_world_size(group) > 1:
+        dist.all_reduce(partials, op=dist.ReduceOp.SUM, group=group)
+    return partials
+
+
+def finalize_metrics(partials: torch.Tensor, names: Sequence[str]) -> Dict[str, float]:
+    p = partials.detach().to('cpu', torch.float64).view(-1, 2)
+    return {n: (float(p[i, 0] / p[i, 1]) if p[i, 1] > 0 else float('nan')) for i, n in enumerate(names)}

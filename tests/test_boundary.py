@@ -1,0 +1,146 @@
+"""CPU-side checks of the drop-in boundary: the C-ABI library loads and exports every symbol the header declares,
+the Python mirror keeps the reference's names, the product never touches the oracle, and the host-side sharding /
+reduction logic (world_size 2 over gloo)."""
+import os
+import re
+import subprocess
+import sys
+
+import numpy as np
+import pytest
+import torch
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+
+
+def _declared_functions():
+    text = open(os.path.join(ROOT, 'include', 'miner_b200.h')).read()
+    text = re.sub(r'/\*.*?\*/', '', text, flags=re.S)
+    return sorted(set(re.findall(r'\b(miner_[a-z0-9_]+)\s*\(', text)))
+
+
+def test_library_loads_and_exports_every_declared_symbol():
+    from miner_b200 import _lib
+    lib = _lib.load()
+    declared = _declared_functions()
+    assert len(declared) >= 15
+    for name in declared:
+        assert hasattr(lib, name), f'{name} declared in include/miner_b200.h but not exported'
+    assert sorted(_lib.EXPORTS) == declared
+    assert lib.miner_abi_version() == _lib.ABI_VERSION
+
+
+def test_built_for_sm100a_with_blackwell_instructions():
+    from miner_b200 import _lib
+    _lib.load()
+    out = subprocess.run(['cuobjdump', '-sass', _lib.LIB_PATH], capture_output=True, text=True)
+    if out.returncode != 0:
+        pytest.skip('cuobjdump unavailable')
+    assert 'sm_100a' in out.stdout
+    for mnemonic in ('UTCHMMA', 'UTMALDG', 'LDTM', 'LDGSTS'):
+        assert mnemonic in out.stdout, f'{mnemonic} missing from SASS'
+
+
+def test_product_never_imports_the_oracle():
+    for root, _, files in os.walk(os.path.join(ROOT, 'miner_b200')):
+        for f in files:
+            if f.endswith(('.py', '.cu', '.cuh', '.h')):
+                src = open(os.path.join(root, f)).read()
+                assert 'import oracle' not in src and 'from oracle' not in src and 'miner_oracle' not in src.replace(
+                    'oracle/miner_oracle.py', ''), f
+
+
+def test_reference_api_names_and_state_dict_keys():
+    import inspect
+    import miner_b200 as mb
+    enc = mb.TableNewsEncoder(torch.zeros(5, 64))
+    m = mb.Miner(enc, True, 8, 24, 'weighted', 0.2, num_category=7, category_embed_dim=10, category_pad_token_id=0)
+    keys = set(m.state_dict().keys())
+    # parameter names a reference checkpoint carries (checkpoint row)
+    assert {'poly_attn.linear.weight', 'poly_attn.context_codes', 'target_aware_attn.linear.weight',
+            'category_embedding.weight'} <= keys
+    assert m.poly_attn.linear.weight.shape == (24, 64) and m.poly_attn.context_codes.shape == (8, 24)
+    assert m.target_aware_attn.linear.weight.shape == (64, 64)
+    sig = inspect.signature(mb.Miner.forward)
+    assert list(sig.parameters)[1:] == ['title', 'title_mask', 'his_title', 'his_title_mask', 'his_mask', 'sapo', 'sapo_mask',
+                                        'his_sapo', 'his_sapo_mask', 'category', 'his_category']
+    assert list(inspect.signature(mb.Miner.__init__).parameters)[1:] == [
+        'news_encoder', 'use_category_bias', 'num_context_codes', 'context_code_dim', 'score_type', 'dropout', 'num_category',
+        'category_embed_dim', 'category_pad_token_id', 'category_embed']
+    assert list(inspect.signature(mb.PolyAttention.forward).parameters)[1:] == ['embeddings', 'attn_mask', 'bias']
+    assert list(inspect.signature(mb.TargetAwareAttention.forward).parameters)[1:] == ['query', 'key', 'value']
+    assert enc.embed_dim == 64
+    with pytest.raises(AssertionError):
+        mb.Miner(enc, True, 8, 24, 'weighted', 0.2)            # assert num_category is not None (model.py:49)
+
+
+def test_cpu_tensors_fail_loudly():
+    import miner_b200 as mb
+    from miner_b200 import ops, _lib
+    with pytest.raises(_lib.MinerError, match='no CPU fallback'):
+        ops.gather(torch.zeros(4, 8), torch.zeros(3, dtype=torch.int64))
+    enc = mb.TableNewsEncoder(torch.zeros(5, 64))
+    m = mb.Miner(enc, False, 8, 24, 'weighted', 0.2).eval()
+    z = torch.zeros(2, 3, 1, dtype=torch.long)
+    zh = torch.zeros(2, 4, 1, dtype=torch.long)
+    with pytest.raises(_lib.MinerError):
+        m(z, z, zh, zh, torch.ones(2, 4, dtype=torch.bool), z, z, zh, zh)
+    m.score_type = 'median'
+    with pytest.raises(ValueError, match='Invalid method of aggregating matching score'):
+        m(z, z, zh, zh, torch.ones(2, 4, dtype=torch.bool), z, z, zh, zh)
+
+
+def test_shard_bounds_balance_and_cover():
+    from miner_b200.parallel import shard_bounds, local_shard
+    g = torch.Generator().manual_seed(0)
+    counts = torch.randint(2, 300, (1000,), generator=g)
+    offs = torch.zeros(1001, dtype=torch.int64)
+    offs[1:] = torch.cumsum(counts, 0)
+    for ws in (1, 2, 4, 8):
+        b = shard_bounds(offs, ws, his_len=50)
+        assert b[0][0] == 0 and b[-1][1] == 1000
+        assert all(b[i][1] == b[i + 1][0] for i in range(ws - 1))
+        cost = [int(offs[e] - offs[s]) + 50 * (e - s) for s, e in b]
+        assert max(cost) - min(cost) <= 350 + 50, cost
+    s, e, loc = local_shard(offs, 1, 4, 50)
+    assert loc[0] == 0 and loc.numel() == e - s + 1 and int(loc[-1]) == int(offs[e] - offs[s])
+    assert shard_bounds(torch.zeros(1, dtype=torch.int64), 4) == [(0, 0)] * 4
+
+
+WORKER = r'''
+import os, sys, torch, torch.distributed as dist
+sys.path.insert(0, sys.argv[1])
+from miner_b200.parallel import shard_bounds, allreduce_partials, finalize_metrics
+from oracle import miner_oracle as O
+import numpy as np
+rank, world = int(os.environ['RANK']), int(os.environ['WORLD_SIZE'])
+dist.init_process_group('gloo', rank=rank, world_size=world)
+g = np.load(os.path.join(sys.argv[1], 'tests', 'golden', 'metrics.npz'))
+offs = torch.from_numpy(g['offsets'])
+s, e = shard_bounds(offs, world, 50)[rank]
+names = ['group_auc', 'mrr', 'ndcg@5', 'ndcg@10', 'hit@5', 'hit@10']
+per = O.per_impression_metrics(g['labels'], g['probs'], g['offsets'][s:e + 1])   # CPU stand-in for the per-rank kernel output
+part = torch.zeros(2 * len(names), dtype=torch.float64)
+for i, n in enumerate(names):
+    v = per[n]
+    part[2 * i] = np.nansum(v); part[2 * i + 1] = np.count_nonzero(~np.isnan(v))
+allreduce_partials(part)
+res = finalize_metrics(part, names)
+if rank == 0:
+    for n in names:
+        assert abs(res[n] - float(g['agg_' + n])) < 1e-12, (n, res[n], float(g['agg_' + n]))
+    print('OK')
+dist.destroy_process_group()
+'''
+
+
+def test_two_rank_metric_reduction_gloo(tmp_path):
+    """world_size 2 over gloo: sharded per-impression metrics + all-reduce of [sum,count] equal the single-process means."""
+    script = tmp_path / 'worker.py'
+    script.write_text(WORKER)
+    env = dict(os.environ, MASTER_ADDR='127.0.0.1', MASTER_PORT='29611', WORLD_SIZE='2')
+    procs = [subprocess.Popen([sys.executable, str(script), ROOT], env=dict(env, RANK=str(r)), stdout=subprocess.PIPE,
+                              stderr=subprocess.STDOUT, text=True) for r in range(2)]
+    outs = [p.communicate(timeout=240)[0] for p in procs]
+    assert all(p.returncode == 0 for p in procs), outs
+    assert 'OK' in outs[0]

@@ -1,0 +1,486 @@
+"""Parity of the CUDA path (through the C ABI) with the oracle and with the golden vectors produced by the
+reference itself.  Everything here needs a B200: ``pytest -m gpu``.
+
+Tolerances (north_star): bit-exact for gathered embeddings and for the ranking derived from given scores;
+scores/metrics within 1e-3 relative.  The fp32 family is held to 1e-4 (it differs from aten only by summation
+order); the tensor-core family (bf16 operands in the two projection GEMMs, fp32 everywhere else) to 1e-3 of the
+score scale.
+"""
+import numpy as np
+import pytest
+import torch
+
+from conftest import load_golden, golden_model_inputs
+from oracle import miner_oracle as O
+
+pytestmark = pytest.mark.gpu
+
+DEV = 'cuda:0'
+MODELS = ['model_small', 'model_odd', 'model_full']
+
+
+def close_fp32(a, b, tol=1e-4):
+    a, b = np.asarray(a, dtype=np.float64), np.asarray(b, dtype=np.float64)
+    scale = max(np.nanmax(np.abs(b)), 1e-30)
+    np.testing.assert_allclose(a, b, rtol=tol, atol=tol * scale, equal_nan=True)
+
+
+def close_norm(a, b, tol):
+    a, b = np.asarray(a, dtype=np.float64), np.asarray(b, dtype=np.float64)
+    err = np.nanmax(np.abs(a - b)) / max(np.nanmax(np.abs(b)), 1e-30)
+    assert err <= tol, f'normwise error {err:.3e} > {tol}'
+    return err
+
+
+def build_miner(x, score_type, use_bias=False, table_dtype=torch.float32):
+    import miner_b200 as mb
+    table = x['table'].to(DEV).to(table_dtype)
+    kw = {}
+    if use_bias:
+        kw = dict(num_category=x['cat_emb'].shape[0], category_embed_dim=x['cat_emb'].shape[1], category_pad_token_id=0)
+    K, Dc = x['codes'].shape
+    m = mb.Miner(mb.TableNewsEncoder(table), use_bias, K, Dc, score_type, 0.2, **kw).to(DEV).eval()
+    with torch.no_grad():
+        m.poly_attn.linear.weight.copy_(x['w_proj'])
+        m.poly_attn.context_codes.copy_(x['codes'])
+        if score_type == 'weighted':
+            m.target_aware_attn.linear.weight.copy_(x['w_target'])
+        if use_bias:
+            m.category_embedding.weight.copy_(x['cat_emb'])
+    return m
+
+
+def run_forward(m, x, category=None, his_category=None):
+    B, C = x['cand'].shape
+    H = x['his_ids'].shape[1]
+    z = torch.zeros(B, C, 1, dtype=torch.long, device=DEV)
+    zh = torch.zeros(B, H, 1, dtype=torch.long, device=DEV)
+    with torch.no_grad():
+        return m(title=x['cand'].to(DEV)[..., None], title_mask=z, his_title=x['his_ids'].to(DEV)[..., None], his_title_mask=zh,
+                 his_mask=x['his_mask'].to(DEV), sapo=z, sapo_mask=z, his_sapo=zh, his_sapo_mask=zh,
+                 category=None if category is None else category.to(DEV),
+                 his_category=None if his_category is None else his_category.to(DEV))
+
+
+# ------------------------------------------------------------------------------------------------ gather (a1)
+@pytest.mark.parametrize('dtype', [torch.float32, torch.bfloat16])
+@pytest.mark.parametrize('idt', [torch.int64, torch.int32])
+@pytest.mark.parametrize('dim', [768, 256, 64, 40, 7, 1000])
+def test_gather_bit_exact(dtype, idt, dim):
+    from miner_b200 import ops
+    g = torch.Generator().manual_seed(dim)
+    table = torch.randn(1001, dim, generator=g).to(dtype).to(DEV)
+    ids = torch.randint(0, 1001, (37, 50), generator=g).to(idt).to(DEV)
+    out = ops.gather(table, ids)
+    assert out.dtype == dtype and out.shape == (37, 50, dim)
+    assert torch.equal(out, table[ids.long()])
+
+
+def test_gather_edge_cases():
+    from miner_b200 import ops
+    table = torch.randn(10, 64, device=DEV)
+    assert ops.gather(table, torch.zeros(0, dtype=torch.int64, device=DEV)).shape == (0, 64)
+    ids = torch.tensor([0, 9, 10, -1, 3], device=DEV)
+    with pytest.raises(IndexError):
+        ops.gather(table, ids, check_bounds=True)
+    out = ops.gather(table, ids)                       # unchecked: out-of-range rows are zero-filled, others exact
+    assert torch.equal(out[[0, 1, 4]], table[[0, 9, 3]]) and float(out[2:4].abs().sum()) == 0.0
+    big = torch.randint(0, 10, (300_000,), device=DEV)      # more rows than resident warps: grid-stride path
+    assert torch.equal(ops.gather(table, big), table[big])
+    # misaligned base pointer -> scalar kernel
+    base = torch.randn(10 * 64 + 1, device=DEV)[1:].view(10, 64)
+    assert torch.equal(ops.gather(base, ids[:2]), base[ids[:2]])
+
+
+def test_newsencoder_contract():
+    import miner_b200 as mb
+    table = torch.randn(50, 128, device=DEV)
+    enc = mb.TableNewsEncoder(table)
+    ids = torch.randint(0, 50, (12, 1), device=DEV)
+    z = torch.zeros_like(ids)
+    out = enc(title_encoding=ids, title_attn_mask=z, sapo_encoding=z, sapo_attn_mask=z)
+    assert torch.equal(out, table[ids[:, 0]]) and enc.embed_dim == 128
+
+
+# ------------------------------------------------------------------------------------------------ op level (a2..a5)
+@pytest.mark.parametrize('name', MODELS)
+def test_category_bias(name):
+    from miner_b200 import ops, utils
+    g = load_golden(name)
+    x = golden_model_inputs(g)
+    mean, full = ops.category_bias(x['cat_emb'].to(DEV), x['his_cat'].to(DEV), x['cand_cat'].to(DEV), want_full=True)
+    close_fp32(full.cpu().numpy(), g['category_bias'], 1e-5)
+    ref_mean = torch.from_numpy(g['category_bias']).mean(dim=2).numpy()
+    close_fp32(mean.cpu().numpy(), ref_mean, 1e-5)
+    full2 = utils.category_cosine_bias(x['cat_emb'].to(DEV), x['his_cat'].to(DEV), x['cand_cat'].to(DEV))
+    assert torch.equal(torch.nan_to_num(full2), torch.nan_to_num(full))
+    # pad categories (zero embedding row) give NaN, as the reference
+    assert np.isnan(g['category_bias']).any() == bool(torch.isnan(full).any())
+
+
+@pytest.mark.parametrize('name', ['model_small', 'model_odd'])
+def test_poly_attention_module(name):
+    import miner_b200 as mb
+    g = load_golden(name)
+    x = golden_model_inputs(g)
+    D = x['table'].shape[1]
+    K, Dc = x['codes'].shape
+    pa = mb.PolyAttention(D, K, Dc).to(DEV)
+    with torch.no_grad():
+        pa.linear.weight.copy_(x['w_proj'])
+        pa.context_codes.copy_(x['codes'])
+        E = x['table'][x['his_ids']].to(DEV)
+        out = pa(embeddings=E, attn_mask=x['his_mask'].to(DEV), bias=None)
+        close_fp32(out.cpu().numpy(), g['poly_direct'])
+        bias = torch.from_numpy(np.nan_to_num(g['category_bias'])).to(DEV)
+        out_b = pa(embeddings=E, attn_mask=x['his_mask'].to(DEV), bias=bias)
+    ref = O.poly_attention(x['table'][x['his_ids']], x['his_mask'], x['w_proj'], x['codes'], bias.cpu())
+    close_fp32(out_b.cpu().numpy(), ref.numpy())
+
+
+def test_poly_attention_weights_and_mask_quirk():
+    """Masked slots are filled with 1e-30, not -inf: pads keep softmax mass (reference model.py:180)."""
+    from miner_b200 import ops
+    g = torch.Generator().manual_seed(5)
+    B, H, D, K, Dc = 3, 50, 128, 32, 40
+    E = torch.randn(B, H, D, generator=g)
+    mask = torch.zeros(B, H, dtype=torch.bool)
+    mask[:, -5:] = True                                   # 5 real clicks of 50
+    wp = torch.randn(Dc, D, generator=g) * 0.05
+    codes = torch.randn(K, Dc, generator=g) * 0.3
+    out, w = ops.poly_attention(E.to(DEV), mask.to(DEV), wp.to(DEV), codes.to(DEV), return_weights=True)
+    ref, wref = O.poly_attention(E, mask, wp, codes, return_weights=True)
+    close_fp32(w.cpu().numpy(), wref.numpy())
+    close_fp32(out.cpu().numpy(), ref.numpy())
+    assert float(w[:, :, :45].sum(dim=2).min()) > 0.5     # the 45 pads hold most of the mass
+    # all-masked and none-masked rows
+    for mk in (torch.zeros(B, H, dtype=torch.bool), torch.ones(B, H, dtype=torch.bool)):
+        o = ops.poly_attention(E.to(DEV), mk.to(DEV), wp.to(DEV), codes.to(DEV))
+        close_fp32(o.cpu().numpy(), O.poly_attention(E, mk, wp, codes).numpy())
+
+
+@pytest.mark.parametrize('name', ['model_small', 'model_odd'])
+def test_target_aware_attention_module(name):
+    import miner_b200 as mb
+    g = load_golden(name)
+    x = golden_model_inputs(g)
+    D = x['table'].shape[1]
+    ta = mb.TargetAwareAttention(D).to(DEV)
+    I = torch.from_numpy(g['interests'])
+    cr = x['table'][x['cand']]
+    match = torch.matmul(cr, I.permute(0, 2, 1))
+    with torch.no_grad():
+        ta.linear.weight.copy_(x['w_target'])
+        out = ta(query=I.to(DEV), key=cr.to(DEV), value=match.to(DEV))
+        close_fp32(out.cpu().numpy(), g['target_direct'])
+        # `value` is honoured even when it is not key . query^T
+        v2 = torch.randn_like(match)
+        out2 = ta(query=I.to(DEV), key=cr.to(DEV), value=v2.to(DEV))
+    close_fp32(out2.cpu().numpy(), O.target_aware_attention(I, cr, v2, x['w_target']).numpy())
+
+
+# ------------------------------------------------------------------------------------------------ Miner.forward (a1..a6)
+@pytest.mark.parametrize('name', MODELS)
+@pytest.mark.parametrize('score_type', ['weighted', 'max', 'mean'])
+def test_miner_forward_fp32_matches_reference(name, score_type):
+    g = load_golden(name)
+    x = golden_model_inputs(g)
+    m = build_miner(x, score_type)
+    I, S = run_forward(m, x)
+    close_fp32(S.cpu().numpy(), g[f'scores_{score_type}'])
+    if score_type == 'weighted':
+        close_fp32(I.cpu().numpy(), g['interests'])
+        # bit-exact ranking order against the reference's scores on these impressions
+        assert np.array_equal(np.argsort(S.cpu().numpy(), axis=1), np.argsort(g['scores_weighted'], axis=1))
+
+
+@pytest.mark.parametrize('name', MODELS)
+def test_miner_forward_per_candidate_rows(name):
+    """Reference eval layout: one row per candidate (src/reader.py:376-379)."""
+    g = load_golden(name)
+    x = golden_model_inputs(g)
+    B, C = x['cand'].shape
+    x1 = dict(x, cand=x['cand'].reshape(-1, 1), his_ids=x['his_ids'].repeat_interleave(C, 0),
+              his_mask=x['his_mask'].repeat_interleave(C, 0))
+    _, S = run_forward(build_miner(x, 'weighted'), x1)
+    close_fp32(S.reshape(B, C).cpu().numpy(), g['scores_weighted_c1'])
+
+
+@pytest.mark.parametrize('name', MODELS)
+def test_miner_forward_category_bias_and_nan(name):
+    g = load_golden(name)
+    x = golden_model_inputs(g)
+    m = build_miner(x, 'weighted', use_bias=True)
+    I, S = run_forward(m, x, category=x['cand_cat'], his_category=x['his_cat'])
+    close_fp32(S.cpu().numpy(), g['scores_bias'])
+    cc = x['cand_cat'].clone()
+    cc[0, 0] = 0                                           # pad category on a candidate NaNs its whole row
+    _, S = run_forward(m, x, category=cc, his_category=x['his_cat'])
+    S = S.cpu().numpy()
+    assert np.isnan(S[0]).all() and np.isnan(g['scores_bias_padcand'][0]).all()
+    close_fp32(S[1:], g['scores_bias_padcand'][1:])
+
+
+@pytest.mark.parametrize('name', ['model_small', 'model_full'])
+def test_miner_forward_tensor_family(name):
+    """bf16 table -> tcgen05 projections.  Checked against the reference run on the same bf16-valued table."""
+    from miner_b200 import ops, _lib
+    g = load_golden(name)
+    x = golden_model_inputs(g)
+    m = build_miner(x, 'weighted', table_dtype=torch.bfloat16)
+    assert ops.default_math(m.news_encoder.table, m.news_encoder.embed_dim) == _lib.MATH_TENSOR
+    I, S = run_forward(m, x)
+    err = close_norm(S.cpu().numpy(), g['scores_weighted_bf16table'], 1e-3)
+    print(f'{name}: tensor-family normwise score error {err:.2e}')
+    # the fp32 family on the same bf16 table is the tighter check of everything but the two GEMMs
+    w = m._weights(True)
+    his, cand = x['his_ids'].to(DEV), x['cand'].to(DEV)
+    _, S32 = ops.score(m.news_encoder.table, his, x['his_mask'].to(DEV), cand, w, 'weighted', math=_lib.MATH_FP32)
+    close_fp32(S32.cpu().numpy(), g['scores_weighted_bf16table'])
+    for st in ('max', 'mean'):
+        mm = build_miner(x, st, table_dtype=torch.bfloat16)
+        _, Sm = run_forward(mm, x)
+        ref = O.miner_forward(x['table'].to(torch.bfloat16), x['his_ids'], x['his_mask'], x['cand'], x['w_proj'], x['codes'], None, st)[1]
+        close_norm(Sm.cpu().numpy(), ref.numpy(), 1e-3)
+
+
+def test_generic_encoder_path_equals_table_path():
+    """Any nn.Module honouring the NewsEncoder contract drops in: the op-level kernels take its dense outputs."""
+    import miner_b200 as mb
+    g = load_golden('model_small')
+    x = golden_model_inputs(g)
+
+    class Enc(torch.nn.Module):
+        def __init__(s, table):
+            super().__init__()
+            s.table = table
+
+        @property
+        def embed_dim(s):
+            return s.table.shape[1]
+
+        def forward(s, title_encoding, title_attn_mask, sapo_encoding=None, sapo_attn_mask=None):
+            return s.table[title_encoding[:, 0]]
+
+    m = build_miner(x, 'weighted')
+    m.news_encoder = Enc(x['table'].to(DEV))
+    I, S = run_forward(m, x)
+    close_fp32(S.cpu().numpy(), g['scores_weighted'])
+    close_fp32(I.cpu().numpy(), g['interests'])
+
+
+def test_backward_fails_loudly():
+    g = load_golden('model_small')
+    x = golden_model_inputs(g)
+    m = build_miner(x, 'weighted').train()
+    B, C = x['cand'].shape
+    H = x['his_ids'].shape[1]
+    z = torch.zeros(B, C, 1, dtype=torch.long, device=DEV)
+    zh = torch.zeros(B, H, 1, dtype=torch.long, device=DEV)
+    I, S = m(x['cand'].to(DEV)[..., None], z, x['his_ids'].to(DEV)[..., None], zh, x['his_mask'].to(DEV), z, z, zh, zh)
+    assert S.requires_grad
+    with pytest.raises(NotImplementedError):
+        S.sum().backward()
+
+
+# ------------------------------------------------------------------------------------------------ CSR scoring
+def _csr_problem(B, H, N, D, K, Dc, seed, dtype):
+    from miner_b200 import synth
+    table = synth.make_table(N, D, seed).to(dtype)
+    w = synth.make_weights(D, K, Dc, seed)
+    eb = synth.make_eval_batch(B, H, N, seed, mean_cands=12.0, max_cands=70)
+    return table, w, eb
+
+
+@pytest.mark.parametrize('math_name', ['fp32', 'tensor'])
+def test_score_impressions_csr(math_name):
+    import miner_b200 as mb
+    from miner_b200 import _lib
+    dtype = torch.float32 if math_name == 'fp32' else torch.bfloat16
+    B, H, N, D, K, Dc = 300, 50, 5000, 256, 32, 48
+    table, w, eb = _csr_problem(B, H, N, D, K, Dc, 3, dtype)
+    m = mb.Miner(mb.TableNewsEncoder(table.to(DEV)), False, K, Dc, 'weighted', 0.2).to(DEV).eval()
+    with torch.no_grad():
+        m.poly_attn.linear.weight.copy_(w.w_proj)
+        m.poly_attn.context_codes.copy_(w.context_codes)
+        m.target_aware_attn.linear.weight.copy_(w.w_target)
+    s = m.score_impressions(eb.his_ids.to(DEV), eb.his_mask.to(DEV), eb.cand_ids.to(DEV), eb.offsets.to(DEV), chunk=128)
+    ref = O.miner_forward_csr(table, eb.his_ids, eb.his_mask, eb.cand_ids, eb.offsets.numpy(), w.w_proj, w.context_codes, w.w_target)
+    if math_name == 'fp32':
+        close_fp32(s.cpu().numpy(), ref.numpy())
+    else:
+        close_norm(s.cpu().numpy(), ref.numpy(), 1e-3)
+    # chunking is invisible
+    s2 = m.score_impressions(eb.his_ids.to(DEV), eb.his_mask.to(DEV), eb.cand_ids.to(DEV), eb.offsets.to(DEV), chunk=77)
+    assert torch.equal(s, s2)
+    # int32 ids give the same bits
+    s3 = m.score_impressions(eb.his_ids.int().to(DEV), eb.his_mask.to(DEV), eb.cand_ids.int().to(DEV), eb.offsets.to(DEV), chunk=128)
+    assert torch.equal(s, s3)
+
+
+# ------------------------------------------------------------------------------------------------ tcgen05 GEMM alone
+@pytest.mark.parametrize('M,N,K', [(128, 256, 64), (128, 16, 64), (300, 200, 768), (1000, 768, 768), (77, 48, 256), (4096, 208, 768)])
+@pytest.mark.parametrize('epi', [0, 1, 2])
+def test_tc_gemm(M, N, K, epi):
+    from miner_b200 import ops
+    g = torch.Generator().manual_seed(M + N + K)
+    a = (torch.randn(M, K, generator=g) * 0.5).to(torch.bfloat16)
+    b = (torch.randn(N, K, generator=g) * (1.0 / K ** 0.5)).to(torch.bfloat16)
+    ref = a.float() @ b.float().T
+    ref = {0: lambda t: t, 1: torch.tanh, 2: torch.nn.functional.gelu}[epi](ref)
+    c, cb = ops.tc_gemm(a.to(DEV), b.to(DEV), epilogue=epi, want_bf16=True)
+    close_norm(c.cpu().numpy(), ref.numpy(), 2e-5)
+    assert torch.equal(cb.cpu(), c.cpu().to(torch.bfloat16))
+
+
+def test_tc_gemm_gathered_rows():
+    from miner_b200 import ops
+    g = torch.Generator().manual_seed(9)
+    table = (torch.randn(5000, 768, generator=g) * 0.2).to(torch.bfloat16)
+    w = (torch.randn(200, 768, generator=g) * 0.03).to(torch.bfloat16)
+    ids = torch.randint(0, 5000, (1234,), generator=g)
+    ids[7] = 5000                                          # out of range -> zero row
+    c = ops.tc_gemm(table.to(DEV), w.to(DEV), epilogue=1, a_ids=ids.to(DEV))
+    a = table[ids.clamp(max=4999)].float()
+    a[7] = 0
+    close_norm(c.cpu().numpy(), torch.tanh(a @ w.float().T).numpy(), 2e-5)
+
+
+# ------------------------------------------------------------------------------------------------ ranking metrics (a7..a12)
+def test_rank_metrics_match_reference_per_impression():
+    from miner_b200 import ops
+    g = load_golden('metrics')
+    logits = torch.from_numpy(g['logits']).to(DEV)
+    labels = torch.from_numpy(g['labels']).to(torch.int8).to(DEV)
+    offs = torch.from_numpy(g['offsets']).to(DEV)
+    names = ops.metric_names((5, 10))
+    # (1) given probabilities (no transform): pure comparisons -> identical ranking, float64 metric arithmetic
+    probs32 = torch.from_numpy(g['probs']).float().to(DEV)
+    partials, per = ops.rank_metrics_raw(probs32, labels, offs, 'none', (5, 10), per_impression=True)
+    per = per.cpu().numpy()
+    for i, n in enumerate(names):
+        np.testing.assert_allclose(per[:, i], g[f'per_{n}'], rtol=1e-12, atol=0, err_msg=n)
+    p = partials.cpu().numpy().reshape(-1, 2)
+    for i, n in enumerate(names):
+        assert abs(p[i, 0] / p[i, 1] - float(g[f'agg_{n}'])) < 1e-12, n
+    # (2) sigmoid inside the kernel (SlowEvaluator): same per-impression values on this tie-free data
+    res = ops.rank_metrics(logits, labels, offs, 'sigmoid', (5, 10))
+    for n in names:
+        assert abs(res[n] - float(g[f'agg_{n}'])) < 1e-9, n
+
+
+def test_rank_metrics_ties_nan_and_long_impressions():
+    from miner_b200 import ops
+    g = load_golden('metrics')
+    # ties + an impression without positives + one longer than the shared-memory staging capacity
+    rng = np.random.default_rng(3)
+    long_n = 1500
+    ys = [g['tie_y'], np.array([0, 1, 0, 0, 1, 0]), np.zeros(4, dtype=np.int64), (rng.random(long_n) < 0.1).astype(np.int64),
+          g['ka_y']]
+    ss = [g['tie_s'], np.full(6, .3), np.array([.1, .2, .3, .4]), np.round(rng.random(long_n), 2), g['ka_s']]
+    offs = np.concatenate([[0], np.cumsum([len(y) for y in ys])])
+    y = np.concatenate(ys)
+    s = np.concatenate(ss).astype(np.float32)
+    _, per = ops.rank_metrics_raw(torch.from_numpy(s).to(DEV), torch.from_numpy(y).to(torch.int8).to(DEV),
+                                  torch.from_numpy(offs).to(DEV), 'none', (1, 2, 5, 10), per_impression=True)
+    per = per.cpu().numpy()
+    ref = O.per_impression_metrics(y, s.astype(np.float64), offs, ks=(1, 2, 5, 10))
+    from miner_b200.ops import metric_names
+    for i, n in enumerate(metric_names((1, 2, 5, 10))):
+        np.testing.assert_allclose(per[:, i], ref[n], rtol=1e-12, atol=0, equal_nan=True, err_msg=n)
+    assert np.isnan(per[2, 0]) and np.isnan(per[2, 1]) and np.isnan(per[2, 2])       # no positives: auc, mrr, ndcg NaN
+    assert per[4, 1] == 0.625 and per[4, 0] == 0.75                                   # known answers
+    agg = ops.rank_metrics(torch.from_numpy(s).to(DEV), torch.from_numpy(y).to(torch.int8).to(DEV), torch.from_numpy(offs).to(DEV),
+                           'none', (1, 2, 5, 10))
+    for n in agg:
+        assert abs(agg[n] - np.nanmean(ref[n])) < 1e-12
+
+
+def test_slow_and_fast_evaluators():
+    from types import SimpleNamespace
+    import miner_b200 as mb
+    g = load_golden('metrics')
+    metrics = ['auc', 'group_auc', 'mrr', 'ndcg@5', 'ndcg@10', 'hit@5', 'hit@10']
+    samples = [SimpleNamespace(impression=SimpleNamespace(impression_id=int(i), label=[int(l)])) for i, l in zip(g['imp_ids'], g['labels'])]
+    ev = mb.SlowEvaluator(SimpleNamespace(samples=samples))
+    lt, it = torch.from_numpy(g['logits']).to(DEV), torch.from_numpy(g['imp_ids']).to(DEV)
+    for s in range(0, lt.numel(), 32):                      # eval_batch_size 32, as the shipped configs
+        ev.eval_batch(lt[s:s + 32].reshape(-1, 1), it[s:s + 32])
+    sc = ev.compute_scores(metrics, save_result=False)
+    for m in metrics:
+        assert abs(sc[m] - float(g[f'agg_{m}'])) < 1e-7, (m, sc[m], float(g[f'agg_{m}']))
+    fsamples = [SimpleNamespace(impression=SimpleNamespace(impression_id=i, label=[int(v) for v in row])) for i, row in enumerate(g['fast_labels'])]
+    fev = mb.FastEvaluator(SimpleNamespace(samples=fsamples))
+    fl = torch.from_numpy(g['fast_logits']).to(DEV)
+    fev.eval_batch(fl[:40], None)
+    fev.eval_batch(fl[40:], None)
+    fs = fev.compute_scores(metrics, save_result=False)
+    for m in metrics:
+        assert abs(fs[m] - float(g[f'fast_{m}'])) < 1e-6, (m, fs[m], float(g[f'fast_{m}']))
+
+
+# ------------------------------------------------------------------------------------------------ losses (a13, a14)
+@pytest.mark.parametrize('name', MODELS)
+def test_losses(name):
+    import torch.nn as nn
+    import miner_b200 as mb
+    g = load_golden(name)
+    I = torch.from_numpy(g['interests']).to(DEV)
+    S = torch.from_numpy(g['scores_weighted']).to(DEV)
+    loss = mb.Loss(nn.CrossEntropyLoss(reduction='mean')).compute(I, S, torch.from_numpy(g['labels']).to(DEV))
+    assert abs(loss.item() - float(g['loss'])) < 1e-4 * max(1.0, abs(float(g['loss'])))
+    ev = mb.Loss.compute_eval_loss(I, S, torch.from_numpy(g['eval_labels']).to(DEV))
+    assert abs(ev - float(g['eval_loss'])) < 1e-4 * max(1.0, abs(float(g['eval_loss'])))
+    with pytest.raises(NotImplementedError):
+        mb.Loss(nn.CrossEntropyLoss(reduction='sum'))
+
+
+# ------------------------------------------------------------------------------------------------ size-independent properties at scale
+def test_properties_at_scale():
+    """64k impressions x ~20 candidates, full dims: properties that need no oracle run."""
+    import miner_b200 as mb
+    from miner_b200 import synth, ops, _lib
+    B, H, N, D, K, Dc = 65536, 50, 100000, 768, 32, 200
+    table = synth.make_table(N, D, 36, torch.bfloat16).to(DEV)
+    w = synth.make_weights(D, K, Dc, 36)
+    eb = synth.make_eval_batch(B, H, N, 36)
+    m = mb.Miner(mb.TableNewsEncoder(table), False, K, Dc, 'weighted', 0.2).to(DEV).eval()
+    with torch.no_grad():
+        m.poly_attn.linear.weight.copy_(w.w_proj)
+        m.poly_attn.context_codes.copy_(w.context_codes)
+        m.target_aware_attn.linear.weight.copy_(w.w_target)
+    his, msk, cand, offs = eb.his_ids.to(DEV), eb.his_mask.to(DEV), eb.cand_ids.to(DEV), eb.offsets.to(DEV)
+    s = m.score_impressions(his, msk, cand, offs)
+    assert torch.isfinite(s).all()
+    # (1) a sample of impressions against the oracle
+    pick = torch.arange(0, B, B // 64)[:64]
+    sub_offs = [0]
+    sub_c = []
+    for i in pick.tolist():
+        a, b = int(eb.offsets[i]), int(eb.offsets[i + 1])
+        sub_c.append(eb.cand_ids[a:b])
+        sub_offs.append(sub_offs[-1] + b - a)
+    ref = O.miner_forward_csr(table.cpu(), eb.his_ids[pick], eb.his_mask[pick], torch.cat(sub_c), np.array(sub_offs), w.w_proj,
+                              w.context_codes, w.w_target)
+    got = torch.cat([s[int(eb.offsets[i]):int(eb.offsets[i + 1])] for i in pick.tolist()]).cpu()
+    close_norm(got.numpy(), ref.numpy(), 1e-3)
+    # (2) tensor family vs fp32 family on the whole block
+    s32 = m.score_impressions(his, msk, cand, offs, math=_lib.MATH_FP32)
+    close_norm(s.cpu().numpy(), s32.cpu().numpy(), 1e-3)
+    # (3) reversing the candidates inside every impression permutes the scores the same way (fp32 family: bit-exact)
+    T = cand.numel()
+    seg = torch.repeat_interleave(torch.arange(B, device=DEV), offs[1:] - offs[:-1])
+    rev = offs[seg] + (offs[seg + 1] - 1 - torch.arange(T, device=DEV))
+    s_rev = m.score_impressions(his, msk, cand[rev], offs, math=_lib.MATH_FP32)
+    assert torch.equal(s_rev, s32[rev])
+    # (4) metrics: invariant to the order of impressions; hit@k monotone in k; values inside [0,1]
+    labels = eb.labels.to(DEV)
+    r = ops.rank_metrics(s, labels, offs, 'sigmoid', (5, 10))
+    assert all(0.0 <= v <= 1.0 for v in r.values()) and r['hit@5'] <= r['hit@10'] and r['ndcg@5'] <= r['ndcg@10'] + 1e-12
+    half = B // 2
+    o1, o2 = offs[:half + 1], offs[half:] - offs[half]
+    p1, _ = ops.rank_metrics_raw(s[:int(offs[half])], labels[:int(offs[half])], o1, 'sigmoid', (5, 10))
+    p2, _ = ops.rank_metrics_raw(s[int(offs[half]):], labels[int(offs[half]):], o2, 'sigmoid', (5, 10))
+    tot = (p1 + p2).cpu().view(-1, 2)
+    for i, n in enumerate(ops.metric_names((5, 10))):
+        assert abs(float(tot[i, 0] / tot[i, 1]) - r[n]) < 1e-12          # sharded partials add up (what ranks all-reduce)
