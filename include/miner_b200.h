@@ -133,6 +133,21 @@ int miner_cast_f32_to_bf16(const float* src, void* dst, int64_t n, void* stream)
 int miner_tc_gemm(const void* a_bf16, const void* a_ids, int id_dtype, int64_t a_rows_in_table, const void* b_bf16,
                   float* c, void* c_bf16, int64_t M, int64_t N, int64_t K, int epilogue, void* stream);
 
+/* The two kernels of the fused tensor-core path on their own (tests / profiling).
+ *   miner_hist_interests_fwd: PolyAttention.forward (model.py:159-185) straight from a bf16 table: gathers table[his_ids],
+ *      projects on tcgen05, softmax over the history, weighted sum on tcgen05.  Writes the interests split as two bf16 arrays
+ *      i_hi + i_lo (B*K, D) and, if out_interests != NULL, as fp32 (B,K,D).  Needs H <= 128, K in {8,16,32}, Dc <= 256, D % 64 == 0.
+ *   miner_cand_score_fwd: matching scores + TargetAwareAttention (model.py:127,200-216, score_type 'weighted') from
+ *      i_hi / i_lo and table[cand_ids]; CSR offsets (B+1) or NULL for dense C per row.  out_scores (T) fp32. */
+size_t miner_hist_interests_workspace_bytes(int64_t Dc);
+int miner_hist_interests_fwd(const void* table_bf16, int64_t n_rows, const void* his_ids, int id_dtype, const uint8_t* his_mask,
+                             const float* bias_mean, const void* w_proj_bf16, const float* codes,
+                             int64_t B, int64_t H, int64_t K, int64_t Dc, int64_t D,
+                             void* i_hi, void* i_lo, float* out_interests, void* workspace, size_t workspace_bytes, void* stream);
+int miner_cand_score_fwd(const void* i_hi, const void* i_lo, const void* w_target_bf16, const void* table_bf16, int64_t n_rows,
+                         const void* cand_ids, int id_dtype, const int64_t* cand_offsets,
+                         int64_t B, int64_t C, int64_t K, int64_t D, float* out_scores, void* stream);
+
 /* ---- (a7..a12) segmented per-impression ranking metrics: replaces SlowEvaluator/FastEvaluator +
  *      compute_scores (evaluation.py:36-84,87-175) and compute_mrr/dcg/ndcg_score, is_hit (:177-249).
  *      scores (T) fp32 logits; labels (T) int8; offsets (B+1) int64; transform: 0 none, 1 sigmoid (SlowEvaluator,

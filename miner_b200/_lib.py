@@ -29,7 +29,7 @@ EXPORTS = [
     'miner_poly_attn_workspace_bytes', 'miner_poly_attn_fwd', 'miner_target_score_workspace_bytes',
     'miner_target_score_fwd', 'miner_score_workspace_bytes', 'miner_score_fwd', 'miner_cast_f32_to_bf16',
     'miner_tc_gemm', 'miner_rank_metrics_workspace_bytes', 'miner_rank_metrics', 'miner_loss_workspace_bytes',
-    'miner_loss_fwd',
+    'miner_loss_fwd', 'miner_hist_interests_workspace_bytes', 'miner_hist_interests_fwd', 'miner_cand_score_fwd',
 ]
 
 
@@ -81,6 +81,10 @@ def _declare(lib: C.CDLL) -> None:
     lib.miner_loss_workspace_bytes.argtypes = [i64, i64]
     lib.miner_loss_workspace_bytes.restype = sz
     lib.miner_loss_fwd.argtypes = [vp, vp, vp, i64, i64, i64, i64, i32, vp, vp, sz, vp]
+    lib.miner_hist_interests_workspace_bytes.argtypes = [i64]
+    lib.miner_hist_interests_workspace_bytes.restype = sz
+    lib.miner_hist_interests_fwd.argtypes = [vp, i64, vp, i32, vp, vp, vp, vp, i64, i64, i64, i64, i64, vp, vp, vp, vp, sz, vp]
+    lib.miner_cand_score_fwd.argtypes = [vp, vp, vp, vp, i64, vp, i32, vp, i64, i64, i64, i64, vp, vp]
 
 
 def load(build_if_missing: bool = True) -> C.CDLL:

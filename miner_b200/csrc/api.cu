@@ -5,6 +5,7 @@
 
 #include "common.cuh"
 #include "tc/tc_gemm.cuh"
+#include "tc/fused.cuh"
 
 namespace miner {
 
@@ -34,12 +35,33 @@ int sm_count() {
 
 struct ScoreWs {
   size_t proj, interests, interests_bf16, target_proj, total;
+  // fused tensor-core path (hist_kernel -> cand_kernel)
+  bool fused;
+  size_t i_hi, i_lo, codes_t;
 };
+
+// The fused tcgen05 path covers the tensor family for the shapes the two kernels support; everything else (and the
+// fp32 family) runs the 4-kernel pipeline.
+static bool use_fused(const miner_score_params* p) {
+  return p->math == MINER_MATH_TENSOR && hist_kernel_supported(p->H, p->K, p->Dc, p->D) &&
+         (p->score_type != MINER_SCORE_WEIGHTED || cand_kernel_supported(p->K, p->D));
+}
 
 static ScoreWs score_ws_layout(const miner_score_params* p, int64_t chunk) {
   ScoreWs w{};
   size_t off = 0;
   auto take = [&](size_t bytes) { size_t o = off; off += align_up(bytes, 256); return o; };
+  w.fused = use_fused(p);
+  if (w.fused) {
+    const size_t rows = (size_t)chunk * p->K;
+    w.i_hi = take(2 * rows * p->D);
+    w.i_lo = take(2 * rows * p->D);
+    w.codes_t = take(hist_kernel_ws_bytes(p->Dc));
+    // 'max' / 'mean' aggregate fp32 interests with the CUDA-core kernel
+    w.interests = take((p->out_interests || p->score_type == MINER_SCORE_WEIGHTED) ? 0 : sizeof(float) * rows * p->D);
+    w.total = off;
+    return w;
+  }
   w.proj = take(sizeof(float) * chunk * p->H * p->Dc);
   w.interests = take(p->out_interests ? 0 : sizeof(float) * chunk * p->K * p->D);
   const bool weighted = p->score_type == MINER_SCORE_WEIGHTED;
@@ -196,6 +218,28 @@ extern "C" int miner_score_fwd(const miner_score_params* p, int64_t chunk, void*
     const float* bias = p->bias_mean ? p->bias_mean + b0 * p->H : nullptr;
     float* interests = p->out_interests ? p->out_interests + b0 * p->K * p->D : reinterpret_cast<float*>(ws + w.interests);
     const int stages = p->stage_mask ? p->stage_mask : 15;
+    if (w.fused) {
+      float* i_f32 = p->out_interests ? interests : (weighted ? nullptr : interests);
+      // steps 1+2: interests straight from the table (model.py:104-111,159-185)
+      if (stages & 1) {
+        rc = launch_hist_kernel(p->table, p->n_rows, his, p->id_dtype, msk, bias, p->w_proj_bf16, p->codes, nb, p->H, p->K, p->Dc, p->D,
+                                ws + w.i_hi, ws + w.i_lo, i_f32, reinterpret_cast<float*>(ws + w.codes_t), st);
+        if (rc) return rc;
+      }
+      if (!(stages & 8)) continue;
+      // steps 3+4: matching scores, target-aware attention, per-candidate score (model.py:127-136,200-216)
+      const void* cids = p->cand_offsets ? p->cand_ids : static_cast<const void*>(static_cast<const char*>(p->cand_ids) + b0 * p->C * id_sz);
+      const int64_t* coffs = p->cand_offsets ? p->cand_offsets + b0 : nullptr;
+      float* outs = p->cand_offsets ? p->out_scores : p->out_scores + b0 * p->C;
+      if (weighted)
+        rc = launch_cand_kernel(ws + w.i_hi, ws + w.i_lo, p->w_target_bf16, p->table, p->n_rows, cids, p->id_dtype, coffs, nb, p->C, p->K,
+                                p->D, outs, st);
+      else
+        rc = launch_target_score(i_f32, nullptr, nullptr, nullptr, p->table, p->table_dtype, cids, p->id_dtype, p->n_rows, coffs, nb,
+                                 p->cand_offsets ? 0 : p->C, p->K, p->D, p->score_type, outs, st);
+      if (rc) return rc;
+      continue;
+    }
     // step 1+2a: proj = tanh(table[his_ids] Wp^T)     (model.py:104-111,171)
     if (!(stages & 1)) rc = MINER_OK;
     else if (tensor)
@@ -227,4 +271,33 @@ extern "C" int miner_score_fwd(const miner_score_params* p, int64_t chunk, void*
     if (rc) return rc;
   }
   return MINER_OK;
+}
+
+extern "C" size_t miner_hist_interests_workspace_bytes(int64_t Dc) { return hist_kernel_ws_bytes(Dc); }
+
+extern "C" int miner_hist_interests_fwd(const void* table, int64_t n_rows, const void* his_ids, int id_dtype, const uint8_t* his_mask,
+                                        const float* bias_mean, const void* w_proj_bf16, const float* codes, int64_t B, int64_t H,
+                                        int64_t K, int64_t Dc, int64_t D, void* i_hi, void* i_lo, float* out_interests,
+                                        void* workspace, size_t workspace_bytes, void* stream) {
+  MINER_CHECK_ARG(B >= 0 && n_rows > 0, "hist_interests: bad sizes");
+  if (B == 0) return MINER_OK;
+  MINER_CHECK_ARG(table && his_ids && his_mask && w_proj_bf16 && codes && i_hi && i_lo, "hist_interests: null pointer");
+  MINER_CHECK_ARG(id_dtype == MINER_I32 || id_dtype == MINER_I64, "hist_interests: id dtype must be int32 or int64");
+  if (!workspace || workspace_bytes < hist_kernel_ws_bytes(Dc)) {
+    set_error("hist_interests: workspace too small (%zu bytes needed)", hist_kernel_ws_bytes(Dc));
+    return MINER_ERR_WORKSPACE;
+  }
+  return launch_hist_kernel(table, n_rows, his_ids, id_dtype, his_mask, bias_mean, w_proj_bf16, codes, B, H, K, Dc, D, i_hi, i_lo,
+                            out_interests, static_cast<float*>(workspace), static_cast<cudaStream_t>(stream));
+}
+
+extern "C" int miner_cand_score_fwd(const void* i_hi, const void* i_lo, const void* w_target_bf16, const void* table, int64_t n_rows,
+                                    const void* cand_ids, int id_dtype, const int64_t* cand_offsets, int64_t B, int64_t C, int64_t K,
+                                    int64_t D, float* out_scores, void* stream) {
+  MINER_CHECK_ARG(B >= 0 && n_rows > 0 && (cand_offsets || C > 0), "cand_score: bad sizes");
+  if (B == 0) return MINER_OK;
+  MINER_CHECK_ARG(i_hi && i_lo && w_target_bf16 && table && cand_ids && out_scores, "cand_score: null pointer");
+  MINER_CHECK_ARG(id_dtype == MINER_I32 || id_dtype == MINER_I64, "cand_score: id dtype must be int32 or int64");
+  return launch_cand_kernel(i_hi, i_lo, w_target_bf16, table, n_rows, cand_ids, id_dtype, cand_offsets, B, C, K, D, out_scores,
+                            static_cast<cudaStream_t>(stream));
 }

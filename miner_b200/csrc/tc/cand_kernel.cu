@@ -1,0 +1,395 @@
+// Candidate side of the fused tensor-core scoring path (sm_100a: tcgen05 + TMEM + TMA), score_type = 'weighted':
+//
+//   P      = gelu(I Wt^T)                          TargetAwareAttention.linear + gelu   (reference src/model/model.py:212)
+//   a[c,k] = cand[c,:] . P[k,:]                    attention logits                      (model.py:213)
+//   m[c,k] = cand[c,:] . I[k,:]                    matching scores                       (model.py:127)
+//   score[c] = sum_k softmax_k(a[c,:])[k] m[c,k]                                         (model.py:213-214)
+//
+// One persistent CTA per SM works on groups of 128 interest rows = IPG impressions x K context codes (K in {8,16,32}).
+// Interests arrive from the history kernel split as I = I_hi + I_lo (two bf16 arrays): I_hi feeds the projection GEMM,
+// I_hi + I_lo together give the matching scores fp32-level accuracy on the tensor cores.  Per group:
+//   - the projection runs in N-chunks of 192 output features; each chunk's K-loop streams I_hi and Wt k-blocks (TMA,
+//     SWIZZLE_128B) through a 3-stage ring into a 128 x 192 fp32 accumulator in tensor memory;
+//   - during chunk 0 the same I_hi k-block (plus the I_lo k-block) is also multiplied with the candidate rows of the group
+//     (gathered from the embedding table by cp.async, k-block by k-block) into the matching-score accumulator m[(i,k), c];
+//   - the 8 epilogue warps turn each finished chunk into bf16 gelu(P) tiles in shared memory, 64 features at a time, and
+//     the MMA warp multiplies them with the matching candidate feature block into the attention accumulator a[(i,k), c];
+//   - finally rows (i, 0..K-1) of a and m sit in K adjacent TMEM lanes = K lanes of one warp: the softmax over K and the
+//     weighted sum are warp-shuffle reductions, one score per candidate column.
+// Candidates of other impressions of the group produce cross terms in a and m that are simply never read (block-diagonal use).
+// Groups with more than 128 candidates run several passes of 128 candidate columns.
+#include <cuda.h>
+
+#include "fused.cuh"
+#include "umma.cuh"
+
+namespace miner {
+
+namespace {
+
+constexpr int CM = 128;                 // interest rows per group (UMMA M)
+constexpr int CKB = 64;                 // k-block (one 128-byte swizzle row of bf16)
+constexpr int NCH = 192;                // projection N-chunk (fp32 accumulator columns)
+constexpr int CST = 3;                  // main ring depth
+constexpr int CA_BYTES = CM * CKB * 2;  // 16 KB  I k-block
+constexpr int CB_BYTES = NCH * CKB * 2; // 24 KB  Wt k-block
+constexpr int CMAXC = 128;              // candidate columns per pass
+constexpr int CC_BYTES = CMAXC * CKB * 2;
+constexpr int RING2 = 2;                // depth of the I_lo / P-tile / candidate rings
+constexpr int C_THREADS = 14 * 32;      // 4 gather warps, TMA warp, MMA warp, 8 epilogue warps
+constexpr int C_EPI_THREADS = 256;
+constexpr int COL_P = 0, COL_A = NCH, COL_M = NCH + CMAXC;   // TMEM columns: 192 + 128 + 128 = 448 of 512
+constexpr int C_SMEM = 1024 + CST * (CA_BYTES + CB_BYTES) + RING2 * (CA_BYTES + CA_BYTES + CC_BYTES) + 512;
+
+struct CBarriers {
+  uint64_t full[CST], empty[CST];
+  uint64_t lo_full[RING2], lo_empty[RING2];
+  uint64_t c_full[RING2], c_empty[RING2];
+  uint64_t pb_full[RING2], pb_empty[RING2];
+  uint64_t p_full, p_empty, fin_full, fin_empty;
+  uint32_t tmem_base;
+};
+
+struct CandArgs {
+  const uint16_t* table; int64_t n_rows;
+  const void* cand_ids; int id_dtype; const int64_t* cand_offsets;
+  int64_t B, C;
+  int K, D;
+  float* out;
+};
+
+__device__ __forceinline__ int64_t cand_off(const CandArgs& a, int64_t i) {
+  if (i > a.B) i = a.B;
+  return a.cand_offsets ? a.cand_offsets[i] : i * a.C;
+}
+
+// erf via Abramowitz-Stegun 7.1.26 (|abs err| <= 1.5e-7): gelu(x) = 0.5 x (1 + erf(x / sqrt 2)).  P is rounded to bf16
+// right after, so this is far below what survives.
+__device__ __forceinline__ float gelu_fast(float x) {
+  const float z = fabsf(x) * 0.70710678118654752440f;
+  const float t = __frcp_rn(fmaf(0.3275911f, z, 1.0f));
+  float p = fmaf(t, 1.061405429f, -1.453152027f);
+  p = fmaf(p, t, 1.421413741f);
+  p = fmaf(p, t, -0.284496736f);
+  p = fmaf(p, t, 0.254829592f);
+  p *= t;
+  const float e = exp2f(-1.4426950408889634f * z * z);
+  const float erf_abs = fmaf(-p, e, 1.0f);
+  return 0.5f * x * (1.0f + copysignf(erf_abs, x));
+}
+
+__device__ __forceinline__ uint32_t pack_bf16x2(float lo, float hi) {
+  __nv_bfloat162 v = __floats2bfloat162_rn(lo, hi);
+  return *reinterpret_cast<uint32_t*>(&v);
+}
+
+template <int W>
+__device__ __forceinline__ float group_max(float v) {
+#pragma unroll
+  for (int o = W / 2; o > 0; o >>= 1) v = fmaxf(v, __shfl_xor_sync(0xffffffffu, v, o));
+  return v;
+}
+template <int W>
+__device__ __forceinline__ float group_sum(float v) {
+#pragma unroll
+  for (int o = W / 2; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
+  return v;
+}
+
+template <int K>
+__global__ void __launch_bounds__(C_THREADS, 1)
+cand_kernel(const __grid_constant__ CUtensorMap tmap_ihi, const __grid_constant__ CUtensorMap tmap_ilo,
+            const __grid_constant__ CUtensorMap tmap_wt, const CandArgs args, int n_groups) {
+  constexpr int IPG = CM / K;
+  extern __shared__ uint8_t smem_raw[];
+  uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~static_cast<uintptr_t>(1023));
+  uint8_t* st_a = smem;                                   // [CST][16 KB]
+  uint8_t* st_b = st_a + CST * CA_BYTES;                  // [CST][24 KB]
+  uint8_t* lo_t = st_b + CST * CB_BYTES;                  // [2][16 KB]
+  uint8_t* pb_t = lo_t + RING2 * CA_BYTES;                // [2][16 KB]
+  uint8_t* cd_t = pb_t + RING2 * CA_BYTES;                // [2][16 KB]
+  CBarriers* bars = reinterpret_cast<CBarriers*>(cd_t + RING2 * CC_BYTES);
+
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int D = args.D;
+  const int KB = D / CKB;
+  const int n_chunks = (D + NCH - 1) / NCH;
+
+  if (threadIdx.x == 0) {
+    for (int s = 0; s < CST; ++s) { tc::mbar_init(&bars->full[s], 1); tc::mbar_init(&bars->empty[s], 1); }
+    for (int s = 0; s < RING2; ++s) {
+      tc::mbar_init(&bars->lo_full[s], 1);  tc::mbar_init(&bars->lo_empty[s], 1);
+      tc::mbar_init(&bars->c_full[s], 128); tc::mbar_init(&bars->c_empty[s], 1);
+      tc::mbar_init(&bars->pb_full[s], C_EPI_THREADS); tc::mbar_init(&bars->pb_empty[s], 1);
+    }
+    tc::mbar_init(&bars->p_full, 1);   tc::mbar_init(&bars->p_empty, C_EPI_THREADS);
+    tc::mbar_init(&bars->fin_full, 1); tc::mbar_init(&bars->fin_empty, C_EPI_THREADS);
+    tc::fence_barrier_init();
+  }
+  if (warp == 4 && lane == 0) { tc::tma_prefetch_desc(&tmap_ihi); tc::tma_prefetch_desc(&tmap_ilo); tc::tma_prefetch_desc(&tmap_wt); }
+  if (warp == 5) { tc::tmem_alloc(&bars->tmem_base, 512); tc::tmem_relinquish(); }
+  tc::tcgen05_fence_before();
+  __syncthreads();
+  tc::tcgen05_fence_after();
+  const uint32_t tmem = bars->tmem_base;
+
+  if (warp < 4) {
+    // ------------------------------------------------------------------ candidate gather (cp.async, 16 B per request)
+    const int chunk = lane & 7;
+    uint32_t issued = 0, signalled = 0;
+    for (int g = blockIdx.x; g < n_groups; g += gridDim.x) {
+      const int64_t c0 = cand_off(args, static_cast<int64_t>(g) * IPG), c1 = cand_off(args, static_cast<int64_t>(g + 1) * IPG);
+      for (int64_t pc0 = c0; pc0 < c1; pc0 += CMAXC) {
+        const int nc = static_cast<int>(c1 - pc0 < CMAXC ? c1 - pc0 : CMAXC);
+        const uint16_t* src[8];
+        uint32_t nbytes[8], dst_off[8];
+#pragma unroll
+        for (int j = 0; j < 8; ++j) {
+          const int r = warp * 32 + j * 4 + (lane >> 3);
+          bool ok = r < nc;
+          int64_t row = 0;
+          if (ok) {
+            row = load_id(args.cand_ids, pc0 + r, args.id_dtype);
+            if (row < 0 || row >= args.n_rows) { ok = false; row = 0; }     // out-of-range id: zero row (gather semantics)
+          }
+          src[j] = args.table + row * D + chunk * 8;
+          nbytes[j] = ok ? 16u : 0u;
+          dst_off[j] = tc::sw128_offset(r, chunk);
+        }
+        // feature blocks in the order the MMA warp consumes them: all KB during chunk 0 (matching scores), then the
+        // blocks of each projection chunk (attention logits)
+        for (int n = 0; n < n_chunks; ++n) {
+          const int first = n == 0 ? 0 : n * (NCH / CKB);
+          const int nn = (D - n * NCH < NCH ? D - n * NCH : NCH) / CKB;
+          const int count = n == 0 ? KB + nn : nn;
+          for (int t = 0; t < count; ++t) {
+            const int fb = (n == 0) ? (t < KB ? t : t - KB) : first + t;
+            const uint32_t s = issued % RING2, ph = (issued / RING2) & 1;
+            tc::mbar_wait(&bars->c_empty[s], ph ^ 1);
+            const uint32_t base = tc::smem_u32(cd_t + s * CC_BYTES);
+#pragma unroll
+            for (int j = 0; j < 8; ++j) tc::cp_async_16(base + dst_off[j], src[j] + fb * CKB, nbytes[j]);
+            tc::cp_async_commit();
+            ++issued;
+            if (issued - signalled > 1) {
+              tc::cp_async_wait<1>();
+              tc::fence_proxy_async_smem();
+              tc::mbar_arrive(&bars->c_full[signalled % RING2]);
+              ++signalled;
+            }
+          }
+        }
+      }
+    }
+    tc::cp_async_wait<0>();
+    tc::fence_proxy_async_smem();
+    while (signalled < issued) { tc::mbar_arrive(&bars->c_full[signalled % RING2]); ++signalled; }
+  } else if (warp == 4) {
+    // ------------------------------------------------------------------ TMA producer: I_hi / Wt k-blocks, I_lo in chunk 0
+    if (lane == 0) {
+      uint32_t it = 0, lo_it = 0;
+      for (int g = blockIdx.x; g < n_groups; g += gridDim.x) {
+        const int64_t c0 = cand_off(args, static_cast<int64_t>(g) * IPG), c1 = cand_off(args, static_cast<int64_t>(g + 1) * IPG);
+        for (int64_t pc0 = c0; pc0 < c1; pc0 += CMAXC) {
+          for (int n = 0; n < n_chunks; ++n) {
+            for (int kb = 0; kb < KB; ++kb, ++it) {
+              const uint32_t s = it % CST, ph = (it / CST) & 1;
+              tc::mbar_wait(&bars->empty[s], ph ^ 1);
+              tc::mbar_arrive_expect_tx(&bars->full[s], CA_BYTES + CB_BYTES);
+              tc::tma_load_2d(&tmap_ihi, &bars->full[s], tc::smem_u32(st_a + s * CA_BYTES), kb * CKB, g * CM);
+              tc::tma_load_2d(&tmap_wt, &bars->full[s], tc::smem_u32(st_b + s * CB_BYTES), kb * CKB, n * NCH);
+              if (n == 0) {
+                const uint32_t ls = lo_it % RING2, lph = (lo_it / RING2) & 1;
+                tc::mbar_wait(&bars->lo_empty[ls], lph ^ 1);
+                tc::mbar_arrive_expect_tx(&bars->lo_full[ls], CA_BYTES);
+                tc::tma_load_2d(&tmap_ilo, &bars->lo_full[ls], tc::smem_u32(lo_t + ls * CA_BYTES), kb * CKB, g * CM);
+                ++lo_it;
+              }
+            }
+          }
+        }
+      }
+    }
+  } else if (warp == 5) {
+    // ------------------------------------------------------------------ MMA issuer
+    if (lane == 0) {
+      uint32_t it = 0, lo_it = 0, c_it = 0, pb_it = 0, ch_it = 0, grp_it = 0;
+      for (int g = blockIdx.x; g < n_groups; g += gridDim.x) {
+        const int64_t c0 = cand_off(args, static_cast<int64_t>(g) * IPG), c1 = cand_off(args, static_cast<int64_t>(g + 1) * IPG);
+        for (int64_t pc0 = c0; pc0 < c1; pc0 += CMAXC, ++grp_it) {
+          const int nc = static_cast<int>(c1 - pc0 < CMAXC ? c1 - pc0 : CMAXC);
+          const int nc16 = nc <= 16 ? 16 : (nc + 15) & ~15;
+          const uint32_t idesc_c = tc::make_idesc_bf16_f32(CM, nc16);
+          tc::mbar_wait(&bars->fin_empty, (grp_it & 1) ^ 1);        // previous pass's scores have been read out of a / m
+          tc::tcgen05_fence_after();
+          for (int n = 0; n < n_chunks; ++n, ++ch_it) {
+            const int nn_cols = D - n * NCH < NCH ? D - n * NCH : NCH;
+            const uint32_t idesc_p = tc::make_idesc_bf16_f32(CM, nn_cols);
+            tc::mbar_wait(&bars->p_empty, (ch_it & 1) ^ 1);         // epilogue has drained the previous chunk
+            tc::tcgen05_fence_after();
+            for (int kb = 0; kb < KB; ++kb, ++it) {
+              const uint32_t s = it % CST, ph = (it / CST) & 1;
+              tc::mbar_wait(&bars->full[s], ph);
+              const uint64_t a_desc = tc::make_smem_desc_sw128(tc::smem_u32(st_a + s * CA_BYTES));
+              const uint64_t b_desc = tc::make_smem_desc_sw128(tc::smem_u32(st_b + s * CB_BYTES));
+              if (n == 0) {
+                const uint32_t ls = lo_it % RING2, lph = (lo_it / RING2) & 1;
+                const uint32_t cs = c_it % RING2, cph = (c_it / RING2) & 1;
+                tc::mbar_wait(&bars->lo_full[ls], lph);
+                tc::mbar_wait(&bars->c_full[cs], cph);
+                tc::tcgen05_fence_after();
+                const uint64_t l_desc = tc::make_smem_desc_sw128(tc::smem_u32(lo_t + ls * CA_BYTES));
+                const uint64_t c_desc = tc::make_smem_desc_sw128(tc::smem_u32(cd_t + cs * CC_BYTES));
+#pragma unroll
+                for (int k = 0; k < CKB / 16; ++k) {
+                  tc::umma_bf16(tmem + COL_M, a_desc + 2 * k, c_desc + 2 * k, idesc_c, (kb | k) != 0 ? 1u : 0u);
+                  tc::umma_bf16(tmem + COL_M, l_desc + 2 * k, c_desc + 2 * k, idesc_c, 1u);
+                }
+                tc::umma_commit(&bars->lo_empty[ls]);
+                tc::umma_commit(&bars->c_empty[cs]);
+                ++lo_it; ++c_it;
+              } else {
+                tc::tcgen05_fence_after();
+              }
+#pragma unroll
+              for (int k = 0; k < CKB / 16; ++k)
+                tc::umma_bf16(tmem + COL_P, a_desc + 2 * k, b_desc + 2 * k, idesc_p, (kb | k) != 0 ? 1u : 0u);
+              tc::umma_commit(&bars->empty[s]);
+            }
+            tc::umma_commit(&bars->p_full);
+            // attention logits: a += gelu(P)[:, 64-feature block] . cand[:, same block]^T
+            for (int sb = 0; sb < nn_cols / CKB; ++sb, ++pb_it, ++c_it) {
+              const uint32_t ps = pb_it % RING2, pph = (pb_it / RING2) & 1;
+              const uint32_t cs = c_it % RING2, cph = (c_it / RING2) & 1;
+              tc::mbar_wait(&bars->pb_full[ps], pph);
+              tc::mbar_wait(&bars->c_full[cs], cph);
+              tc::tcgen05_fence_after();
+              const uint64_t p_desc = tc::make_smem_desc_sw128(tc::smem_u32(pb_t + ps * CA_BYTES));
+              const uint64_t c_desc = tc::make_smem_desc_sw128(tc::smem_u32(cd_t + cs * CC_BYTES));
+#pragma unroll
+              for (int k = 0; k < CKB / 16; ++k)
+                tc::umma_bf16(tmem + COL_A, p_desc + 2 * k, c_desc + 2 * k, idesc_c, (n | sb | k) != 0 ? 1u : 0u);
+              tc::umma_commit(&bars->pb_empty[ps]);
+              tc::umma_commit(&bars->c_empty[cs]);
+            }
+          }
+          tc::umma_commit(&bars->fin_full);
+        }
+      }
+    }
+  } else {
+    // ------------------------------------------------------------------ epilogue warps 6..13
+    const int ew = warp - 6;
+    const int q = warp & 3;                     // TMEM lane quarter this warp may access
+    const int half = ew >> 2;                   // which 32 columns of a 64-column block
+    const int r = q * 32 + lane;                // row of the group = TMEM lane
+    const uint32_t lane_addr = static_cast<uint32_t>(q * 32) << 16;
+    uint32_t pb_it = 0, ch_it = 0, grp_it = 0;
+    for (int g = blockIdx.x; g < n_groups; g += gridDim.x) {
+      const int64_t c0 = cand_off(args, static_cast<int64_t>(g) * IPG), c1 = cand_off(args, static_cast<int64_t>(g + 1) * IPG);
+      for (int64_t pc0 = c0; pc0 < c1; pc0 += CMAXC, ++grp_it) {
+        for (int n = 0; n < n_chunks; ++n, ++ch_it) {
+          const int nn_cols = D - n * NCH < NCH ? D - n * NCH : NCH;
+          tc::mbar_wait(&bars->p_full, ch_it & 1);
+          tc::tcgen05_fence_after();
+          for (int sb = 0; sb < nn_cols / CKB; ++sb, ++pb_it) {
+            const uint32_t ps = pb_it % RING2, pph = (pb_it / RING2) & 1;
+            uint32_t v[32];
+            tc::tmem_ld_32x32(tmem + lane_addr + COL_P + sb * CKB + half * 32, v);
+            tc::tmem_ld_wait();
+            uint32_t pk[16];
+#pragma unroll
+            for (int j = 0; j < 16; ++j)
+              pk[j] = pack_bf16x2(gelu_fast(__uint_as_float(v[2 * j])), gelu_fast(__uint_as_float(v[2 * j + 1])));
+            tc::mbar_wait(&bars->pb_empty[ps], pph ^ 1);
+            uint8_t* tile = pb_t + ps * CA_BYTES;
+#pragma unroll
+            for (int c = 0; c < 4; ++c)
+              *reinterpret_cast<uint4*>(tile + tc::sw128_offset(r, half * 4 + c)) = make_uint4(pk[4 * c], pk[4 * c + 1], pk[4 * c + 2], pk[4 * c + 3]);
+            tc::fence_proxy_async_smem();
+            tc::mbar_arrive(&bars->pb_full[ps]);
+          }
+          tc::tcgen05_fence_before();
+          tc::mbar_arrive(&bars->p_empty);
+        }
+        // ---- scores of this pass: softmax over the K lanes of an impression, weighted sum of matching scores
+        tc::mbar_wait(&bars->fin_full, grp_it & 1);
+        tc::tcgen05_fence_after();
+        if (half == 0) {
+          const int64_t imp = static_cast<int64_t>(g) * IPG + r / K;
+          const int k = r % K;
+          const int64_t o0 = cand_off(args, imp), o1 = cand_off(args, imp + 1);
+          const int64_t q0 = cand_off(args, static_cast<int64_t>(g) * IPG + (q * 32) / K);
+          const int64_t q1 = cand_off(args, static_cast<int64_t>(g) * IPG + (q * 32 + 31) / K + 1);
+          const int nc = static_cast<int>(c1 - pc0 < CMAXC ? c1 - pc0 : CMAXC);
+          int lo_col = static_cast<int>(q0 - pc0), hi_col = static_cast<int>(q1 - pc0 < nc ? q1 - pc0 : nc);
+          if (q0 - pc0 < 0) lo_col = 0;
+          if (q1 <= pc0) hi_col = 0;
+          for (int cb = 0; cb < CMAXC / 32; ++cb) {
+            if (cb * 32 >= hi_col || cb * 32 + 32 <= lo_col) continue;       // warp-uniform
+            uint32_t av[32], mv[32];
+            tc::tmem_ld_32x32(tmem + lane_addr + COL_A + cb * 32, av);
+            tc::tmem_ld_32x32(tmem + lane_addr + COL_M + cb * 32, mv);
+            tc::tmem_ld_wait();
+#pragma unroll
+            for (int j = 0; j < 32; ++j) {
+              const int col = cb * 32 + j;
+              if (col < lo_col || col >= hi_col) continue;                     // warp-uniform
+              const float a = __uint_as_float(av[j]);
+              const float mx = group_max<K>(a);
+              const float e = expf(a - mx);
+              const float se = group_sum<K>(e);
+              const float sm = group_sum<K>(e * __uint_as_float(mv[j]));
+              const int64_t f = pc0 + col;
+              if (k == 0 && f >= o0 && f < o1) args.out[f] = sm / se;
+            }
+          }
+        }
+        tc::tcgen05_fence_before();
+        tc::mbar_arrive(&bars->fin_empty);
+      }
+    }
+  }
+
+  tc::tcgen05_fence_before();
+  __syncthreads();
+  if (warp == 5) tc::tmem_dealloc(tmem, 512);
+}
+
+}  // namespace
+
+bool cand_kernel_supported(int64_t K, int64_t D) { return (K == 8 || K == 16 || K == 32) && D >= 64 && D % 64 == 0 && D <= 4096; }
+
+int launch_cand_kernel(const void* i_hi, const void* i_lo, const void* wt_bf16, const void* table, int64_t n_rows,
+                       const void* cand_ids, int id_dtype, const int64_t* cand_offsets, int64_t B, int64_t C, int64_t K, int64_t D,
+                       float* out_scores, cudaStream_t stream) {
+  if (B == 0) return MINER_OK;
+  if (!cand_kernel_supported(K, D)) {
+    set_error("cand_kernel: unsupported shape K=%lld D=%lld (need K in {8,16,32}, D %% 64 == 0)", (long long)K, (long long)D);
+    return MINER_ERR_UNSUPPORTED;
+  }
+  CUtensorMap m_hi, m_lo, m_wt;
+  int rc = make_tmap_2d_bf16(&m_hi, i_hi, static_cast<uint64_t>(B * K), static_cast<uint64_t>(D), CM, CKB);
+  if (rc) return rc;
+  rc = make_tmap_2d_bf16(&m_lo, i_lo, static_cast<uint64_t>(B * K), static_cast<uint64_t>(D), CM, CKB);
+  if (rc) return rc;
+  rc = make_tmap_2d_bf16(&m_wt, wt_bf16, static_cast<uint64_t>(D), static_cast<uint64_t>(D), NCH, CKB);
+  if (rc) return rc;
+  const int ipg = static_cast<int>(CM / K);
+  const int64_t n_groups = (B + ipg - 1) / ipg;
+  const int grid = static_cast<int>(n_groups < sm_count() ? n_groups : sm_count());
+  CandArgs a{static_cast<const uint16_t*>(table), n_rows, cand_ids, id_dtype, cand_offsets, B, C, static_cast<int>(K), static_cast<int>(D), out_scores};
+#define MINER_CAND(KK)                                                                                              \
+  do {                                                                                                              \
+    MINER_CUDA_OK(cudaFuncSetAttribute(cand_kernel<KK>, cudaFuncAttributeMaxDynamicSharedMemorySize, C_SMEM));      \
+    cand_kernel<KK><<<grid, C_THREADS, C_SMEM, stream>>>(m_hi, m_lo, m_wt, a, static_cast<int>(n_groups));          \
+  } while (0)
+  if (K == 32) MINER_CAND(32);
+  else if (K == 16) MINER_CAND(16);
+  else MINER_CAND(8);
+#undef MINER_CAND
+  MINER_LAUNCH_OK("cand_kernel");
+  return MINER_OK;
+}
+
+}  // namespace miner

@@ -118,6 +118,43 @@ __device__ __forceinline__ void umma_bf16(uint32_t tmem_d, uint64_t desc_a, uint
       "l"(desc_a), "l"(desc_b), "r"(idesc), "r"(accumulate)
       : "memory");
 }
+// Same physical layout (8-row x 128-byte swizzle atoms stacked every 1024 bytes) read as an MN-major operand: the 64
+// contiguous bf16 of a row run along M (or N), the rows run along K.  One MMA (K = 16) covers two 8-row groups, SBO =
+// 1024 B apart; the operand is one 64-element atom wide along MN, so LBO (distance between MN atoms) is unused.
+// Needs the a_major / b_major bit of the instruction descriptor set (make_idesc_bf16_f32(..., a_mn, b_mn)).
+__device__ __forceinline__ uint64_t make_smem_desc_sw128_mn(uint32_t smem_addr) {
+  uint64_t d = 0;
+  d |= static_cast<uint64_t>((smem_addr & 0x3FFFFu) >> 4);
+  d |= static_cast<uint64_t>(1) << 16;                          // LBO (unused: one atom along MN)
+  d |= static_cast<uint64_t>(1024 >> 4) << 32;                  // SBO: next group of 8 K-rows
+  d |= static_cast<uint64_t>(1) << 46;
+  d |= static_cast<uint64_t>(2) << 61;
+  return d;
+}
+__host__ __device__ constexpr uint32_t make_idesc_bf16_f32_major(int M, int N, bool a_mn_major, bool b_mn_major) {
+  return make_idesc_bf16_f32(M, N) | (a_mn_major ? (1u << 15) : 0u) | (b_mn_major ? (1u << 16) : 0u);
+}
+
+// 32 lanes x 16 consecutive 32-bit columns
+__device__ __forceinline__ void tmem_ld_32x16(uint32_t taddr, uint32_t (&r)[16]) {
+  asm volatile(
+      "tcgen05.ld.sync.aligned.32x32b.x16.b32 "
+      "{%0, %1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15}, [%16];"
+      : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]), "=r"(r[4]), "=r"(r[5]), "=r"(r[6]), "=r"(r[7]), "=r"(r[8]), "=r"(r[9]),
+        "=r"(r[10]), "=r"(r[11]), "=r"(r[12]), "=r"(r[13]), "=r"(r[14]), "=r"(r[15])
+      : "r"(taddr)
+      : "memory");
+}
+
+// named barrier over a subset of the CTA's warps (id 1..15; id 0 is __syncthreads)
+__device__ __forceinline__ void named_bar_sync(uint32_t id, uint32_t n_threads) {
+  asm volatile("bar.sync %0, %1;" ::"r"(id), "r"(n_threads) : "memory");
+}
+
+// byte offset of element (row r, 16-byte chunk c) inside a K-major / MN-major SWIZZLE_128B tile of 128-byte rows
+__device__ __forceinline__ uint32_t sw128_offset(uint32_t r, uint32_t c) {
+  return (r >> 3) * 1024u + (r & 7u) * 128u + ((c ^ (r & 7u)) << 4);
+}
 // mbarrier arrive once every previously issued tcgen05.mma of this thread has completed (implies fence::before_thread_sync)
 __device__ __forceinline__ void umma_commit(uint64_t* bar) {
   asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(smem_u32(bar)) : "memory");

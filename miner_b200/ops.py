@@ -248,6 +248,53 @@ def score(table: torch.Tensor, his_ids: torch.Tensor, his_mask: torch.Tensor, ca
     return interests, scores
 
 
+def hist_interests(table: torch.Tensor, his_ids: torch.Tensor, his_mask: torch.Tensor, w_proj_bf16: torch.Tensor, codes: torch.Tensor,
+                   bias_mean: Optional[torch.Tensor] = None, want_f32: bool = True):
+    """History kernel of the fused tensor-core path on its own: ``(i_hi, i_lo, interests_f32 or None)``."""
+    dev = _need_cuda(table, his_ids, his_mask, w_proj_bf16, codes, bias_mean)
+    lib = L.load()
+    assert table.dtype == torch.bfloat16 and w_proj_bf16.dtype == torch.bfloat16
+    table, wp = table.contiguous(), w_proj_bf16.contiguous()
+    B, H = his_ids.shape
+    D = table.shape[1]
+    K, Dc = codes.shape
+    hid, it = _ids(his_ids)
+    m, cd = _mask_u8(his_mask), _f32(codes)
+    bm = _f32(bias_mean) if bias_mean is not None else None
+    i_hi = torch.empty(B * K, D, dtype=torch.bfloat16, device=dev)
+    i_lo = torch.empty(B * K, D, dtype=torch.bfloat16, device=dev)
+    out = torch.empty(B, K, D, dtype=torch.float32, device=dev) if want_f32 else None
+    ws_bytes = lib.miner_hist_interests_workspace_bytes(Dc)
+    ws = torch.empty(max(ws_bytes, 1), dtype=torch.uint8, device=dev)
+    with torch.cuda.device(dev):
+        L.check(lib.miner_hist_interests_fwd(_ptr(table), table.shape[0], _ptr(hid), it, _ptr(m), _ptr(bm), _ptr(wp), _ptr(cd), B, H, K, Dc, D,
+                                             _ptr(i_hi), _ptr(i_lo), _ptr(out), _ptr(ws), ws_bytes, _stream()))
+    return i_hi, i_lo, out
+
+
+def cand_score(i_hi: torch.Tensor, i_lo: torch.Tensor, w_target_bf16: torch.Tensor, table: torch.Tensor, cand_ids: torch.Tensor, K: int,
+               cand_offsets: Optional[torch.Tensor] = None) -> torch.Tensor:
+    """Candidate kernel of the fused tensor-core path on its own (score_type 'weighted')."""
+    dev = _need_cuda(i_hi, i_lo, w_target_bf16, table, cand_ids, cand_offsets)
+    lib = L.load()
+    assert i_hi.dtype == torch.bfloat16 and i_lo.dtype == torch.bfloat16 and w_target_bf16.dtype == torch.bfloat16 and table.dtype == torch.bfloat16
+    D = table.shape[1]
+    B = i_hi.shape[0] // K
+    cid, it = _ids(cand_ids)
+    if cand_offsets is None:
+        Cn = cand_ids.shape[1]
+        offs = None
+        out = torch.empty(B, Cn, dtype=torch.float32, device=dev)
+    else:
+        Cn = 0
+        offs = cand_offsets.to(torch.int64).contiguous()
+        out = torch.empty(cid.numel(), dtype=torch.float32, device=dev)
+    with torch.cuda.device(dev):
+        L.check(lib.miner_cand_score_fwd(_ptr(i_hi.contiguous()), _ptr(i_lo.contiguous()), _ptr(w_target_bf16.contiguous()), _ptr(table.contiguous()),
+                                         table.shape[0], _ptr(cid), it, _ptr(offs), B, Cn, K, D, _ptr(out), _stream()))
+    return out
+
+
 def tc_gemm(a_bf16: torch.Tensor, b_bf16: torch.Tensor, epilogue: int = 0, a_ids: Optional[torch.Tensor] = None,
             want_bf16: bool = False):
     """The tcgen05 projection GEMM on its own: epi(A B^T) with optional row gather of A (tests / profiling)."""
