@@ -248,10 +248,13 @@ def main():
     pk = peaks()
     kernels, roofline = None, None
     if rank == 0 and not args.no_breakdown:
-        stages = [('tc_gemm: tanh(table[his] Wp^T) [gather fused]', 1), ('poly_softmax_wsum', 2), ('tc_gemm: gelu(I Wt^T)', 4),
-                  ('target_score [cand gather fused]', 8)]
-        if math == _lib.MATH_FP32:
-            stages = [(n.replace('tc_gemm', 'sgemm'), m) for n, m in stages]
+        if math == _lib.MATH_TENSOR:
+            # fused tcgen05 path: two kernels per wave of `chunk` impressions
+            stages = [('hist_kernel: gather + tanh(E Wp^T) + logits/softmax + weighted sum (tcgen05)', 1),
+                      ('cand_kernel: gelu(I Wt^T) + matching/attention MMAs + softmax_K + score (tcgen05)', 8)]
+        else:
+            stages = [('sgemm: tanh(table[his] Wp^T) [gather fused]', 1), ('poly_softmax_wsum', 2), ('sgemm: gelu(I Wt^T)', 4),
+                      ('target_score [cand gather fused]', 8)]
         nchunks = (B + chunk - 1) // chunk
         kernels = []
         for name, mask in stages:
@@ -272,18 +275,25 @@ def main():
             k['share'] = k['ms_per_step'] / tot
         # algorithmic work per impression of each stage
         c_mean = T / B
-        flops = {1: 2 * H * D * DC, 2: 2 * H * DC * K + 2 * K * H * D, 4: 2 * K * D * D, 8: 4 * c_mean * K * D}
-        byts = {1: H * D * 2 + H * 8, 2: H * D * 2 + H * 8 + H, 4: 0, 8: c_mean * D * 2 + c_mean * 8 + c_mean * 4}
-        top = max(range(4), key=lambda i: kernels[i]['ms_per_step'])
+        if math == _lib.MATH_TENSOR:
+            flops = {1: 2 * H * D * DC + 2 * H * DC * K + 2 * K * H * D, 8: 2 * K * D * D + 4 * c_mean * K * D}
+            byts = {1: H * D * 2 + H * 8 + H, 8: c_mean * D * 2 + c_mean * 8 + c_mean * 4}
+            tensor_stage = (1, 8)
+        else:
+            flops = {1: 2 * H * D * DC, 2: 2 * H * DC * K + 2 * K * H * D, 4: 2 * K * D * D, 8: 4 * c_mean * K * D}
+            byts = {1: H * D * 2 + H * 8, 2: H * D * 2 + H * 8 + H, 4: 0, 8: c_mean * D * 2 + c_mean * 8 + c_mean * 4}
+            tensor_stage = ()
+        top = max(range(len(stages)), key=lambda i: kernels[i]['ms_per_step'])
         mask = stages[top][1]
         sec_per_launch = kernels[top]['ms_per_step'] * 1e-3 / nchunks
         per_launch_impr = B / nchunks
         tf = flops[mask] * per_launch_impr / sec_per_launch / 1e12
         gbs = byts[mask] * per_launch_impr / sec_per_launch / 1e9
         peak_tf = pk.get('bf16_tflops_sustained', pk['bf16_tflops'])
-        if mask in (1, 4):
+        if mask in tensor_stage:
             roofline = {'kernel': stages[top][0], 'bound': 'tensor', 'achieved': tf, 'peak': peak_tf, 'unit': 'TFLOP/s',
-                        'frac': tf / peak_tf, 'traffic': None, 'peak_source': pk['_source'] + ' (sustained bf16)'}
+                        'frac': tf / peak_tf, 'traffic': None, 'peak_source': pk['_source'] + ' (sustained bf16)',
+                        'algorithmic_flops_per_launch': flops[mask] * per_launch_impr, 'ms_per_launch': sec_per_launch * 1e3}
         else:
             roofline = {'kernel': stages[top][0], 'bound': 'hbm', 'achieved': gbs, 'peak': pk['hbm_gbs'], 'unit': 'GB/s',
                         'frac': gbs / pk['hbm_gbs'], 'traffic': None, 'peak_source': pk['_source'], 'achieved_tflops_fp32': tf}

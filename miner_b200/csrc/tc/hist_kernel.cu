@@ -36,7 +36,9 @@ constexpr int LROW = 33;                // padded row of the logits tile
 constexpr int H_THREADS = 14 * 32;      // 4 gather warps, TMA warp, MMA warp, 8 epilogue warps
 constexpr int H_EPI = 256;
 constexpr int RCOLS = 192;              // TMEM columns of one pass-2 round (3 feature blocks)
-constexpr int WT_BYTES = 4 * HA_BYTES;  // w tiles: {hi, lo} x {history rows 0-63, 64-127}, each 128 rows x 128 B
+constexpr int WA_BYTES = 64 * 128;      // one w tile atom: 64 interest rows x 64 history slots (bf16).  The MMA reads M = 128 rows, i.e.
+                                        // 8 KB past each atom: those accumulator rows are garbage and never read
+constexpr int WT_BYTES = 4 * WA_BYTES;  // w tiles: {hi, lo} x {history rows 0-63, 64-127}
 
 struct HBarriers {
   uint64_t full[HST], empty[HST];
@@ -81,7 +83,8 @@ hist_kernel(const __grid_constant__ CUtensorMap tmap_wp, const HistArgs args, in
   uint8_t* st_a = smem;                                    // [HST][16 KB]      gathered E k-block
   uint8_t* st_b = st_a + HST * HA_BYTES;                   // [HST][b_bytes]    Wp k-block
   uint8_t* w_t = st_b + HST * args.b_bytes;                // 4 x 16 KB         softmax weights, bf16 hi/lo
-  float* L = reinterpret_cast<float*>(w_t + WT_BYTES);     // [128][33]         logits / softmax scratch
+  float* codes_s = reinterpret_cast<float*>(w_t + WT_BYTES);   // [Dc][32]      context codes, transposed + zero padded
+  float* L = codes_s + args.Dc * KP;                       // [128][33]         logits / softmax scratch
   HBarriers* bars = reinterpret_cast<HBarriers*>(reinterpret_cast<uint8_t*>(L) + HM * LROW * 4);
 
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
@@ -92,6 +95,8 @@ hist_kernel(const __grid_constant__ CUtensorMap tmap_wp, const HistArgs args, in
   const int NR = (KB + 2) / 3;                             // pass-2 rounds per tile
 
   for (int i = threadIdx.x; i < WT_BYTES / 16; i += H_THREADS) reinterpret_cast<uint4*>(w_t)[i] = make_uint4(0, 0, 0, 0);
+  for (int i = threadIdx.x; i < args.Dc * KP / 4; i += H_THREADS)
+    reinterpret_cast<float4*>(codes_s)[i] = __ldg(reinterpret_cast<const float4*>(args.codes_t) + i);
   tc::fence_proxy_async_smem();
   if (threadIdx.x == 0) {
     for (int s = 0; s < HST; ++s) { tc::mbar_init(&bars->full[s], 128 + 1); tc::mbar_init(&bars->empty[s], 1); }
@@ -111,7 +116,7 @@ hist_kernel(const __grid_constant__ CUtensorMap tmap_wp, const HistArgs args, in
   if (warp < 4) {
     // ------------------------------------------------------------------ E gather (both passes)
     const int chunk = lane & 7;
-    uint32_t issued = 0, signalled = 0;
+    uint32_t issued = 0;
     for (int tile = blockIdx.x; tile < n_tiles; tile += gridDim.x) {
       const uint16_t* src[8];
       uint32_t nbytes[8], dst_off[8];
@@ -137,19 +142,11 @@ hist_kernel(const __grid_constant__ CUtensorMap tmap_wp, const HistArgs args, in
         const uint32_t base = tc::smem_u32(st_a + s * HA_BYTES);
 #pragma unroll
         for (int j = 0; j < 8; ++j) tc::cp_async_16(base + dst_off[j], src[j] + kb * HKB, nbytes[j]);
-        tc::cp_async_commit();
+        tc::cp_async_mbar_arrive_noinc(&bars->full[s]);     // arrives by itself once this thread's 8 copies have landed
         ++issued;
-        if (issued - signalled > 2) {
-          tc::cp_async_wait<2>();
-          tc::fence_proxy_async_smem();
-          tc::mbar_arrive(&bars->full[signalled % HST]);
-          ++signalled;
-        }
       }
     }
-    tc::cp_async_wait<0>();
-    tc::fence_proxy_async_smem();
-    while (signalled < issued) { tc::mbar_arrive(&bars->full[signalled % HST]); ++signalled; }
+    tc::cp_async_wait_all();
   } else if (warp == 4) {
     // ------------------------------------------------------------------ Wp k-blocks by TMA (pass 1); plain arrive in pass 2
     if (lane == 0) {
@@ -179,6 +176,7 @@ hist_kernel(const __grid_constant__ CUtensorMap tmap_wp, const HistArgs args, in
         for (int kb = 0; kb < KB; ++kb, ++it) {
           const uint32_t s = it % HST, ph = (it / HST) & 1;
           tc::mbar_wait(&bars->full[s], ph);
+          tc::fence_proxy_async_smem();                      // cp.async (generic proxy) writes -> tcgen05.mma (async proxy) reads
           tc::tcgen05_fence_after();
           const uint64_t a_desc = tc::make_smem_desc_sw128(tc::smem_u32(st_a + s * HA_BYTES));
           const uint64_t b_desc = tc::make_smem_desc_sw128(tc::smem_u32(st_b + s * args.b_bytes));
@@ -197,6 +195,7 @@ hist_kernel(const __grid_constant__ CUtensorMap tmap_wp, const HistArgs args, in
           for (int db = 0; db < nd; ++db, ++it) {
             const uint32_t s = it % HST, ph = (it / HST) & 1;
             tc::mbar_wait(&bars->full[s], ph);
+            tc::fence_proxy_async_smem();
             tc::tcgen05_fence_after();
             const uint64_t e_desc = tc::make_smem_desc_sw128_mn(tc::smem_u32(st_a + s * HA_BYTES));
             const uint32_t d_tmem = tmem + buf * RCOLS + db * HKB;
@@ -204,7 +203,7 @@ hist_kernel(const __grid_constant__ CUtensorMap tmap_wp, const HistArgs args, in
             for (int hl = 0; hl < 2; ++hl) {
 #pragma unroll
               for (int ks = 0; ks < HM / 16; ++ks) {
-                const uint64_t w_desc = tc::make_smem_desc_sw128(tc::smem_u32(w_t + (hl * 2 + (ks >> 2)) * HA_BYTES)) + 2 * (ks & 3);
+                const uint64_t w_desc = tc::make_smem_desc_sw128(tc::smem_u32(w_t + (hl * 2 + (ks >> 2)) * WA_BYTES)) + 2 * (ks & 3);
                 tc::umma_bf16(d_tmem, w_desc, e_desc + ks * (2048 >> 4), idesc2, (hl | ks) != 0 ? 1u : 0u);
               }
             }
@@ -224,7 +223,7 @@ hist_kernel(const __grid_constant__ CUtensorMap tmap_wp, const HistArgs args, in
     const uint32_t lane_addr = static_cast<uint32_t>(q * 32) << 16;
     const int n_cc = (N1 + 31) / 32;
     const int cc_begin = half == 0 ? 0 : (n_cc + 1) / 2, cc_end = half == 0 ? (n_cc + 1) / 2 : n_cc;
-    const float4* codes4 = reinterpret_cast<const float4*>(args.codes_t);
+    const float4* codes4 = reinterpret_cast<const float4*>(codes_s);
     uint32_t tile_it = 0, rnd_it = 0;
     for (int tile = blockIdx.x; tile < n_tiles; tile += gridDim.x, ++tile_it) {
       // ---- epilogue 1: tanh, logits against the context codes, bias / mask, softmax over the history
@@ -244,7 +243,7 @@ hist_kernel(const __grid_constant__ CUtensorMap tmap_wp, const HistArgs args, in
             const float t = tanh_acc(__uint_as_float(v[j]));                   // model.py:171
 #pragma unroll
             for (int k4 = 0; k4 < KP / 4; ++k4) {
-              const float4 c = __ldg(codes4 + dc * (KP / 4) + k4);
+              const float4 c = codes4[dc * (KP / 4) + k4];
               acc[4 * k4 + 0] = fmaf(t, c.x, acc[4 * k4 + 0]);
               acc[4 * k4 + 1] = fmaf(t, c.y, acc[4 * k4 + 1]);
               acc[4 * k4 + 2] = fmaf(t, c.z, acc[4 * k4 + 2]);
@@ -295,9 +294,9 @@ hist_kernel(const __grid_constant__ CUtensorMap tmap_wp, const HistArgs args, in
             const __nv_bfloat16 whi = __float2bfloat16_rn(w);
             const __nv_bfloat16 wlo = __float2bfloat16_rn(w - __bfloat162float(whi));
             const int hc = i * HP + h;
-            const uint32_t off = (hc >> 6) * HA_BYTES + tc::sw128_offset(R, (hc & 63) >> 3) + (hc & 7) * 2;
+            const uint32_t off = (hc >> 6) * WA_BYTES + tc::sw128_offset(R, (hc & 63) >> 3) + (hc & 7) * 2;
             *reinterpret_cast<__nv_bfloat16*>(w_t + off) = whi;
-            *reinterpret_cast<__nv_bfloat16*>(w_t + 2 * HA_BYTES + off) = wlo;
+            *reinterpret_cast<__nv_bfloat16*>(w_t + 2 * WA_BYTES + off) = wlo;
           }
         }
       }
@@ -391,7 +390,7 @@ int launch_hist_kernel(const void* table, int64_t n_rows, const void* his_ids, i
   const int ipt = H <= 64 ? 2 : 1;
   const int64_t n_tiles = (B + ipt - 1) / ipt;
   const int grid = static_cast<int>(n_tiles < sm_count() ? n_tiles : sm_count());
-  const int smem = 1024 + HST * (HA_BYTES + a.b_bytes) + WT_BYTES + HM * LROW * 4 + 256;
+  const int smem = 1024 + HST * (HA_BYTES + a.b_bytes) + WT_BYTES + static_cast<int>(Dc) * KP * 4 + HM * LROW * 4 + 256;
   MINER_CUDA_OK(cudaFuncSetAttribute(hist_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
   hist_kernel<<<grid, H_THREADS, smem, stream>>>(m_wp, a, static_cast<int>(n_tiles));
   MINER_LAUNCH_OK("hist_kernel");
