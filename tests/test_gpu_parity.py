@@ -484,3 +484,103 @@ def test_properties_at_scale():
     tot = (p1 + p2).cpu().view(-1, 2)
     for i, n in enumerate(ops.metric_names((5, 10))):
         assert abs(float(tot[i, 0] / tot[i, 1]) - r[n]) < 1e-12          # sharded partials add up (what ranks all-reduce)
+
+
+# ------------------------------------------------------------------------------------------------ fused tcgen05 kernels on their own
+def _nerr(a, b):
+    a, b = a.double(), b.double()
+    return float((a - b).abs().max() / b.abs().max().clamp_min(1e-30))
+
+
+@pytest.mark.parametrize('B,H,D,K,Dc', [(6, 12, 64, 8, 24), (37, 50, 768, 32, 200), (301, 50, 256, 32, 48), (33, 100, 128, 16, 40),
+                                         (5, 64, 64, 32, 16), (3, 128, 192, 8, 256), (1, 1, 64, 16, 1)])
+def test_hist_kernel_interests(B, H, D, K, Dc):
+    """History kernel alone: fp32 interests and the bf16 hi+lo split against PolyAttention on the same bf16-valued inputs."""
+    from miner_b200 import ops, synth
+    N = 700
+    table = synth.make_table(N, D, 5, torch.bfloat16)
+    w = synth.make_weights(D, K, Dc, 5)
+    g = torch.Generator().manual_seed(B + H)
+    his, mask, _ = synth.make_history(B, H, N, g)
+    wp16 = w.w_proj.to(torch.bfloat16)
+    bias = torch.randn(B, H, generator=g) * 0.3
+    for bm in (None, bias):
+        ref = O.poly_attention(table.float()[his], mask, wp16.float(), w.context_codes,
+                               None if bm is None else bm[:, :, None])
+        ihi, ilo, out = ops.hist_interests(table.to(DEV), his.to(DEV), mask.to(DEV), wp16.to(DEV), w.context_codes.to(DEV),
+                                           bias_mean=None if bm is None else bm.to(DEV))
+        assert _nerr(out.cpu(), ref) < 5e-5
+        assert _nerr((ihi.float() + ilo.float()).cpu().view(B, K, D), ref) < 5e-5
+        assert torch.equal(ihi.cpu().view(B, K, D), out.cpu().to(torch.bfloat16))          # hi is the bf16 rounding of the fp32 value
+    # int32 ids: same bits; out-of-range id: that history row contributes a zero vector
+    ihi32, _, _ = ops.hist_interests(table.to(DEV), his.int().to(DEV), mask.to(DEV), wp16.to(DEV), w.context_codes.to(DEV), bias_mean=bias.to(DEV))
+    assert torch.equal(ihi32, ihi)
+    his_bad = his.clone()
+    his_bad[0, -1] = N + 5
+    tz = torch.cat([table, torch.zeros(6, D, dtype=torch.bfloat16)])
+    ref = O.poly_attention(tz.float()[his_bad], mask, wp16.float(), w.context_codes)
+    _, _, out = ops.hist_interests(table.to(DEV), his_bad.to(DEV), mask.to(DEV), wp16.to(DEV), w.context_codes.to(DEV))
+    assert _nerr(out.cpu(), ref) < 5e-5
+
+
+@pytest.mark.parametrize('B,D,K,mean_c,max_c', [(6, 64, 8, 20.0, 300), (37, 768, 32, 20.0, 300), (301, 256, 32, 12.0, 70), (33, 128, 16, 20.0, 300),
+                                                 (9, 768, 32, 150.0, 300), (2, 64, 32, 3.0, 4)])
+def test_cand_kernel_scores(B, D, K, mean_c, max_c):
+    """Candidate kernel alone (weighted score) against the oracle's aggregate_scores on the same interests / bf16-valued Wt."""
+    from miner_b200 import ops, synth
+    N = 900
+    table = synth.make_table(N, D, 7, torch.bfloat16)
+    w = synth.make_weights(D, K, 24, 7)
+    eb = synth.make_eval_batch(B, 20, N, 7, mean_cands=mean_c, max_cands=max_c)
+    I = O.poly_attention(table.float()[eb.his_ids], eb.his_mask, w.w_proj, w.context_codes)
+    ihi = I.to(torch.bfloat16)
+    ilo = (I - ihi.float()).to(torch.bfloat16)
+    wt16 = w.w_target.to(torch.bfloat16)
+    offs = eb.offsets.numpy()
+    ref = torch.empty(int(offs[-1]))
+    for i in range(B):
+        cr = table.float()[eb.cand_ids[offs[i]:offs[i + 1]]][None]
+        ref[offs[i]:offs[i + 1]] = O.aggregate_scores(I[i:i + 1], cr, 'weighted', wt16.float())[0]
+    args = (ihi.view(B * K, D).to(DEV), ilo.view(B * K, D).to(DEV), wt16.to(DEV), table.to(DEV))
+    s = ops.cand_score(*args, eb.cand_ids.to(DEV), K, cand_offsets=eb.offsets.to(DEV))
+    assert _nerr(s.cpu(), ref) < 3e-4
+    # dense (B, C) layout gives the same bits as its CSR restatement
+    Cd = 5
+    cd = torch.randint(1, N + 1, (B, Cd), generator=torch.Generator().manual_seed(1))
+    s_dense = ops.cand_score(*args, cd.to(DEV), K)
+    s_csr = ops.cand_score(*args, cd.reshape(-1).to(DEV), K, cand_offsets=(torch.arange(B + 1) * Cd).to(DEV))
+    assert torch.equal(s_dense.reshape(-1), s_csr)
+    assert torch.equal(ops.cand_score(*args, cd.int().to(DEV), K), s_dense)
+
+
+def test_fused_path_is_chunk_and_layout_invariant():
+    """The tile / group an impression lands in must not change its scores (bit-exact), nor may the chunking of the wave."""
+    import miner_b200 as mb
+    from miner_b200 import synth
+    B, H, N, D, K, Dc = 203, 50, 3000, 768, 32, 200
+    table = synth.make_table(N, D, 36, torch.bfloat16).to(DEV)
+    w = synth.make_weights(D, K, Dc, 36)
+    eb = synth.make_eval_batch(B, H, N, 36)
+    m = mb.Miner(mb.TableNewsEncoder(table), False, K, Dc, 'weighted', 0.2).to(DEV).eval()
+    with torch.no_grad():
+        m.poly_attn.linear.weight.copy_(w.w_proj)
+        m.poly_attn.context_codes.copy_(w.context_codes)
+        m.target_aware_attn.linear.weight.copy_(w.w_target)
+    his, msk, cand, offs = eb.his_ids.to(DEV), eb.his_mask.to(DEV), eb.cand_ids.to(DEV), eb.offsets.to(DEV)
+    s = m.score_impressions(his, msk, cand, offs, chunk=4096)
+    for chunk in (1, 7, 64):
+        assert torch.equal(m.score_impressions(his, msk, cand, offs, chunk=chunk), s)
+    # drop the first impression: every other impression changes tile / group partner but not its scores
+    c1 = int(eb.offsets[1])
+    s1 = m.score_impressions(his[1:], msk[1:], cand[c1:], offs[1:] - c1)
+    assert torch.equal(s1, s[c1:])
+    ref = O.miner_forward_csr(table.cpu(), eb.his_ids, eb.his_mask, eb.cand_ids, eb.offsets.numpy(), w.w_proj, w.context_codes, w.w_target)
+    assert _nerr(s.cpu(), ref) < 1e-3
+    # ranking order per impression equals the fp32 reference order wherever the reference's own gap exceeds the error bound
+    sc, rc = s.cpu().numpy(), ref.numpy()
+    o = eb.offsets.numpy()
+    for i in range(B):
+        a, b = rc[o[i]:o[i + 1]], sc[o[i]:o[i + 1]]
+        order = np.argsort(a)
+        if np.min(np.diff(a[order])) > 2e-4 * np.abs(rc).max():
+            assert np.array_equal(order, np.argsort(b)), i
