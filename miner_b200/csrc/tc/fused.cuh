@@ -15,7 +15,12 @@ bool hist_kernel_supported(int64_t H, int64_t K, int64_t Dc, int64_t D);
 int launch_hist_kernel(const void* table, int64_t n_rows, const void* his_ids, int id_dtype, const uint8_t* his_mask,
                        const float* bias_mean, const void* w_proj_bf16, const float* codes, int64_t B, int64_t H, int64_t K,
                        int64_t Dc, int64_t D, void* i_hi, void* i_lo, float* out_interests, float* codes_t_ws, cudaStream_t stream);
-size_t hist_kernel_ws_bytes(int64_t Dc);   // transposed, zero-padded codes [DcPad][32] fp32
+size_t hist_kernel_ws_bytes(int64_t Dc);
+// software-pipelined variant with tensor-core logits (hist_kernel2.cu), Dc <= 224; launch_hist_kernel dispatches to it
+bool hist_kernel2_supported(int64_t H, int64_t K, int64_t Dc, int64_t D);
+int launch_hist_kernel2(const void* table, int64_t n_rows, const void* his_ids, int id_dtype, const uint8_t* his_mask,
+                        const float* bias_mean, const void* w_proj_bf16, const float* codes, int64_t B, int64_t H, int64_t K,
+                        int64_t Dc, int64_t D, void* i_hi, void* i_lo, float* out_interests, cudaStream_t stream);   // transposed, zero-padded codes [DcPad][32] fp32
 
 // Candidate side: scores for score_type = 'weighted' (model.py:127,200-216) from I_hi/I_lo and table[cand_ids].
 bool cand_kernel_supported(int64_t K, int64_t D);

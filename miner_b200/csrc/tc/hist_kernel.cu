@@ -19,6 +19,7 @@
 //           bf16 hi + lo (I = hi + lo to ~2^-17; hi feeds the candidate kernel's projection GEMM, hi + lo its matching
 //           scores) and, on request, the fp32 interests themselves.
 #include <cuda.h>
+#include <stdlib.h>
 
 #include "fused.cuh"
 #include "umma.cuh"
@@ -375,6 +376,10 @@ int launch_hist_kernel(const void* table, int64_t n_rows, const void* his_ids, i
     set_error("hist_kernel: unsupported shape H=%lld K=%lld Dc=%lld D=%lld", (long long)H, (long long)K, (long long)Dc, (long long)D);
     return MINER_ERR_UNSUPPORTED;
   }
+  static const bool force_v1 = getenv("MINER_HIST_V1") != nullptr;      // A/B switch for profiling
+  if (!force_v1 && hist_kernel2_supported(H, K, Dc, D))
+    return launch_hist_kernel2(table, n_rows, his_ids, id_dtype, his_mask, bias_mean, w_proj_bf16, codes, B, H, K, Dc, D, i_hi, i_lo,
+                               out_interests, stream);
   const int N1 = static_cast<int>((Dc + 15) / 16 * 16);
   CUtensorMap m_wp;
   int rc = make_tmap_2d_bf16(&m_wp, w_proj_bf16, static_cast<uint64_t>(Dc), static_cast<uint64_t>(D), N1, HKB);

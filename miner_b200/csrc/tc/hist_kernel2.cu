@@ -1,0 +1,428 @@
+// History side of the fused tensor-core scoring path, software-pipelined across tiles (sm_100a: tcgen05 + TMEM + TMA).
+// Same contract as hist_kernel.cu (PolyAttention.forward, reference src/model/model.py:159-185, straight from the table),
+// used when Dc <= 208.  Differences:
+//   * the logits against the context codes run on the tensor cores too: the epilogue warps write tanh(proj) back to
+//     tensor memory as packed bf16 hi + lo (tcgen05.st) and the MMA warp multiplies it, as a TMEM-resident A operand (TS
+//     form), with the context codes (bf16 hi + lo K-major tiles in shared memory) into a 128 x 32 accumulator
+//     (T_hi C_hi + T_lo C_hi + T_hi C_lo: ~2^-17 relative, i.e. fp32-level logits);
+//   * as soon as the epilogue warps have turned the projection of tile t into T, the projection accumulator is free: the
+//     MMA warp accumulates the projection of tile t+1 while tile t goes through softmax, weighted sum and draining, so
+//     the gather / TMA pipeline keeps running across the phase boundaries.  The issue order of one step is fixed and
+//     shared by the three roles:
+//         LG(t)  P1(t+1)[0..2]  { P2(t)[j], P1(t+1)[3 + j] }  rest of P1(t+1)
+//     P1 = one projection k-block (gathered E tile + Wp tile), LG = logits MMAs, P2 = one 64-feature block of the interests
+//     (A = softmax weights hi|lo from shared memory, B = the re-gathered E tile read MN-major);
+//   * TMEM map (512 columns): projection [0,208) | T_hi [208,312) | T_lo [312,416) | logits [416,448) | interests block [448,512).
+#include <cuda.h>
+
+#include "fused.cuh"
+#include "umma.cuh"
+
+namespace miner {
+
+namespace {
+
+constexpr int HM = 128, HKB = 64, HST = 3;
+constexpr int HA_BYTES = HM * HKB * 2;       // 16 KB gathered E k-block
+constexpr int KP = 32;
+constexpr int LROW = 33;
+constexpr int H_THREADS = 14 * 32;
+constexpr int H_EPI = 256;
+constexpr int N1_MAX = 208;                  // projection accumulator columns (Dc padded to 16)
+constexpr int TH_COL = N1_MAX, TL_COL = TH_COL + N1_MAX / 2, LG_COL = TL_COL + N1_MAX / 2, IA_COL = LG_COL + KP;
+constexpr int WA_BYTES = 64 * 128;           // softmax-weight atom (64 interest rows x 64 history slots); the MMA reads 8 KB past it
+constexpr int WT_BYTES = 4 * WA_BYTES;
+constexpr int CT_ATOM = KP * 128;            // codes tile atom: 32 codes x 64 features
+constexpr int CT_BYTES = 4 * CT_ATOM;        // per hi / lo tile (Dc <= 256)
+
+enum { OP_P1 = 0, OP_LG = 1, OP_P2 = 2 };
+
+struct H2Barriers {
+  uint64_t full[HST], empty[HST];
+  uint64_t p1_full, t_ready, lg_full, w_ready;
+  uint64_t ia_full, ia_free;
+  uint32_t tmem_base;
+};
+
+struct Hist2Args {
+  const uint16_t* table; int64_t n_rows;
+  const void* his_ids; int id_dtype;
+  const uint8_t* mask; const float* bias_mean;
+  const float* codes;                          // (K, Dc) fp32
+  int64_t B;
+  int H, K, Dc, D, N1, b_bytes;
+  __nv_bfloat16* i_hi; __nv_bfloat16* i_lo; float* out_interests;
+};
+
+// issue order of one step; `has_cur` false = prologue (only the projection of the first tile)
+template <class F>
+__device__ __forceinline__ void for_each_op(bool has_cur, bool has_next, int KB, F&& f) {
+  int p1 = 0;
+  auto p1n = [&](int n) {
+    for (int i = 0; i < n && has_next && p1 < KB; ++i) f(OP_P1, p1++);
+  };
+  if (!has_cur) { p1n(KB); return; }
+  f(OP_LG, 0);
+  p1n(3);
+  for (int j = 0; j < KB; ++j) {
+    f(OP_P2, j);
+    p1n(1);
+  }
+  p1n(KB);
+}
+
+__device__ __forceinline__ float tanh_acc2(float x) {
+  const float ax = fabsf(x);
+  const float e = __expf(-2.0f * ax);
+  return copysignf(__fdividef(1.0f - e, 1.0f + e), x);
+}
+__device__ __forceinline__ uint32_t pack2b(float a, float b) {
+  __nv_bfloat162 v = __floats2bfloat162_rn(a, b);
+  return *reinterpret_cast<uint32_t*>(&v);
+}
+
+__global__ void __launch_bounds__(H_THREADS, 1)
+hist_kernel2(const __grid_constant__ CUtensorMap tmap_wp, const Hist2Args args, int n_tiles) {
+  extern __shared__ uint8_t smem_raw[];
+  uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~static_cast<uintptr_t>(1023));
+  uint8_t* st_a = smem;                                    // [HST][16 KB]      gathered E k-block
+  uint8_t* st_b = st_a + HST * HA_BYTES;                   // [HST][b_bytes]    Wp k-block
+  uint8_t* w_t = st_b + HST * args.b_bytes;                // 4 x 8 KB          softmax weights, bf16 {hi,lo} x {rows 0-63, 64-127}
+  uint8_t* c_hi = w_t + WT_BYTES;                          // 16 KB             context codes bf16 hi, K-major SW128 atoms
+  uint8_t* c_lo = c_hi + CT_BYTES;                         // 16 KB             ... lo
+  float* L = reinterpret_cast<float*>(c_lo + CT_BYTES);    // [128][33]         logits / softmax scratch
+  H2Barriers* bars = reinterpret_cast<H2Barriers*>(reinterpret_cast<uint8_t*>(L) + HM * LROW * 4);
+
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int H = args.H, K = args.K, D = args.D, Dc = args.Dc, N1 = args.N1;
+  const int KB = D / HKB;
+  const int IPT = H <= 64 ? 2 : 1;
+  const int HP = HM / IPT;
+  const int n_local = (n_tiles - static_cast<int>(blockIdx.x) + static_cast<int>(gridDim.x) - 1) / static_cast<int>(gridDim.x);
+
+  for (int i = threadIdx.x; i < (WT_BYTES + 2 * CT_BYTES) / 16; i += H_THREADS) reinterpret_cast<uint4*>(w_t)[i] = make_uint4(0, 0, 0, 0);
+  __syncthreads();
+  for (int i = threadIdx.x; i < K * Dc; i += H_THREADS) {
+    const int k = i / Dc, dc = i - k * Dc;
+    const float c = args.codes[i];
+    const __nv_bfloat16 hi = __float2bfloat16_rn(c);
+    const uint32_t off = (dc >> 6) * CT_ATOM + tc::sw128_offset(k, (dc & 63) >> 3) + (dc & 7) * 2;
+    *reinterpret_cast<__nv_bfloat16*>(c_hi + off) = hi;
+    *reinterpret_cast<__nv_bfloat16*>(c_lo + off) = __float2bfloat16_rn(c - __bfloat162float(hi));
+  }
+  tc::fence_proxy_async_smem();
+  if (threadIdx.x == 0) {
+    for (int s = 0; s < HST; ++s) { tc::mbar_init(&bars->full[s], 128 + 1); tc::mbar_init(&bars->empty[s], 1); }
+    tc::mbar_init(&bars->p1_full, 1);
+    tc::mbar_init(&bars->t_ready, H_EPI);
+    tc::mbar_init(&bars->lg_full, 1);
+    tc::mbar_init(&bars->w_ready, H_EPI);
+    tc::mbar_init(&bars->ia_full, 1);
+    tc::mbar_init(&bars->ia_free, H_EPI);
+    tc::fence_barrier_init();
+  }
+  if (warp == 4 && lane == 0) tc::tma_prefetch_desc(&tmap_wp);
+  if (warp == 5) { tc::tmem_alloc(&bars->tmem_base, 512); tc::tmem_relinquish(); }
+  tc::tcgen05_fence_before();
+  __syncthreads();
+  tc::tcgen05_fence_after();
+  const uint32_t tmem = bars->tmem_base;
+
+  if (warp < 4) {
+    // ------------------------------------------------------------------ E gather for P1 (next tile) and P2 (current tile)
+    const int chunk = lane & 7;
+    uint32_t dst_off[8];
+#pragma unroll
+    for (int j = 0; j < 8; ++j) dst_off[j] = tc::sw128_offset(warp * 32 + j * 4 + (lane >> 3), chunk);
+    const uint16_t* src_cur[8];
+    const uint16_t* src_nxt[8];
+#pragma unroll
+    for (int j = 0; j < 8; ++j) src_cur[j] = src_nxt[j] = args.table;
+    uint32_t nb_cur = 0, nb_nxt = 0;          // bit j set = row j of this thread is a real history row
+    auto setup = [&](int lt, const uint16_t* (&src)[8], uint32_t& nb) {
+      const int tile = static_cast<int>(blockIdx.x) + lt * static_cast<int>(gridDim.x);
+      nb = 0;
+#pragma unroll
+      for (int j = 0; j < 8; ++j) {
+        const int r = warp * 32 + j * 4 + (lane >> 3);
+        const int64_t imp = static_cast<int64_t>(tile) * IPT + r / HP;
+        const int h = r % HP;
+        bool ok = h < H && imp < args.B;
+        int64_t row = 0;
+        if (ok) {
+          row = load_id(args.his_ids, imp * H + h, args.id_dtype);
+          if (row < 0 || row >= args.n_rows) { ok = false; row = 0; }       // out-of-range id: zero row (gather semantics)
+        }
+        src[j] = args.table + row * D + chunk * 8;
+        nb |= ok ? (1u << j) : 0u;
+      }
+    };
+    uint32_t issued = 0;
+    for (int st = -1; st < n_local; ++st) {
+      const bool has_next = st + 1 < n_local;
+#pragma unroll
+      for (int j = 0; j < 8; ++j) src_cur[j] = src_nxt[j];
+      nb_cur = nb_nxt;
+      if (has_next) setup(st + 1, src_nxt, nb_nxt);
+      for_each_op(st >= 0, has_next, KB, [&](int kind, int idx) {
+        if (kind == OP_LG) return;
+        const uint32_t s = issued % HST, ph = (issued / HST) & 1;
+        tc::mbar_wait(&bars->empty[s], ph ^ 1);
+        const uint32_t base = tc::smem_u32(st_a + s * HA_BYTES);
+        if (kind == OP_P1) {
+#pragma unroll
+          for (int j = 0; j < 8; ++j) tc::cp_async_16(base + dst_off[j], src_nxt[j] + idx * HKB, ((nb_nxt >> j) & 1u) ? 16u : 0u);
+        } else {
+#pragma unroll
+          for (int j = 0; j < 8; ++j) tc::cp_async_16(base + dst_off[j], src_cur[j] + idx * HKB, ((nb_cur >> j) & 1u) ? 16u : 0u);
+        }
+        tc::cp_async_mbar_arrive_noinc(&bars->full[s]);
+        ++issued;
+      });
+    }
+    tc::cp_async_wait_all();
+  } else if (warp == 4) {
+    // ------------------------------------------------------------------ Wp k-blocks by TMA for P1 ops; plain arrive for P2 ops
+    if (lane == 0) {
+      uint32_t it = 0;
+      for (int st = -1; st < n_local; ++st) {
+        for_each_op(st >= 0, st + 1 < n_local, KB, [&](int kind, int idx) {
+          if (kind == OP_LG) return;
+          const uint32_t s = it % HST, ph = (it / HST) & 1;
+          tc::mbar_wait(&bars->empty[s], ph ^ 1);
+          if (kind == OP_P1) {
+            tc::mbar_arrive_expect_tx(&bars->full[s], static_cast<uint32_t>(N1 * HKB * 2));
+            tc::tma_load_2d(&tmap_wp, &bars->full[s], tc::smem_u32(st_b + s * args.b_bytes), idx * HKB, 0);
+          } else {
+            tc::mbar_arrive(&bars->full[s]);
+          }
+          ++it;
+        });
+      }
+    }
+  } else if (warp == 5) {
+    // ------------------------------------------------------------------ MMA issuer
+    if (lane == 0) {
+      const uint32_t idesc1 = tc::make_idesc_bf16_f32(HM, N1);
+      const uint32_t idesc_lg = tc::make_idesc_bf16_f32(HM, KP);
+      const uint32_t idesc2 = tc::make_idesc_bf16_f32_major(HM, HKB, false, true);     // B = E k-block read MN-major
+      uint32_t it = 0, gj = 0;
+      for (int st = -1; st < n_local; ++st) {
+        const int lt = st, ln = st + 1;                      // local index of the current / next tile
+        for_each_op(st >= 0, ln < n_local, KB, [&](int kind, int idx) {
+          if (kind == OP_P1) {
+            // the projection accumulator is free: LG(lt) (issued before, after t_ready) means tile lt has been turned into T
+            const uint32_t s = it % HST, ph = (it / HST) & 1;
+            tc::mbar_wait(&bars->full[s], ph);
+            tc::fence_proxy_async_smem();                    // cp.async (generic proxy) writes -> tcgen05.mma (async proxy) reads
+            tc::tcgen05_fence_after();
+            const uint64_t a_desc = tc::make_smem_desc_sw128(tc::smem_u32(st_a + s * HA_BYTES));
+            const uint64_t b_desc = tc::make_smem_desc_sw128(tc::smem_u32(st_b + s * args.b_bytes));
+#pragma unroll
+            for (int k = 0; k < HKB / 16; ++k) tc::umma_bf16(tmem, a_desc + 2 * k, b_desc + 2 * k, idesc1, (idx | k) != 0 ? 1u : 0u);
+            tc::umma_commit(&bars->empty[s]);
+            if (idx == KB - 1) tc::umma_commit(&bars->p1_full);
+            ++it;
+          } else if (kind == OP_LG) {
+            tc::mbar_wait(&bars->t_ready, lt & 1);           // tanh(proj) of the current tile sits in T_hi / T_lo as packed bf16
+            tc::tcgen05_fence_after();
+            for (int ks = 0; ks < N1 / 16; ++ks) {
+              const uint32_t off = (ks >> 2) * CT_ATOM;
+              const uint64_t h_desc = tc::make_smem_desc_sw128(tc::smem_u32(c_hi + off)) + 2 * (ks & 3);
+              const uint64_t l_desc = tc::make_smem_desc_sw128(tc::smem_u32(c_lo + off)) + 2 * (ks & 3);
+              tc::umma_bf16_ts(tmem + LG_COL, tmem + TH_COL + 8 * ks, h_desc, idesc_lg, ks != 0 ? 1u : 0u);
+              tc::umma_bf16_ts(tmem + LG_COL, tmem + TL_COL + 8 * ks, h_desc, idesc_lg, 1u);
+              tc::umma_bf16_ts(tmem + LG_COL, tmem + TH_COL + 8 * ks, l_desc, idesc_lg, 1u);
+            }
+            tc::umma_commit(&bars->lg_full);
+          } else {
+            if (idx == 0) {
+              tc::mbar_wait(&bars->w_ready, lt & 1);         // softmax weights of the current tile are in shared memory
+              tc::tcgen05_fence_after();
+            }
+            tc::mbar_wait(&bars->ia_free, (gj & 1) ^ 1);     // the previous 64-feature block has been drained
+            const uint32_t s = it % HST, ph = (it / HST) & 1;
+            tc::mbar_wait(&bars->full[s], ph);
+            tc::fence_proxy_async_smem();
+            tc::tcgen05_fence_after();
+            const uint64_t e_desc = tc::make_smem_desc_sw128_mn(tc::smem_u32(st_a + s * HA_BYTES));
+#pragma unroll
+            for (int hl = 0; hl < 2; ++hl) {
+#pragma unroll
+              for (int ks = 0; ks < HM / 16; ++ks) {
+                const uint64_t w_desc = tc::make_smem_desc_sw128(tc::smem_u32(w_t + (hl * 2 + (ks >> 2)) * WA_BYTES)) + 2 * (ks & 3);
+                tc::umma_bf16(tmem + IA_COL, w_desc, e_desc + ks * (2048 >> 4), idesc2, (hl | ks) != 0 ? 1u : 0u);
+              }
+            }
+            tc::umma_commit(&bars->empty[s]);
+            tc::umma_commit(&bars->ia_full);
+            ++it; ++gj;
+          }
+        });
+      }
+    }
+  } else {
+    // ------------------------------------------------------------------ epilogue warps 6..13
+    const int ew = warp - 6;
+    const int q = warp & 3;
+    const int half = ew >> 2;
+    const int r = q * 32 + lane;                           // tile row = TMEM lane
+    const int et = ew * 32 + lane;                         // 0..255
+    const uint32_t lane_addr = static_cast<uint32_t>(q * 32) << 16;
+    const int n_cu = N1 / 16;
+    const int cu_begin = half == 0 ? 0 : (n_cu + 1) / 2, cu_end = half == 0 ? (n_cu + 1) / 2 : n_cu;
+    uint32_t gj = 0;
+    for (int lt = 0; lt < n_local; ++lt) {
+      const int tile = static_cast<int>(blockIdx.x) + lt * static_cast<int>(gridDim.x);
+      // ---- E1a: tanh(proj) -> packed bf16 hi / lo in tensor memory (model.py:171)
+      tc::mbar_wait(&bars->p1_full, lt & 1);
+      tc::tcgen05_fence_after();
+      for (int cu = cu_begin; cu < cu_end; ++cu) {                             // units of 16 projection columns
+        uint32_t v[16];
+        tc::tmem_ld_32x16(tmem + lane_addr + cu * 16, v);
+        tc::tmem_ld_wait();
+        uint32_t hi[8], lo[8];
+#pragma unroll
+        for (int j = 0; j < 8; ++j) {
+          const float t0 = tanh_acc2(__uint_as_float(v[2 * j])), t1 = tanh_acc2(__uint_as_float(v[2 * j + 1]));
+          const __nv_bfloat16 h0 = __float2bfloat16_rn(t0), h1 = __float2bfloat16_rn(t1);
+          hi[j] = pack2b(t0, t1);
+          lo[j] = pack2b(t0 - __bfloat162float(h0), t1 - __bfloat162float(h1));
+        }
+        tc::tmem_st_32x8(tmem + lane_addr + TH_COL + cu * 8, hi);
+        tc::tmem_st_32x8(tmem + lane_addr + TL_COL + cu * 8, lo);
+      }
+      tc::tmem_st_wait();
+      tc::tcgen05_fence_before();
+      tc::mbar_arrive(&bars->t_ready);
+      // ---- E1b: logits (+bias), 1e-30 mask fill, softmax over the history (model.py:174-181)
+      tc::mbar_wait(&bars->lg_full, lt & 1);
+      tc::tcgen05_fence_after();
+      {
+        uint32_t lg[16];
+        tc::tmem_ld_32x16(tmem + lane_addr + LG_COL + half * 16, lg);
+        tc::tmem_ld_wait();
+        const int64_t imp = static_cast<int64_t>(tile) * IPT + r / HP;
+        const int h = r % HP;
+        const bool valid = h < H && imp < args.B;
+        const bool keep = valid && args.mask[imp * H + h] != 0;
+        const float bias = (valid && args.bias_mean) ? args.bias_mean[imp * H + h] : 0.f;
+#pragma unroll
+        for (int j = 0; j < 16; ++j) {
+          float v = __uint_as_float(lg[j]) + bias;
+          if (!keep) v = kMaskFill;                                            // model.py:180 (1e-30, not -inf)
+          if (!valid) v = -INFINITY;                                           // tile padding: not part of the history
+          L[r * LROW + half * 16 + j] = v;
+        }
+      }
+      tc::tcgen05_fence_before();
+      tc::named_bar_sync(1, H_EPI);
+      {
+        const int pair = et >> 2, part = et & 3;
+        const bool active = pair < IPT * K;
+        const int i = active ? pair / K : 0, k = active ? pair % K : 0;
+        const float* col = L + (i * HP) * LROW + k;
+        float mx = -INFINITY;
+        for (int h = part; h < HP; h += 4) mx = fmaxf(mx, col[h * LROW]);
+        mx = fmaxf(mx, __shfl_xor_sync(0xffffffffu, mx, 1));
+        mx = fmaxf(mx, __shfl_xor_sync(0xffffffffu, mx, 2));
+        const bool dead = mx == -INFINITY;                                     // impression past the end of the batch
+        float sum = 0.f;
+        for (int h = part; h < HP; h += 4) sum += dead ? 0.f : expf(col[h * LROW] - mx);
+        sum += __shfl_xor_sync(0xffffffffu, sum, 1);
+        sum += __shfl_xor_sync(0xffffffffu, sum, 2);
+        if (active) {
+          const int R = i * K + k;
+          for (int h = part; h < HP; h += 4) {
+            const float w = dead ? 0.f : expf(col[h * LROW] - mx) / sum;       // model.py:181
+            const __nv_bfloat16 whi = __float2bfloat16_rn(w);
+            const __nv_bfloat16 wlo = __float2bfloat16_rn(w - __bfloat162float(whi));
+            const int hc = i * HP + h;
+            const uint32_t off = (hc >> 6) * WA_BYTES + tc::sw128_offset(R, (hc & 63) >> 3) + (hc & 7) * 2;
+            *reinterpret_cast<__nv_bfloat16*>(w_t + off) = whi;
+            *reinterpret_cast<__nv_bfloat16*>(w_t + 2 * WA_BYTES + off) = wlo;
+          }
+        }
+      }
+      tc::fence_proxy_async_smem();
+      tc::mbar_arrive(&bars->w_ready);
+      // ---- E2: drain the interests, one 64-feature block at a time (model.py:182)
+      const bool row_ok = r < IPT * K;
+      const int64_t imp2 = static_cast<int64_t>(tile) * IPT + r / K;
+      const bool store_ok = row_ok && imp2 < args.B;
+      const int64_t grow = static_cast<int64_t>(tile) * IPT * K + r;            // = imp * K + k
+      for (int j = 0; j < KB; ++j, ++gj) {
+        tc::mbar_wait(&bars->ia_full, gj & 1);
+        tc::tcgen05_fence_after();
+        if (q * 32 < IPT * K) {                                                // warp-uniform: this lane quarter holds interest rows
+          uint32_t v[32];
+          tc::tmem_ld_32x32(tmem + lane_addr + IA_COL + half * 32, v);
+          tc::tmem_ld_wait();
+          if (store_ok) {
+            const int64_t o = grow * D + j * HKB + half * 32;
+            uint32_t hi[16], lo[16];
+#pragma unroll
+            for (int c = 0; c < 16; ++c) {
+              const float x0 = __uint_as_float(v[2 * c]), x1 = __uint_as_float(v[2 * c + 1]);
+              const __nv_bfloat16 h0 = __float2bfloat16_rn(x0), h1 = __float2bfloat16_rn(x1);
+              hi[c] = pack2b(x0, x1);
+              lo[c] = pack2b(x0 - __bfloat162float(h0), x1 - __bfloat162float(h1));
+            }
+            uint4* ph = reinterpret_cast<uint4*>(args.i_hi + o);
+            uint4* pl = reinterpret_cast<uint4*>(args.i_lo + o);
+#pragma unroll
+            for (int c = 0; c < 4; ++c) {
+              ph[c] = make_uint4(hi[4 * c], hi[4 * c + 1], hi[4 * c + 2], hi[4 * c + 3]);
+              pl[c] = make_uint4(lo[4 * c], lo[4 * c + 1], lo[4 * c + 2], lo[4 * c + 3]);
+            }
+            if (args.out_interests) {
+              float4* pf = reinterpret_cast<float4*>(args.out_interests + o);
+#pragma unroll
+              for (int c = 0; c < 8; ++c)
+                pf[c] = make_float4(__uint_as_float(v[4 * c]), __uint_as_float(v[4 * c + 1]), __uint_as_float(v[4 * c + 2]),
+                                    __uint_as_float(v[4 * c + 3]));
+            }
+          }
+        }
+        tc::tcgen05_fence_before();
+        tc::mbar_arrive(&bars->ia_free);
+      }
+    }
+  }
+
+  tc::tcgen05_fence_before();
+  __syncthreads();
+  if (warp == 5) tc::tmem_dealloc(tmem, 512);
+}
+
+}  // namespace
+
+bool hist_kernel2_supported(int64_t H, int64_t K, int64_t Dc, int64_t D) {
+  return H >= 1 && H <= 128 && (K == 8 || K == 16 || K == 32) && Dc >= 1 && Dc <= N1_MAX && D >= 64 && D % 64 == 0 && D <= 4096;
+}
+
+int launch_hist_kernel2(const void* table, int64_t n_rows, const void* his_ids, int id_dtype, const uint8_t* his_mask,
+                        const float* bias_mean, const void* w_proj_bf16, const float* codes, int64_t B, int64_t H, int64_t K,
+                        int64_t Dc, int64_t D, void* i_hi, void* i_lo, float* out_interests, cudaStream_t stream) {
+  if (B == 0) return MINER_OK;
+  const int N1 = static_cast<int>((Dc + 15) / 16 * 16);
+  CUtensorMap m_wp;
+  int rc = make_tmap_2d_bf16(&m_wp, w_proj_bf16, static_cast<uint64_t>(Dc), static_cast<uint64_t>(D), N1, HKB);
+  if (rc) return rc;
+  Hist2Args a;
+  a.table = static_cast<const uint16_t*>(table); a.n_rows = n_rows;
+  a.his_ids = his_ids; a.id_dtype = id_dtype; a.mask = his_mask; a.bias_mean = bias_mean; a.codes = codes;
+  a.B = B; a.H = static_cast<int>(H); a.K = static_cast<int>(K); a.Dc = static_cast<int>(Dc); a.D = static_cast<int>(D); a.N1 = N1;
+  a.b_bytes = N1 * HKB * 2;
+  a.i_hi = static_cast<__nv_bfloat16*>(i_hi); a.i_lo = static_cast<__nv_bfloat16*>(i_lo); a.out_interests = out_interests;
+  const int ipt = H <= 64 ? 2 : 1;
+  const int64_t n_tiles = (B + ipt - 1) / ipt;
+  const int grid = static_cast<int>(n_tiles < sm_count() ? n_tiles : sm_count());
+  const int smem = 1024 + HST * (HA_BYTES + a.b_bytes) + WT_BYTES + 2 * CT_BYTES + HM * LROW * 4 + 512;
+  MINER_CUDA_OK(cudaFuncSetAttribute(hist_kernel2, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
+  hist_kernel2<<<grid, H_THREADS, smem, stream>>>(m_wp, a, static_cast<int>(n_tiles));
+  MINER_LAUNCH_OK("hist_kernel2");
+  return MINER_OK;
+}
+
+}  // namespace miner
