@@ -11,7 +11,7 @@ import os
 from typing import Optional
 
 _PKG = os.path.dirname(os.path.abspath(__file__))
-LIB_PATH = os.path.join(_PKG, 'libminer_b200.so')
+LIB_PATH = os.environ.get('MINER_B200_LIB') or os.path.join(_PKG, 'libminer_b200.so')   # override: instrumented builds
 
 # constants mirrored from include/miner_b200.h
 OK, ERR_INVALID_ARG, ERR_SCORE_TYPE, ERR_CUDA, ERR_WORKSPACE, ERR_UNSUPPORTED = 0, 1, 2, 3, 4, 5

@@ -34,7 +34,12 @@ def _deps_mtime() -> float:
     return m
 
 
-def build(force: bool = False, verbose: bool = False) -> str:
+def build(force: bool = False, verbose: bool = False, extra_flags=(), out: str = None) -> str:
+    """`extra_flags` / `out`: instrumented variants (e.g. -DMINER_HIST_PROF -> libminer_b200_prof.so, objects in build_<name>/)."""
+    global OBJ, LIB
+    if out:
+        LIB = os.path.join(PKG, out)
+        OBJ = os.path.join(PKG, 'build_' + os.path.splitext(out)[0])
     if not force and os.path.exists(LIB) and os.path.getmtime(LIB) >= _deps_mtime():
         return LIB
     os.makedirs(OBJ, exist_ok=True)
@@ -43,7 +48,7 @@ def build(force: bool = False, verbose: bool = False) -> str:
 
     def compile_one(src):
         obj = os.path.join(OBJ, src.replace('/', '_') + '.o')
-        cmd = [nvcc, *NVCC_FLAGS, '-c', os.path.join(CSRC, src), '-o', obj]
+        cmd = [nvcc, *NVCC_FLAGS, *extra_flags, '-c', os.path.join(CSRC, src), '-o', obj]
         r = subprocess.run(cmd, capture_output=True, text=True)
         logs[src] = r.stderr
         if r.returncode != 0:
@@ -66,4 +71,5 @@ def build(force: bool = False, verbose: bool = False) -> str:
 
 
 if __name__ == '__main__':
-    print(build(force='--force' in sys.argv, verbose='-v' in sys.argv))
+    print(build(force='--force' in sys.argv, verbose='-v' in sys.argv, extra_flags=[a for a in sys.argv[1:] if a.startswith('-D')],
+                out=next((a.split('=', 1)[1] for a in sys.argv[1:] if a.startswith('--out=')), None)))

@@ -301,3 +301,6 @@ extern "C" int miner_cand_score_fwd(const void* i_hi, const void* i_lo, const vo
   return launch_cand_kernel(i_hi, i_lo, w_target_bf16, table, n_rows, cand_ids, id_dtype, cand_offsets, B, C, K, D, out_scores,
                             static_cast<cudaStream_t>(stream));
 }
+
+// profiling hook (not part of the documented ABI): device buffer of 148*3*16 int64 for -DMINER_HIST_PROF builds
+extern "C" void miner_debug_set_hist_prof(void* p) { set_hist_prof_buffer(static_cast<long long*>(p)); }

@@ -173,7 +173,7 @@ cand_kernel(const __grid_constant__ CUtensorMap tmap_ihi, const __grid_constant_
     tc::cp_async_wait_all();
   } else if (warp == 4) {
     // ------------------------------------------------------------------ TMA producer: I_hi / Wt k-blocks, I_lo in chunk 0
-    if (lane == 0) {
+    {
       uint32_t it = 0, lo_it = 0;
       for (int g = blockIdx.x; g < n_groups; g += gridDim.x) {
         const int64_t c0 = cand_off(args, static_cast<int64_t>(g) * IPG), c1 = cand_off(args, static_cast<int64_t>(g + 1) * IPG);
@@ -182,14 +182,20 @@ cand_kernel(const __grid_constant__ CUtensorMap tmap_ihi, const __grid_constant_
             for (int kb = 0; kb < KB; ++kb, ++it) {
               const uint32_t s = it % CST, ph = (it / CST) & 1;
               tc::mbar_wait(&bars->empty[s], ph ^ 1);
-              tc::mbar_arrive_expect_tx(&bars->full[s], CA_BYTES + CB_BYTES);
-              tc::tma_load_2d(&tmap_ihi, &bars->full[s], tc::smem_u32(st_a + s * CA_BYTES), kb * CKB, g * CM);
-              tc::tma_load_2d(&tmap_wt, &bars->full[s], tc::smem_u32(st_b + s * CB_BYTES), kb * CKB, n * NCH);
+              if (tc::elect_one()) {
+                tc::mbar_arrive_expect_tx(&bars->full[s], CA_BYTES + CB_BYTES);
+                tc::tma_load_2d(&tmap_ihi, &bars->full[s], tc::smem_u32(st_a + s * CA_BYTES), kb * CKB, g * CM);
+                tc::tma_load_2d(&tmap_wt, &bars->full[s], tc::smem_u32(st_b + s * CB_BYTES), kb * CKB, n * NCH);
+              }
+              __syncwarp();
               if (n == 0) {
                 const uint32_t ls = lo_it % RING2, lph = (lo_it / RING2) & 1;
                 tc::mbar_wait(&bars->lo_empty[ls], lph ^ 1);
-                tc::mbar_arrive_expect_tx(&bars->lo_full[ls], CA_BYTES);
-                tc::tma_load_2d(&tmap_ilo, &bars->lo_full[ls], tc::smem_u32(lo_t + ls * CA_BYTES), kb * CKB, g * CM);
+                if (tc::elect_one()) {
+                  tc::mbar_arrive_expect_tx(&bars->lo_full[ls], CA_BYTES);
+                  tc::tma_load_2d(&tmap_ilo, &bars->lo_full[ls], tc::smem_u32(lo_t + ls * CA_BYTES), kb * CKB, g * CM);
+                }
+                __syncwarp();
                 ++lo_it;
               }
             }
@@ -198,8 +204,8 @@ cand_kernel(const __grid_constant__ CUtensorMap tmap_ihi, const __grid_constant_
       }
     }
   } else if (warp == 5) {
-    // ------------------------------------------------------------------ MMA issuer
-    if (lane == 0) {
+    // ------------------------------------------------------------------ MMA issuer (warp-uniform; one elected lane issues)
+    {
       uint32_t it = 0, lo_it = 0, c_it = 0, pb_it = 0, ch_it = 0, grp_it = 0;
       for (int g = blockIdx.x; g < n_groups; g += gridDim.x) {
         const int64_t c0 = cand_off(args, static_cast<int64_t>(g) * IPG), c1 = cand_off(args, static_cast<int64_t>(g + 1) * IPG);
@@ -224,45 +230,52 @@ cand_kernel(const __grid_constant__ CUtensorMap tmap_ihi, const __grid_constant_
                 const uint32_t cs = c_it % RING2, cph = (c_it / RING2) & 1;
                 tc::mbar_wait(&bars->lo_full[ls], lph);
                 tc::mbar_wait(&bars->c_full[cs], cph);
-                tc::fence_proxy_async_smem();                // cp.async (generic proxy) writes -> tcgen05.mma (async proxy) reads
                 tc::tcgen05_fence_after();
                 const uint64_t l_desc = tc::make_smem_desc_sw128(tc::smem_u32(lo_t + ls * CA_BYTES));
                 const uint64_t c_desc = tc::make_smem_desc_sw128(tc::smem_u32(cd_t + cs * CC_BYTES));
+                if (tc::elect_one()) {
 #pragma unroll
-                for (int k = 0; k < CKB / 16; ++k) {
-                  tc::umma_bf16(tmem + COL_M, a_desc + 2 * k, c_desc + 2 * k, idesc_c, (kb | k) != 0 ? 1u : 0u);
-                  tc::umma_bf16(tmem + COL_M, l_desc + 2 * k, c_desc + 2 * k, idesc_c, 1u);
+                  for (int k = 0; k < CKB / 16; ++k) {
+                    tc::umma_bf16(tmem + COL_M, a_desc + 2 * k, c_desc + 2 * k, idesc_c, (kb | k) != 0 ? 1u : 0u);
+                    tc::umma_bf16(tmem + COL_M, l_desc + 2 * k, c_desc + 2 * k, idesc_c, 1u);
+                  }
+                  tc::umma_commit(&bars->lo_empty[ls]);
+                  tc::umma_commit(&bars->c_empty[cs]);
                 }
-                tc::umma_commit(&bars->lo_empty[ls]);
-                tc::umma_commit(&bars->c_empty[cs]);
+                __syncwarp();
                 ++lo_it; ++c_it;
               } else {
                 tc::tcgen05_fence_after();
               }
+              if (tc::elect_one()) {
 #pragma unroll
-              for (int k = 0; k < CKB / 16; ++k)
-                tc::umma_bf16(tmem + COL_P, a_desc + 2 * k, b_desc + 2 * k, idesc_p, (kb | k) != 0 ? 1u : 0u);
-              tc::umma_commit(&bars->empty[s]);
+                for (int k = 0; k < CKB / 16; ++k)
+                  tc::umma_bf16(tmem + COL_P, a_desc + 2 * k, b_desc + 2 * k, idesc_p, (kb | k) != 0 ? 1u : 0u);
+                tc::umma_commit(&bars->empty[s]);
+                if (kb == KB - 1) tc::umma_commit(&bars->p_full);
+              }
+              __syncwarp();
             }
-            tc::umma_commit(&bars->p_full);
             // attention logits: a += gelu(P)[:, 64-feature block] . cand[:, same block]^T
             for (int sb = 0; sb < nn_cols / CKB; ++sb, ++pb_it, ++c_it) {
               const uint32_t ps = pb_it % RING2, pph = (pb_it / RING2) & 1;
               const uint32_t cs = c_it % RING2, cph = (c_it / RING2) & 1;
               tc::mbar_wait(&bars->pb_full[ps], pph);
               tc::mbar_wait(&bars->c_full[cs], cph);
-              tc::fence_proxy_async_smem();
               tc::tcgen05_fence_after();
               const uint64_t p_desc = tc::make_smem_desc_sw128(tc::smem_u32(pb_t + ps * CA_BYTES));
               const uint64_t c_desc = tc::make_smem_desc_sw128(tc::smem_u32(cd_t + cs * CC_BYTES));
+              if (tc::elect_one()) {
 #pragma unroll
-              for (int k = 0; k < CKB / 16; ++k)
-                tc::umma_bf16(tmem + COL_A, p_desc + 2 * k, c_desc + 2 * k, idesc_c, (n | sb | k) != 0 ? 1u : 0u);
-              tc::umma_commit(&bars->pb_empty[ps]);
-              tc::umma_commit(&bars->c_empty[cs]);
+                for (int k = 0; k < CKB / 16; ++k)
+                  tc::umma_bf16(tmem + COL_A, p_desc + 2 * k, c_desc + 2 * k, idesc_c, (n | sb | k) != 0 ? 1u : 0u);
+                tc::umma_commit(&bars->pb_empty[ps]);
+                tc::umma_commit(&bars->c_empty[cs]);
+                if (n == n_chunks - 1 && sb == nn_cols / CKB - 1) tc::umma_commit(&bars->fin_full);
+              }
+              __syncwarp();
             }
           }
-          tc::umma_commit(&bars->fin_full);
         }
       }
     }

@@ -22,6 +22,8 @@ int launch_hist_kernel2(const void* table, int64_t n_rows, const void* his_ids, 
                         const float* bias_mean, const void* w_proj_bf16, const float* codes, int64_t B, int64_t H, int64_t K,
                         int64_t Dc, int64_t D, void* i_hi, void* i_lo, float* out_interests, cudaStream_t stream);   // transposed, zero-padded codes [DcPad][32] fp32
 
+void set_hist_prof_buffer(long long* p);   // -DMINER_HIST_PROF builds only: where hist_kernel2 writes its cycle counters
+
 // Candidate side: scores for score_type = 'weighted' (model.py:127,200-216) from I_hi/I_lo and table[cand_ids].
 bool cand_kernel_supported(int64_t K, int64_t D);
 int launch_cand_kernel(const void* i_hi, const void* i_lo, const void* wt_bf16, const void* table, int64_t n_rows,

@@ -177,7 +177,6 @@ hist_kernel(const __grid_constant__ CUtensorMap tmap_wp, const HistArgs args, in
         for (int kb = 0; kb < KB; ++kb, ++it) {
           const uint32_t s = it % HST, ph = (it / HST) & 1;
           tc::mbar_wait(&bars->full[s], ph);
-          tc::fence_proxy_async_smem();                      // cp.async (generic proxy) writes -> tcgen05.mma (async proxy) reads
           tc::tcgen05_fence_after();
           const uint64_t a_desc = tc::make_smem_desc_sw128(tc::smem_u32(st_a + s * HA_BYTES));
           const uint64_t b_desc = tc::make_smem_desc_sw128(tc::smem_u32(st_b + s * args.b_bytes));
@@ -196,7 +195,6 @@ hist_kernel(const __grid_constant__ CUtensorMap tmap_wp, const HistArgs args, in
           for (int db = 0; db < nd; ++db, ++it) {
             const uint32_t s = it % HST, ph = (it / HST) & 1;
             tc::mbar_wait(&bars->full[s], ph);
-            tc::fence_proxy_async_smem();
             tc::tcgen05_fence_after();
             const uint64_t e_desc = tc::make_smem_desc_sw128_mn(tc::smem_u32(st_a + s * HA_BYTES));
             const uint32_t d_tmem = tmem + buf * RCOLS + db * HKB;

@@ -9,16 +9,19 @@
 //     MMA warp accumulates the projection of tile t+1 while tile t goes through softmax, weighted sum and draining, so
 //     the gather / TMA pipeline keeps running across the phase boundaries.  The issue order of one step is fixed and
 //     shared by the three roles:
-//         LG(t)  P1(t+1)[0..2]  { P2(t)[j], P1(t+1)[3 + j] }  rest of P1(t+1)
+//         LG(t)  P1(t+1)[0..7]  { P2(t)[j], P1(t+1)[8 + j] }  rest of P1(t+1)
 //     P1 = one projection k-block (gathered E tile + Wp tile), LG = logits MMAs, P2 = one 64-feature block of the interests
 //     (A = softmax weights hi|lo from shared memory, B = the re-gathered E tile read MN-major);
-//   * TMEM map (512 columns): projection [0,208) | T_hi [208,312) | T_lo [312,416) | logits [416,448) | interests block [448,512).
+//   * TMEM map (512 columns): projection [0,208) | T_hi [208,312) | T_lo [312,416) | logits [416,448); once the logits MMAs
+//     are done the T region is dead and holds three 64-column interest buffers [208,400), drained round-robin.
 #include <cuda.h>
 
 #include "fused.cuh"
 #include "umma.cuh"
 
 namespace miner {
+
+long long* hist_prof_buffer();
 
 namespace {
 
@@ -29,7 +32,9 @@ constexpr int LROW = 33;
 constexpr int H_THREADS = 14 * 32;
 constexpr int H_EPI = 256;
 constexpr int N1_MAX = 208;                  // projection accumulator columns (Dc padded to 16)
-constexpr int TH_COL = N1_MAX, TL_COL = TH_COL + N1_MAX / 2, LG_COL = TL_COL + N1_MAX / 2, IA_COL = LG_COL + KP;
+constexpr int TH_COL = N1_MAX, TL_COL = TH_COL + N1_MAX / 2, LG_COL = TL_COL + N1_MAX / 2;
+// the three 64-column interest buffers live in the T_hi / T_lo region, which is dead once the logits MMAs of the tile are done
+constexpr int IA_COL = TH_COL, IA_BUFS = 3;
 constexpr int WA_BYTES = 64 * 128;           // softmax-weight atom (64 interest rows x 64 history slots); the MMA reads 8 KB past it
 constexpr int WT_BYTES = 4 * WA_BYTES;
 constexpr int CT_ATOM = KP * 128;            // codes tile atom: 32 codes x 64 features
@@ -37,10 +42,22 @@ constexpr int CT_BYTES = 4 * CT_ATOM;        // per hi / lo tile (Dc <= 256)
 
 enum { OP_P1 = 0, OP_LG = 1, OP_P2 = 2 };
 
+// Optional cycle accounting (build with -DMINER_HIST_PROF): per CTA, 16 counters each for the MMA thread, one epilogue
+// thread and one gather thread, written to args.prof at the end (scripts/prof_hist.py prints them).
+#ifdef MINER_HIST_PROF
+#define PROF_DECL long long prof_c[16] = {0}; long long prof_t0 = clock64(), prof_start = prof_t0
+#define PROF_ADD(i) do { const long long prof_t1 = clock64(); prof_c[i] += prof_t1 - prof_t0; prof_t0 = prof_t1; } while (0)
+#define PROF_STORE(role) do { if (args.prof) { prof_c[15] = clock64() - prof_start; for (int i_ = 0; i_ < 16; ++i_) args.prof[(blockIdx.x * 3 + (role)) * 16 + i_] = prof_c[i_]; } } while (0)
+#else
+#define PROF_DECL
+#define PROF_ADD(i)
+#define PROF_STORE(role)
+#endif
+
 struct H2Barriers {
   uint64_t full[HST], empty[HST];
   uint64_t p1_full, t_ready, lg_full, w_ready;
-  uint64_t ia_full, ia_free;
+  uint64_t ia_full[IA_BUFS], ia_free[IA_BUFS];
   uint32_t tmem_base;
 };
 
@@ -52,6 +69,7 @@ struct Hist2Args {
   int64_t B;
   int H, K, Dc, D, N1, b_bytes;
   __nv_bfloat16* i_hi; __nv_bfloat16* i_lo; float* out_interests;
+  long long* prof;
 };
 
 // issue order of one step; `has_cur` false = prologue (only the projection of the first tile)
@@ -63,7 +81,7 @@ __device__ __forceinline__ void for_each_op(bool has_cur, bool has_next, int KB,
   };
   if (!has_cur) { p1n(KB); return; }
   f(OP_LG, 0);
-  p1n(3);
+  p1n(8);
   for (int j = 0; j < KB; ++j) {
     f(OP_P2, j);
     p1n(1);
@@ -117,8 +135,7 @@ hist_kernel2(const __grid_constant__ CUtensorMap tmap_wp, const Hist2Args args, 
     tc::mbar_init(&bars->t_ready, H_EPI);
     tc::mbar_init(&bars->lg_full, 1);
     tc::mbar_init(&bars->w_ready, H_EPI);
-    tc::mbar_init(&bars->ia_full, 1);
-    tc::mbar_init(&bars->ia_free, H_EPI);
+    for (int b = 0; b < IA_BUFS; ++b) { tc::mbar_init(&bars->ia_full[b], 1); tc::mbar_init(&bars->ia_free[b], H_EPI); }
     tc::fence_barrier_init();
   }
   if (warp == 4 && lane == 0) tc::tma_prefetch_desc(&tmap_wp);
@@ -139,35 +156,46 @@ hist_kernel2(const __grid_constant__ CUtensorMap tmap_wp, const Hist2Args args, 
 #pragma unroll
     for (int j = 0; j < 8; ++j) src_cur[j] = src_nxt[j] = args.table;
     uint32_t nb_cur = 0, nb_nxt = 0;          // bit j set = row j of this thread is a real history row
-    auto setup = [&](int lt, const uint16_t* (&src)[8], uint32_t& nb) {
+    // ids of a tile are fetched one step before its row pointers are needed (the loads are issued together, unconditionally)
+    int64_t ids_pre[8];
+    auto fetch_ids = [&](int lt) {
       const int tile = static_cast<int>(blockIdx.x) + lt * static_cast<int>(gridDim.x);
-      nb = 0;
 #pragma unroll
       for (int j = 0; j < 8; ++j) {
         const int r = warp * 32 + j * 4 + (lane >> 3);
         const int64_t imp = static_cast<int64_t>(tile) * IPT + r / HP;
         const int h = r % HP;
-        bool ok = h < H && imp < args.B;
-        int64_t row = 0;
-        if (ok) {
-          row = load_id(args.his_ids, imp * H + h, args.id_dtype);
-          if (row < 0 || row >= args.n_rows) { ok = false; row = 0; }       // out-of-range id: zero row (gather semantics)
-        }
-        src[j] = args.table + row * D + chunk * 8;
+        const bool ok = h < H && imp < args.B;
+        ids_pre[j] = load_id(args.his_ids, ok ? imp * H + h : 0, args.id_dtype);
+        if (!ok) ids_pre[j] = -1;
+      }
+    };
+    auto setup = [&](const uint16_t* (&src)[8], uint32_t& nb) {
+      nb = 0;
+#pragma unroll
+      for (int j = 0; j < 8; ++j) {
+        const int64_t row = ids_pre[j];
+        const bool ok = row >= 0 && row < args.n_rows;                      // padding slot or out-of-range id: zero row (gather semantics)
+        src[j] = args.table + (ok ? row : 0) * D + chunk * 8;
         nb |= ok ? (1u << j) : 0u;
       }
     };
+    if (n_local > 0) fetch_ids(0);
     uint32_t issued = 0;
+    PROF_DECL;
     for (int st = -1; st < n_local; ++st) {
       const bool has_next = st + 1 < n_local;
 #pragma unroll
       for (int j = 0; j < 8; ++j) src_cur[j] = src_nxt[j];
       nb_cur = nb_nxt;
-      if (has_next) setup(st + 1, src_nxt, nb_nxt);
+      if (has_next) setup(src_nxt, nb_nxt);
+      if (st + 2 < n_local) fetch_ids(st + 2);
+      PROF_ADD(0);
       for_each_op(st >= 0, has_next, KB, [&](int kind, int idx) {
         if (kind == OP_LG) return;
         const uint32_t s = issued % HST, ph = (issued / HST) & 1;
         tc::mbar_wait(&bars->empty[s], ph ^ 1);
+        PROF_ADD(1);
         const uint32_t base = tc::smem_u32(st_a + s * HA_BYTES);
         if (kind == OP_P1) {
 #pragma unroll
@@ -178,88 +206,115 @@ hist_kernel2(const __grid_constant__ CUtensorMap tmap_wp, const Hist2Args args, 
         }
         tc::cp_async_mbar_arrive_noinc(&bars->full[s]);
         ++issued;
+        PROF_ADD(2);
       });
     }
     tc::cp_async_wait_all();
+    if (threadIdx.x == 0) PROF_STORE(2);
   } else if (warp == 4) {
     // ------------------------------------------------------------------ Wp k-blocks by TMA for P1 ops; plain arrive for P2 ops
-    if (lane == 0) {
+    {
       uint32_t it = 0;
       for (int st = -1; st < n_local; ++st) {
         for_each_op(st >= 0, st + 1 < n_local, KB, [&](int kind, int idx) {
           if (kind == OP_LG) return;
           const uint32_t s = it % HST, ph = (it / HST) & 1;
           tc::mbar_wait(&bars->empty[s], ph ^ 1);
-          if (kind == OP_P1) {
-            tc::mbar_arrive_expect_tx(&bars->full[s], static_cast<uint32_t>(N1 * HKB * 2));
-            tc::tma_load_2d(&tmap_wp, &bars->full[s], tc::smem_u32(st_b + s * args.b_bytes), idx * HKB, 0);
-          } else {
-            tc::mbar_arrive(&bars->full[s]);
+          if (tc::elect_one()) {
+            if (kind == OP_P1) {
+              tc::mbar_arrive_expect_tx(&bars->full[s], static_cast<uint32_t>(N1 * HKB * 2));
+              tc::tma_load_2d(&tmap_wp, &bars->full[s], tc::smem_u32(st_b + s * args.b_bytes), idx * HKB, 0);
+            } else {
+              tc::mbar_arrive(&bars->full[s]);
+            }
           }
+          __syncwarp();
           ++it;
         });
       }
     }
   } else if (warp == 5) {
-    // ------------------------------------------------------------------ MMA issuer
-    if (lane == 0) {
+    // ------------------------------------------------------------------ MMA issuer (warp-uniform; one elected lane issues)
+    {
       const uint32_t idesc1 = tc::make_idesc_bf16_f32(HM, N1);
       const uint32_t idesc_lg = tc::make_idesc_bf16_f32(HM, KP);
       const uint32_t idesc2 = tc::make_idesc_bf16_f32_major(HM, HKB, false, true);     // B = E k-block read MN-major
       uint32_t it = 0, gj = 0;
+      PROF_DECL;
       for (int st = -1; st < n_local; ++st) {
         const int lt = st, ln = st + 1;                      // local index of the current / next tile
         for_each_op(st >= 0, ln < n_local, KB, [&](int kind, int idx) {
           if (kind == OP_P1) {
             // the projection accumulator is free: LG(lt) (issued before, after t_ready) means tile lt has been turned into T
             const uint32_t s = it % HST, ph = (it / HST) & 1;
+            PROF_ADD(0);
             tc::mbar_wait(&bars->full[s], ph);
-            tc::fence_proxy_async_smem();                    // cp.async (generic proxy) writes -> tcgen05.mma (async proxy) reads
+            PROF_ADD(1);
             tc::tcgen05_fence_after();
             const uint64_t a_desc = tc::make_smem_desc_sw128(tc::smem_u32(st_a + s * HA_BYTES));
             const uint64_t b_desc = tc::make_smem_desc_sw128(tc::smem_u32(st_b + s * args.b_bytes));
+            if (tc::elect_one()) {
 #pragma unroll
-            for (int k = 0; k < HKB / 16; ++k) tc::umma_bf16(tmem, a_desc + 2 * k, b_desc + 2 * k, idesc1, (idx | k) != 0 ? 1u : 0u);
-            tc::umma_commit(&bars->empty[s]);
-            if (idx == KB - 1) tc::umma_commit(&bars->p1_full);
-            ++it;
-          } else if (kind == OP_LG) {
-            tc::mbar_wait(&bars->t_ready, lt & 1);           // tanh(proj) of the current tile sits in T_hi / T_lo as packed bf16
-            tc::tcgen05_fence_after();
-            for (int ks = 0; ks < N1 / 16; ++ks) {
-              const uint32_t off = (ks >> 2) * CT_ATOM;
-              const uint64_t h_desc = tc::make_smem_desc_sw128(tc::smem_u32(c_hi + off)) + 2 * (ks & 3);
-              const uint64_t l_desc = tc::make_smem_desc_sw128(tc::smem_u32(c_lo + off)) + 2 * (ks & 3);
-              tc::umma_bf16_ts(tmem + LG_COL, tmem + TH_COL + 8 * ks, h_desc, idesc_lg, ks != 0 ? 1u : 0u);
-              tc::umma_bf16_ts(tmem + LG_COL, tmem + TL_COL + 8 * ks, h_desc, idesc_lg, 1u);
-              tc::umma_bf16_ts(tmem + LG_COL, tmem + TH_COL + 8 * ks, l_desc, idesc_lg, 1u);
+              for (int k = 0; k < HKB / 16; ++k) tc::umma_bf16(tmem, a_desc + 2 * k, b_desc + 2 * k, idesc1, (idx | k) != 0 ? 1u : 0u);
+              tc::umma_commit(&bars->empty[s]);
+              if (idx == KB - 1) tc::umma_commit(&bars->p1_full);
             }
-            tc::umma_commit(&bars->lg_full);
+            __syncwarp();
+            ++it;
+            PROF_ADD(2);
+          } else if (kind == OP_LG) {
+            PROF_ADD(0);
+            tc::mbar_wait(&bars->t_ready, lt & 1);           // tanh(proj) of the current tile sits in T_hi / T_lo as packed bf16
+            PROF_ADD(3);
+            tc::tcgen05_fence_after();
+            const uint64_t ch_desc = tc::make_smem_desc_sw128(tc::smem_u32(c_hi));
+            const uint64_t cl_desc = tc::make_smem_desc_sw128(tc::smem_u32(c_lo));
+            if (tc::elect_one()) {
+              for (int ks = 0; ks < N1 / 16; ++ks) {
+                const uint32_t adv = (ks >> 2) * (CT_ATOM >> 4) + 2 * (ks & 3);
+                tc::umma_bf16_ts(tmem + LG_COL, tmem + TH_COL + 8 * ks, ch_desc + adv, idesc_lg, ks != 0 ? 1u : 0u);
+                tc::umma_bf16_ts(tmem + LG_COL, tmem + TL_COL + 8 * ks, ch_desc + adv, idesc_lg, 1u);
+                tc::umma_bf16_ts(tmem + LG_COL, tmem + TH_COL + 8 * ks, cl_desc + adv, idesc_lg, 1u);
+              }
+              tc::umma_commit(&bars->lg_full);
+            }
+            __syncwarp();
+            PROF_ADD(4);
           } else {
+            PROF_ADD(0);
             if (idx == 0) {
               tc::mbar_wait(&bars->w_ready, lt & 1);         // softmax weights of the current tile are in shared memory
               tc::tcgen05_fence_after();
             }
-            tc::mbar_wait(&bars->ia_free, (gj & 1) ^ 1);     // the previous 64-feature block has been drained
+            PROF_ADD(5);
+            const uint32_t slot = gj % IA_BUFS;
+            tc::mbar_wait(&bars->ia_free[slot], ((gj / IA_BUFS) & 1) ^ 1);     // its previous 64-feature block has been drained
+            PROF_ADD(6);
             const uint32_t s = it % HST, ph = (it / HST) & 1;
             tc::mbar_wait(&bars->full[s], ph);
-            tc::fence_proxy_async_smem();
+            PROF_ADD(7);
             tc::tcgen05_fence_after();
             const uint64_t e_desc = tc::make_smem_desc_sw128_mn(tc::smem_u32(st_a + s * HA_BYTES));
+            const uint64_t w_desc0 = tc::make_smem_desc_sw128(tc::smem_u32(w_t));
+            if (tc::elect_one()) {
 #pragma unroll
-            for (int hl = 0; hl < 2; ++hl) {
+              for (int hl = 0; hl < 2; ++hl) {
 #pragma unroll
-              for (int ks = 0; ks < HM / 16; ++ks) {
-                const uint64_t w_desc = tc::make_smem_desc_sw128(tc::smem_u32(w_t + (hl * 2 + (ks >> 2)) * WA_BYTES)) + 2 * (ks & 3);
-                tc::umma_bf16(tmem + IA_COL, w_desc, e_desc + ks * (2048 >> 4), idesc2, (hl | ks) != 0 ? 1u : 0u);
+                for (int ks = 0; ks < HM / 16; ++ks) {
+                  const uint64_t w_desc = w_desc0 + ((hl * 2 + (ks >> 2)) * (WA_BYTES >> 4) + 2 * (ks & 3));
+                  tc::umma_bf16(tmem + IA_COL + slot * HKB, w_desc, e_desc + ks * (2048 >> 4), idesc2, (hl | ks) != 0 ? 1u : 0u);
+                }
               }
+              tc::umma_commit(&bars->empty[s]);
+              tc::umma_commit(&bars->ia_full[slot]);
             }
-            tc::umma_commit(&bars->empty[s]);
-            tc::umma_commit(&bars->ia_full);
+            __syncwarp();
             ++it; ++gj;
+            PROF_ADD(8);
           }
         });
       }
+      if (lane == 0) PROF_STORE(0);
     }
   } else {
     // ------------------------------------------------------------------ epilogue warps 6..13
@@ -272,10 +327,13 @@ hist_kernel2(const __grid_constant__ CUtensorMap tmap_wp, const Hist2Args args, 
     const int n_cu = N1 / 16;
     const int cu_begin = half == 0 ? 0 : (n_cu + 1) / 2, cu_end = half == 0 ? (n_cu + 1) / 2 : n_cu;
     uint32_t gj = 0;
+    PROF_DECL;
     for (int lt = 0; lt < n_local; ++lt) {
       const int tile = static_cast<int>(blockIdx.x) + lt * static_cast<int>(gridDim.x);
       // ---- E1a: tanh(proj) -> packed bf16 hi / lo in tensor memory (model.py:171)
+      PROF_ADD(0);
       tc::mbar_wait(&bars->p1_full, lt & 1);
+      PROF_ADD(1);
       tc::tcgen05_fence_after();
       for (int cu = cu_begin; cu < cu_end; ++cu) {                             // units of 16 projection columns
         uint32_t v[16];
@@ -295,8 +353,10 @@ hist_kernel2(const __grid_constant__ CUtensorMap tmap_wp, const Hist2Args args, 
       tc::tmem_st_wait();
       tc::tcgen05_fence_before();
       tc::mbar_arrive(&bars->t_ready);
+      PROF_ADD(2);
       // ---- E1b: logits (+bias), 1e-30 mask fill, softmax over the history (model.py:174-181)
       tc::mbar_wait(&bars->lg_full, lt & 1);
+      PROF_ADD(3);
       tc::tcgen05_fence_after();
       {
         uint32_t lg[16];
@@ -327,36 +387,51 @@ hist_kernel2(const __grid_constant__ CUtensorMap tmap_wp, const Hist2Args args, 
         mx = fmaxf(mx, __shfl_xor_sync(0xffffffffu, mx, 1));
         mx = fmaxf(mx, __shfl_xor_sync(0xffffffffu, mx, 2));
         const bool dead = mx == -INFINITY;                                     // impression past the end of the batch
+        float ev[HM / 4];                                                      // this thread's exp values (HP / 4 <= 32 slots)
         float sum = 0.f;
-        for (int h = part; h < HP; h += 4) sum += dead ? 0.f : expf(col[h * LROW] - mx);
+#pragma unroll
+        for (int t = 0; t < HM / 4; ++t) {
+          const int h = part + 4 * t;
+          ev[t] = (h < HP && !dead) ? expf(col[h * LROW] - mx) : 0.f;
+          sum += ev[t];
+        }
         sum += __shfl_xor_sync(0xffffffffu, sum, 1);
         sum += __shfl_xor_sync(0xffffffffu, sum, 2);
         if (active) {
           const int R = i * K + k;
-          for (int h = part; h < HP; h += 4) {
-            const float w = dead ? 0.f : expf(col[h * LROW] - mx) / sum;       // model.py:181
-            const __nv_bfloat16 whi = __float2bfloat16_rn(w);
-            const __nv_bfloat16 wlo = __float2bfloat16_rn(w - __bfloat162float(whi));
-            const int hc = i * HP + h;
-            const uint32_t off = (hc >> 6) * WA_BYTES + tc::sw128_offset(R, (hc & 63) >> 3) + (hc & 7) * 2;
-            *reinterpret_cast<__nv_bfloat16*>(w_t + off) = whi;
-            *reinterpret_cast<__nv_bfloat16*>(w_t + 2 * WA_BYTES + off) = wlo;
+          const float inv = 1.0f / sum;
+#pragma unroll
+          for (int t = 0; t < HM / 4; ++t) {
+            const int h = part + 4 * t;
+            if (h < HP) {
+              const float w = dead ? 0.f : ev[t] / sum;                        // model.py:181
+              const __nv_bfloat16 whi = __float2bfloat16_rn(w);
+              const __nv_bfloat16 wlo = __float2bfloat16_rn(w - __bfloat162float(whi));
+              const int hc = i * HP + h;
+              const uint32_t off = (hc >> 6) * WA_BYTES + tc::sw128_offset(R, (hc & 63) >> 3) + (hc & 7) * 2;
+              *reinterpret_cast<__nv_bfloat16*>(w_t + off) = whi;
+              *reinterpret_cast<__nv_bfloat16*>(w_t + 2 * WA_BYTES + off) = wlo;
+            }
           }
+          (void)inv;
         }
       }
       tc::fence_proxy_async_smem();
       tc::mbar_arrive(&bars->w_ready);
+      PROF_ADD(4);
       // ---- E2: drain the interests, one 64-feature block at a time (model.py:182)
       const bool row_ok = r < IPT * K;
       const int64_t imp2 = static_cast<int64_t>(tile) * IPT + r / K;
       const bool store_ok = row_ok && imp2 < args.B;
       const int64_t grow = static_cast<int64_t>(tile) * IPT * K + r;            // = imp * K + k
       for (int j = 0; j < KB; ++j, ++gj) {
-        tc::mbar_wait(&bars->ia_full, gj & 1);
+        const uint32_t slot = gj % IA_BUFS;
+        tc::mbar_wait(&bars->ia_full[slot], (gj / IA_BUFS) & 1);
+        PROF_ADD(5);
         tc::tcgen05_fence_after();
         if (q * 32 < IPT * K) {                                                // warp-uniform: this lane quarter holds interest rows
           uint32_t v[32];
-          tc::tmem_ld_32x32(tmem + lane_addr + IA_COL + half * 32, v);
+          tc::tmem_ld_32x32(tmem + lane_addr + IA_COL + slot * HKB + half * 32, v);
           tc::tmem_ld_wait();
           if (store_ok) {
             const int64_t o = grow * D + j * HKB + half * 32;
@@ -385,9 +460,11 @@ hist_kernel2(const __grid_constant__ CUtensorMap tmap_wp, const Hist2Args args, 
           }
         }
         tc::tcgen05_fence_before();
-        tc::mbar_arrive(&bars->ia_free);
+        tc::mbar_arrive(&bars->ia_free[slot]);
+        PROF_ADD(6);
       }
     }
+    if (et == 0) PROF_STORE(1);
   }
 
   tc::tcgen05_fence_before();
@@ -396,6 +473,11 @@ hist_kernel2(const __grid_constant__ CUtensorMap tmap_wp, const Hist2Args args, 
 }
 
 }  // namespace
+
+// debug buffer for -DMINER_HIST_PROF builds (148 CTAs x 3 roles x 16 counters), set through miner_debug_set_hist_prof
+static long long* g_hist_prof = nullptr;
+long long* hist_prof_buffer() { return g_hist_prof; }
+void set_hist_prof_buffer(long long* p) { g_hist_prof = p; }
 
 bool hist_kernel2_supported(int64_t H, int64_t K, int64_t Dc, int64_t D) {
   return H >= 1 && H <= 128 && (K == 8 || K == 16 || K == 32) && Dc >= 1 && Dc <= N1_MAX && D >= 64 && D % 64 == 0 && D <= 4096;
@@ -415,6 +497,7 @@ int launch_hist_kernel2(const void* table, int64_t n_rows, const void* his_ids, 
   a.B = B; a.H = static_cast<int>(H); a.K = static_cast<int>(K); a.Dc = static_cast<int>(Dc); a.D = static_cast<int>(D); a.N1 = N1;
   a.b_bytes = N1 * HKB * 2;
   a.i_hi = static_cast<__nv_bfloat16*>(i_hi); a.i_lo = static_cast<__nv_bfloat16*>(i_lo); a.out_interests = out_interests;
+  a.prof = hist_prof_buffer();
   const int ipt = H <= 64 ? 2 : 1;
   const int64_t n_tiles = (B + ipt - 1) / ipt;
   const int grid = static_cast<int>(n_tiles < sm_count() ? n_tiles : sm_count());

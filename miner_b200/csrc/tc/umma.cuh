@@ -9,6 +9,19 @@ namespace tc {
 
 __device__ __forceinline__ uint32_t smem_u32(const void* p) { return static_cast<uint32_t>(__cvta_generic_to_shared(p)); }
 
+// One lane of the (converged) warp.  The MMA / TMA issuing warps run their loops warp-uniformly and only wrap the issuing
+// instructions in `if (elect_one())`: tcgen05.mma / TMA take their operands from uniform registers, and code inside a
+// divergent `if (lane == 0)` region forces a per-instruction R2UR waterfall loop (seen in the SASS as ELECT / R2UR / BRA.U.ANY).
+__device__ __forceinline__ bool elect_one() {
+  uint32_t pred;
+  asm volatile(
+      "{\n\t.reg .b32 rx;\n\t.reg .pred px;\n\t"
+      "elect.sync rx|px, 0xffffffff;\n\t"
+      "selp.u32 %0, 1, 0, px;\n\t}"
+      : "=r"(pred));
+  return pred != 0;
+}
+
 // ----------------------------------------------------------------------------------------------- mbarrier
 __device__ __forceinline__ void mbar_init(uint64_t* bar, uint32_t count) {
   asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(smem_u32(bar)), "r"(count) : "memory");

@@ -1,0 +1,35 @@
+"""Cycle accounting of hist_kernel2 (needs the -DMINER_HIST_PROF build):
+    python -m miner_b200.build --force -DMINER_HIST_PROF --out=libminer_b200_prof.so
+    MINER_B200_LIB=miner_b200/libminer_b200_prof.so python scripts/prof_hist.py
+"""
+import os, sys
+sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
+import ctypes as C
+import torch
+from miner_b200 import ops, synth, _lib
+
+dev = 'cuda:0'
+B, H, N, D, K, Dc = 4096, 50, 100000, 768, 32, 200
+table = synth.make_table(N, D, 36, torch.bfloat16).to(dev)
+w = synth.make_weights(D, K, Dc, 36)
+eb = synth.make_eval_batch(B, H, N, 36)
+lib = _lib.load()
+prof = torch.zeros(148 * 3 * 16, dtype=torch.int64, device=dev)
+lib.miner_debug_set_hist_prof.argtypes = [C.c_void_p]
+lib.miner_debug_set_hist_prof(prof.data_ptr())
+wp16 = w.w_proj.to(torch.bfloat16).to(dev)
+args = (table, eb.his_ids.to(dev), eb.his_mask.to(dev), wp16, w.context_codes.to(dev))
+for _ in range(3):
+    ops.hist_interests(*args, want_f32=False)
+torch.cuda.synchronize()
+p = prof.cpu().view(148, 3, 16).double()
+tiles = (B / 2) / 148
+names = {0: ['other/issue-gap', 'wait full (P1)', 'issue P1', 'wait t_ready', 'issue LG', 'wait w_ready', 'wait ia_free', 'wait full (P2)', 'issue P2'],
+         1: ['gap', 'wait p1_full', 'E1a tanh->T', 'wait lg_full', 'E1b softmax', 'wait ia_full', 'drain'],
+         2: ['setup ids', 'wait empty', 'issue cp.async']}
+for role, rn in ((0, 'MMA thread'), (1, 'epilogue thread'), (2, 'gather thread')):
+    tot = p[:, role, 15].mean()
+    print(f'{rn}: total {tot:.0f} cycles = {tot / tiles:.0f} per tile')
+    for i, n in enumerate(names[role]):
+        v = p[:, role, i].mean()
+        print(f'    {n:18s} {v / tiles:9.0f} cycles/tile  {100 * v / tot:5.1f}%')
