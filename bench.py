@@ -290,13 +290,20 @@ def main():
         tf = flops[mask] * per_launch_impr / sec_per_launch / 1e12
         gbs = byts[mask] * per_launch_impr / sec_per_launch / 1e9
         peak_tf = pk.get('bf16_tflops_sustained', pk['bf16_tflops'])
+        traffic, traffic_src = None, None
+        tpath = os.path.join(ROOT, 'profiles', 'traffic.json')
+        if os.path.exists(tpath) and math == _lib.MATH_TENSOR:       # DRAM bytes per impression from the committed ncu capture
+            tj = json.load(open(tpath)).get('hist_kernel' if mask == 1 else 'cand_kernel')
+            if tj:
+                traffic, traffic_src = tj['dram_bytes_per_impression'] * per_launch_impr, tj['source']
         if mask in tensor_stage:
             roofline = {'kernel': stages[top][0], 'bound': 'tensor', 'achieved': tf, 'peak': peak_tf, 'unit': 'TFLOP/s',
-                        'frac': tf / peak_tf, 'traffic': None, 'peak_source': pk['_source'] + ' (sustained bf16)',
+                        'frac': tf / peak_tf, 'traffic': traffic, 'traffic_source': traffic_src, 'peak_source': pk['_source'] + ' (sustained bf16)',
+                        'achieved_hbm_gbs': gbs, 'hbm_frac': gbs / pk['hbm_gbs'],
                         'algorithmic_flops_per_launch': flops[mask] * per_launch_impr, 'ms_per_launch': sec_per_launch * 1e3}
         else:
             roofline = {'kernel': stages[top][0], 'bound': 'hbm', 'achieved': gbs, 'peak': pk['hbm_gbs'], 'unit': 'GB/s',
-                        'frac': gbs / pk['hbm_gbs'], 'traffic': None, 'peak_source': pk['_source'], 'achieved_tflops_fp32': tf}
+                        'frac': gbs / pk['hbm_gbs'], 'traffic': traffic, 'peak_source': pk['_source'], 'achieved_tflops_fp32': tf}
 
     # ---- CPU baseline (rank 0, N=1 only)
     cpu_baseline = None

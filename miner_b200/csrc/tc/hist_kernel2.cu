@@ -25,7 +25,9 @@ long long* hist_prof_buffer();
 
 namespace {
 
-constexpr int HM = 128, HKB = 64, HST = 3;
+constexpr int HM = 128, HKB = 64;
+constexpr int NA = 5;                        // ring of gathered E k-blocks (projection AND weighted-sum passes; HBM latency)
+constexpr int NB = 2;                        // ring of Wp k-blocks (projection pass only; L2-hot)
 constexpr int HA_BYTES = HM * HKB * 2;       // 16 KB gathered E k-block
 constexpr int KP = 32;
 constexpr int LROW = 33;
@@ -55,7 +57,7 @@ enum { OP_P1 = 0, OP_LG = 1, OP_P2 = 2 };
 #endif
 
 struct H2Barriers {
-  uint64_t full[HST], empty[HST];
+  uint64_t full_a[NA], empty_a[NA], full_b[NB], empty_b[NB];
   uint64_t p1_full, t_ready, lg_full, w_ready;
   uint64_t ia_full[IA_BUFS], ia_free[IA_BUFS];
   uint32_t tmem_base;
@@ -103,9 +105,9 @@ __global__ void __launch_bounds__(H_THREADS, 1)
 hist_kernel2(const __grid_constant__ CUtensorMap tmap_wp, const Hist2Args args, int n_tiles) {
   extern __shared__ uint8_t smem_raw[];
   uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~static_cast<uintptr_t>(1023));
-  uint8_t* st_a = smem;                                    // [HST][16 KB]      gathered E k-block
-  uint8_t* st_b = st_a + HST * HA_BYTES;                   // [HST][b_bytes]    Wp k-block
-  uint8_t* w_t = st_b + HST * args.b_bytes;                // 4 x 8 KB          softmax weights, bf16 {hi,lo} x {rows 0-63, 64-127}
+  uint8_t* st_a = smem;                                    // [NA][16 KB]       gathered E k-block
+  uint8_t* st_b = st_a + NA * HA_BYTES;                    // [NB][b_bytes]     Wp k-block
+  uint8_t* w_t = st_b + NB * args.b_bytes;                 // 4 x 8 KB          softmax weights, bf16 {hi,lo} x {rows 0-63, 64-127}
   uint8_t* c_hi = w_t + WT_BYTES;                          // 16 KB             context codes bf16 hi, K-major SW128 atoms
   uint8_t* c_lo = c_hi + CT_BYTES;                         // 16 KB             ... lo
   float* L = reinterpret_cast<float*>(c_lo + CT_BYTES);    // [128][33]         logits / softmax scratch
@@ -130,7 +132,8 @@ hist_kernel2(const __grid_constant__ CUtensorMap tmap_wp, const Hist2Args args, 
   }
   tc::fence_proxy_async_smem();
   if (threadIdx.x == 0) {
-    for (int s = 0; s < HST; ++s) { tc::mbar_init(&bars->full[s], 128 + 1); tc::mbar_init(&bars->empty[s], 1); }
+    for (int s = 0; s < NA; ++s) { tc::mbar_init(&bars->full_a[s], 128); tc::mbar_init(&bars->empty_a[s], 1); }
+    for (int s = 0; s < NB; ++s) { tc::mbar_init(&bars->full_b[s], 1); tc::mbar_init(&bars->empty_b[s], 1); }
     tc::mbar_init(&bars->p1_full, 1);
     tc::mbar_init(&bars->t_ready, H_EPI);
     tc::mbar_init(&bars->lg_full, 1);
@@ -193,8 +196,8 @@ hist_kernel2(const __grid_constant__ CUtensorMap tmap_wp, const Hist2Args args, 
       PROF_ADD(0);
       for_each_op(st >= 0, has_next, KB, [&](int kind, int idx) {
         if (kind == OP_LG) return;
-        const uint32_t s = issued % HST, ph = (issued / HST) & 1;
-        tc::mbar_wait(&bars->empty[s], ph ^ 1);
+        const uint32_t s = issued % NA, ph = (issued / NA) & 1;
+        tc::mbar_wait(&bars->empty_a[s], ph ^ 1);
         PROF_ADD(1);
         const uint32_t base = tc::smem_u32(st_a + s * HA_BYTES);
         if (kind == OP_P1) {
@@ -204,7 +207,7 @@ hist_kernel2(const __grid_constant__ CUtensorMap tmap_wp, const Hist2Args args, 
 #pragma unroll
           for (int j = 0; j < 8; ++j) tc::cp_async_16(base + dst_off[j], src_cur[j] + idx * HKB, ((nb_cur >> j) & 1u) ? 16u : 0u);
         }
-        tc::cp_async_mbar_arrive_noinc(&bars->full[s]);
+        tc::cp_async_mbar_arrive_noinc(&bars->full_a[s]);
         ++issued;
         PROF_ADD(2);
       });
@@ -212,21 +215,17 @@ hist_kernel2(const __grid_constant__ CUtensorMap tmap_wp, const Hist2Args args, 
     tc::cp_async_wait_all();
     if (threadIdx.x == 0) PROF_STORE(2);
   } else if (warp == 4) {
-    // ------------------------------------------------------------------ Wp k-blocks by TMA for P1 ops; plain arrive for P2 ops
+    // ------------------------------------------------------------------ Wp k-blocks by TMA (projection ops only)
     {
       uint32_t it = 0;
       for (int st = -1; st < n_local; ++st) {
         for_each_op(st >= 0, st + 1 < n_local, KB, [&](int kind, int idx) {
-          if (kind == OP_LG) return;
-          const uint32_t s = it % HST, ph = (it / HST) & 1;
-          tc::mbar_wait(&bars->empty[s], ph ^ 1);
+          if (kind != OP_P1) return;
+          const uint32_t s = it % NB, ph = (it / NB) & 1;
+          tc::mbar_wait(&bars->empty_b[s], ph ^ 1);
           if (tc::elect_one()) {
-            if (kind == OP_P1) {
-              tc::mbar_arrive_expect_tx(&bars->full[s], static_cast<uint32_t>(N1 * HKB * 2));
-              tc::tma_load_2d(&tmap_wp, &bars->full[s], tc::smem_u32(st_b + s * args.b_bytes), idx * HKB, 0);
-            } else {
-              tc::mbar_arrive(&bars->full[s]);
-            }
+            tc::mbar_arrive_expect_tx(&bars->full_b[s], static_cast<uint32_t>(N1 * HKB * 2));
+            tc::tma_load_2d(&tmap_wp, &bars->full_b[s], tc::smem_u32(st_b + s * args.b_bytes), idx * HKB, 0);
           }
           __syncwarp();
           ++it;
@@ -239,28 +238,31 @@ hist_kernel2(const __grid_constant__ CUtensorMap tmap_wp, const Hist2Args args, 
       const uint32_t idesc1 = tc::make_idesc_bf16_f32(HM, N1);
       const uint32_t idesc_lg = tc::make_idesc_bf16_f32(HM, KP);
       const uint32_t idesc2 = tc::make_idesc_bf16_f32_major(HM, HKB, false, true);     // B = E k-block read MN-major
-      uint32_t it = 0, gj = 0;
+      uint32_t it = 0, ib = 0, gj = 0;
       PROF_DECL;
       for (int st = -1; st < n_local; ++st) {
         const int lt = st, ln = st + 1;                      // local index of the current / next tile
         for_each_op(st >= 0, ln < n_local, KB, [&](int kind, int idx) {
           if (kind == OP_P1) {
             // the projection accumulator is free: LG(lt) (issued before, after t_ready) means tile lt has been turned into T
-            const uint32_t s = it % HST, ph = (it / HST) & 1;
+            const uint32_t s = it % NA, ph = (it / NA) & 1;
+            const uint32_t sb = ib % NB, phb = (ib / NB) & 1;
             PROF_ADD(0);
-            tc::mbar_wait(&bars->full[s], ph);
+            tc::mbar_wait(&bars->full_a[s], ph);
+            tc::mbar_wait(&bars->full_b[sb], phb);
             PROF_ADD(1);
             tc::tcgen05_fence_after();
             const uint64_t a_desc = tc::make_smem_desc_sw128(tc::smem_u32(st_a + s * HA_BYTES));
-            const uint64_t b_desc = tc::make_smem_desc_sw128(tc::smem_u32(st_b + s * args.b_bytes));
+            const uint64_t b_desc = tc::make_smem_desc_sw128(tc::smem_u32(st_b + sb * args.b_bytes));
             if (tc::elect_one()) {
 #pragma unroll
               for (int k = 0; k < HKB / 16; ++k) tc::umma_bf16(tmem, a_desc + 2 * k, b_desc + 2 * k, idesc1, (idx | k) != 0 ? 1u : 0u);
-              tc::umma_commit(&bars->empty[s]);
+              tc::umma_commit(&bars->empty_a[s]);
+              tc::umma_commit(&bars->empty_b[sb]);
               if (idx == KB - 1) tc::umma_commit(&bars->p1_full);
             }
             __syncwarp();
-            ++it;
+            ++it; ++ib;
             PROF_ADD(2);
           } else if (kind == OP_LG) {
             PROF_ADD(0);
@@ -290,8 +292,8 @@ hist_kernel2(const __grid_constant__ CUtensorMap tmap_wp, const Hist2Args args, 
             const uint32_t slot = gj % IA_BUFS;
             tc::mbar_wait(&bars->ia_free[slot], ((gj / IA_BUFS) & 1) ^ 1);     // its previous 64-feature block has been drained
             PROF_ADD(6);
-            const uint32_t s = it % HST, ph = (it / HST) & 1;
-            tc::mbar_wait(&bars->full[s], ph);
+            const uint32_t s = it % NA, ph = (it / NA) & 1;
+            tc::mbar_wait(&bars->full_a[s], ph);
             PROF_ADD(7);
             tc::tcgen05_fence_after();
             const uint64_t e_desc = tc::make_smem_desc_sw128_mn(tc::smem_u32(st_a + s * HA_BYTES));
@@ -305,7 +307,7 @@ hist_kernel2(const __grid_constant__ CUtensorMap tmap_wp, const Hist2Args args, 
                   tc::umma_bf16(tmem + IA_COL + slot * HKB, w_desc, e_desc + ks * (2048 >> 4), idesc2, (hl | ks) != 0 ? 1u : 0u);
                 }
               }
-              tc::umma_commit(&bars->empty[s]);
+              tc::umma_commit(&bars->empty_a[s]);
               tc::umma_commit(&bars->ia_full[slot]);
             }
             __syncwarp();
@@ -501,7 +503,7 @@ int launch_hist_kernel2(const void* table, int64_t n_rows, const void* his_ids, 
   const int ipt = H <= 64 ? 2 : 1;
   const int64_t n_tiles = (B + ipt - 1) / ipt;
   const int grid = static_cast<int>(n_tiles < sm_count() ? n_tiles : sm_count());
-  const int smem = 1024 + HST * (HA_BYTES + a.b_bytes) + WT_BYTES + 2 * CT_BYTES + HM * LROW * 4 + 512;
+  const int smem = 1024 + NA * HA_BYTES + NB * a.b_bytes + WT_BYTES + 2 * CT_BYTES + HM * LROW * 4 + 512;
   MINER_CUDA_OK(cudaFuncSetAttribute(hist_kernel2, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
   hist_kernel2<<<grid, H_THREADS, smem, stream>>>(m_wp, a, static_cast<int>(n_tiles));
   MINER_LAUNCH_OK("hist_kernel2");
