@@ -91,10 +91,21 @@ __device__ __forceinline__ void for_each_op(bool has_cur, bool has_next, int KB,
   p1n(KB);
 }
 
-__device__ __forceinline__ float tanh_acc2(float x) {
+__device__ __forceinline__ float tanh_acc2(float x) {          // exp form, any x
   const float ax = fabsf(x);
   const float e = __expf(-2.0f * ax);
   return copysignf(__fdividef(1.0f - e, 1.0f + e), x);
+}
+// tanh to ~1.5e-7 absolute on |x| <= 1: odd minimax polynomial, FMA pipe only (the projection pre-activations are small);
+// the caller falls back to tanh_acc2 for a whole unit if any |x| exceeds 1
+__device__ __forceinline__ float tanh_poly(float x, float s) {
+  float p = fmaf(s, 1.045553543e-03f, -6.217069879e-03f);
+  p = fmaf(p, s, 2.030551945e-02f);
+  p = fmaf(p, s, -5.346517736e-02f);
+  p = fmaf(p, s, 1.332539784e-01f);
+  p = fmaf(p, s, -3.333285609e-01f);
+  p = fmaf(p, s, 9.999999527e-01f);
+  return x * p;
 }
 __device__ __forceinline__ uint32_t pack2b(float a, float b) {
   __nv_bfloat162 v = __floats2bfloat162_rn(a, b);
@@ -342,9 +353,20 @@ hist_kernel2(const __grid_constant__ CUtensorMap tmap_wp, const Hist2Args args, 
         tc::tmem_ld_32x16(tmem + lane_addr + cu * 16, v);
         tc::tmem_ld_wait();
         uint32_t hi[8], lo[8];
+        float t[16], smax = 0.f;
+#pragma unroll
+        for (int j = 0; j < 16; ++j) {
+          const float x = __uint_as_float(v[j]), sq = x * x;
+          smax = fmaxf(smax, sq);
+          t[j] = tanh_poly(x, sq);
+        }
+        if (smax > 1.0f) {                                                     // rare: large pre-activations
+#pragma unroll
+          for (int j = 0; j < 16; ++j) t[j] = tanh_acc2(__uint_as_float(v[j]));
+        }
 #pragma unroll
         for (int j = 0; j < 8; ++j) {
-          const float t0 = tanh_acc2(__uint_as_float(v[2 * j])), t1 = tanh_acc2(__uint_as_float(v[2 * j + 1]));
+          const float t0 = t[2 * j], t1 = t[2 * j + 1];
           const __nv_bfloat16 h0 = __float2bfloat16_rn(t0), h1 = __float2bfloat16_rn(t1);
           hi[j] = pack2b(t0, t1);
           lo[j] = pack2b(t0 - __bfloat162float(h0), t1 - __bfloat162float(h1));
