@@ -190,7 +190,7 @@ def main():
     host = {k: getattr(eb, k).pin_memory() for k in ('his_ids', 'his_mask', 'cand_ids', 'labels', 'offsets')}
     h2d_bytes = sum(t.numel() * t.element_size() for t in host.values())
     names = ops.metric_names(KS)
-    chunk = args.chunk if args.chunk > 0 else 4096
+    chunk = args.chunk if args.chunk > 0 else 32768
     sw = model._weights(with_bf16=(math == _lib.MATH_TENSOR))
     scores_buf = torch.empty(T, dtype=torch.float32, device=dev)
 
@@ -232,10 +232,11 @@ def main():
     metrics_out = parallel.finalize_metrics(partials, names)
 
     # ---- e2e: public API with host buffers, H2D + D2H inside the timed region
+    # public API: HostEvaluator copies waves of impressions H2D on a copy stream while the previous wave is scored
+    evaluator = mb.HostEvaluator(model, wave=2 * chunk, chunk=chunk, ks=KS, transform='sigmoid', math=math)
+
     def e2e_step():
-        d = {k: v.to(dev, non_blocking=True) for k, v in host.items()}
-        s = model.score_impressions(d['his_ids'], d['his_mask'], d['cand_ids'], d['offsets'], chunk=chunk, math=math)
-        p, _ = ops.rank_metrics_raw(s, d['labels'], d['offsets'], 'sigmoid', KS)
+        p, _ = evaluator.evaluate(host)
         parallel.allreduce_partials(p)
         return p.cpu()
 

@@ -7,5 +7,6 @@ Public API mirrors the reference's ``src/model`` / ``src/evaluation`` / ``src/lo
 from .model import Miner, PolyAttention, TargetAwareAttention, TableNewsEncoder  # noqa: F401
 from .evaluation import SlowEvaluator, FastEvaluator  # noqa: F401
 from .loss import Loss  # noqa: F401
+from .pipeline import HostEvaluator  # noqa: F401
 
-__all__ = ['Miner', 'PolyAttention', 'TargetAwareAttention', 'TableNewsEncoder', 'SlowEvaluator', 'FastEvaluator', 'Loss']
+__all__ = ['Miner', 'PolyAttention', 'TargetAwareAttention', 'TableNewsEncoder', 'SlowEvaluator', 'FastEvaluator', 'Loss', 'HostEvaluator']

@@ -221,7 +221,7 @@ class Miner(nn.Module):
     # -- grouped (CSR) evaluation entry: extension beyond the reference API ---------------------------------------
     @torch.no_grad()
     def score_impressions(self, his_ids: Tensor, his_mask: Tensor, cand_ids: Tensor, cand_offsets: Tensor,
-                          chunk: int = 4096, math: Optional[int] = None) -> Tensor:
+                          chunk: int = 16384, math: Optional[int] = None) -> Tensor:
         """Scores of every candidate of every impression, CSR layout (``cand_offsets`` (B+1,) into flat ``cand_ids``).
 
         Equals the reference's per-candidate eval rows (src/reader.py:376-379: one sample per candidate, interests

@@ -190,7 +190,7 @@ def default_math(table: torch.Tensor, D: int) -> int:
 
 def score(table: torch.Tensor, his_ids: torch.Tensor, his_mask: torch.Tensor, cand_ids: torch.Tensor, weights: ScoreWeights,
           score_type: str = 'weighted', cand_offsets: Optional[torch.Tensor] = None, bias_mean: Optional[torch.Tensor] = None,
-          math: Optional[int] = None, want_interests: bool = False, chunk: int = 4096,
+          math: Optional[int] = None, want_interests: bool = False, chunk: int = 16384,
           out_scores: Optional[torch.Tensor] = None, stage_mask: int = 0, workspace: Optional[torch.Tensor] = None):
     """Miner.forward for a block of impressions straight from the embedding table (reference model.py:61-138).
 
