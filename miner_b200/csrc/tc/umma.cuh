@@ -81,6 +81,25 @@ __device__ __forceinline__ void tma_load_2d(const void* tmap, uint64_t* bar, uin
       : "memory");
 }
 
+// ----------------------------------------------------------------------------------------------- thread-block clusters
+__device__ __forceinline__ uint32_t cluster_ctarank() { uint32_t r; asm volatile("mov.u32 %0, %%cluster_ctarank;" : "=r"(r)); return r; }
+__device__ __forceinline__ void cluster_sync_all() {
+  asm volatile("barrier.cluster.arrive.release.aligned;\n\tbarrier.cluster.wait.acquire.aligned;" ::: "memory");
+}
+// TMA 2D tile load delivered to the same shared-memory offset (and signalling the mbarrier at the same offset) in every
+// CTA of `cta_mask`
+__device__ __forceinline__ void tma_load_2d_multicast(const void* tmap, uint64_t* bar, uint32_t dst_smem, int32_t x, int32_t y, uint16_t cta_mask) {
+  asm volatile(
+      "cp.async.bulk.tensor.2d.shared::cluster.global.mbarrier::complete_tx::bytes.multicast::cluster [%0], [%1, {%4, %5}], [%2], %3;" ::"r"(dst_smem),
+      "l"(reinterpret_cast<uint64_t>(tmap)), "r"(smem_u32(bar)), "h"(cta_mask), "r"(x), "r"(y)
+      : "memory");
+}
+// tcgen05.commit arriving on the mbarrier at this offset in every CTA of `cta_mask`
+__device__ __forceinline__ void umma_commit_multicast(uint64_t* bar, uint16_t cta_mask) {
+  asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.multicast::cluster.b64 [%0], %1;" ::"r"(smem_u32(bar)), "h"(cta_mask)
+               : "memory");
+}
+
 // ----------------------------------------------------------------------------------------------- TMEM
 // whole-warp instructions; `cols` is a power of two >= 32
 __device__ __forceinline__ void tmem_alloc(uint32_t* dst_smem, uint32_t cols) {
