@@ -35,8 +35,9 @@ constexpr int H_THREADS = 14 * 32;
 constexpr int H_EPI = 256;
 constexpr int N1_MAX = 208;                  // projection accumulator columns (Dc padded to 16)
 constexpr int TH_COL = N1_MAX, TL_COL = TH_COL + N1_MAX / 2, LG_COL = TL_COL + N1_MAX / 2;
-// the three 64-column interest buffers live in the T_hi / T_lo region, which is dead once the logits MMAs of the tile are done
-constexpr int IA_COL = TH_COL, IA_BUFS = 3;
+// one 64-column interest buffer after the logits: the T region must stay free so that tanh(proj) of tile t+1 can be written
+// while the interests of tile t are still being produced
+constexpr int IA_COL = LG_COL + KP, IA_BUFS = 1;
 constexpr int WA_BYTES = 64 * 128;           // softmax-weight atom (64 interest rows x 64 history slots); the MMA reads 8 KB past it
 constexpr int WT_BYTES = 4 * WA_BYTES;
 constexpr int CT_ATOM = KP * 128;            // codes tile atom: 32 codes x 64 features
@@ -59,7 +60,7 @@ enum { OP_P1 = 0, OP_LG = 1, OP_P2 = 2 };
 struct H2Barriers {
   uint64_t full_a[NA], empty_a[NA], full_b[NB], empty_b[NB];
   uint64_t p1_full, t_ready, lg_full, w_ready;
-  uint64_t ia_full[IA_BUFS], ia_free[IA_BUFS];
+  uint64_t ia_full, ia_free;
   uint32_t tmem_base;
 };
 
@@ -74,19 +75,22 @@ struct Hist2Args {
   long long* prof;
 };
 
-// issue order of one step; `has_cur` false = prologue (only the projection of the first tile)
+// issue order of one step; `has_cur` false = prologue (only the projection of the first tile).  Every projection block of
+// tile t+1 is issued before interest block `first` of tile t: from there on the epilogue warps interleave the tanh
+// conversion of tile t+1 with the remaining drains of tile t.
 template <class F>
-__device__ __forceinline__ void for_each_op(bool has_cur, bool has_next, int KB, F&& f) {
+__device__ __forceinline__ void for_each_op(bool has_cur, bool has_next, int KB, int first, F&& f) {
   int p1 = 0;
   auto p1n = [&](int n) {
     for (int i = 0; i < n && has_next && p1 < KB; ++i) f(OP_P1, p1++);
   };
   if (!has_cur) { p1n(KB); return; }
   f(OP_LG, 0);
-  p1n(8);
+  p1n(first == 0 ? KB : KB / 2);
+  const int per = first > 0 ? (KB - KB / 2 + first - 1) / first : 0;
   for (int j = 0; j < KB; ++j) {
     f(OP_P2, j);
-    p1n(1);
+    if (j < first) p1n(per);
   }
   p1n(KB);
 }
@@ -130,6 +134,8 @@ hist_kernel2(const __grid_constant__ CUtensorMap tmap_wp, const Hist2Args args, 
   const int IPT = H <= 64 ? 2 : 1;
   const int HP = HM / IPT;
   const int n_local = (n_tiles - static_cast<int>(blockIdx.x) + static_cast<int>(gridDim.x) - 1) / static_cast<int>(gridDim.x);
+  const int n_cu = N1 / 16;                                // 16-column units of the projection
+  const int first = KB - (n_cu + 1) / 2 > 0 ? KB - (n_cu + 1) / 2 : 0;   // first interest block whose drain is paired with a tanh unit of the next tile
 
   for (int i = threadIdx.x; i < (WT_BYTES + 2 * CT_BYTES) / 16; i += H_THREADS) reinterpret_cast<uint4*>(w_t)[i] = make_uint4(0, 0, 0, 0);
   __syncthreads();
@@ -149,7 +155,8 @@ hist_kernel2(const __grid_constant__ CUtensorMap tmap_wp, const Hist2Args args, 
     tc::mbar_init(&bars->t_ready, H_EPI);
     tc::mbar_init(&bars->lg_full, 1);
     tc::mbar_init(&bars->w_ready, H_EPI);
-    for (int b = 0; b < IA_BUFS; ++b) { tc::mbar_init(&bars->ia_full[b], 1); tc::mbar_init(&bars->ia_free[b], H_EPI); }
+    tc::mbar_init(&bars->ia_full, 1);
+    tc::mbar_init(&bars->ia_free, H_EPI);
     tc::fence_barrier_init();
   }
   if (warp == 4 && lane == 0) tc::tma_prefetch_desc(&tmap_wp);
@@ -205,7 +212,7 @@ hist_kernel2(const __grid_constant__ CUtensorMap tmap_wp, const Hist2Args args, 
       if (has_next) setup(src_nxt, nb_nxt);
       if (st + 2 < n_local) fetch_ids(st + 2);
       PROF_ADD(0);
-      for_each_op(st >= 0, has_next, KB, [&](int kind, int idx) {
+      for_each_op(st >= 0, has_next, KB, first, [&](int kind, int idx) {
         if (kind == OP_LG) return;
         const uint32_t s = issued % NA, ph = (issued / NA) & 1;
         tc::mbar_wait(&bars->empty_a[s], ph ^ 1);
@@ -230,7 +237,7 @@ hist_kernel2(const __grid_constant__ CUtensorMap tmap_wp, const Hist2Args args, 
     {
       uint32_t it = 0;
       for (int st = -1; st < n_local; ++st) {
-        for_each_op(st >= 0, st + 1 < n_local, KB, [&](int kind, int idx) {
+        for_each_op(st >= 0, st + 1 < n_local, KB, first, [&](int kind, int idx) {
           if (kind != OP_P1) return;
           const uint32_t s = it % NB, ph = (it / NB) & 1;
           tc::mbar_wait(&bars->empty_b[s], ph ^ 1);
@@ -253,7 +260,7 @@ hist_kernel2(const __grid_constant__ CUtensorMap tmap_wp, const Hist2Args args, 
       PROF_DECL;
       for (int st = -1; st < n_local; ++st) {
         const int lt = st, ln = st + 1;                      // local index of the current / next tile
-        for_each_op(st >= 0, ln < n_local, KB, [&](int kind, int idx) {
+        for_each_op(st >= 0, ln < n_local, KB, first, [&](int kind, int idx) {
           if (kind == OP_P1) {
             // the projection accumulator is free: LG(lt) (issued before, after t_ready) means tile lt has been turned into T
             const uint32_t s = it % NA, ph = (it / NA) & 1;
@@ -300,8 +307,7 @@ hist_kernel2(const __grid_constant__ CUtensorMap tmap_wp, const Hist2Args args, 
               tc::tcgen05_fence_after();
             }
             PROF_ADD(5);
-            const uint32_t slot = gj % IA_BUFS;
-            tc::mbar_wait(&bars->ia_free[slot], ((gj / IA_BUFS) & 1) ^ 1);     // its previous 64-feature block has been drained
+            tc::mbar_wait(&bars->ia_free, (gj & 1) ^ 1);                    // the previous 64-feature block is out of the accumulator
             PROF_ADD(6);
             const uint32_t s = it % NA, ph = (it / NA) & 1;
             tc::mbar_wait(&bars->full_a[s], ph);
@@ -315,11 +321,11 @@ hist_kernel2(const __grid_constant__ CUtensorMap tmap_wp, const Hist2Args args, 
 #pragma unroll
                 for (int ks = 0; ks < HM / 16; ++ks) {
                   const uint64_t w_desc = w_desc0 + ((hl * 2 + (ks >> 2)) * (WA_BYTES >> 4) + 2 * (ks & 3));
-                  tc::umma_bf16(tmem + IA_COL + slot * HKB, w_desc, e_desc + ks * (2048 >> 4), idesc2, (hl | ks) != 0 ? 1u : 0u);
+                  tc::umma_bf16(tmem + IA_COL, w_desc, e_desc + ks * (2048 >> 4), idesc2, (hl | ks) != 0 ? 1u : 0u);
                 }
               }
               tc::umma_commit(&bars->empty_a[s]);
-              tc::umma_commit(&bars->ia_full[slot]);
+              tc::umma_commit(&bars->ia_full);
             }
             __syncwarp();
             ++it; ++gj;
@@ -337,47 +343,54 @@ hist_kernel2(const __grid_constant__ CUtensorMap tmap_wp, const Hist2Args args, 
     const int r = q * 32 + lane;                           // tile row = TMEM lane
     const int et = ew * 32 + lane;                         // 0..255
     const uint32_t lane_addr = static_cast<uint32_t>(q * 32) << 16;
-    const int n_cu = N1 / 16;
     const int cu_begin = half == 0 ? 0 : (n_cu + 1) / 2, cu_end = half == 0 ? (n_cu + 1) / 2 : n_cu;
+    const int n_u = cu_end - cu_begin;
     uint32_t gj = 0;
     PROF_DECL;
-    for (int lt = 0; lt < n_local; ++lt) {
-      const int tile = static_cast<int>(blockIdx.x) + lt * static_cast<int>(gridDim.x);
-      // ---- E1a: tanh(proj) -> packed bf16 hi / lo in tensor memory (model.py:171)
-      PROF_ADD(0);
-      tc::mbar_wait(&bars->p1_full, lt & 1);
-      PROF_ADD(1);
-      tc::tcgen05_fence_after();
-      for (int cu = cu_begin; cu < cu_end; ++cu) {                             // units of 16 projection columns
-        uint32_t v[16];
-        tc::tmem_ld_32x16(tmem + lane_addr + cu * 16, v);
-        tc::tmem_ld_wait();
-        uint32_t hi[8], lo[8];
-        float t[16], smax = 0.f;
+    // one 16-column unit of E1a: tanh(proj) -> packed bf16 hi / lo in tensor memory (model.py:171)
+    auto e1a_unit = [&](int cu) {
+      uint32_t v[16];
+      tc::tmem_ld_32x16(tmem + lane_addr + cu * 16, v);
+      tc::tmem_ld_wait();
+      uint32_t hi[8], lo[8];
+      float t[16], smax = 0.f;
 #pragma unroll
-        for (int j = 0; j < 16; ++j) {
-          const float x = __uint_as_float(v[j]), sq = x * x;
-          smax = fmaxf(smax, sq);
-          t[j] = tanh_poly(x, sq);
-        }
-        if (smax > 1.0f) {                                                     // rare: large pre-activations
-#pragma unroll
-          for (int j = 0; j < 16; ++j) t[j] = tanh_acc2(__uint_as_float(v[j]));
-        }
-#pragma unroll
-        for (int j = 0; j < 8; ++j) {
-          const float t0 = t[2 * j], t1 = t[2 * j + 1];
-          const __nv_bfloat16 h0 = __float2bfloat16_rn(t0), h1 = __float2bfloat16_rn(t1);
-          hi[j] = pack2b(t0, t1);
-          lo[j] = pack2b(t0 - __bfloat162float(h0), t1 - __bfloat162float(h1));
-        }
-        tc::tmem_st_32x8(tmem + lane_addr + TH_COL + cu * 8, hi);
-        tc::tmem_st_32x8(tmem + lane_addr + TL_COL + cu * 8, lo);
+      for (int j = 0; j < 16; ++j) {
+        const float x = __uint_as_float(v[j]), sq = x * x;
+        smax = fmaxf(smax, sq);
+        t[j] = tanh_poly(x, sq);
       }
+      if (smax > 1.0f) {                                                       // rare: large pre-activations
+#pragma unroll
+        for (int j = 0; j < 16; ++j) t[j] = tanh_acc2(__uint_as_float(v[j]));
+      }
+#pragma unroll
+      for (int j = 0; j < 8; ++j) {
+        const float t0 = t[2 * j], t1 = t[2 * j + 1];
+        const __nv_bfloat16 h0 = __float2bfloat16_rn(t0), h1 = __float2bfloat16_rn(t1);
+        hi[j] = pack2b(t0, t1);
+        lo[j] = pack2b(t0 - __bfloat162float(h0), t1 - __bfloat162float(h1));
+      }
+      tc::tmem_st_32x8(tmem + lane_addr + TH_COL + cu * 8, hi);
+      tc::tmem_st_32x8(tmem + lane_addr + TL_COL + cu * 8, lo);
+    };
+    auto e1a_done = [&]() {
       tc::tmem_st_wait();
       tc::tcgen05_fence_before();
       tc::mbar_arrive(&bars->t_ready);
+    };
+    // prologue: the first tile is converted in one go
+    if (n_local > 0) {
+      tc::mbar_wait(&bars->p1_full, 0);
+      PROF_ADD(1);
+      tc::tcgen05_fence_after();
+      for (int cu = cu_begin; cu < cu_end; ++cu) e1a_unit(cu);
+      e1a_done();
       PROF_ADD(2);
+    }
+    for (int lt = 0; lt < n_local; ++lt) {
+      const int tile = static_cast<int>(blockIdx.x) + lt * static_cast<int>(gridDim.x);
+      const bool has_next = lt + 1 < n_local;
       // ---- E1b: logits (+bias), 1e-30 mask fill, softmax over the history (model.py:174-181)
       tc::mbar_wait(&bars->lg_full, lt & 1);
       PROF_ADD(3);
@@ -423,7 +436,6 @@ hist_kernel2(const __grid_constant__ CUtensorMap tmap_wp, const Hist2Args args, 
         sum += __shfl_xor_sync(0xffffffffu, sum, 2);
         if (active) {
           const int R = i * K + k;
-          const float inv = 1.0f / sum;
 #pragma unroll
           for (int t = 0; t < HM / 4; ++t) {
             const int h = part + 4 * t;
@@ -437,26 +449,33 @@ hist_kernel2(const __grid_constant__ CUtensorMap tmap_wp, const Hist2Args args, 
               *reinterpret_cast<__nv_bfloat16*>(w_t + 2 * WA_BYTES + off) = wlo;
             }
           }
-          (void)inv;
         }
       }
       tc::fence_proxy_async_smem();
       tc::mbar_arrive(&bars->w_ready);
       PROF_ADD(4);
-      // ---- E2: drain the interests, one 64-feature block at a time (model.py:182)
+      // ---- E2: drain the interests one 64-feature block at a time (model.py:182); from block `first` on, each drain is
+      //      followed by one tanh unit of the NEXT tile, whose projection is complete by then
       const bool row_ok = r < IPT * K;
       const int64_t imp2 = static_cast<int64_t>(tile) * IPT + r / K;
       const bool store_ok = row_ok && imp2 < args.B;
       const int64_t grow = static_cast<int64_t>(tile) * IPT * K + r;            // = imp * K + k
+      int next_cu = cu_begin;
       for (int j = 0; j < KB; ++j, ++gj) {
-        const uint32_t slot = gj % IA_BUFS;
-        tc::mbar_wait(&bars->ia_full[slot], (gj / IA_BUFS) & 1);
+        if (has_next && j == first) {
+          tc::mbar_wait(&bars->p1_full, (lt + 1) & 1);
+          PROF_ADD(1);
+          tc::tcgen05_fence_after();
+        }
+        tc::mbar_wait(&bars->ia_full, gj & 1);
         PROF_ADD(5);
         tc::tcgen05_fence_after();
         if (q * 32 < IPT * K) {                                                // warp-uniform: this lane quarter holds interest rows
           uint32_t v[32];
-          tc::tmem_ld_32x32(tmem + lane_addr + IA_COL + slot * HKB + half * 32, v);
+          tc::tmem_ld_32x32(tmem + lane_addr + IA_COL + half * 32, v);
           tc::tmem_ld_wait();
+          tc::tcgen05_fence_before();
+          tc::mbar_arrive(&bars->ia_free);                                     // the accumulator is in registers: release it first
           if (store_ok) {
             const int64_t o = grow * D + j * HKB + half * 32;
             uint32_t hi[16], lo[16];
@@ -482,10 +501,24 @@ hist_kernel2(const __grid_constant__ CUtensorMap tmap_wp, const Hist2Args args, 
                                     __uint_as_float(v[4 * c + 3]));
             }
           }
+        } else {
+          tc::tcgen05_fence_before();
+          tc::mbar_arrive(&bars->ia_free);
         }
-        tc::tcgen05_fence_before();
-        tc::mbar_arrive(&bars->ia_free[slot]);
         PROF_ADD(6);
+        if (has_next && j >= first && next_cu < cu_end) {
+          e1a_unit(next_cu++);
+          PROF_ADD(2);
+        }
+      }
+      if (has_next) {
+        if (first >= KB) {                                                     // KB == 0 cannot happen; defensive: projection not yet awaited
+          tc::mbar_wait(&bars->p1_full, (lt + 1) & 1);
+          tc::tcgen05_fence_after();
+        }
+        for (; next_cu < cu_end; ++next_cu) e1a_unit(next_cu);
+        e1a_done();
+        PROF_ADD(2);
       }
     }
     if (et == 0) PROF_STORE(1);
