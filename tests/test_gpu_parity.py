@@ -610,3 +610,41 @@ def test_host_evaluator_pipeline():
         assert torch.allclose(p, p_ref, rtol=1e-12, atol=0)
     p0, _ = mb.HostEvaluator(m).evaluate({k: v[:0] if k != 'offsets' else v[:1] for k, v in host.items()})
     assert float(p0.abs().sum()) == 0.0
+
+
+# ------------------------------------------------------------------------------------------------ sweep (BASELINE config 4) and Fastformer-style scoring (config 5)
+@pytest.mark.parametrize('H', [50, 100, 200])
+@pytest.mark.parametrize('K', [8, 16, 32, 64])
+def test_sweep_history_and_codes(H, K):
+    """History 50-200 x K 8-64: whichever kernel family the shape selects (fused tcgen05 for H <= 128 and K <= 32, the
+    tc_gemm + CUDA-core pipeline beyond) must match the oracle."""
+    import miner_b200 as mb
+    from miner_b200 import synth
+    B, N, D, Dc = 40, 2000, 768, 200
+    table = synth.make_table(N, D, 36, torch.bfloat16).to(DEV)
+    w = synth.make_weights(D, K, Dc, 36)
+    eb = synth.make_eval_batch(B, H, N, H * 100 + K)
+    m = mb.Miner(mb.TableNewsEncoder(table), False, K, Dc, 'weighted', 0.2).to(DEV).eval()
+    with torch.no_grad():
+        m.poly_attn.linear.weight.copy_(w.w_proj)
+        m.poly_attn.context_codes.copy_(w.context_codes)
+        m.target_aware_attn.linear.weight.copy_(w.w_target)
+    s = m.score_impressions(eb.his_ids.to(DEV), eb.his_mask.to(DEV), eb.cand_ids.to(DEV), eb.offsets.to(DEV))
+    ref = O.miner_forward_csr(table.cpu(), eb.his_ids, eb.his_mask, eb.cand_ids, eb.offsets.numpy(), w.w_proj, w.context_codes, w.w_target)
+    assert _nerr(s.cpu(), ref) < 1e-3
+
+
+def test_fastformer_style_dot_score():
+    """Config 5: a pooled 256-d user vector (Fastformer, reference model.py:326-341: score = cand . user) scored against
+    gathered candidates with the same gather + dot-score kernels (K = 1 interest, 'mean' aggregation)."""
+    from miner_b200 import ops
+    g = torch.Generator().manual_seed(4)
+    N, D, B, C = 3000, 256, 64, 9
+    table = torch.randn(N, D, generator=g) * 0.2
+    user = torch.randn(B, 1, D, generator=g) * 0.2
+    cand_ids = torch.randint(0, N, (B, C), generator=g)
+    cand = ops.gather(table.to(DEV), cand_ids.to(DEV))
+    assert torch.equal(cand.cpu(), table[cand_ids])
+    s = ops.target_score(user.to(DEV), cand, None, 'mean')
+    ref = torch.matmul(table[cand_ids], user.permute(0, 2, 1)).squeeze(2)            # model.py:339
+    close_fp32(s.cpu().numpy(), ref.numpy())
