@@ -164,6 +164,10 @@ def main():
         return 0
 
     # ---------------------------------------------------------------------------------------------- our arm
+    # stdout carries exactly one JSON line: anything libraries print there (e.g. NCCL's version banner) goes to stderr
+    sys.stdout.flush()
+    saved_stdout = os.dup(1)
+    os.dup2(2, 1)
     import torch.distributed as dist
     import miner_b200 as mb
     from miner_b200 import ops, synth, parallel, _lib
@@ -345,7 +349,10 @@ def main():
             'cpu_baseline': cpu_baseline,
             'metrics': metrics_out,
         }
-        print(json.dumps(line))
+        sys.stdout.flush()
+        os.dup2(saved_stdout, 1)
+        print(json.dumps(line), flush=True)
+        os.dup2(2, 1)
     if world > 1:
         dist.destroy_process_group()
     return 0
