@@ -15,6 +15,7 @@
 //   * TMEM map (512 columns): projection [0,208) | T_hi [208,312) | T_lo [312,416) | logits [416,448); once the logits MMAs
 //     are done the T region is dead and holds three 64-column interest buffers [208,400), drained round-robin.
 #include <cuda.h>
+#include <stdlib.h>
 
 #include "fused.cuh"
 #include "umma.cuh"
@@ -70,7 +71,7 @@ struct Hist2Args {
   const uint8_t* mask; const float* bias_mean;
   const float* codes;                          // (K, Dc) fp32
   int64_t B;
-  int H, K, Dc, D, N1, b_bytes;
+  int H, K, Dc, D, N1, b_bytes, first;
   __nv_bfloat16* i_hi; __nv_bfloat16* i_lo; float* out_interests;
   long long* prof;
 };
@@ -86,11 +87,12 @@ __device__ __forceinline__ void for_each_op(bool has_cur, bool has_next, int KB,
   };
   if (!has_cur) { p1n(KB); return; }
   f(OP_LG, 0);
-  p1n(first == 0 ? KB : KB / 2);
-  const int per = first > 0 ? (KB - KB / 2 + first - 1) / first : 0;
+  // `first` interest blocks are paired 1:1 with projection blocks (continuous ingest); what does not fit is front-loaded
+  // while the epilogue warps run the softmax of the current tile
+  p1n(KB > first ? KB - first : 0);
   for (int j = 0; j < KB; ++j) {
     f(OP_P2, j);
-    if (j < first) p1n(per);
+    if (j < first) p1n(1);
   }
   p1n(KB);
 }
@@ -135,7 +137,7 @@ hist_kernel2(const __grid_constant__ CUtensorMap tmap_wp, const Hist2Args args, 
   const int HP = HM / IPT;
   const int n_local = (n_tiles - static_cast<int>(blockIdx.x) + static_cast<int>(gridDim.x) - 1) / static_cast<int>(gridDim.x);
   const int n_cu = N1 / 16;                                // 16-column units of the projection
-  const int first = KB - (n_cu + 1) / 2 > 0 ? KB - (n_cu + 1) / 2 : 0;   // first interest block whose drain is paired with a tanh unit of the next tile
+  const int first = args.first < KB ? args.first : KB - 1;   // first interest block whose drain is paired with tanh units of the next tile
 
   for (int i = threadIdx.x; i < (WT_BYTES + 2 * CT_BYTES) / 16; i += H_THREADS) reinterpret_cast<uint4*>(w_t)[i] = make_uint4(0, 0, 0, 0);
   __syncthreads();
@@ -215,7 +217,7 @@ hist_kernel2(const __grid_constant__ CUtensorMap tmap_wp, const Hist2Args args, 
       for_each_op(st >= 0, has_next, KB, first, [&](int kind, int idx) {
         if (kind == OP_LG) return;
         const uint32_t s = issued % NA, ph = (issued / NA) & 1;
-        tc::mbar_wait(&bars->empty_a[s], ph ^ 1);
+        tc::mbar_wait_relaxed(&bars->empty_a[s], ph ^ 1);
         PROF_ADD(1);
         const uint32_t base = tc::smem_u32(st_a + s * HA_BYTES);
         if (kind == OP_P1) {
@@ -240,7 +242,7 @@ hist_kernel2(const __grid_constant__ CUtensorMap tmap_wp, const Hist2Args args, 
         for_each_op(st >= 0, st + 1 < n_local, KB, first, [&](int kind, int idx) {
           if (kind != OP_P1) return;
           const uint32_t s = it % NB, ph = (it / NB) & 1;
-          tc::mbar_wait(&bars->empty_b[s], ph ^ 1);
+          tc::mbar_wait_relaxed(&bars->empty_b[s], ph ^ 1);
           if (tc::elect_one()) {
             tc::mbar_arrive_expect_tx(&bars->full_b[s], static_cast<uint32_t>(N1 * HKB * 2));
             tc::tma_load_2d(&tmap_wp, &bars->full_b[s], tc::smem_u32(st_b + s * args.b_bytes), idx * HKB, 0);
@@ -267,8 +269,9 @@ hist_kernel2(const __grid_constant__ CUtensorMap tmap_wp, const Hist2Args args, 
             const uint32_t sb = ib % NB, phb = (ib / NB) & 1;
             PROF_ADD(0);
             tc::mbar_wait(&bars->full_a[s], ph);
-            tc::mbar_wait(&bars->full_b[sb], phb);
             PROF_ADD(1);
+            tc::mbar_wait(&bars->full_b[sb], phb);
+            PROF_ADD(9);
             tc::tcgen05_fence_after();
             const uint64_t a_desc = tc::make_smem_desc_sw128(tc::smem_u32(st_a + s * HA_BYTES));
             const uint64_t b_desc = tc::make_smem_desc_sw128(tc::smem_u32(st_b + sb * args.b_bytes));
@@ -345,6 +348,7 @@ hist_kernel2(const __grid_constant__ CUtensorMap tmap_wp, const Hist2Args args, 
     const uint32_t lane_addr = static_cast<uint32_t>(q * 32) << 16;
     const int cu_begin = half == 0 ? 0 : (n_cu + 1) / 2, cu_end = half == 0 ? (n_cu + 1) / 2 : n_cu;
     const int n_u = cu_end - cu_begin;
+    const int upd = (n_u + (KB - first) - 1) / (KB - first);      // tanh units per paired drain
     uint32_t gj = 0;
     PROF_DECL;
     // one 16-column unit of E1a: tanh(proj) -> packed bf16 hi / lo in tensor memory (model.py:171)
@@ -392,6 +396,12 @@ hist_kernel2(const __grid_constant__ CUtensorMap tmap_wp, const Hist2Args args, 
       const int tile = static_cast<int>(blockIdx.x) + lt * static_cast<int>(gridDim.x);
       const bool has_next = lt + 1 < n_local;
       // ---- E1b: logits (+bias), 1e-30 mask fill, softmax over the history (model.py:174-181)
+      // mask / bias of this row are fetched before the wait so that their latency hides behind the logits MMAs
+      const int64_t imp_r = static_cast<int64_t>(tile) * IPT + r / HP;
+      const int h_r = r % HP;
+      const bool valid = h_r < H && imp_r < args.B;
+      const bool keep = valid && args.mask[imp_r * H + h_r] != 0;
+      const float bias = (valid && args.bias_mean) ? args.bias_mean[imp_r * H + h_r] : 0.f;
       tc::mbar_wait(&bars->lg_full, lt & 1);
       PROF_ADD(3);
       tc::tcgen05_fence_after();
@@ -399,11 +409,6 @@ hist_kernel2(const __grid_constant__ CUtensorMap tmap_wp, const Hist2Args args, 
         uint32_t lg[16];
         tc::tmem_ld_32x16(tmem + lane_addr + LG_COL + half * 16, lg);
         tc::tmem_ld_wait();
-        const int64_t imp = static_cast<int64_t>(tile) * IPT + r / HP;
-        const int h = r % HP;
-        const bool valid = h < H && imp < args.B;
-        const bool keep = valid && args.mask[imp * H + h] != 0;
-        const float bias = (valid && args.bias_mean) ? args.bias_mean[imp * H + h] : 0.f;
 #pragma unroll
         for (int j = 0; j < 16; ++j) {
           float v = __uint_as_float(lg[j]) + bias;
@@ -506,8 +511,8 @@ hist_kernel2(const __grid_constant__ CUtensorMap tmap_wp, const Hist2Args args, 
           tc::mbar_arrive(&bars->ia_free);
         }
         PROF_ADD(6);
-        if (has_next && j >= first && next_cu < cu_end) {
-          e1a_unit(next_cu++);
+        if (has_next && j >= first) {
+          for (int u = 0; u < upd && next_cu < cu_end; ++u) e1a_unit(next_cu++);
           PROF_ADD(2);
         }
       }
@@ -553,6 +558,13 @@ int launch_hist_kernel2(const void* table, int64_t n_rows, const void* his_ids, 
   a.his_ids = his_ids; a.id_dtype = id_dtype; a.mask = his_mask; a.bias_mean = bias_mean; a.codes = codes;
   a.B = B; a.H = static_cast<int>(H); a.K = static_cast<int>(K); a.Dc = static_cast<int>(Dc); a.D = static_cast<int>(D); a.N1 = N1;
   a.b_bytes = N1 * HKB * 2;
+  {
+    const int kb = static_cast<int>(D / HKB);
+    static const char* env_first = getenv("MINER_HIST_FIRST");          // tuning knob; default keeps 2/3 of the blocks paired
+    a.first = env_first ? atoi(env_first) : (2 * kb) / 3;
+    if (a.first < 0) a.first = 0;
+    if (a.first > kb - 1) a.first = kb - 1;
+  }
   a.i_hi = static_cast<__nv_bfloat16*>(i_hi); a.i_lo = static_cast<__nv_bfloat16*>(i_lo); a.out_interests = out_interests;
   a.prof = hist_prof_buffer();
   const int ipt = H <= 64 ? 2 : 1;

@@ -49,6 +49,11 @@ __device__ __forceinline__ void mbar_wait(uint64_t* bar, uint32_t parity) {
   while (!mbar_try_wait(bar, parity)) {
   }
 }
+// for warps that are far ahead of their consumer (producers waiting for a free stage): back off between probes so the
+// polling does not take issue slots from the warps doing the math on the same scheduler
+__device__ __forceinline__ void mbar_wait_relaxed(uint64_t* bar, uint32_t parity) {
+  while (!mbar_try_wait(bar, parity)) __nanosleep(64);
+}
 
 // ----------------------------------------------------------------------------------------------- proxies / fences
 // generic-proxy writes to shared memory (st.shared / cp.async) -> visible to the async proxy (tcgen05.mma, TMA)

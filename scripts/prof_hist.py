@@ -24,7 +24,7 @@ for _ in range(3):
 torch.cuda.synchronize()
 p = prof.cpu().view(148, 3, 16).double()
 tiles = (B / 2) / 148
-names = {0: ['other/issue-gap', 'wait full (P1)', 'issue P1', 'wait t_ready', 'issue LG', 'wait w_ready', 'wait ia_free', 'wait full (P2)', 'issue P2'],
+names = {0: ['other/issue-gap', 'wait E tile (P1)', 'issue P1', 'wait t_ready', 'issue LG', 'wait w_ready', 'wait ia_free', 'wait full (P2)', 'issue P2', 'wait Wp tile (P1)'],
          1: ['gap', 'wait p1_full', 'E1a tanh->T', 'wait lg_full', 'E1b softmax', 'wait ia_full', 'drain'],
          2: ['setup ids', 'wait empty', 'issue cp.async']}
 for role, rn in ((0, 'MMA thread'), (1, 'epilogue thread'), (2, 'gather thread')):
