@@ -304,3 +304,4 @@ extern "C" int miner_cand_score_fwd(const void* i_hi, const void* i_lo, const vo
 
 // profiling hook (not part of the documented ABI): device buffer of 148*3*16 int64 for -DMINER_HIST_PROF builds
 extern "C" void miner_debug_set_hist_prof(void* p) { set_hist_prof_buffer(static_cast<long long*>(p)); }
+extern "C" void miner_debug_set_cand_pair(int on) { set_cand_pair(on); }

@@ -30,4 +30,11 @@ int launch_cand_kernel(const void* i_hi, const void* i_lo, const void* wt_bf16, 
                        const void* cand_ids, int id_dtype, const int64_t* cand_offsets, int64_t B, int64_t C, int64_t K, int64_t D,
                        float* out_scores, cudaStream_t stream);
 
+bool cand_pair_enabled();
+void set_cand_pair(int on);
+// CTA-pair variant (cand_kernel2.cu): tcgen05.mma.cta_group::2 projection with Wt split across two SMs; launch_cand_kernel dispatches to it
+int launch_cand_kernel2(const void* i_hi, const void* i_lo, const void* wt_bf16, const void* table, int64_t n_rows,
+                        const void* cand_ids, int id_dtype, const int64_t* cand_offsets, int64_t B, int64_t C, int64_t K, int64_t D,
+                        float* out_scores, cudaStream_t stream);
+
 }  // namespace miner

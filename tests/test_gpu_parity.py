@@ -648,3 +648,28 @@ def test_fastformer_style_dot_score():
     s = ops.target_score(user.to(DEV), cand, None, 'mean')
     ref = torch.matmul(table[cand_ids], user.permute(0, 2, 1)).squeeze(2)            # model.py:339
     close_fp32(s.cpu().numpy(), ref.numpy())
+
+
+def test_cand_pair_kernel_matches_single_cta_kernel():
+    """cand_kernel2 (tcgen05 cta_group::2: the projection of two groups as one M = 256 MMA, Wt split across a CTA pair) is
+    opt-in; it must give the scores of the default kernel (same arithmetic, same accumulation order per row)."""
+    import ctypes as C
+    from miner_b200 import ops, synth, _lib
+    lib = _lib.load()
+    lib.miner_debug_set_cand_pair.argtypes = [C.c_int]
+    B, D, K, N = 75, 768, 32, 900
+    table = synth.make_table(N, D, 7, torch.bfloat16)
+    w = synth.make_weights(D, K, 24, 7)
+    eb = synth.make_eval_batch(B, 20, N, 7, mean_cands=40.0, max_cands=300)
+    I = O.poly_attention(table.float()[eb.his_ids], eb.his_mask, w.w_proj, w.context_codes)
+    ihi = I.to(torch.bfloat16)
+    ilo = (I - ihi.float()).to(torch.bfloat16)
+    args = (ihi.view(B * K, D).to(DEV), ilo.view(B * K, D).to(DEV), w.w_target.to(torch.bfloat16).to(DEV), table.to(DEV), eb.cand_ids.to(DEV), K)
+    s1 = ops.cand_score(*args, cand_offsets=eb.offsets.to(DEV))
+    try:
+        lib.miner_debug_set_cand_pair(1)
+        s2 = ops.cand_score(*args, cand_offsets=eb.offsets.to(DEV))
+        torch.cuda.synchronize()
+    finally:
+        lib.miner_debug_set_cand_pair(0)
+    assert torch.equal(s1, s2)
