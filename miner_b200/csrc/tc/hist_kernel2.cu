@@ -17,6 +17,8 @@
 #include <cuda.h>
 #include <stdlib.h>
 
+#include <cuda_fp16.h>
+
 #include "fused.cuh"
 #include "umma.cuh"
 
@@ -27,18 +29,19 @@ long long* hist_prof_buffer();
 namespace {
 
 constexpr int HM = 128, HKB = 64;
-constexpr int NA = 5;                        // ring of gathered E k-blocks (projection AND weighted-sum passes; HBM latency)
+constexpr int NA = 3;                        // ring of gathered E k-blocks of the projection pipeline
+constexpr int NA2 = 2;                       // ring of gathered E k-blocks of the weighted-sum pipeline
 constexpr int NB = 2;                        // ring of Wp k-blocks (projection pass only; L2-hot)
 constexpr int HA_BYTES = HM * HKB * 2;       // 16 KB gathered E k-block
 constexpr int KP = 32;
 constexpr int LROW = 33;
-constexpr int H_THREADS = 14 * 32;
+constexpr int H_THREADS = 15 * 32;           // 4 gather warps, TMA warp, 2 MMA warps (5 and 14), 8 epilogue warps (6..13)
 constexpr int H_EPI = 256;
 constexpr int N1_MAX = 208;                  // projection accumulator columns (Dc padded to 16)
-constexpr int TH_COL = N1_MAX, TL_COL = TH_COL + N1_MAX / 2, LG_COL = TL_COL + N1_MAX / 2;
-// one 64-column interest buffer after the logits: the T region must stay free so that tanh(proj) of tile t+1 can be written
-// while the interests of tile t are still being produced
-constexpr int IA_COL = LG_COL + KP, IA_BUFS = 1;
+// TMEM map (512 columns): projection [0,208) | T = tanh(proj) as packed fp16 [208,312) | logits [312,344) | two 64-column
+// interest buffers [344,408), [408,472)
+constexpr int TH_COL = N1_MAX, LG_COL = TH_COL + N1_MAX / 2;
+constexpr int IA_COL = LG_COL + KP, IA_BUFS = 2;
 constexpr int WA_BYTES = 64 * 128;           // softmax-weight atom (64 interest rows x 64 history slots); the MMA reads 8 KB past it
 constexpr int WT_BYTES = 4 * WA_BYTES;
 constexpr int CT_ATOM = KP * 128;            // codes tile atom: 32 codes x 64 features
@@ -51,7 +54,7 @@ enum { OP_P1 = 0, OP_LG = 1, OP_P2 = 2 };
 #ifdef MINER_HIST_PROF
 #define PROF_DECL long long prof_c[16] = {0}; long long prof_t0 = clock64(), prof_start = prof_t0
 #define PROF_ADD(i) do { const long long prof_t1 = clock64(); prof_c[i] += prof_t1 - prof_t0; prof_t0 = prof_t1; } while (0)
-#define PROF_STORE(role) do { if (args.prof) { prof_c[15] = clock64() - prof_start; for (int i_ = 0; i_ < 16; ++i_) args.prof[(blockIdx.x * 3 + (role)) * 16 + i_] = prof_c[i_]; } } while (0)
+#define PROF_STORE(role) do { if (args.prof) { prof_c[15] = clock64() - prof_start; for (int i_ = 0; i_ < 16; ++i_) args.prof[(blockIdx.x * 4 + (role)) * 16 + i_] = prof_c[i_]; } } while (0)
 #else
 #define PROF_DECL
 #define PROF_ADD(i)
@@ -59,9 +62,9 @@ enum { OP_P1 = 0, OP_LG = 1, OP_P2 = 2 };
 #endif
 
 struct H2Barriers {
-  uint64_t full_a[NA], empty_a[NA], full_b[NB], empty_b[NB];
+  uint64_t full_a[NA], empty_a[NA], full_a2[NA2], empty_a2[NA2], full_b[NB], empty_b[NB];
   uint64_t p1_full, t_ready, lg_full, w_ready;
-  uint64_t ia_full, ia_free;
+  uint64_t ia_full[IA_BUFS], ia_free[IA_BUFS];
   uint32_t tmem_base;
 };
 
@@ -123,7 +126,8 @@ hist_kernel2(const __grid_constant__ CUtensorMap tmap_wp, const Hist2Args args, 
   extern __shared__ uint8_t smem_raw[];
   uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~static_cast<uintptr_t>(1023));
   uint8_t* st_a = smem;                                    // [NA][16 KB]       gathered E k-block
-  uint8_t* st_b = st_a + NA * HA_BYTES;                    // [NB][b_bytes]     Wp k-block
+  uint8_t* st_a2 = st_a + NA * HA_BYTES;                   // [NA2][16 KB]      gathered E k-block of the weighted-sum pipeline
+  uint8_t* st_b = st_a2 + NA2 * HA_BYTES;                  // [NB][b_bytes]     Wp k-block
   uint8_t* w_t = st_b + NB * args.b_bytes;                 // 4 x 8 KB          softmax weights, bf16 {hi,lo} x {rows 0-63, 64-127}
   uint8_t* c_hi = w_t + WT_BYTES;                          // 16 KB             context codes bf16 hi, K-major SW128 atoms
   uint8_t* c_lo = c_hi + CT_BYTES;                         // 16 KB             ... lo
@@ -144,21 +148,21 @@ hist_kernel2(const __grid_constant__ CUtensorMap tmap_wp, const Hist2Args args, 
   for (int i = threadIdx.x; i < K * Dc; i += H_THREADS) {
     const int k = i / Dc, dc = i - k * Dc;
     const float c = args.codes[i];
-    const __nv_bfloat16 hi = __float2bfloat16_rn(c);
+    const __half hi = __float2half_rn(c);
     const uint32_t off = (dc >> 6) * CT_ATOM + tc::sw128_offset(k, (dc & 63) >> 3) + (dc & 7) * 2;
-    *reinterpret_cast<__nv_bfloat16*>(c_hi + off) = hi;
-    *reinterpret_cast<__nv_bfloat16*>(c_lo + off) = __float2bfloat16_rn(c - __bfloat162float(hi));
+    *reinterpret_cast<__half*>(c_hi + off) = hi;
+    *reinterpret_cast<__half*>(c_lo + off) = __float2half_rn(c - __half2float(hi));
   }
   tc::fence_proxy_async_smem();
   if (threadIdx.x == 0) {
-    for (int s = 0; s < NA; ++s) { tc::mbar_init(&bars->full_a[s], 128); tc::mbar_init(&bars->empty_a[s], 1); }
+    for (int s = 0; s < NA; ++s) { tc::mbar_init(&bars->full_a[s], 64); tc::mbar_init(&bars->empty_a[s], 1); }
+    for (int s = 0; s < NA2; ++s) { tc::mbar_init(&bars->full_a2[s], 64); tc::mbar_init(&bars->empty_a2[s], 1); }
     for (int s = 0; s < NB; ++s) { tc::mbar_init(&bars->full_b[s], 1); tc::mbar_init(&bars->empty_b[s], 1); }
     tc::mbar_init(&bars->p1_full, 1);
     tc::mbar_init(&bars->t_ready, H_EPI);
     tc::mbar_init(&bars->lg_full, 1);
     tc::mbar_init(&bars->w_ready, H_EPI);
-    tc::mbar_init(&bars->ia_full, 1);
-    tc::mbar_init(&bars->ia_free, H_EPI);
+    for (int b = 0; b < IA_BUFS; ++b) { tc::mbar_init(&bars->ia_full[b], 1); tc::mbar_init(&bars->ia_free[b], H_EPI); }
     tc::fence_barrier_init();
   }
   if (warp == 4 && lane == 0) tc::tma_prefetch_desc(&tmap_wp);
@@ -169,175 +173,164 @@ hist_kernel2(const __grid_constant__ CUtensorMap tmap_wp, const Hist2Args args, 
   const uint32_t tmem = bars->tmem_base;
 
   if (warp < 4) {
-    // ------------------------------------------------------------------ E gather for P1 (next tile) and P2 (current tile)
-    const int chunk = lane & 7;
-    uint32_t dst_off[8];
+    // ------------------------------------------------------------------ E gathers: warps 0-1 feed the projection ring with the
+    //        rows of tile lt + 1 ... no: of every tile in turn, warps 2-3 feed the weighted-sum ring; the two pipelines only meet
+    //        through the epilogue warps' barriers.  64 threads per ring: 16 rows x one 16-byte chunk each per stage.
+    const int ring = warp >> 1;                          // 0: projection (P1), 1: weighted sum (P2)
+    const int t64 = (warp & 1) * 32 + lane;
+    const int chunk = t64 & 7;
+    uint32_t dst_off[16];
 #pragma unroll
-    for (int j = 0; j < 8; ++j) dst_off[j] = tc::sw128_offset(warp * 32 + j * 4 + (lane >> 3), chunk);
-    const uint16_t* src_cur[8];
-    const uint16_t* src_nxt[8];
-#pragma unroll
-    for (int j = 0; j < 8; ++j) src_cur[j] = src_nxt[j] = args.table;
-    uint32_t nb_cur = 0, nb_nxt = 0;          // bit j set = row j of this thread is a real history row
-    // ids of a tile are fetched one step before its row pointers are needed (the loads are issued together, unconditionally)
-    int64_t ids_pre[8];
+    for (int j = 0; j < 16; ++j) dst_off[j] = tc::sw128_offset((t64 >> 3) + 8 * j, chunk);
+    int32_t ids_pre[16];                                 // row of the table, -1 = zero row (padding slot / out-of-range id)
     auto fetch_ids = [&](int lt) {
       const int tile = static_cast<int>(blockIdx.x) + lt * static_cast<int>(gridDim.x);
 #pragma unroll
-      for (int j = 0; j < 8; ++j) {
-        const int r = warp * 32 + j * 4 + (lane >> 3);
+      for (int j = 0; j < 16; ++j) {
+        const int r = (t64 >> 3) + 8 * j;
         const int64_t imp = static_cast<int64_t>(tile) * IPT + r / HP;
         const int h = r % HP;
         const bool ok = h < H && imp < args.B;
-        ids_pre[j] = load_id(args.his_ids, ok ? imp * H + h : 0, args.id_dtype);
-        if (!ok) ids_pre[j] = -1;
+        const int64_t id = load_id(args.his_ids, ok ? imp * H + h : 0, args.id_dtype);
+        ids_pre[j] = (ok && id >= 0 && id < args.n_rows) ? static_cast<int32_t>(id) : -1;
       }
     };
-    auto setup = [&](const uint16_t* (&src)[8], uint32_t& nb) {
-      nb = 0;
-#pragma unroll
-      for (int j = 0; j < 8; ++j) {
-        const int64_t row = ids_pre[j];
-        const bool ok = row >= 0 && row < args.n_rows;                      // padding slot or out-of-range id: zero row (gather semantics)
-        src[j] = args.table + (ok ? row : 0) * D + chunk * 8;
-        nb |= ok ? (1u << j) : 0u;
-      }
-    };
-    if (n_local > 0) fetch_ids(0);
+    uint8_t* stage0 = ring == 0 ? st_a : st_a2;
+    uint64_t* fullb = ring == 0 ? bars->full_a : bars->full_a2;
+    uint64_t* emptyb = ring == 0 ? bars->empty_a : bars->empty_a2;
+    const int depth = ring == 0 ? NA : NA2;
     uint32_t issued = 0;
     PROF_DECL;
-    for (int st = -1; st < n_local; ++st) {
-      const bool has_next = st + 1 < n_local;
+    if (n_local > 0) fetch_ids(0);
+    for (int lt = 0; lt < n_local; ++lt) {
+      const uint16_t* src[16];
+      uint32_t nb = 0;
 #pragma unroll
-      for (int j = 0; j < 8; ++j) src_cur[j] = src_nxt[j];
-      nb_cur = nb_nxt;
-      if (has_next) setup(src_nxt, nb_nxt);
-      if (st + 2 < n_local) fetch_ids(st + 2);
+      for (int j = 0; j < 16; ++j) {
+        const bool ok = ids_pre[j] >= 0;
+        src[j] = args.table + static_cast<int64_t>(ok ? ids_pre[j] : 0) * D + chunk * 8;
+        nb |= ok ? (1u << j) : 0u;
+      }
+      if (lt + 1 < n_local) fetch_ids(lt + 1);
       PROF_ADD(0);
-      for_each_op(st >= 0, has_next, KB, first, [&](int kind, int idx) {
-        if (kind == OP_LG) return;
-        const uint32_t s = issued % NA, ph = (issued / NA) & 1;
-        tc::mbar_wait_relaxed(&bars->empty_a[s], ph ^ 1);
+      for (int kb = 0; kb < KB; ++kb) {
+        const uint32_t s = issued % depth, ph = (issued / depth) & 1;
+        tc::mbar_wait_relaxed(&emptyb[s], ph ^ 1);
         PROF_ADD(1);
-        const uint32_t base = tc::smem_u32(st_a + s * HA_BYTES);
-        if (kind == OP_P1) {
+        const uint32_t base = tc::smem_u32(stage0 + s * HA_BYTES);
 #pragma unroll
-          for (int j = 0; j < 8; ++j) tc::cp_async_16(base + dst_off[j], src_nxt[j] + idx * HKB, ((nb_nxt >> j) & 1u) ? 16u : 0u);
-        } else {
-#pragma unroll
-          for (int j = 0; j < 8; ++j) tc::cp_async_16(base + dst_off[j], src_cur[j] + idx * HKB, ((nb_cur >> j) & 1u) ? 16u : 0u);
-        }
-        tc::cp_async_mbar_arrive_noinc(&bars->full_a[s]);
+        for (int j = 0; j < 16; ++j) tc::cp_async_16(base + dst_off[j], src[j] + kb * HKB, ((nb >> j) & 1u) ? 16u : 0u);
+        tc::cp_async_mbar_arrive_noinc(&fullb[s]);
         ++issued;
         PROF_ADD(2);
-      });
+      }
     }
     tc::cp_async_wait_all();
     if (threadIdx.x == 0) PROF_STORE(2);
   } else if (warp == 4) {
-    // ------------------------------------------------------------------ Wp k-blocks by TMA (projection ops only)
-    {
-      uint32_t it = 0;
-      for (int st = -1; st < n_local; ++st) {
-        for_each_op(st >= 0, st + 1 < n_local, KB, first, [&](int kind, int idx) {
-          if (kind != OP_P1) return;
-          const uint32_t s = it % NB, ph = (it / NB) & 1;
-          tc::mbar_wait_relaxed(&bars->empty_b[s], ph ^ 1);
-          if (tc::elect_one()) {
-            tc::mbar_arrive_expect_tx(&bars->full_b[s], static_cast<uint32_t>(N1 * HKB * 2));
-            tc::tma_load_2d(&tmap_wp, &bars->full_b[s], tc::smem_u32(st_b + s * args.b_bytes), idx * HKB, 0);
-          }
-          __syncwarp();
-          ++it;
-        });
+    // ------------------------------------------------------------------ Wp k-blocks by TMA (projection pipeline)
+    uint32_t it = 0;
+    for (int lt = 0; lt < n_local; ++lt) {
+      for (int kb = 0; kb < KB; ++kb, ++it) {
+        const uint32_t s = it % NB, ph = (it / NB) & 1;
+        tc::mbar_wait_relaxed(&bars->empty_b[s], ph ^ 1);
+        if (tc::elect_one()) {
+          tc::mbar_arrive_expect_tx(&bars->full_b[s], static_cast<uint32_t>(N1 * HKB * 2));
+          tc::tma_load_2d(&tmap_wp, &bars->full_b[s], tc::smem_u32(st_b + s * args.b_bytes), kb * HKB, 0);
+        }
+        __syncwarp();
       }
     }
   } else if (warp == 5) {
-    // ------------------------------------------------------------------ MMA issuer (warp-uniform; one elected lane issues)
-    {
-      const uint32_t idesc1 = tc::make_idesc_bf16_f32(HM, N1);
-      const uint32_t idesc_lg = tc::make_idesc_bf16_f32(HM, KP);
-      const uint32_t idesc2 = tc::make_idesc_bf16_f32_major(HM, HKB, false, true);     // B = E k-block read MN-major
-      uint32_t it = 0, ib = 0, gj = 0;
-      PROF_DECL;
-      for (int st = -1; st < n_local; ++st) {
-        const int lt = st, ln = st + 1;                      // local index of the current / next tile
-        for_each_op(st >= 0, ln < n_local, KB, first, [&](int kind, int idx) {
-          if (kind == OP_P1) {
-            // the projection accumulator is free: LG(lt) (issued before, after t_ready) means tile lt has been turned into T
-            const uint32_t s = it % NA, ph = (it / NA) & 1;
-            const uint32_t sb = ib % NB, phb = (ib / NB) & 1;
-            PROF_ADD(0);
-            tc::mbar_wait(&bars->full_a[s], ph);
-            PROF_ADD(1);
-            tc::mbar_wait(&bars->full_b[sb], phb);
-            PROF_ADD(9);
-            tc::tcgen05_fence_after();
-            const uint64_t a_desc = tc::make_smem_desc_sw128(tc::smem_u32(st_a + s * HA_BYTES));
-            const uint64_t b_desc = tc::make_smem_desc_sw128(tc::smem_u32(st_b + sb * args.b_bytes));
-            if (tc::elect_one()) {
-#pragma unroll
-              for (int k = 0; k < HKB / 16; ++k) tc::umma_bf16(tmem, a_desc + 2 * k, b_desc + 2 * k, idesc1, (idx | k) != 0 ? 1u : 0u);
-              tc::umma_commit(&bars->empty_a[s]);
-              tc::umma_commit(&bars->empty_b[sb]);
-              if (idx == KB - 1) tc::umma_commit(&bars->p1_full);
-            }
-            __syncwarp();
-            ++it; ++ib;
-            PROF_ADD(2);
-          } else if (kind == OP_LG) {
-            PROF_ADD(0);
-            tc::mbar_wait(&bars->t_ready, lt & 1);           // tanh(proj) of the current tile sits in T_hi / T_lo as packed bf16
-            PROF_ADD(3);
-            tc::tcgen05_fence_after();
-            const uint64_t ch_desc = tc::make_smem_desc_sw128(tc::smem_u32(c_hi));
-            const uint64_t cl_desc = tc::make_smem_desc_sw128(tc::smem_u32(c_lo));
-            if (tc::elect_one()) {
-              for (int ks = 0; ks < N1 / 16; ++ks) {
-                const uint32_t adv = (ks >> 2) * (CT_ATOM >> 4) + 2 * (ks & 3);
-                tc::umma_bf16_ts(tmem + LG_COL, tmem + TH_COL + 8 * ks, ch_desc + adv, idesc_lg, ks != 0 ? 1u : 0u);
-                tc::umma_bf16_ts(tmem + LG_COL, tmem + TL_COL + 8 * ks, ch_desc + adv, idesc_lg, 1u);
-                tc::umma_bf16_ts(tmem + LG_COL, tmem + TH_COL + 8 * ks, cl_desc + adv, idesc_lg, 1u);
-              }
-              tc::umma_commit(&bars->lg_full);
-            }
-            __syncwarp();
-            PROF_ADD(4);
-          } else {
-            PROF_ADD(0);
-            if (idx == 0) {
-              tc::mbar_wait(&bars->w_ready, lt & 1);         // softmax weights of the current tile are in shared memory
-              tc::tcgen05_fence_after();
-            }
-            PROF_ADD(5);
-            tc::mbar_wait(&bars->ia_free, (gj & 1) ^ 1);                    // the previous 64-feature block is out of the accumulator
-            PROF_ADD(6);
-            const uint32_t s = it % NA, ph = (it / NA) & 1;
-            tc::mbar_wait(&bars->full_a[s], ph);
-            PROF_ADD(7);
-            tc::tcgen05_fence_after();
-            const uint64_t e_desc = tc::make_smem_desc_sw128_mn(tc::smem_u32(st_a + s * HA_BYTES));
-            const uint64_t w_desc0 = tc::make_smem_desc_sw128(tc::smem_u32(w_t));
-            if (tc::elect_one()) {
-#pragma unroll
-              for (int hl = 0; hl < 2; ++hl) {
-#pragma unroll
-                for (int ks = 0; ks < HM / 16; ++ks) {
-                  const uint64_t w_desc = w_desc0 + ((hl * 2 + (ks >> 2)) * (WA_BYTES >> 4) + 2 * (ks & 3));
-                  tc::umma_bf16(tmem + IA_COL, w_desc, e_desc + ks * (2048 >> 4), idesc2, (hl | ks) != 0 ? 1u : 0u);
-                }
-              }
-              tc::umma_commit(&bars->empty_a[s]);
-              tc::umma_commit(&bars->ia_full);
-            }
-            __syncwarp();
-            ++it; ++gj;
-            PROF_ADD(8);
-          }
-        });
+    // ------------------------------------------------------------------ MMA issuer of the projection pipeline (P1)
+    const uint32_t idesc1 = tc::make_idesc_bf16_f32(HM, N1);
+    uint32_t it = 0;
+    PROF_DECL;
+    for (int lt = 0; lt < n_local; ++lt) {
+      if (lt > 0) {
+        PROF_ADD(0);
+        tc::mbar_wait(&bars->t_ready, (lt - 1) & 1);       // tile lt-1 has been turned into T: the projection accumulator is free
+        PROF_ADD(3);
+        tc::tcgen05_fence_after();
       }
-      if (lane == 0) PROF_STORE(0);
+      for (int kb = 0; kb < KB; ++kb, ++it) {
+        const uint32_t s = it % NA, ph = (it / NA) & 1;
+        const uint32_t sb = it % NB, phb = (it / NB) & 1;
+        PROF_ADD(0);
+        tc::mbar_wait(&bars->full_a[s], ph);
+        PROF_ADD(1);
+        tc::mbar_wait(&bars->full_b[sb], phb);
+        PROF_ADD(9);
+        tc::tcgen05_fence_after();
+        const uint64_t a_desc = tc::make_smem_desc_sw128(tc::smem_u32(st_a + s * HA_BYTES));
+        const uint64_t b_desc = tc::make_smem_desc_sw128(tc::smem_u32(st_b + sb * args.b_bytes));
+        if (tc::elect_one()) {
+#pragma unroll
+          for (int k = 0; k < HKB / 16; ++k) tc::umma_bf16(tmem, a_desc + 2 * k, b_desc + 2 * k, idesc1, (kb | k) != 0 ? 1u : 0u);
+          tc::umma_commit(&bars->empty_a[s]);
+          tc::umma_commit(&bars->empty_b[sb]);
+          if (kb == KB - 1) tc::umma_commit(&bars->p1_full);
+        }
+        __syncwarp();
+        PROF_ADD(2);
+      }
     }
+    if (lane == 0) PROF_STORE(0);
+  } else if (warp == 14) {
+    // ------------------------------------------------------------------ MMA issuer of the logits (LG) and weighted-sum (P2) pipeline
+    const uint32_t idesc_lg = tc::make_idesc_f16_f32(HM, KP);         // T and the context codes are fp16 (11-bit mantissa)
+    const uint32_t idesc2 = tc::make_idesc_bf16_f32_major(HM, HKB, false, true);     // B = E k-block read MN-major
+    uint32_t it = 0, gj = 0;
+    PROF_DECL;
+    for (int lt = 0; lt < n_local; ++lt) {
+      PROF_ADD(0);
+      tc::mbar_wait(&bars->t_ready, lt & 1);               // tanh(proj) of this tile sits in T as packed fp16
+      PROF_ADD(3);
+      tc::tcgen05_fence_after();
+      {
+        const uint64_t ch_desc = tc::make_smem_desc_sw128(tc::smem_u32(c_hi));
+        const uint64_t cl_desc = tc::make_smem_desc_sw128(tc::smem_u32(c_lo));
+        if (tc::elect_one()) {
+          for (int ks = 0; ks < N1 / 16; ++ks) {
+            const uint32_t adv = (ks >> 2) * (CT_ATOM >> 4) + 2 * (ks & 3);
+            tc::umma_bf16_ts(tmem + LG_COL, tmem + TH_COL + 8 * ks, ch_desc + adv, idesc_lg, ks != 0 ? 1u : 0u);
+            tc::umma_bf16_ts(tmem + LG_COL, tmem + TH_COL + 8 * ks, cl_desc + adv, idesc_lg, 1u);
+          }
+          tc::umma_commit(&bars->lg_full);
+        }
+        __syncwarp();
+      }
+      PROF_ADD(4);
+      tc::mbar_wait(&bars->w_ready, lt & 1);               // softmax weights of this tile are in shared memory
+      PROF_ADD(5);
+      tc::tcgen05_fence_after();
+      for (int j = 0; j < KB; ++j, ++it, ++gj) {
+        const uint32_t slot = gj & 1;
+        tc::mbar_wait(&bars->ia_free[slot], ((gj >> 1) & 1) ^ 1);       // its previous 64-feature block is out of this accumulator
+        PROF_ADD(6);
+        const uint32_t s = it % NA2, ph = (it / NA2) & 1;
+        tc::mbar_wait(&bars->full_a2[s], ph);
+        PROF_ADD(7);
+        tc::tcgen05_fence_after();
+        const uint64_t e_desc = tc::make_smem_desc_sw128_mn(tc::smem_u32(st_a2 + s * HA_BYTES));
+        const uint64_t w_desc0 = tc::make_smem_desc_sw128(tc::smem_u32(w_t));
+        if (tc::elect_one()) {
+#pragma unroll
+          for (int hl = 0; hl < 2; ++hl) {
+#pragma unroll
+            for (int ks = 0; ks < HM / 16; ++ks) {
+              const uint64_t w_desc = w_desc0 + ((hl * 2 + (ks >> 2)) * (WA_BYTES >> 4) + 2 * (ks & 3));
+              tc::umma_bf16(tmem + IA_COL + slot * HKB, w_desc, e_desc + ks * (2048 >> 4), idesc2, (hl | ks) != 0 ? 1u : 0u);
+            }
+          }
+          tc::umma_commit(&bars->empty_a2[s]);
+          tc::umma_commit(&bars->ia_full[slot]);
+        }
+        __syncwarp();
+        PROF_ADD(8);
+      }
+    }
+    if (lane == 0) PROF_STORE(3);
   } else {
     // ------------------------------------------------------------------ epilogue warps 6..13
     const int ew = warp - 6;
@@ -356,7 +349,7 @@ hist_kernel2(const __grid_constant__ CUtensorMap tmap_wp, const Hist2Args args, 
       uint32_t v[16];
       tc::tmem_ld_32x16(tmem + lane_addr + cu * 16, v);
       tc::tmem_ld_wait();
-      uint32_t hi[8], lo[8];
+      uint32_t pk[8];
       float t[16], smax = 0.f;
 #pragma unroll
       for (int j = 0; j < 16; ++j) {
@@ -370,13 +363,10 @@ hist_kernel2(const __grid_constant__ CUtensorMap tmap_wp, const Hist2Args args, 
       }
 #pragma unroll
       for (int j = 0; j < 8; ++j) {
-        const float t0 = t[2 * j], t1 = t[2 * j + 1];
-        const __nv_bfloat16 h0 = __float2bfloat16_rn(t0), h1 = __float2bfloat16_rn(t1);
-        hi[j] = pack2b(t0, t1);
-        lo[j] = pack2b(t0 - __bfloat162float(h0), t1 - __bfloat162float(h1));
+        const __half2 h = __floats2half2_rn(t[2 * j], t[2 * j + 1]);           // |tanh| <= 1: fp16 keeps 11 bits
+        pk[j] = *reinterpret_cast<const uint32_t*>(&h);
       }
-      tc::tmem_st_32x8(tmem + lane_addr + TH_COL + cu * 8, hi);
-      tc::tmem_st_32x8(tmem + lane_addr + TL_COL + cu * 8, lo);
+      tc::tmem_st_32x8(tmem + lane_addr + TH_COL + cu * 8, pk);
     };
     auto e1a_done = [&]() {
       tc::tmem_st_wait();
@@ -472,15 +462,16 @@ hist_kernel2(const __grid_constant__ CUtensorMap tmap_wp, const Hist2Args args, 
           PROF_ADD(1);
           tc::tcgen05_fence_after();
         }
-        tc::mbar_wait(&bars->ia_full, gj & 1);
+        const uint32_t slot = gj & 1;
+        tc::mbar_wait(&bars->ia_full[slot], (gj >> 1) & 1);
         PROF_ADD(5);
         tc::tcgen05_fence_after();
         if (q * 32 < IPT * K) {                                                // warp-uniform: this lane quarter holds interest rows
           uint32_t v[32];
-          tc::tmem_ld_32x32(tmem + lane_addr + IA_COL + half * 32, v);
+          tc::tmem_ld_32x32(tmem + lane_addr + IA_COL + slot * HKB + half * 32, v);
           tc::tmem_ld_wait();
           tc::tcgen05_fence_before();
-          tc::mbar_arrive(&bars->ia_free);                                     // the accumulator is in registers: release it first
+          tc::mbar_arrive(&bars->ia_free[slot]);                               // the accumulator is in registers: release it first
           if (store_ok) {
             const int64_t o = grow * D + j * HKB + half * 32;
             uint32_t hi[16], lo[16];
@@ -508,7 +499,7 @@ hist_kernel2(const __grid_constant__ CUtensorMap tmap_wp, const Hist2Args args, 
           }
         } else {
           tc::tcgen05_fence_before();
-          tc::mbar_arrive(&bars->ia_free);
+          tc::mbar_arrive(&bars->ia_free[slot]);
         }
         PROF_ADD(6);
         if (has_next && j >= first) {
@@ -570,7 +561,7 @@ int launch_hist_kernel2(const void* table, int64_t n_rows, const void* his_ids, 
   const int ipt = H <= 64 ? 2 : 1;
   const int64_t n_tiles = (B + ipt - 1) / ipt;
   const int grid = static_cast<int>(n_tiles < sm_count() ? n_tiles : sm_count());
-  const int smem = 1024 + NA * HA_BYTES + NB * a.b_bytes + WT_BYTES + 2 * CT_BYTES + HM * LROW * 4 + 512;
+  const int smem = 1024 + (NA + NA2) * HA_BYTES + NB * a.b_bytes + WT_BYTES + 2 * CT_BYTES + HM * LROW * 4 + 512;
   MINER_CUDA_OK(cudaFuncSetAttribute(hist_kernel2, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
   hist_kernel2<<<grid, H_THREADS, smem, stream>>>(m_wp, a, static_cast<int>(n_tiles));
   MINER_LAUNCH_OK("hist_kernel2");

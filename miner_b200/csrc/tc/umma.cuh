@@ -178,6 +178,10 @@ __device__ __forceinline__ uint64_t make_smem_desc_sw128_mn(uint32_t smem_addr) 
   d |= static_cast<uint64_t>(2) << 61;
   return d;
 }
+// same with fp16 A and B operands
+__host__ __device__ constexpr uint32_t make_idesc_f16_f32(int M, int N) {
+  return (1u << 4) | (static_cast<uint32_t>(N >> 3) << 17) | (static_cast<uint32_t>(M >> 4) << 24);
+}
 __host__ __device__ constexpr uint32_t make_idesc_bf16_f32_major(int M, int N, bool a_mn_major, bool b_mn_major) {
   return make_idesc_bf16_f32(M, N) | (a_mn_major ? (1u << 15) : 0u) | (b_mn_major ? (1u << 16) : 0u);
 }

@@ -33,7 +33,7 @@ def run_hist(B, H, N, D, K, Dc):
     e_f32 = nerr(out.cpu(), ref)
     e_split = nerr((ihi.float() + ilo.float()).cpu().view(B, K, D), ref)
     print(f'hist B={B} H={H} D={D} K={K} Dc={Dc}: f32 err {e_f32:.2e}  hi+lo err {e_split:.2e}  ({time.time()-t0:.2f}s)', flush=True)
-    return e_f32 < 1e-4 and e_split < 1e-4
+    return e_f32 < 3e-4 and e_split < 3e-4
 
 
 def run_cand(B, H, N, D, K, Dc, mean_c=20.0, max_c=300):

@@ -14,7 +14,7 @@ table = synth.make_table(N, D, 36, torch.bfloat16).to(dev)
 w = synth.make_weights(D, K, Dc, 36)
 eb = synth.make_eval_batch(B, H, N, 36)
 lib = _lib.load()
-prof = torch.zeros(148 * 3 * 16, dtype=torch.int64, device=dev)
+prof = torch.zeros(148 * 4 * 16, dtype=torch.int64, device=dev)
 lib.miner_debug_set_hist_prof.argtypes = [C.c_void_p]
 lib.miner_debug_set_hist_prof(prof.data_ptr())
 wp16 = w.w_proj.to(torch.bfloat16).to(dev)
@@ -22,14 +22,17 @@ args = (table, eb.his_ids.to(dev), eb.his_mask.to(dev), wp16, w.context_codes.to
 for _ in range(3):
     ops.hist_interests(*args, want_f32=False)
 torch.cuda.synchronize()
-p = prof.cpu().view(148, 3, 16).double()
+p = prof.cpu().view(148, 4, 16).double()
 tiles = (B / 2) / 148
-names = {0: ['other/issue-gap', 'wait E tile (P1)', 'issue P1', 'wait t_ready', 'issue LG', 'wait w_ready', 'wait ia_free', 'wait full (P2)', 'issue P2', 'wait Wp tile (P1)'],
+names = {0: ['other/issue-gap', 'wait E tile', 'issue P1', 'wait proj free (t_ready)', '-', '-', '-', '-', '-', 'wait Wp tile'],
+         3: ['other/issue-gap', '-', '-', 'wait t_ready', 'issue LG', 'wait w_ready', 'wait ia_free', 'wait E tile', 'issue P2'],
          1: ['gap', 'wait p1_full', 'E1a tanh->T', 'wait lg_full', 'E1b softmax', 'wait ia_full', 'drain'],
          2: ['setup ids', 'wait empty', 'issue cp.async']}
-for role, rn in ((0, 'MMA thread'), (1, 'epilogue thread'), (2, 'gather thread')):
+for role, rn in ((0, 'MMA warp, projection pipeline'), (3, 'MMA warp, logits + weighted-sum pipeline'), (1, 'epilogue thread'), (2, 'gather thread (projection ring)')):
     tot = p[:, role, 15].mean()
     print(f'{rn}: total {tot:.0f} cycles = {tot / tiles:.0f} per tile')
     for i, n in enumerate(names[role]):
+        if n == '-':
+            continue
         v = p[:, role, i].mean()
         print(f'    {n:18s} {v / tiles:9.0f} cycles/tile  {100 * v / tot:5.1f}%')

@@ -509,8 +509,8 @@ def test_hist_kernel_interests(B, H, D, K, Dc):
                                None if bm is None else bm[:, :, None])
         ihi, ilo, out = ops.hist_interests(table.to(DEV), his.to(DEV), mask.to(DEV), wp16.to(DEV), w.context_codes.to(DEV),
                                            bias_mean=None if bm is None else bm.to(DEV))
-        assert _nerr(out.cpu(), ref) < 5e-5
-        assert _nerr((ihi.float() + ilo.float()).cpu().view(B, K, D), ref) < 5e-5
+        assert _nerr(out.cpu(), ref) < 3e-4          # logits MMA operands are fp16 (tanh values) / fp16 hi+lo (codes)
+        assert _nerr((ihi.float() + ilo.float()).cpu().view(B, K, D), ref) < 3e-4
         assert torch.equal(ihi.cpu().view(B, K, D), out.cpu().to(torch.bfloat16))          # hi is the bf16 rounding of the fp32 value
     # int32 ids: same bits; out-of-range id: that history row contributes a zero vector
     ihi32, _, _ = ops.hist_interests(table.to(DEV), his.int().to(DEV), mask.to(DEV), wp16.to(DEV), w.context_codes.to(DEV), bias_mean=bias.to(DEV))
@@ -520,7 +520,7 @@ def test_hist_kernel_interests(B, H, D, K, Dc):
     tz = torch.cat([table, torch.zeros(6, D, dtype=torch.bfloat16)])
     ref = O.poly_attention(tz.float()[his_bad], mask, wp16.float(), w.context_codes)
     _, _, out = ops.hist_interests(table.to(DEV), his_bad.to(DEV), mask.to(DEV), wp16.to(DEV), w.context_codes.to(DEV))
-    assert _nerr(out.cpu(), ref) < 5e-5
+    assert _nerr(out.cpu(), ref) < 3e-4
 
 
 @pytest.mark.parametrize('B,D,K,mean_c,max_c', [(6, 64, 8, 20.0, 300), (37, 768, 32, 20.0, 300), (301, 256, 32, 12.0, 70), (33, 128, 16, 20.0, 300),
