@@ -86,6 +86,18 @@ __device__ __forceinline__ void tma_load_2d(const void* tmap, uint64_t* bar, uin
       : "memory");
 }
 
+// TMA row gather (sm_100a tile::gather4): 4 rows of a 2D row-major tensor, chosen by index, 64 bf16 each starting at
+// column x, land in 4 consecutive 128-byte shared-memory rows (SWIZZLE_128B keyed on the destination row, i.e. exactly the
+// layout the UMMA descriptors above read).  The tensor map must have box {64, 1}.  A row index past the end of the tensor is
+// zero-filled.  Verified on B200 by scripts/probes/tma_gather4_probe.cu.
+__device__ __forceinline__ void tma_gather4(const void* tmap, uint64_t* bar, uint32_t dst_smem, int32_t x, int32_t r0, int32_t r1, int32_t r2,
+                                            int32_t r3) {
+  asm volatile(
+      "cp.async.bulk.tensor.2d.shared::cta.global.tile::gather4.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4, %5, %6, %7}], [%2];" ::"r"(dst_smem),
+      "l"(reinterpret_cast<uint64_t>(tmap)), "r"(smem_u32(bar)), "r"(x), "r"(r0), "r"(r1), "r"(r2), "r"(r3)
+      : "memory");
+}
+
 // ----------------------------------------------------------------------------------------------- thread-block clusters
 __device__ __forceinline__ uint32_t cluster_ctarank() { uint32_t r; asm volatile("mov.u32 %0, %%cluster_ctarank;" : "=r"(r)); return r; }
 __device__ __forceinline__ void cluster_sync_all() {
