@@ -18,7 +18,12 @@ prof = torch.zeros(148 * 4 * 16, dtype=torch.int64, device=dev)
 lib.miner_debug_set_hist_prof.argtypes = [C.c_void_p]
 lib.miner_debug_set_hist_prof(prof.data_ptr())
 wp16 = w.w_proj.to(torch.bfloat16).to(dev)
-args = (table, eb.his_ids.to(dev), eb.his_mask.to(dev), wp16, w.context_codes.to(dev))
+his = eb.his_ids.to(dev)
+if '--same-ids' in sys.argv:          # ablation: every history row is table row 1 (gathers hit L2 / one DRAM page)
+    his = torch.ones_like(his)
+if '--few-ids' in sys.argv:           # ablation: ids from a 2000-row window (L2-resident)
+    his = his % 2000
+args = (table, his, eb.his_mask.to(dev), wp16, w.context_codes.to(dev))
 for _ in range(3):
     ops.hist_interests(*args, want_f32=False)
 torch.cuda.synchronize()
