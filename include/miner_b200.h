@@ -148,6 +148,26 @@ int miner_cand_score_fwd(const void* i_hi, const void* i_lo, const void* w_targe
                          const void* cand_ids, int id_dtype, const int64_t* cand_offsets,
                          int64_t B, int64_t C, int64_t K, int64_t D, float* out_scores, void* stream);
 
+/* ---- Table-level mode of the scoring path (opt-in; same results to fp32 rounding, different operation order).
+ *      The two nn.Linear layers of the path act row-wise on gathered news vectors (model.py:171 PolyAttention.linear,
+ *      model.py:212 TargetAwareAttention.linear applied to sum_h w[k,h] E[h]), so they can be applied once per TABLE row
+ *      instead of once per gathered row:
+ *        lg (n_rows,K) fp32 = tanh(table Wp^T) codes^T      (model.py:171,174)
+ *        tw (n_rows,D) bf16 = table Wt^T                     (model.py:212 before the gelu; NULL unless score_type WEIGHTED)
+ *      miner_table_project computes them (once per weight version / table; bench.py does it inside every timed step);
+ *      miner_score_table_fwd is Miner.forward (model.py:61-138) for B impressions from table, lg, tw in one kernel:
+ *      masked softmax over the history (1e-30 fill, model.py:180), interests, gelu, matching scores, softmax over K, score.
+ *      Needs a bf16 table, H <= 64, K <= 32, D % 64 == 0.  out_interests (B,K,D) fp32 or NULL. */
+size_t miner_table_project_workspace_bytes(int64_t n_rows, int64_t Dc);
+int miner_table_project(const void* table_bf16, int64_t n_rows, int64_t D, const void* w_proj_bf16, const float* codes,
+                        const void* w_target_bf16, int64_t K, int64_t Dc, float* out_lg, void* out_tw,
+                        void* workspace, size_t workspace_bytes, void* stream);
+int miner_score_table_supported(int64_t H, int64_t K, int64_t D);
+int miner_score_table_fwd(const void* table_bf16, const void* tw_bf16, const float* lg, int64_t n_rows,
+                          const void* his_ids, const uint8_t* his_mask, const void* cand_ids, const int64_t* cand_offsets,
+                          int id_dtype, const float* bias_mean, int64_t B, int64_t H, int64_t C, int64_t K, int64_t D,
+                          int score_type, float* out_scores, float* out_interests, void* stream);
+
 /* ---- (a7..a12) segmented per-impression ranking metrics: replaces SlowEvaluator/FastEvaluator +
  *      compute_scores (evaluation.py:36-84,87-175) and compute_mrr/dcg/ndcg_score, is_hit (:177-249).
  *      scores (T) fp32 logits; labels (T) int8; offsets (B+1) int64; transform: 0 none, 1 sigmoid (SlowEvaluator,

@@ -302,6 +302,41 @@ extern "C" int miner_cand_score_fwd(const void* i_hi, const void* i_lo, const vo
                             static_cast<cudaStream_t>(stream));
 }
 
+extern "C" size_t miner_table_project_workspace_bytes(int64_t n_rows, int64_t Dc) { return table_project_ws_bytes(n_rows, Dc); }
+
+extern "C" int miner_table_project(const void* table, int64_t n_rows, int64_t D, const void* w_proj_bf16, const float* codes,
+                                   const void* w_target_bf16, int64_t K, int64_t Dc, float* out_lg, void* out_tw, void* workspace,
+                                   size_t workspace_bytes, void* stream) {
+  MINER_CHECK_ARG(n_rows >= 0 && D > 0 && K > 0 && Dc > 0, "table_project: bad sizes");
+  if (n_rows == 0) return MINER_OK;
+  MINER_CHECK_ARG(table && w_proj_bf16 && codes && out_lg && (!out_tw || w_target_bf16), "table_project: null pointer");
+  if (!workspace || workspace_bytes < table_project_ws_bytes(n_rows, Dc)) {
+    set_error("table_project: workspace too small (%zu bytes needed)", table_project_ws_bytes(n_rows, Dc));
+    return MINER_ERR_WORKSPACE;
+  }
+  return launch_table_project(table, n_rows, D, w_proj_bf16, codes, w_target_bf16, K, Dc, out_lg, out_tw, static_cast<float*>(workspace),
+                              static_cast<cudaStream_t>(stream));
+}
+
+extern "C" int miner_score_table_supported(int64_t H, int64_t K, int64_t D) { return tscore_kernel_supported(H, K, D) ? 1 : 0; }
+
+extern "C" int miner_score_table_fwd(const void* table, const void* tw, const float* lg, int64_t n_rows, const void* his_ids,
+                                     const uint8_t* his_mask, const void* cand_ids, const int64_t* cand_offsets, int id_dtype,
+                                     const float* bias_mean, int64_t B, int64_t H, int64_t C, int64_t K, int64_t D, int score_type,
+                                     float* out_scores, float* out_interests, void* stream) {
+  MINER_CHECK_ARG(B >= 0 && n_rows > 0 && H > 0 && K > 0 && D > 0 && (cand_offsets || C > 0), "score_table: bad sizes");
+  if (score_type != MINER_SCORE_MAX && score_type != MINER_SCORE_MEAN && score_type != MINER_SCORE_WEIGHTED) {
+    set_error("Invalid method of aggregating matching score");
+    return MINER_ERR_SCORE_TYPE;
+  }
+  if (B == 0) return MINER_OK;
+  MINER_CHECK_ARG(table && lg && his_ids && his_mask && cand_ids && out_scores, "score_table: null pointer");
+  MINER_CHECK_ARG(tw || score_type != MINER_SCORE_WEIGHTED, "score_table: 'weighted' needs the tw table");
+  MINER_CHECK_ARG(id_dtype == MINER_I32 || id_dtype == MINER_I64, "score_table: id dtype must be int32 or int64");
+  return launch_tscore_kernel(table, tw ? tw : table, lg, n_rows, his_ids, id_dtype, his_mask, bias_mean, cand_ids, cand_offsets, B, H, C, K,
+                              D, score_type, out_scores, out_interests, static_cast<cudaStream_t>(stream));
+}
+
 // profiling hook (not part of the documented ABI): device buffer of 148*3*16 int64 for -DMINER_HIST_PROF builds
 extern "C" void miner_debug_set_hist_prof(void* p) { set_hist_prof_buffer(static_cast<long long*>(p)); }
 extern "C" void miner_debug_set_cand_pair(int on) { set_cand_pair(on); }

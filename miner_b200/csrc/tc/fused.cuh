@@ -37,4 +37,15 @@ int launch_cand_kernel2(const void* i_hi, const void* i_lo, const void* wt_bf16,
                         const void* cand_ids, int id_dtype, const int64_t* cand_offsets, int64_t B, int64_t C, int64_t K, int64_t D,
                         float* out_scores, cudaStream_t stream);
 
+// Table-level mode (table_project.cu, tscore_kernel.cu): projections hoisted to the news table, one scoring kernel.
+size_t table_project_ws_bytes(int64_t n_rows, int64_t Dc);
+int launch_table_project(const void* table, int64_t n_rows, int64_t D, const void* w_proj_bf16, const float* codes,
+                         const void* w_target_bf16, int64_t K, int64_t Dc, float* out_lg, void* out_tw, float* proj_ws,
+                         cudaStream_t stream);
+bool tscore_kernel_supported(int64_t H, int64_t K, int64_t D);
+int launch_tscore_kernel(const void* table, const void* tw, const float* lg, int64_t n_rows, const void* his_ids, int id_dtype,
+                         const uint8_t* his_mask, const float* bias_mean, const void* cand_ids, const int64_t* cand_offsets,
+                         int64_t B, int64_t H, int64_t C, int64_t K, int64_t D, int score_type, float* out_scores, float* out_interests,
+                         cudaStream_t stream);
+
 }  // namespace miner

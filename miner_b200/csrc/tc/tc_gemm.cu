@@ -189,13 +189,14 @@ tc_gemm_kernel(const __grid_constant__ CUtensorMap tmap_b, const uint16_t* __res
         tc::tmem_ld_32x32(tmem_base + (static_cast<uint32_t>(q * 32) << 16) + as * GN + c * 32, r);
         tc::tmem_ld_wait();
         if (m < M) {
-          float* crow = C + m * N + n0 + c * 32;
+          float* crow = C ? C + m * N + n0 + c * 32 : nullptr;
           __nv_bfloat16* brow = Cb ? Cb + m * N + n0 + c * 32 : nullptr;
           const int valid = n_cols - c * 32 < 32 ? n_cols - c * 32 : 32;
           float v[32];
 #pragma unroll
           for (int j = 0; j < 32; ++j) v[j] = apply_epilogue(__uint_as_float(r[j]), epi);
-          if (valid == 32 && vec_ok) {
+          if (!C) {
+          } else if (valid == 32 && vec_ok) {
 #pragma unroll
             for (int j = 0; j < 32; j += 4) *reinterpret_cast<float4*>(crow + j) = make_float4(v[j], v[j + 1], v[j + 2], v[j + 3]);
           } else {
@@ -204,9 +205,19 @@ tc_gemm_kernel(const __grid_constant__ CUtensorMap tmap_b, const uint16_t* __res
               if (j < valid) crow[j] = v[j];
           }
           if (brow) {
+            if (valid == 32 && N % 8 == 0) {
 #pragma unroll
-            for (int j = 0; j < 32; ++j)
-              if (j < valid) brow[j] = __float2bfloat16_rn(v[j]);
+              for (int j = 0; j < 32; j += 8) {
+                __nv_bfloat162 h0 = __floats2bfloat162_rn(v[j], v[j + 1]), h1 = __floats2bfloat162_rn(v[j + 2], v[j + 3]);
+                __nv_bfloat162 h2 = __floats2bfloat162_rn(v[j + 4], v[j + 5]), h3 = __floats2bfloat162_rn(v[j + 6], v[j + 7]);
+                *reinterpret_cast<uint4*>(brow + j) = make_uint4(*reinterpret_cast<uint32_t*>(&h0), *reinterpret_cast<uint32_t*>(&h1),
+                                                                 *reinterpret_cast<uint32_t*>(&h2), *reinterpret_cast<uint32_t*>(&h3));
+              }
+            } else {
+#pragma unroll
+              for (int j = 0; j < 32; ++j)
+                if (j < valid) brow[j] = __float2bfloat16_rn(v[j]);
+            }
           }
         }
       }
@@ -242,13 +253,13 @@ bool tc_gemm_supported(int64_t K, int64_t N) { return K >= GK && K % GK == 0 && 
 int launch_tc_gemm(const void* A, const void* a_ids, int id_dtype, int64_t a_rows_in_table, const void* B, float* C, void* c_bf16,
                    int64_t M, int64_t N, int64_t K, int epilogue, cudaStream_t stream) {
   if (M == 0) return MINER_OK;
-  MINER_CHECK_ARG(A && B && C, "tc_gemm: null pointer");
+  MINER_CHECK_ARG(A && B && (C || c_bf16), "tc_gemm: null pointer");
   if (!tc_gemm_supported(K, N)) {
     set_error("tc_gemm: unsupported shape N=%lld K=%lld (need K %% 64 == 0, N >= 16)", (long long)N, (long long)K);
     return MINER_ERR_UNSUPPORTED;
   }
   MINER_CHECK_ARG(reinterpret_cast<uintptr_t>(A) % 16 == 0 && reinterpret_cast<uintptr_t>(B) % 16 == 0 &&
-                      reinterpret_cast<uintptr_t>(C) % 16 == 0,
+                      reinterpret_cast<uintptr_t>(C) % 16 == 0 && reinterpret_cast<uintptr_t>(c_bf16) % 16 == 0,
                   "tc_gemm: operands must be 16-byte aligned");
   EncodeTiledFn encode = encode_tiled_fn();
   if (!encode) {

@@ -248,6 +248,84 @@ def score(table: torch.Tensor, his_ids: torch.Tensor, his_mask: torch.Tensor, ca
     return interests, scores
 
 
+# ------------------------------------------------------------------------------------------------ table-level mode
+class TableProjections:
+    """``lg (N,K) fp32 = tanh(table Wp^T) codes^T`` and ``tw (N,D) bf16 = table Wt^T``: the two nn.Linear layers of the path
+    (reference model.py:171,174 and :212) applied once per table row instead of once per gathered row."""
+
+    def __init__(self, table: torch.Tensor, lg: torch.Tensor, tw: Optional[torch.Tensor]):
+        self.table, self.lg, self.tw = table, lg, tw
+
+
+def table_project(table: torch.Tensor, weights: 'ScoreWeights', weighted: bool = True,
+                  out: Optional[TableProjections] = None, workspace: Optional[torch.Tensor] = None) -> TableProjections:
+    """Compute the table-level projections (``miner_table_project``).  ``out`` / ``workspace`` let a caller reuse buffers."""
+    dev = _need_cuda(table)
+    lib = L.load()
+    if table.dtype != torch.bfloat16:
+        raise L.MinerError('table-level mode needs a bfloat16 table')
+    if weights.w_proj_bf16 is None:
+        raise L.MinerError('table-level mode needs weights prepared with bf16 copies')
+    table = table.detach().contiguous()
+    N, D = table.shape
+    K, Dc = weights.codes.shape
+    want_tw = weighted and weights.w_target_bf16 is not None
+    if out is None:
+        lg = torch.empty(N, K, dtype=torch.float32, device=dev)
+        tw = torch.empty(N, D, dtype=torch.bfloat16, device=dev) if want_tw else None
+        out = TableProjections(table, lg, tw)
+    ws_bytes = lib.miner_table_project_workspace_bytes(N, Dc)
+    ws = workspace if (workspace is not None and workspace.numel() >= ws_bytes) else torch.empty(max(ws_bytes, 1), dtype=torch.uint8, device=dev)
+    with torch.cuda.device(dev):
+        L.check(lib.miner_table_project(_ptr(table), N, D, _ptr(weights.w_proj_bf16), _ptr(weights.codes),
+                                        _ptr(weights.w_target_bf16) if want_tw else None, K, Dc, _ptr(out.lg),
+                                        _ptr(out.tw) if want_tw else None, _ptr(ws), ws.numel(), _stream()))
+    out.table = table
+    return out
+
+
+def score_table_supported(H: int, K: int, D: int) -> bool:
+    return bool(L.load().miner_score_table_supported(H, K, D))
+
+
+def score_table(proj: TableProjections, his_ids: torch.Tensor, his_mask: torch.Tensor, cand_ids: torch.Tensor,
+                score_type: str = 'weighted', cand_offsets: Optional[torch.Tensor] = None, bias_mean: Optional[torch.Tensor] = None,
+                want_interests: bool = False, out_scores: Optional[torch.Tensor] = None):
+    """Miner.forward (reference model.py:61-138) for a block of impressions in one kernel from the table-level projections.
+
+    Dense layout: ``cand_ids`` (B,C).  CSR layout: ``cand_ids`` (T,) + ``cand_offsets`` (B+1,) int64.
+    Returns ``(interests (B,K,D) or None, scores)``.
+    """
+    dev = _need_cuda(proj.table, his_ids, his_mask, cand_ids, cand_offsets, bias_mean)
+    lib = L.load()
+    st = L.SCORE_TYPES.get(score_type, -1)
+    if st < 0:
+        raise ValueError('Invalid method of aggregating matching score')
+    B, H = his_ids.shape
+    N, D = proj.table.shape
+    K = proj.lg.shape[1]
+    hid, it = _ids(his_ids)
+    cid, it2 = _ids(cand_ids)
+    if it != it2:
+        cid, it2 = _ids(cand_ids.to(his_ids.dtype))
+    m = _mask_u8(his_mask)
+    if cand_offsets is None:
+        Cn = cand_ids.shape[1]
+        offs = None
+        out_shape = (B, Cn)
+    else:
+        Cn = 0
+        offs = cand_offsets.to(torch.int64).contiguous()
+        out_shape = (cid.numel(),)
+    bm = _f32(bias_mean) if bias_mean is not None else None
+    scores = out_scores if out_scores is not None else torch.empty(out_shape, dtype=torch.float32, device=dev)
+    interests = torch.empty(B, K, D, dtype=torch.float32, device=dev) if want_interests else None
+    with torch.cuda.device(dev):
+        L.check(lib.miner_score_table_fwd(_ptr(proj.table), _ptr(proj.tw), _ptr(proj.lg), N, _ptr(hid), _ptr(m), _ptr(cid), _ptr(offs), it,
+                                          _ptr(bm), B, H, Cn, K, D, st, _ptr(scores), _ptr(interests), _stream()))
+    return interests, scores
+
+
 def hist_interests(table: torch.Tensor, his_ids: torch.Tensor, his_mask: torch.Tensor, w_proj_bf16: torch.Tensor, codes: torch.Tensor,
                    bias_mean: Optional[torch.Tensor] = None, want_f32: bool = True):
     """History kernel of the fused tensor-core path on its own: ``(i_hi, i_lo, interests_f32 or None)``."""
