@@ -135,7 +135,10 @@ def main():
     ap.add_argument('--impressions', type=int, default=1_000_000, help='impressions per GPU per step')
     ap.add_argument('--chunk', type=int, default=0, help='impressions per kernel wave (0 = library default)')
     ap.add_argument('--cpu-sample', type=int, default=4000, help='impressions in the CPU baseline sample')
-    ap.add_argument('--math', default='tensor', choices=['tensor', 'fp32'])
+    ap.add_argument('--math', default='table', choices=['table', 'tensor', 'fp32'],
+                    help='table: projections applied once per table row inside every step + one fused scoring kernel (default); '
+                         'tensor / fp32: reference operation order')
+    ap.add_argument('--no-reference-order', action='store_true', help='skip the extra reference-order (tensor family) timing')
     ap.add_argument('--no-cpu-baseline', action='store_true')
     ap.add_argument('--no-breakdown', action='store_true')
     args = ap.parse_args()
@@ -179,7 +182,7 @@ def main():
         dist.init_process_group('nccl', device_id=dev)
     B = args.impressions
     seed = 36
-    math = _lib.MATH_TENSOR if args.math == 'tensor' else _lib.MATH_FP32
+    math = {'table': _lib.MATH_TABLE, 'tensor': _lib.MATH_TENSOR, 'fp32': _lib.MATH_FP32}[args.math]
 
     # replicated table + weights; this rank's own impressions (weak scaling)
     table = synth.make_table(N_NEWS, D, seed, torch.bfloat16).to(dev)
@@ -195,12 +198,22 @@ def main():
     h2d_bytes = sum(t.numel() * t.element_size() for t in host.values())
     names = ops.metric_names(KS)
     chunk = args.chunk if args.chunk > 0 else 32768
-    sw = model._weights(with_bf16=(math == _lib.MATH_TENSOR))
+    sw = model._weights(with_bf16=(math != _lib.MATH_FP32))
     scores_buf = torch.empty(T, dtype=torch.float32, device=dev)
 
-    def device_step(d):
-        ops.score(table, d['his_ids'], d['his_mask'], d['cand_ids'], sw, 'weighted', cand_offsets=d['offsets'], math=math,
-                  chunk=chunk, out_scores=scores_buf)
+    proj = ops.table_project(table, sw) if math == _lib.MATH_TABLE else None          # buffers; recomputed inside every step
+    proj_ws = torch.empty(max(_lib.load().miner_table_project_workspace_bytes(table.shape[0], DC), 1), dtype=torch.uint8, device=dev)
+
+    def score_step(d, m):
+        if m == _lib.MATH_TABLE:
+            ops.table_project(table, sw, out=proj, workspace=proj_ws)       # part of the step: nothing is carried over between steps
+            ops.score_table(proj, d['his_ids'], d['his_mask'], d['cand_ids'], 'weighted', cand_offsets=d['offsets'], out_scores=scores_buf)
+        else:
+            ops.score(table, d['his_ids'], d['his_mask'], d['cand_ids'], sw, 'weighted', cand_offsets=d['offsets'], math=m,
+                      chunk=chunk, out_scores=scores_buf)
+
+    def device_step(d, m=None):
+        score_step(d, math if m is None else m)
         partials, _ = ops.rank_metrics_raw(scores_buf, d['labels'], d['offsets'], 'sigmoid', KS)
         parallel.allreduce_partials(partials)
         return partials
@@ -234,6 +247,16 @@ def main():
     ms_dev, partials = timed(lambda: device_step(resident), args.steps)
     launches = ops.launch_count() - l0
     metrics_out = parallel.finalize_metrics(partials, names)
+    reference_order = None
+    if math == _lib.MATH_TABLE and not args.no_reference_order:
+        # the same step in the reference's operation order (tensor family: per-row projections on tcgen05), for comparison
+        for _ in range(2):
+            device_step(resident, _lib.MATH_TENSOR)
+        ms_ro, p_ro = timed(lambda: device_step(resident, _lib.MATH_TENSOR), max(1, min(args.steps, 3)))
+        m_ro = parallel.finalize_metrics(p_ro, names)
+        reference_order = {'value': B * world / (ms_ro * 1e-3), 'unit': 'impressions/s', 'ms_per_step': ms_ro,
+                           'kernels': 'hist_kernel2 + cand_kernel (tcgen05, per-row projections), rank_metrics',
+                           'max_metric_abs_diff_vs_table_mode': max(abs(m_ro[k] - metrics_out[k]) for k in names)}
 
     # ---- e2e: public API with host buffers, H2D + D2H inside the timed region
     # public API: HostEvaluator copies waves of impressions H2D on a copy stream while the previous wave is scored
@@ -253,23 +276,32 @@ def main():
     pk = peaks()
     kernels, roofline = None, None
     if rank == 0 and not args.no_breakdown:
-        if math == _lib.MATH_TENSOR:
+        if math == _lib.MATH_TABLE:
+            stages = [('table_project: tc_gemm tanh(table Wp^T) + table_logits + tc_gemm table Wt^T (once per step, N rows)', 'proj'),
+                      ('tscore_kernel: gather table/tw/cand rows + softmax_H + interests + gelu + matching/attention MMAs + softmax_K + score (tcgen05)', 'score')]
+        elif math == _lib.MATH_TENSOR:
             # fused tcgen05 path: two kernels per wave of `chunk` impressions
             stages = [('hist_kernel: gather + tanh(E Wp^T) + logits/softmax + weighted sum (tcgen05)', 1),
                       ('cand_kernel: gelu(I Wt^T) + matching/attention MMAs + softmax_K + score (tcgen05)', 8)]
         else:
             stages = [('sgemm: tanh(table[his] Wp^T) [gather fused]', 1), ('poly_softmax_wsum', 2), ('sgemm: gelu(I Wt^T)', 4),
                       ('target_score [cand gather fused]', 8)]
-        nchunks = (B + chunk - 1) // chunk
+        nchunks = 1 if math == _lib.MATH_TABLE else (B + chunk - 1) // chunk
         kernels = []
         for name, mask in stages:
-            fn = lambda: ops.score(table, resident['his_ids'], resident['his_mask'], resident['cand_ids'], sw, 'weighted',
-                                   cand_offsets=resident['offsets'], math=math, chunk=chunk, out_scores=scores_buf, stage_mask=mask)
+            if mask == 'proj':
+                fn = lambda: ops.table_project(table, sw, out=proj, workspace=proj_ws)
+            elif mask == 'score':
+                fn = lambda: ops.score_table(proj, resident['his_ids'], resident['his_mask'], resident['cand_ids'], 'weighted',
+                                             cand_offsets=resident['offsets'], out_scores=scores_buf)
+            else:
+                fn = lambda: ops.score(table, resident['his_ids'], resident['his_mask'], resident['cand_ids'], sw, 'weighted',
+                                       cand_offsets=resident['offsets'], math=math, chunk=chunk, out_scores=scores_buf, stage_mask=mask)
             fn()
             torch.cuda.synchronize()
             e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
             e0.record(); fn(); e1.record(); torch.cuda.synchronize()
-            kernels.append({'kernel': name, 'ms_per_step': e0.elapsed_time(e1), 'launches_per_step': nchunks})
+            kernels.append({'kernel': name, 'ms_per_step': e0.elapsed_time(e1), 'launches_per_step': 3 if mask == 'proj' else nchunks})
         fn = lambda: ops.rank_metrics_raw(scores_buf, resident['labels'], resident['offsets'], 'sigmoid', KS)
         fn(); torch.cuda.synchronize()
         e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
@@ -280,7 +312,14 @@ def main():
             k['share'] = k['ms_per_step'] / tot
         # algorithmic work per impression of each stage
         c_mean = T / B
-        if math == _lib.MATH_TENSOR:
+        if math == _lib.MATH_TABLE:
+            # table-level mode: FLOPs actually issued per impression (weighted sums over E and TW, matching + attention dots) and the
+            # SURVEY 8(d) algorithmic bytes (gathered table rows + ids + mask + scores + labels); the tw rows the kernel also
+            # gathers are extra traffic of this formulation and are reported as `gathered_bytes_per_impression`
+            flops = {'proj': (2 * D * DC + 2 * DC * K + 2 * D * D) * (N_NEWS + 1) / B, 'score': 4 * K * H * D + 4 * c_mean * K * D}
+            byts = {'proj': (N_NEWS + 1) * D * 2 / B, 'score': synth.algorithmic_bytes_per_impression(H, c_mean, D, 2)}
+            tensor_stage = ()
+        elif math == _lib.MATH_TENSOR:
             flops = {1: 2 * H * D * DC + 2 * H * DC * K + 2 * K * H * D, 8: 2 * K * D * D + 4 * c_mean * K * D}
             byts = {1: H * D * 2 + H * 8 + H, 8: c_mean * D * 2 + c_mean * 8 + c_mean * 4}
             tensor_stage = (1, 8)
@@ -297,8 +336,8 @@ def main():
         peak_tf = pk.get('bf16_tflops_sustained', pk['bf16_tflops'])
         traffic, traffic_src = None, None
         tpath = os.path.join(ROOT, 'profiles', 'traffic.json')
-        if os.path.exists(tpath) and math == _lib.MATH_TENSOR:       # DRAM bytes per impression from the committed ncu capture
-            tj = json.load(open(tpath)).get('hist_kernel' if mask == 1 else 'cand_kernel')
+        if os.path.exists(tpath) and math != _lib.MATH_FP32:       # DRAM bytes per impression from the committed ncu capture
+            tj = json.load(open(tpath)).get({1: 'hist_kernel', 8: 'cand_kernel', 'score': 'tscore_kernel'}.get(mask, '-'))
             if tj:
                 traffic, traffic_src = tj['dram_bytes_per_impression'] * per_launch_impr, tj['source']
         if mask in tensor_stage:
@@ -308,7 +347,13 @@ def main():
                         'algorithmic_flops_per_launch': flops[mask] * per_launch_impr, 'ms_per_launch': sec_per_launch * 1e3}
         else:
             roofline = {'kernel': stages[top][0], 'bound': 'hbm', 'achieved': gbs, 'peak': pk['hbm_gbs'], 'unit': 'GB/s',
-                        'frac': gbs / pk['hbm_gbs'], 'traffic': traffic, 'peak_source': pk['_source'], 'achieved_tflops_fp32': tf}
+                        'frac': gbs / pk['hbm_gbs'], 'traffic': traffic, 'traffic_source': traffic_src, 'peak_source': pk['_source'],
+                        'achieved_tflops': tf, 'algorithmic_bytes_per_launch': byts[mask] * per_launch_impr, 'ms_per_launch': sec_per_launch * 1e3}
+            if math == _lib.MATH_TABLE:
+                gathered = (2 * H + c_mean) * D * 2 + H * K * 4 + (H + c_mean) * 8 + H + c_mean * 5     # + tw rows + lg rows
+                roofline['gathered_bytes_per_impression'] = gathered
+                roofline['gathered_gbs'] = gathered * per_launch_impr / sec_per_launch / 1e9
+                roofline['gathered_frac'] = roofline['gathered_gbs'] / pk['hbm_gbs']
 
     # ---- CPU baseline (rank 0, N=1 only)
     cpu_baseline = None
@@ -329,10 +374,11 @@ def main():
         line = {
             'metric': 'impressions scored/sec', 'value': value, 'unit': 'impressions/s', 'n_gpus': world, 'steps': args.steps,
             'warmup': max(args.warmup, 3), 'ms_per_step': ms_dev, 'higher_is_better': True, 'scaling': 'weak', 'vs_baseline': None,
-            'dtype': 'bf16 operands / f32 accumulate (projection GEMMs), f32 elsewhere, f64 metrics' if math == _lib.MATH_TENSOR else 'f32',
+            'dtype': 'f32' if math == _lib.MATH_FP32 else 'bf16 operands / f32 accumulate (tcgen05 MMAs, hi+lo splits where fp32 accuracy matters), f32 elsewhere, f64 metrics',
             'data': 'synthetic',
             'config': {'workload': 'MINER eval scoring on 1xB200 per rank: 1M synthetic impressions, history 50, K=32, Dc=200, D=768, '
                                    '~20 candidates each (CSR), 100k-news bf16 table, score_type=weighted, metrics group_auc/mrr/ndcg@5,10/hit@5,10',
+                       'math': args.math + (' (both nn.Linear layers applied once per table row INSIDE every step, then one fused scoring kernel)' if math == _lib.MATH_TABLE else ' (reference operation order)'),
                        'impressions_per_gpu_per_step': B, 'candidates_per_gpu_per_step': T, 'chunk_impressions': chunk,
                        'l2': 'inputs per step (>600 MB ids + 154 MB table + workspace) exceed the 126 MB L2; no explicit flush',
                        'parallelism': f'dp{world} (impressions sharded, table+weights replicated)'},
@@ -342,10 +388,11 @@ def main():
             'clocks': clocks,
             'roofline': roofline,
             'roofline_path': {'hbm_frac': per_gpu * bytes_per_impr / 1e9 / pk['hbm_gbs'],
-                              'tensor_frac': per_gpu * flops_per_impr / 1e12 / pk.get('bf16_tflops_sustained', pk['bf16_tflops']),
+                              'tensor_frac_reference_order_flops': per_gpu * flops_per_impr / 1e12 / pk.get('bf16_tflops_sustained', pk['bf16_tflops']),
                               'algorithmic_bytes_per_impression': bytes_per_impr, 'algorithmic_flops_per_impression': flops_per_impr,
                               'peak_source': pk['_source']},
             'kernels': kernels,
+            'reference_order': reference_order,
             'cpu_baseline': cpu_baseline,
             'metrics': metrics_out,
         }

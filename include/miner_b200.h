@@ -53,6 +53,9 @@ extern "C" {
 #define MINER_MATH_FP32    0   /* fp32 CUDA-core kernels, reference operation order                     */
 #define MINER_MATH_TENSOR  1   /* tcgen05 bf16 tensor cores (fp32 accumulate) for the two projection
                                   GEMMs; softmax / weighted sums / dot-scores stay fp32               */
+#define MINER_MATH_TABLE   2   /* table-level mode: projections applied once per table row
+                                  (miner_table_project) + one fused scoring kernel (miner_score_table_fwd);
+                                  not a value of miner_score_params.math -- it has its own entry points    */
 
 int         miner_abi_version(void);
 const char* miner_last_error(void);

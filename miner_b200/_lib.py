@@ -18,7 +18,7 @@ OK, ERR_INVALID_ARG, ERR_SCORE_TYPE, ERR_CUDA, ERR_WORKSPACE, ERR_UNSUPPORTED = 
 F32, BF16 = 0, 1
 I32, I64 = 0, 1
 SCORE_MAX, SCORE_MEAN, SCORE_WEIGHTED = 0, 1, 2
-MATH_FP32, MATH_TENSOR = 0, 1
+MATH_FP32, MATH_TENSOR, MATH_TABLE = 0, 1, 2
 EPI_NONE, EPI_TANH, EPI_GELU = 0, 1, 2
 ABI_VERSION = 1
 

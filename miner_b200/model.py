@@ -157,6 +157,8 @@ class Miner(nn.Module):
             self.target_aware_attn = TargetAwareAttention(self.news_embed_dim)
         self.dropout = nn.Dropout(dropout)           # constructed but never applied, as in the reference (model.py:59)
         self._prepared = None                        # (version key, ops.ScoreWeights)
+        self._table_proj = None                      # (version key, ops.TableProjections)
+        self.table_level = False                     # forward(): opt into the table-level mode (score_impressions uses it by default)
 
     # -- parameter staging -------------------------------------------------------------------------------------
     def _weights(self, with_bf16: bool) -> ops.ScoreWeights:
@@ -166,6 +168,18 @@ class Miner(nn.Module):
         if self._prepared is None or self._prepared[0] != key:
             self._prepared = (key, ops.ScoreWeights(params[0], params[1], wt, with_bf16))
         return self._prepared[1]
+
+    def table_projections(self) -> 'ops.TableProjections':
+        """Table-level projections ``lg = tanh(table Wp^T) codes^T`` and ``tw = table Wt^T`` (model.py:171,174,212 applied once per
+        table row), recomputed whenever a parameter or the table changes."""
+        if not isinstance(self.news_encoder, TableNewsEncoder):
+            raise L.MinerError('table-level mode needs a TableNewsEncoder')
+        table = self.news_encoder.table
+        w = self._weights(with_bf16=True)
+        key = (self._prepared[0], table.data_ptr(), table._version)
+        if self._table_proj is None or self._table_proj[0] != key:
+            self._table_proj = (key, ops.table_project(table, w, weighted=self.score_type == 'weighted'))
+        return self._table_proj[1]
 
     def _bias_mean(self, his_category: Tensor, category: Tensor) -> Tensor:
         if self.training and self.category_dropout.p > 0:
@@ -195,6 +209,12 @@ class Miner(nn.Module):
             w = self._weights(with_bf16=(math == L.MATH_TENSOR))
             cand_ids = title.reshape(batch_size, num_candidates, -1)[..., 0]
             his_ids = his_title.reshape(batch_size, his_length, -1)[..., 0]
+            if self.table_level and table.dtype == torch.bfloat16 and ops.score_table_supported(his_length, self.poly_attn.context_codes.shape[0],
+                                                                                               table.shape[1]):
+                interests, scores = ops.score_table(self.table_projections(), his_ids, his_mask, cand_ids, self.score_type,
+                                                    bias_mean=bias_mean, want_interests=True)
+                params = [p for p in self.parameters()]
+                return _attach(interests, *params), _attach(scores, *params)
             interests, scores = ops.score(table, his_ids, his_mask, cand_ids, w, self.score_type, bias_mean=bias_mean,
                                           math=math, want_interests=True)
         else:
@@ -224,6 +244,9 @@ class Miner(nn.Module):
                           chunk: int = 16384, math: Optional[int] = None) -> Tensor:
         """Scores of every candidate of every impression, CSR layout (``cand_offsets`` (B+1,) into flat ``cand_ids``).
 
+        ``math``: ``MATH_TABLE`` (default when the shape allows: bf16 table, H <= 64, K <= 32, D % 64 == 0) applies the two linear
+        layers once per table row and scores in one kernel; ``MATH_TENSOR`` / ``MATH_FP32`` keep the reference operation order.
+
         Equals the reference's per-candidate eval rows (src/reader.py:376-379: one sample per candidate, interests
         recomputed per candidate) when category bias is off, but computes the interests once per impression.
         """
@@ -234,7 +257,10 @@ class Miner(nn.Module):
             raise L.MinerError('score_impressions needs a TableNewsEncoder')
         table = self.news_encoder.table
         if math is None:
-            math = ops.default_math(table, table.shape[1])
+            math = ops.default_eval_math(table, his_ids.shape[1], self.poly_attn.context_codes.shape[0])
+        if math == L.MATH_TABLE:
+            _, scores = ops.score_table(self.table_projections(), his_ids, his_mask, cand_ids, self.score_type, cand_offsets=cand_offsets)
+            return scores
         w = self._weights(with_bf16=(math == L.MATH_TENSOR))
         _, scores = ops.score(table, his_ids, his_mask, cand_ids, w, self.score_type, cand_offsets=cand_offsets, math=math,
                               chunk=chunk)

@@ -188,6 +188,14 @@ def default_math(table: torch.Tensor, D: int) -> int:
     return L.MATH_TENSOR if (table.dtype == torch.bfloat16 and D % 64 == 0 and D >= 64) else L.MATH_FP32
 
 
+def default_eval_math(table: torch.Tensor, H: int, K: int) -> int:
+    """Grouped (CSR) evaluation: the table-level mode whenever its kernel covers the shape, else :func:`default_math`."""
+    D = table.shape[1]
+    if table.dtype == torch.bfloat16 and score_table_supported(H, K, D):
+        return L.MATH_TABLE
+    return default_math(table, D)
+
+
 def score(table: torch.Tensor, his_ids: torch.Tensor, his_mask: torch.Tensor, cand_ids: torch.Tensor, weights: ScoreWeights,
           score_type: str = 'weighted', cand_offsets: Optional[torch.Tensor] = None, bias_mean: Optional[torch.Tensor] = None,
           math: Optional[int] = None, want_interests: bool = False, chunk: int = 16384,

@@ -2,7 +2,7 @@
 host memory and get the ranking metrics back.
 
 Waves of `wave` impressions are copied host->device on a copy stream while the previous wave is being scored
-(hist_kernel -> cand_kernel -> rank_metrics) on the compute stream; the per-wave [sum, count] metric partials add up
+(table-level tscore_kernel, or hist_kernel -> cand_kernel in reference order, then rank_metrics) on the compute stream; the per-wave [sum, count] metric partials add up
 (exactly what ranks all-reduce, parallel.allreduce_partials).  Everything on the device runs in the sm_100a kernels of
 libminer_b200.so; this file is stream / buffer plumbing only.
 """
@@ -27,8 +27,15 @@ class HostEvaluator:
         self.model, self.wave, self.chunk, self.ks, self.transform = model, int(wave), int(chunk), tuple(ks), transform
         self.table = model.news_encoder.table
         self.dev = self.table.device
-        self.math = ops.default_math(self.table, self.table.shape[1]) if math is None else math
+        self._math_arg = math
+        self.math = math
         self.copy_stream = torch.cuda.Stream(device=self.dev)
+
+    def _proj_ws(self) -> torch.Tensor:
+        n = L.load().miner_table_project_workspace_bytes(self.table.shape[0], self.model.poly_attn.context_codes.shape[1])
+        if getattr(self, '_pws', None) is None or self._pws.numel() < n:
+            self._pws = torch.empty(max(n, 1), dtype=torch.uint8, device=self.dev)
+        return self._pws
 
     def _stage(self, host: Dict[str, torch.Tensor], a: int, b: int):
         """Issue the H2D copies of impressions [a, b) on the copy stream; returns device tensors + the event to wait on."""
@@ -50,7 +57,13 @@ class HostEvaluator:
         """host: pinned CPU tensors his_ids (B,H), his_mask (B,H), cand_ids (T,), labels (T,), offsets (B+1,).
         Returns (partials (2*M,) float64 on the device: [sum, count] per metric of ops.metric_names(ks), scores (T,) or None)."""
         B = host['his_ids'].shape[0]
-        w = self.model._weights(with_bf16=(self.math == L.MATH_TENSOR))
+        if self._math_arg is None:
+            self.math = ops.default_eval_math(self.table, host['his_ids'].shape[1], self.model.poly_attn.context_codes.shape[0])
+        w = self.model._weights(with_bf16=(self.math != L.MATH_FP32))
+        if self.math == L.MATH_TABLE:
+            # the table-level projections belong to the call: they are recomputed here, not carried over between calls
+            self._proj = ops.table_project(self.table, w, weighted=self.model.score_type == 'weighted', out=getattr(self, '_proj', None),
+                                           workspace=self._proj_ws())
         compute = torch.cuda.current_stream(self.dev)
         total = None
         scores_all = torch.empty(int(host['offsets'][-1]), dtype=torch.float32, device=self.dev) if want_scores else None
@@ -61,8 +74,11 @@ class HostEvaluator:
             nxt = self._stage(host, bounds[i + 1], bounds[i + 2]) if i + 2 < len(bounds) else None
             compute.wait_event(ev)
             offs = d['offsets'] - d['c0']
-            _, s = ops.score(self.table, d['his_ids'], d['his_mask'], d['cand_ids'], w, self.model.score_type, cand_offsets=offs,
-                             math=self.math, chunk=self.chunk)
+            if self.math == L.MATH_TABLE:
+                _, s = ops.score_table(self._proj, d['his_ids'], d['his_mask'], d['cand_ids'], self.model.score_type, cand_offsets=offs)
+            else:
+                _, s = ops.score(self.table, d['his_ids'], d['his_mask'], d['cand_ids'], w, self.model.score_type, cand_offsets=offs,
+                                 math=self.math, chunk=self.chunk)
             p, _ = ops.rank_metrics_raw(s, d['labels'], offs, self.transform, self.ks)
             total = p if total is None else total + p
             if want_scores:

@@ -673,3 +673,111 @@ def test_cand_pair_kernel_matches_single_cta_kernel():
     finally:
         lib.miner_debug_set_cand_pair(0)
     assert torch.equal(s1, s2)
+
+
+# ------------------------------------------------------------------------------------------------ table-level mode
+@pytest.mark.parametrize('N,D,K,Dc', [(300, 64, 8, 24), (900, 768, 32, 200), (513, 256, 32, 48), (77, 128, 16, 40)])
+def test_table_project(N, D, K, Dc):
+    """lg = tanh(table Wp^T) codes^T (model.py:171,174) and tw = table Wt^T (model.py:212) per table row, against torch fp32 on the
+    same bf16-valued operands.  Tolerances: lg 2e-5 normwise (fp32 accumulation order), tw 2^-8 (bf16 output rounding)."""
+    from miner_b200 import ops, synth
+    table = synth.make_table(N, D, 5, torch.bfloat16)
+    w = synth.make_weights(D, K, Dc, 5)
+    sw = ops.ScoreWeights(w.w_proj.to(DEV), w.context_codes.to(DEV), w.w_target.to(DEV), True)
+    tp = ops.table_project(table.to(DEV), sw)
+    wp, wt = w.w_proj.to(torch.bfloat16).float(), w.w_target.to(torch.bfloat16).float()
+    lg_ref = torch.tanh(table.float() @ wp.T) @ w.context_codes.T
+    tw_ref = table.float() @ wt.T
+    assert tp.lg.shape == (N + 1, K) and tp.tw.shape == (N + 1, D) and tp.tw.dtype == torch.bfloat16
+    assert _nerr(tp.lg.cpu(), lg_ref) < 2e-5
+    assert _nerr(tp.tw.float().cpu(), tw_ref) < 2.0 ** -8
+    # 'max' / 'mean' do not need tw
+    sw2 = ops.ScoreWeights(w.w_proj.to(DEV), w.context_codes.to(DEV), None, True)
+    tp2 = ops.table_project(table.to(DEV), sw2, weighted=False)
+    assert tp2.tw is None and torch.equal(tp2.lg, tp.lg)
+
+
+@pytest.mark.parametrize('B,H,D,K,Dc,mean_c,max_c', [(2, 12, 64, 8, 24, 5.0, 10), (6, 12, 64, 8, 24, 20.0, 300), (37, 50, 768, 32, 200, 20.0, 300),
+                                                      (301, 50, 256, 32, 48, 12.0, 70), (33, 64, 128, 16, 40, 20.0, 300),
+                                                      (9, 50, 768, 32, 200, 150.0, 300), (1, 1, 64, 1, 16, 2.0, 2), (5, 7, 192, 5, 16, 40.0, 100)])
+@pytest.mark.parametrize('score_type', ['weighted', 'max', 'mean'])
+def test_table_level_scores(B, H, D, K, Dc, mean_c, max_c, score_type):
+    """Table-level mode (miner_table_project + miner_score_table_fwd) against the oracle in the reference's operation order on the
+    same bf16-valued weights: CSR impressions of 2..300 candidates (several 96-candidate passes), ragged histories with left
+    padding, with and without the category-bias scalar.  Interests 3e-5, scores 3e-4 normwise (tolerance north_star: 1e-3)."""
+    from miner_b200 import ops, synth
+    N = 900
+    table = synth.make_table(N, D, 5, torch.bfloat16)
+    w = synth.make_weights(D, K, Dc, 5)
+    eb = synth.make_eval_batch(B, H, N, 7, mean_cands=mean_c, max_cands=max_c)
+    sw = ops.ScoreWeights(w.w_proj.to(DEV), w.context_codes.to(DEV), w.w_target.to(DEV), True)
+    tp = ops.table_project(table.to(DEV), sw)
+    wp, wt = w.w_proj.to(torch.bfloat16).float(), w.w_target.to(torch.bfloat16).float()
+    offs = eb.offsets.numpy()
+    bias = torch.randn(B, H, generator=torch.Generator().manual_seed(1)) * 0.3
+    for bm in (None, bias):
+        I, s = ops.score_table(tp, eb.his_ids.to(DEV), eb.his_mask.to(DEV), eb.cand_ids.to(DEV), score_type, cand_offsets=eb.offsets.to(DEV),
+                               bias_mean=None if bm is None else bm.to(DEV), want_interests=True)
+        Iref = O.poly_attention(table.float()[eb.his_ids], eb.his_mask, wp, w.context_codes, None if bm is None else bm[:, :, None])
+        ref = torch.empty(int(offs[-1]))
+        for i in range(B):
+            cr = table.float()[eb.cand_ids[offs[i]:offs[i + 1]]][None]
+            ref[offs[i]:offs[i + 1]] = O.aggregate_scores(Iref[i:i + 1], cr, score_type, wt)[0]
+        assert _nerr(I.cpu(), Iref) < 3e-5
+        assert _nerr(s.cpu(), ref) < 3e-4
+    # int32 ids and the no-interests call give the same bits
+    _, s32 = ops.score_table(tp, eb.his_ids.int().to(DEV), eb.his_mask.to(DEV), eb.cand_ids.int().to(DEV), score_type,
+                             cand_offsets=eb.offsets.to(DEV), bias_mean=bias.to(DEV))
+    assert torch.equal(s32, s)
+
+
+def test_table_level_dense_layout_and_invariance():
+    """Dense (B,C) layout = its CSR restatement (bit-exact); the tile an impression lands in does not change its scores."""
+    from miner_b200 import ops, synth
+    B, H, N, D, K, Dc, Cd = 41, 50, 700, 256, 32, 48, 5
+    table = synth.make_table(N, D, 9, torch.bfloat16)
+    w = synth.make_weights(D, K, Dc, 9)
+    g = torch.Generator().manual_seed(3)
+    his, mask, _ = synth.make_history(B, H, N, g)
+    cd = torch.randint(1, N + 1, (B, Cd), generator=g)
+    sw = ops.ScoreWeights(w.w_proj.to(DEV), w.context_codes.to(DEV), w.w_target.to(DEV), True)
+    tp = ops.table_project(table.to(DEV), sw)
+    _, s_dense = ops.score_table(tp, his.to(DEV), mask.to(DEV), cd.to(DEV))
+    _, s_csr = ops.score_table(tp, his.to(DEV), mask.to(DEV), cd.reshape(-1).to(DEV), cand_offsets=(torch.arange(B + 1) * Cd).to(DEV))
+    assert s_dense.shape == (B, Cd) and torch.equal(s_dense.reshape(-1), s_csr)
+    # drop the first impression: every other impression moves to the other half of its tile
+    _, s_shift = ops.score_table(tp, his[1:].to(DEV), mask[1:].to(DEV), cd[1:].to(DEV))
+    assert torch.equal(s_shift, s_dense[1:])
+    # out-of-range ids contribute zero rows instead of faulting
+    his_bad = his.clone()
+    his_bad[0, -1] = N + 5
+    _, s_bad = ops.score_table(tp, his_bad.to(DEV), mask.to(DEV), cd.to(DEV))
+    assert torch.isfinite(s_bad).all() and torch.equal(s_bad[1:], s_dense[1:])
+    # empty batch / unsupported shapes
+    _, s0 = ops.score_table(tp, his[:0].to(DEV), mask[:0].to(DEV), cd[:0].to(DEV))
+    assert s0.shape == (0, Cd)
+    assert not ops.score_table_supported(100, 32, 256) and not ops.score_table_supported(50, 64, 256) and not ops.score_table_supported(50, 32, 100)
+    with pytest.raises(ValueError, match='Invalid method of aggregating matching score'):
+        ops.score_table(tp, his.to(DEV), mask.to(DEV), cd.to(DEV), 'median')
+
+
+@pytest.mark.parametrize('name', ['model_small', 'model_full'])
+def test_miner_forward_table_level_matches_reference(name):
+    """Miner.forward with table_level = True against the golden outputs of the reference itself (scores 1e-3 normwise)."""
+    g = load_golden(name)
+    x = golden_model_inputs(g)
+    H, K, D = x['his_ids'].shape[1], x['codes'].shape[0], x['table'].shape[1]
+    from miner_b200 import ops
+    if not ops.score_table_supported(H, K, D):
+        pytest.skip('shape outside the table-level kernel')
+    m = build_miner(x, 'weighted', table_dtype=torch.bfloat16)
+    m.table_level = True
+    I, S = run_forward(m, x)
+    err = close_norm(S.cpu().numpy(), g['scores_weighted_bf16table'], 1e-3)
+    print(f'{name}: table-level normwise score error {err:.2e}')
+    ref_I = O.miner_forward(x['table'].to(torch.bfloat16), x['his_ids'], x['his_mask'], x['cand'], x['w_proj'], x['codes'], x['w_target'])[0]
+    close_norm(I.cpu().numpy(), ref_I.numpy(), 1e-3)
+    # and grouped scoring picks the table-level mode by default, same bits as the explicit call
+    B, C = x['cand'].shape
+    s_csr = m.score_impressions(x['his_ids'].to(DEV), x['his_mask'].to(DEV), x['cand'].reshape(-1).to(DEV), (torch.arange(B + 1) * C).to(DEV))
+    assert torch.equal(s_csr.view(B, C), S.detach())
