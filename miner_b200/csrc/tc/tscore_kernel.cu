@@ -12,8 +12,10 @@
 // bound by the gather (HBM / L2 ingest), not by the tensor pipe.
 //
 // One persistent CTA per SM; a tile is IPT = 2 impressions = 128 history slots (64 per impression, H <= 64).  TMEM lanes are
-// (impression i, context code k, part hl): lane 64 i + 2 k + hl, where hl selects the bf16 hi / lo part of the softmax
-// weight -- the two lanes of a pair accumulate  w_hi . E  and  w_lo . E  and are summed in the epilogue (fp32-level weights).
+// (impression i, context code k, part hl): lane 64 i + 16 (k / 8) + 8 hl + k % 8, where hl selects the bf16 hi / lo part of the
+// softmax weight -- the two lanes of a pair accumulate  w_hi . E  and  w_lo . E  and are summed in the epilogue (fp32-level
+// weights).  Keeping a pair 8 lanes apart lets the 16-lane tcgen05.ld / st shapes (16x256b / 16x128b) hand both rows of a pair
+// to ONE thread: the pair sum, the gelu and the hi/lo split need no shuffles and no thread repeats another's work.
 //   warps 0-3   gather: per 64-feature block, table[his] and tw[his] rows (128 slots x 128 B each) and the tile's candidate
 //               rows, 16-byte cp.async straight into the 128B-swizzled layout, completion through mbarriers
 //   warp 4      issues every tcgen05.mma:
@@ -33,6 +35,8 @@
 
 namespace miner {
 
+long long* hist_prof_buffer();
+
 namespace {
 
 constexpr int TM = 128;                      // TMEM lanes = history slots per tile
@@ -46,13 +50,26 @@ constexpr int NC_MAX = 96;                   // candidate columns per pass
 constexpr int C_BYTES = NC_MAX * FB * 2;     // 12 KB
 constexpr int LS = KMAX;                     // logits scratch row stride (floats)
 constexpr int SS = KMAX + 1;                 // score scratch row stride (floats)
-constexpr int T_THREADS = 17 * 32;
-constexpr int T_EPI = 256, T_SMX = 128, T_GAT = 128;
+constexpr int T_EPI = 256, T_SMX = 128, T_GAT = 128;   // 4 gather warps, MMA warp, 8 epilogue warps, 4 softmax warps
+constexpr int T_THREADS = T_GAT + 32 + T_EPI + T_SMX;
+constexpr int W_EPI0 = 5, W_SMX0 = W_EPI0 + T_EPI / 32;
 // TMEM map (512 columns)
 constexpr int AW_COL = 0;                    // softmax weights, packed bf16: 128 slots -> 64 columns
 constexpr int IP_COL = 64;                   // 2 buffers x (I 64 | P 64) fp32; their first 32 columns become the packed A operands
 constexpr int DM_COL = IP_COL + 2 * 128;     // matching scores  m[(i,k,hl), c]
 constexpr int DA_COL = DM_COL + NC_MAX;      // attention logits a[(i,k,hl), c]
+
+// Optional cycle accounting (build with -DMINER_TS_PROF): per CTA, 16 counters for one thread of each role (0 MMA issuer,
+// 1 epilogue (interest half), 2 gather, 3 softmax, 4 epilogue (gelu half)), written to args.prof at the end (scripts/prof_tscore.py prints them).
+#ifdef MINER_TS_PROF
+#define PROF_DECL long long prof_c[16] = {0}; long long prof_t0 = clock64(), prof_start = prof_t0
+#define PROF_ADD(i) do { const long long prof_t1 = clock64(); prof_c[i] += prof_t1 - prof_t0; prof_t0 = prof_t1; } while (0)
+#define PROF_STORE(role) do { if (args.prof) { prof_c[15] = clock64() - prof_start; for (int i_ = 0; i_ < 16; ++i_) args.prof[(blockIdx.x * 5 + (role)) * 16 + i_] = prof_c[i_]; } } while (0)
+#else
+#define PROF_DECL
+#define PROF_ADD(i)
+#define PROF_STORE(role)
+#endif
 
 struct TBarriers {
   uint64_t full1[S1], empty1[S1], full2[S2], empty2[S2];
@@ -67,6 +84,7 @@ struct TScoreArgs {
   int64_t B;
   int H, K, D, C, score_type;
   float* out_scores; float* out_interests;
+  long long* prof;
 };
 
 __device__ __forceinline__ int64_t cand_off(const TScoreArgs& a, int64_t i) { return a.cand_offsets ? a.cand_offsets[i] : i * a.C; }
@@ -134,6 +152,9 @@ tscore_kernel(const TScoreArgs args, int n_tiles) {
     // ------------------------------------------------------------------ gathers
     const int t = threadIdx.x;
     const int chunk = t & 7, r0 = t >> 3;                    // 16-byte chunk of the 128-byte block row; rows r0 + 16 jj
+    const uint32_t row_bytes = static_cast<uint32_t>(D) * 2;
+    const char* table_b = reinterpret_cast<const char*>(args.table);
+    const char* tw_b = reinterpret_cast<const char*>(args.tw);
     uint32_t dst_off[8];
 #pragma unroll
     for (int jj = 0; jj < 8; ++jj) dst_off[jj] = tc::sw128_offset(r0 + 16 * jj, chunk);
@@ -151,15 +172,16 @@ tscore_kernel(const TScoreArgs args, int n_tiles) {
       }
     };
     uint32_t g = 0;
+    PROF_DECL;
     if (n_local > 0) fetch_ids(0);
     for (int lt = 0; lt < n_local; ++lt) {
       const int tile = static_cast<int>(blockIdx.x) + lt * static_cast<int>(gridDim.x);
-      int64_t eoff[8];
+      uint32_t eoff[8];                                      // byte offset of this thread's 16-byte chunk in its rows (table < 4 GB, checked by the launcher)
       uint32_t emask = 0;
 #pragma unroll
       for (int jj = 0; jj < 8; ++jj) {
         const bool ok = ids_pre[jj] >= 0;
-        eoff[jj] = static_cast<int64_t>(ok ? ids_pre[jj] : 0) * D + chunk * 8;
+        eoff[jj] = static_cast<uint32_t>(ok ? ids_pre[jj] : 0) * row_bytes + chunk * 16;
         emask |= ok ? (1u << jj) : 0u;
       }
       if (lt + 1 < n_local) fetch_ids(lt + 1);
@@ -170,7 +192,7 @@ tscore_kernel(const TScoreArgs args, int n_tiles) {
         const int64_t pc0 = cs + static_cast<int64_t>(p) * NC_MAX;
         const int nc = static_cast<int>(ce - pc0 < NC_MAX ? ce - pc0 : NC_MAX);
         const int nc16 = nc <= 16 ? 16 : (nc + 15) & ~15;
-        int64_t coff[6];
+        uint32_t coff[6];
         uint32_t cmask = 0;
 #pragma unroll
         for (int jj = 0; jj < 6; ++jj) {
@@ -178,36 +200,42 @@ tscore_kernel(const TScoreArgs args, int n_tiles) {
           int64_t id = -1;
           if (c < nc) id = load_id(args.cand_ids, pc0 + c, args.id_dtype);
           const bool ok = id >= 0 && id < args.n_rows;
-          coff[jj] = (ok ? id : 0) * D + chunk * 8;
+          coff[jj] = static_cast<uint32_t>(ok ? id : 0) * row_bytes + chunk * 16;
           cmask |= ok ? (1u << jj) : 0u;
         }
         for (int j = 0; j < KB; ++j, ++g) {
           {
             const uint32_t s = g % S1, ph = (g / S1) & 1;
+            PROF_ADD(0);
             tc::mbar_wait_relaxed(&bars->empty1[s], ph ^ 1);
+            PROF_ADD(1);
             const uint32_t base = tc::smem_u32(st1 + s * ST1_BYTES);
+            const uint32_t jb = static_cast<uint32_t>(j) * (FB * 2);
 #pragma unroll
-            for (int jj = 0; jj < 8; ++jj)
-              tc::cp_async_16(base + dst_off[jj], args.table + eoff[jj] + j * FB, ((emask >> jj) & 1u) ? 16u : 0u);
-#pragma unroll
-            for (int jj = 0; jj < 8; ++jj)
-              tc::cp_async_16(base + E_BYTES + dst_off[jj], args.tw + eoff[jj] + j * FB, ((emask >> jj) & 1u) ? 16u : 0u);
+            for (int jj = 0; jj < 8; ++jj) {
+              const uint32_t o = eoff[jj] + jb, sz = ((emask >> jj) & 1u) ? 16u : 0u;
+              tc::cp_async_16(base + dst_off[jj], table_b + o, sz);
+              tc::cp_async_16(base + E_BYTES + dst_off[jj], tw_b + o, sz);
+            }
             tc::cp_async_mbar_arrive_noinc(&bars->full1[s]);
           }
           {
             const uint32_t s = g % S2, ph = (g / S2) & 1;
+            PROF_ADD(2);
             tc::mbar_wait_relaxed(&bars->empty2[s], ph ^ 1);
+            PROF_ADD(3);
             const uint32_t base = tc::smem_u32(st2 + s * C_BYTES);
 #pragma unroll
             for (int jj = 0; jj < 6; ++jj)
               if (r0 + 16 * jj < nc16)
-                tc::cp_async_16(base + dst_off[jj], args.table + coff[jj] + j * FB, ((cmask >> jj) & 1u) ? 16u : 0u);
+                tc::cp_async_16(base + dst_off[jj], table_b + (coff[jj] + static_cast<uint32_t>(j) * (FB * 2)), ((cmask >> jj) & 1u) ? 16u : 0u);
             tc::cp_async_mbar_arrive_noinc(&bars->full2[s]);
           }
         }
       }
     }
     tc::cp_async_wait_all();
+    if (threadIdx.x == 0) PROF_STORE(2);
   } else if (warp == 4) {
     // ------------------------------------------------------------------ MMA issuer
     const uint32_t idesc1 = tc::make_idesc_bf16_f32_major(TM, FB, false, true);        // B = gathered tile, MN-major
@@ -215,12 +243,17 @@ tscore_kernel(const TScoreArgs args, int n_tiles) {
     bool pending = false;
     int pend_j = 0, pend_nc16 = 16;
     uint32_t pend_u = 0;
+    PROF_DECL;
     auto stage2 = [&]() {                                                                // S2 of block g2
       const uint32_t b = g2 & 1;
+      PROF_ADD(0);
       tc::mbar_wait(&bars->a_ready[b], (g2 >> 1) & 1);
+      PROF_ADD(4);
       const uint32_t s = g2 % S2, ph = (g2 / S2) & 1;
       tc::mbar_wait(&bars->full2[s], ph);
+      PROF_ADD(5);
       if (pend_j == 0) tc::mbar_wait(&bars->dma_free, (pend_u & 1) ^ 1);                 // previous unit's scores are out of D_m / D_a
+      PROF_ADD(6);
       tc::tcgen05_fence_after();
       const uint32_t idesc2 = tc::make_idesc_bf16_f32(TM, pend_nc16);
       const uint64_t c_desc = tc::make_smem_desc_sw128(tc::smem_u32(st2 + s * C_BYTES));
@@ -237,6 +270,7 @@ tscore_kernel(const TScoreArgs args, int n_tiles) {
       }
       __syncwarp();
       ++g2;
+      PROF_ADD(7);
     };
     for (int lt = 0; lt < n_local; ++lt) {
       const int tile = static_cast<int>(blockIdx.x) + lt * static_cast<int>(gridDim.x);
@@ -247,11 +281,15 @@ tscore_kernel(const TScoreArgs args, int n_tiles) {
         const int64_t pc0 = cs + static_cast<int64_t>(p) * NC_MAX;
         const int nc = static_cast<int>(ce - pc0 < NC_MAX ? ce - pc0 : NC_MAX);
         const int nc16 = nc <= 16 ? 16 : (nc + 15) & ~15;
+        PROF_ADD(0);
         tc::mbar_wait(&bars->w_ready, u & 1);
+        PROF_ADD(1);
         tc::tcgen05_fence_after();
         for (int j = 0; j < KB; ++j) {
           const uint32_t s = g1 % S1, ph = (g1 / S1) & 1, b = g1 & 1;
+          PROF_ADD(0);
           tc::mbar_wait(&bars->full1[s], ph);
+          PROF_ADD(2);
           tc::tcgen05_fence_after();
           const uint64_t e_desc = tc::make_smem_desc_sw128_mn(tc::smem_u32(st1 + s * ST1_BYTES));
           const uint64_t t_desc = tc::make_smem_desc_sw128_mn(tc::smem_u32(st1 + s * ST1_BYTES + E_BYTES));
@@ -268,24 +306,31 @@ tscore_kernel(const TScoreArgs args, int n_tiles) {
           }
           __syncwarp();
           ++g1;
+          PROF_ADD(3);
           if (pending) stage2();
           pending = true; pend_j = j; pend_nc16 = nc16; pend_u = u;
         }
       }
     }
     if (pending) stage2();
-  } else if (warp < 13) {
+    if (lane == 0) PROF_STORE(0);
+  } else if (warp < W_SMX0) {
     // ------------------------------------------------------------------ epilogue warps 5..12
-    const int ew = warp - 5;
+    const int ew = warp - W_EPI0;
     const int q = warp & 3;                                    // TMEM lane quarter
-    const int half = ew >> 2;                                  // 0: interests / matching scores, 1: gelu(P) / attention logits
+    const int half = ew >> 2;                                  // per block: 16-lane group of the quarter; per pass: 0 = D_m, 1 = D_a
     const int et = ew * 32 + lane;
-    const int tl = q * 32 + lane;                              // TMEM lane = (i, k, hl)
-    const int li = tl / LPI, lk = (tl % LPI) >> 1;
-    const bool lo_part = (tl & 1) != 0;
+    const int tl = q * 32 + lane;                              // TMEM lane = (i, k, hl), see lane_of()
+    const int li = tl / LPI, lk = ((tl % LPI) >> 4) * 8 + (tl & 7);
+    const bool lo_part = (tl & 8) != 0;
     const bool row_ok = lk < K;
     const uint32_t lane_addr = static_cast<uint32_t>(q * 32) << 16;
+    // block epilogue: this warp owns lanes [16 half, 16 half + 16) of its quarter; thread t meets the (hi, lo) rows of code bk
+    const uint32_t grp_addr = static_cast<uint32_t>(q * 32 + half * 16) << 16;
+    const int bk = ((q & 1) * 2 + half) * 8 + (lane >> 2);      // context code of this thread's row pair
+    const int bf = 2 * (lane & 3);                              // its features inside an 8-feature group
     uint32_t g = 0, u = 0;
+    PROF_DECL;
     for (int lt = 0; lt < n_local; ++lt) {
       const int tile = static_cast<int>(blockIdx.x) + lt * static_cast<int>(gridDim.x);
       int64_t cs, ce;
@@ -299,43 +344,55 @@ tscore_kernel(const TScoreArgs args, int n_tiles) {
       for (int p = 0; p < npass; ++p, ++u) {
         const int64_t pc0 = cs + static_cast<int64_t>(p) * NC_MAX;
         const int nc = static_cast<int>(ce - pc0 < NC_MAX ? ce - pc0 : NC_MAX);
+        const bool want_i = args.out_interests != nullptr && p == 0 && bk < K && my_imp < args.B;
         for (int j = 0; j < KB; ++j, ++g) {
           const uint32_t b = g & 1;
+          PROF_ADD(0);
           tc::mbar_wait(&bars->ip_full[b], (g >> 1) & 1);
+          PROF_ADD(1);
           tc::tcgen05_fence_after();
-          const uint32_t acc = tmem + lane_addr + IP_COL + b * 128 + half * 64;
+          const uint32_t acc = tmem + grp_addr + IP_COL + b * 128;
+          uint32_t vi[32], vp[32];
+          tc::tmem_ld_16x256b_x8(acc, vi);                                     // interests block: rows (hi, lo) x 16 of its 64 features
+          tc::tmem_ld_16x256b_x8(acc + 64, vp);                                // same of P = I Wt^T
+          tc::tmem_ld_wait();
+          PROF_ADD(5);
+          uint32_t pk[16];
+          if (want_i) {                                                        // model.py:138 (interests are an output)
+            float* o = args.out_interests + (my_imp * K + bk) * D + j * FB + bf;
 #pragma unroll
-          for (int cc = 0; cc < 2; ++cc) {
-            uint32_t v[32];
-            tc::tmem_ld_32x32(acc + cc * 32, v);
-            tc::tmem_ld_wait();
-            float s[32];
-#pragma unroll
-            for (int c = 0; c < 32; ++c) {
-              const float x = __uint_as_float(v[c]);
-              s[c] = x + __shfl_xor_sync(0xffffffffu, x, 1);                  // w_hi . E + w_lo . E
-            }
-            if (half == 0) {
-              if (args.out_interests && p == 0 && !lo_part && row_ok && my_imp < args.B) {     // model.py:138 (interests are an output)
-                float4* o = reinterpret_cast<float4*>(args.out_interests + (my_imp * K + lk) * D + j * FB + cc * 32);
-#pragma unroll
-                for (int c = 0; c < 8; ++c) o[c] = make_float4(s[4 * c], s[4 * c + 1], s[4 * c + 2], s[4 * c + 3]);
-              }
-            } else {
-#pragma unroll
-              for (int c = 0; c < 32; ++c) s[c] = gelu_fast(s[c]);                              // model.py:212
-            }
-            uint32_t pk[16];
-#pragma unroll
-            for (int c = 0; c < 16; ++c) pk[c] = pack_part(s[2 * c], s[2 * c + 1], lo_part);
-            tc::tmem_st_32x16(acc + cc * 16, pk);                             // in place: these columns have been read
+            for (int n = 0; n < 8; ++n)
+              *reinterpret_cast<float2*>(o + 8 * n) = make_float2(__uint_as_float(vi[4 * n]) + __uint_as_float(vi[4 * n + 2]),
+                                                                  __uint_as_float(vi[4 * n + 1]) + __uint_as_float(vi[4 * n + 3]));
           }
+#pragma unroll
+          for (int n = 0; n < 8; ++n) {
+            const float s0 = __uint_as_float(vi[4 * n]) + __uint_as_float(vi[4 * n + 2]);       // w_hi . E + w_lo . E
+            const float s1 = __uint_as_float(vi[4 * n + 1]) + __uint_as_float(vi[4 * n + 3]);
+            const uint32_t hi = pack2(s0, s1);
+            pk[2 * n] = hi;
+            pk[2 * n + 1] = pack2(s0 - __uint_as_float(hi << 16), s1 - __uint_as_float(hi & 0xffff0000u));
+          }
+          tc::tmem_st_16x128b_x8(acc, pk);                                     // in place: this thread group has read all 64 columns
+#pragma unroll
+          for (int n = 0; n < 8; ++n) {
+            // gelu(P) only feeds the softmax-over-K logits: one bf16 (as cand_kernel.cu), the lo row of the pair stays zero
+            pk[2 * n] = pack2(gelu_fast(__uint_as_float(vp[4 * n]) + __uint_as_float(vp[4 * n + 2])),           // model.py:212
+                              gelu_fast(__uint_as_float(vp[4 * n + 1]) + __uint_as_float(vp[4 * n + 3])));
+            pk[2 * n + 1] = 0u;
+          }
+          PROF_ADD(6);
+          tc::tmem_st_16x128b_x8(acc + 64, pk);
+          PROF_ADD(7);
           tc::tmem_st_wait();
+          PROF_ADD(8);
           tc::tcgen05_fence_before();
           tc::mbar_arrive(&bars->a_ready[b]);
+          PROF_ADD(2);
         }
         // ---- scores of this pass (model.py:127-136,213-214)
         tc::mbar_wait(&bars->dma_full, u & 1);
+        PROF_ADD(3);
         tc::tcgen05_fence_after();
         tc::named_bar_sync(1, T_EPI);                                          // the previous pass's score threads are done with Sm / Sa
         {
@@ -353,7 +410,7 @@ tscore_kernel(const TScoreArgs args, int n_tiles) {
 #pragma unroll
             for (int c = 0; c < 16; ++c) {
               const float x = __uint_as_float(v[c]);
-              const float sum = x + __shfl_xor_sync(0xffffffffu, x, 1);       // A_hi . cand + A_lo . cand
+              const float sum = x + __shfl_xor_sync(0xffffffffu, x, 8);       // A_hi . cand + A_lo . cand
               const int col = c0 + c;
               if (!lo_part && row_ok && col >= c_lo && col < c_hi) S[col * SS + lk] = sum;
             }
@@ -386,24 +443,35 @@ tscore_kernel(const TScoreArgs args, int n_tiles) {
           }
           args.out_scores[pc0 + et] = score;
         }
+        PROF_ADD(4);
       }
     }
+    if (et == 0) PROF_STORE(1);
+    if (et == 128) PROF_STORE(4);
   } else {
     // ------------------------------------------------------------------ softmax warps 13..16
-    const int sw = warp - 13;
+    const int sw = warp - W_SMX0;
     const int q = warp & 3;
-    const int tl = q * 32 + lane;
-    const int li = tl / LPI, lk = (tl % LPI) >> 1;
-    const bool lo_part = (tl & 1) != 0;
-    const bool row_ok = lk < K;
+    const int li = q >> 1;                                     // impression of this quarter's lanes
     const uint32_t lane_addr = static_cast<uint32_t>(q * 32) << 16;
     uint32_t u = 0;
+    PROF_DECL;
+    {
+      // the off-diagonal half of A_w (slots of the other impression) stays zero for the whole kernel
+      uint32_t z[16];
+#pragma unroll
+      for (int c = 0; c < 16; ++c) z[c] = 0u;
+#pragma unroll
+      for (int cc = 0; cc < 4; ++cc) tc::tmem_st_32x16(tmem + lane_addr + AW_COL + cc * 16, z);
+      tc::tmem_st_wait();
+    }
     for (int lt = 0; lt < n_local; ++lt) {
       const int tile = static_cast<int>(blockIdx.x) + lt * static_cast<int>(gridDim.x);
       int64_t cs, ce;
       int npass;
       tile_cands(args, tile, cs, ce, npass);
       for (int p = 0; p < npass; ++p, ++u) {
+        PROF_ADD(0);
         tc::named_bar_sync(2, T_SMX);                                          // previous unit's reads of L are done
         {
           // logits of 32 slots per warp: lg rows are K consecutive floats (model.py:174 hoisted to the table)
@@ -420,59 +488,77 @@ tscore_kernel(const TScoreArgs args, int n_tiles) {
             if (args.bias_mean) bias = args.bias_mean[imp * H + h];
             if (id < 0 || id >= args.n_rows) id = -1;
           }
-          int code = valid ? (keep ? 2 : 1) : 0;
-#pragma unroll 4
-          for (int ss = 0; ss < 32; ++ss) {
+          const int code = valid ? ((keep && id >= 0) ? 2 : (keep ? 3 : 1)) : 0;
+          float v[32];
+#pragma unroll
+          for (int ss = 0; ss < 32; ++ss) {                                    // 32 independent 128-byte row loads in flight
             const long long id_s = __shfl_sync(0xffffffffu, static_cast<long long>(id), ss);
             const int code_s = __shfl_sync(0xffffffffu, code, ss);
+            v[ss] = (code_s == 2 && lane < K) ? args.lg[id_s * K + lane] : 0.f;
+          }
+#pragma unroll
+          for (int ss = 0; ss < 32; ++ss) {
+            const int code_s = __shfl_sync(0xffffffffu, code, ss);
             const float bias_s = __shfl_sync(0xffffffffu, bias, ss);
-            float v = -INFINITY;                                               // tile padding: not part of the history
-            if (code_s == 1) v = kMaskFill;                                    // model.py:180 (1e-30, not -inf)
-            if (code_s == 2) v = ((id_s >= 0 && lane < K) ? args.lg[id_s * K + lane] : 0.f) + bias_s;   // model.py:174-177
-            L[(sw * 32 + ss) * LS + lane] = v;
+            float x = v[ss] + bias_s;                                          // model.py:174-177
+            if (code_s == 1) x = kMaskFill;                                    // model.py:180 (1e-30, not -inf)
+            if (code_s == 0) x = -INFINITY;                                    // tile padding: not part of the history
+            L[(sw * 32 + ss) * LS + lane] = x;
           }
         }
         tc::named_bar_sync(2, T_SMX);
-        uint32_t pk[32];                                                       // this lane's 64 slots, packed bf16 pairs (hi or lo part)
-        {
-          const float* col = L + (li * HP) * LS + (row_ok ? lk : 0);
+        PROF_ADD(1);
+        // softmax over the history (model.py:181): per 16-lane group, thread t owns code k = 8 group + t/4 and the 16 slots
+        // {2c, 2c+1 : c = t%4 + 4n}; the (hi, lo) rows of the pair leave through one 16x128b store
+        uint32_t pk[2][16];
+#pragma unroll
+        for (int hf = 0; hf < 2; ++hf) {
+          const int k = ((q & 1) * 2 + hf) * 8 + (lane >> 2);
+          const bool row_ok = k < K;
+          const float* col = L + (li * HP) * LS + (row_ok ? k : 0);
+          float e[16];
           float mx = -INFINITY;
-          for (int h = 0; h < HP; ++h) mx = fmaxf(mx, col[h * LS]);
-          const bool dead = mx == -INFINITY || !row_ok;
+#pragma unroll
+          for (int n = 0; n < 8; ++n) {
+            const int c = (lane & 3) + 4 * n;
+            e[2 * n] = col[(2 * c) * LS];
+            e[2 * n + 1] = col[(2 * c + 1) * LS];
+            mx = fmaxf(mx, fmaxf(e[2 * n], e[2 * n + 1]));
+          }
+          mx = fmaxf(mx, __shfl_xor_sync(0xffffffffu, mx, 1));
+          mx = fmaxf(mx, __shfl_xor_sync(0xffffffffu, mx, 2));
+          const bool dead = mx == -INFINITY || !row_ok;                        // impression past the end of the batch / unused row
           float sum = 0.f;
-          for (int h = 0; h < HP; ++h) sum += dead ? 0.f : __expf(col[h * LS] - mx);
+#pragma unroll
+          for (int n = 0; n < 16; ++n) {
+            e[n] = dead ? 0.f : __expf(e[n] - mx);
+            sum += e[n];
+          }
+          sum += __shfl_xor_sync(0xffffffffu, sum, 1);
+          sum += __shfl_xor_sync(0xffffffffu, sum, 2);
           const float inv = dead ? 0.f : 1.0f / sum;
 #pragma unroll
-          for (int c = 0; c < HP / 2; ++c) {
-            const float w0 = dead ? 0.f : __expf(col[(2 * c) * LS] - mx) * inv;                  // model.py:181
-            const float w1 = dead ? 0.f : __expf(col[(2 * c + 1) * LS] - mx) * inv;
-            pk[c] = pack_part(w0, w1, lo_part);
+          for (int n = 0; n < 8; ++n) {
+            const float w0 = e[2 * n] * inv, w1 = e[2 * n + 1] * inv;
+            const uint32_t hi = pack2(w0, w1);
+            pk[hf][2 * n] = hi;
+            pk[hf][2 * n + 1] = pack2(w0 - __uint_as_float(hi << 16), w1 - __uint_as_float(hi & 0xffff0000u));
           }
         }
+        PROF_ADD(2);
         if (u > 0) tc::mbar_wait(&bars->w_free, (u - 1) & 1);                  // S1 of the previous unit no longer reads A_w
+        PROF_ADD(3);
         tc::tcgen05_fence_after();
-        {
-          uint32_t z[16];
 #pragma unroll
-          for (int c = 0; c < 16; ++c) z[c] = 0u;
-#pragma unroll
-          for (int cc = 0; cc < 4; ++cc) {                                     // 16 columns = 32 slots per store
-            const bool mine = (cc >> 1) == li;                                 // warp-uniform
-            if (mine) {
-              uint32_t o[16];
-#pragma unroll
-              for (int c = 0; c < 16; ++c) o[c] = (cc & 1) ? pk[16 + c] : pk[c];
-              tc::tmem_st_32x16(tmem + lane_addr + AW_COL + cc * 16, o);
-            } else {
-              tc::tmem_st_32x16(tmem + lane_addr + AW_COL + cc * 16, z);
-            }
-          }
-        }
+        for (int hf = 0; hf < 2; ++hf)
+          tc::tmem_st_16x128b_x8(tmem + (static_cast<uint32_t>(q * 32 + hf * 16) << 16) + AW_COL + li * (HP / 2), pk[hf]);
         tc::tmem_st_wait();
         tc::tcgen05_fence_before();
         tc::mbar_arrive(&bars->w_ready);
+        PROF_ADD(4);
       }
     }
+    if (threadIdx.x == W_SMX0 * 32) PROF_STORE(3);
   }
 
   tc::tcgen05_fence_before();
@@ -498,11 +584,17 @@ int launch_tscore_kernel(const void* table, const void* tw, const float* lg, int
               (long long)D);
     return MINER_ERR_UNSUPPORTED;
   }
+  if (static_cast<uint64_t>(n_rows) * static_cast<uint64_t>(D) * 2 > 0xffffffffull) {
+    set_error("table-level scoring: table of %lld x %lld bf16 exceeds the 4 GB the kernel addresses with 32-bit offsets", (long long)n_rows,
+              (long long)D);
+    return MINER_ERR_UNSUPPORTED;
+  }
   TScoreArgs a;
   a.table = static_cast<const uint16_t*>(table); a.tw = static_cast<const uint16_t*>(tw); a.lg = lg; a.n_rows = n_rows;
   a.his_ids = his_ids; a.cand_ids = cand_ids; a.id_dtype = id_dtype; a.mask = his_mask; a.bias_mean = bias_mean;
   a.cand_offsets = cand_offsets; a.B = B; a.H = static_cast<int>(H); a.K = static_cast<int>(K); a.D = static_cast<int>(D);
   a.C = static_cast<int>(C); a.score_type = score_type; a.out_scores = out_scores; a.out_interests = out_interests;
+  a.prof = hist_prof_buffer();
   const int64_t n_tiles = (B + IPT - 1) / IPT;
   const int grid = static_cast<int>(n_tiles < sm_count() ? n_tiles : sm_count());
   MINER_CUDA_OK(cudaFuncSetAttribute(tscore_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, T_SMEM));
