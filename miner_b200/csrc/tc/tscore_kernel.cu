@@ -16,16 +16,17 @@
 // softmax weight -- the two lanes of a pair accumulate  w_hi . E  and  w_lo . E  and are summed in the epilogue (fp32-level
 // weights).  Keeping a pair 8 lanes apart lets the 16-lane tcgen05.ld / st shapes (16x256b / 16x128b) hand both rows of a pair
 // to ONE thread: the pair sum, the gelu and the hi/lo split need no shuffles and no thread repeats another's work.
-//   warps 0-3   gather: per 64-feature block, table[his] and tw[his] rows (128 slots x 128 B each) and the tile's candidate
-//               rows, 16-byte cp.async straight into the 128B-swizzled layout, completion through mbarriers
-//   warp 4      issues every tcgen05.mma:
+//   warps 0-3   gather: per 64-feature block, table[his] and tw[his] rows (128 slots x 128 B each), 16-byte cp.async straight
+//               into the 128B-swizzled layout, completion through mbarriers;  warps 4-5: the tile's candidate rows, own ring
+//   warp 6      issues every tcgen05.mma:
 //               S1(j): D_I = A_w . E_j, D_P = A_w . TW_j   (A_w = softmax weights in tensor memory, TS form, block diagonal over
 //                      the two impressions; B = the gathered 128 x 64 tile read MN-major)
 //               S2(j): D_m += A_I . cand_j^T, D_a += A_G . cand_j^T  (A = bf16 hi|lo of I / gelu(P), written IN PLACE over the
 //                      fp32 accumulator by the epilogue warps; B = candidate rows, K-major)
-//   warps 5-12  epilogue: per block, pair-sum (shuffle), gelu, bf16 hi/lo split, tcgen05.st; per tile, the softmax over K and
-//               the weighted sum of the matching scores through a shared-memory transpose, one thread per candidate
-//   warps 13-16 softmax over the history from the lg rows (L2-resident 128-byte rows), weights to tensor memory
+//   warps 7-14  epilogue: per block, pair sum, gelu, bf16 hi/lo split, tcgen05.st back in place (16-lane ld / st shapes)
+//   warps 15-18 softmax over the history from the lg rows (L2-resident 128-byte rows), weights to tensor memory; and, per
+//               finished tile, the softmax over K and the weighted sum of the matching scores through a shared-memory
+//               transpose, one thread per candidate
 // Tiles with more than 96 candidates run several passes (the history side is recomputed; rare).
 #include <cuda.h>
 #include <stdlib.h>
@@ -50,9 +51,12 @@ constexpr int NC_MAX = 96;                   // candidate columns per pass
 constexpr int C_BYTES = NC_MAX * FB * 2;     // 12 KB
 constexpr int LS = KMAX;                     // logits scratch row stride (floats)
 constexpr int SS = KMAX + 1;                 // score scratch row stride (floats)
-constexpr int T_EPI = 256, T_SMX = 128, T_GAT = 128;   // 4 gather warps, MMA warp, 8 epilogue warps, 4 softmax warps
-constexpr int T_THREADS = T_GAT + 32 + T_EPI + T_SMX;
-constexpr int W_EPI0 = 5, W_SMX0 = W_EPI0 + T_EPI / 32;
+constexpr int T_EPI = 256, T_SMX = 128;                // 8 epilogue warps, 4 softmax / score warps
+constexpr int T_G1 = 128, T_G2 = 64;                   // gather threads of the (E, TW) ring / of the candidate ring
+constexpr int G1_ROWS = TM * 8 / T_G1, G2_ROWS = NC_MAX * 8 / T_G2;  // rows per thread (a thread moves one 16-byte chunk per row)
+constexpr int G1_STEP = T_G1 / 8, G2_STEP = T_G2 / 8;
+constexpr int W_G2 = T_G1 / 32, W_MMA = W_G2 + T_G2 / 32, W_EPI0 = W_MMA + 1, W_SMX0 = W_EPI0 + T_EPI / 32;
+constexpr int T_THREADS = (W_SMX0 + T_SMX / 32) * 32;
 // TMEM map (512 columns)
 constexpr int AW_COL = 0;                    // softmax weights, packed bf16: 128 slots -> 64 columns
 constexpr int IP_COL = 64;                   // 2 buffers x (I 64 | P 64) fp32; their first 32 columns become the packed A operands
@@ -75,6 +79,9 @@ struct TBarriers {
   uint64_t full1[S1], empty1[S1], full2[S2], empty2[S2];
   uint64_t w_ready, w_free, ip_full[2], a_ready[2], dma_full, dma_free;
   uint32_t tmem_base;
+#ifdef MINER_TS_PROF
+  long long issue_clk[S1][4];   // when lane 0 of each (E, TW) gather warp finished issuing a stage (latency accounting)
+#endif
 };
 
 struct TScoreArgs {
@@ -85,18 +92,40 @@ struct TScoreArgs {
   int H, K, D, C, score_type;
   float* out_scores; float* out_interests;
   long long* prof;
+  int dbg;   // ablations (MINER_TS_DBG): bit 0 no global reads in the gathers (zero fill), bit 1 no tw reads, bit 2 no candidate reads
 };
 
 __device__ __forceinline__ int64_t cand_off(const TScoreArgs& a, int64_t i) { return a.cand_offsets ? a.cand_offsets[i] : i * a.C; }
 
-// candidate range of a tile and its number of passes
-__device__ __forceinline__ void tile_cands(const TScoreArgs& a, int tile, int64_t& cs, int64_t& ce, int& npass) {
+// An id fetched ahead of time stays RAW (the loaded bits, nothing computed from them) until the tile that uses it: any
+// instruction consuming the loaded register -- a range check, a sign extension -- would wait for the load where it was issued
+// and put a DRAM round trip on the gather warps' path at every tile boundary.
+struct RawId { uint32_t lo, hi; };
+__device__ __forceinline__ RawId load_id_raw(const void* ids, int64_t i, int id_dtype) {
+  RawId r;
+  if (id_dtype == MINER_I64) {
+    const uint2 v = reinterpret_cast<const uint2*>(ids)[i];
+    r.lo = v.x; r.hi = v.y;
+  } else {
+    r.lo = reinterpret_cast<const uint32_t*>(ids)[i]; r.hi = 0;
+  }
+  return r;
+}
+__device__ __forceinline__ int64_t id_of(RawId r, int id_dtype) {
+  return id_dtype == MINER_I64 ? static_cast<int64_t>((static_cast<uint64_t>(r.hi) << 32) | r.lo) : static_cast<int64_t>(static_cast<int32_t>(r.lo));
+}
+
+// candidate range of a tile (two loads, nothing else: callers issue them a tile ahead and only look at the values a tile later,
+// so their latency never sits on a role's critical path) and its number of passes
+__device__ __forceinline__ void tile_range(const TScoreArgs& a, int tile, int64_t& cs, int64_t& ce) {
   const int64_t i0 = static_cast<int64_t>(tile) * IPT;
   const int64_t i1 = i0 + IPT < a.B ? i0 + IPT : a.B;
   cs = cand_off(a, i0);
   ce = cand_off(a, i1);
+}
+__device__ __forceinline__ int passes_of(int64_t cs, int64_t ce) {
   const int64_t n = ce - cs;
-  npass = n <= NC_MAX ? 1 : static_cast<int>((n + NC_MAX - 1) / NC_MAX);
+  return n <= NC_MAX ? 1 : static_cast<int>((n + NC_MAX - 1) / NC_MAX);
 }
 
 __device__ __forceinline__ float gelu_fast(float x) {               // tanh form, hardware tanh (see cand_kernel.cu)
@@ -104,18 +133,15 @@ __device__ __forceinline__ float gelu_fast(float x) {               // tanh form
   const float hx = 0.5f * x;
   return fmaf(hx, tc::tanh_approx(u), hx);
 }
+__device__ __forceinline__ float ex2_approx(float x) {
+  float y;
+  asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(y) : "f"(x));
+  return y;
+}
 __device__ __forceinline__ uint32_t pack2(float a, float b) {
   __nv_bfloat162 v = __floats2bfloat162_rn(a, b);
   return *reinterpret_cast<uint32_t*>(&v);
 }
-// bf16 hi (even lanes) or lo = x - hi (odd lanes) of a pair of values
-__device__ __forceinline__ uint32_t pack_part(float x0, float x1, bool lo) {
-  const uint32_t hi = pack2(x0, x1);
-  if (!lo) return hi;
-  const float h0 = __uint_as_float(hi << 16), h1 = __uint_as_float(hi & 0xffff0000u);
-  return pack2(x0 - h0, x1 - h1);
-}
-
 __global__ void __launch_bounds__(T_THREADS, 1)
 tscore_kernel(const TScoreArgs args, int n_tiles) {
   extern __shared__ uint8_t smem_raw[];
@@ -133,112 +159,165 @@ tscore_kernel(const TScoreArgs args, int n_tiles) {
   const int n_local = (n_tiles - static_cast<int>(blockIdx.x) + static_cast<int>(gridDim.x) - 1) / static_cast<int>(gridDim.x);
 
   if (threadIdx.x == 0) {
-    for (int s = 0; s < S1; ++s) { tc::mbar_init(&bars->full1[s], T_GAT); tc::mbar_init(&bars->empty1[s], 1); }
-    for (int s = 0; s < S2; ++s) { tc::mbar_init(&bars->full2[s], T_GAT); tc::mbar_init(&bars->empty2[s], 1); }
+    for (int s = 0; s < S1; ++s) { tc::mbar_init(&bars->full1[s], T_G1); tc::mbar_init(&bars->empty1[s], 1); }
+    for (int s = 0; s < S2; ++s) { tc::mbar_init(&bars->full2[s], T_G2); tc::mbar_init(&bars->empty2[s], 1); }
     tc::mbar_init(&bars->w_ready, T_SMX);
     tc::mbar_init(&bars->w_free, 1);
     for (int b = 0; b < 2; ++b) { tc::mbar_init(&bars->ip_full[b], 1); tc::mbar_init(&bars->a_ready[b], T_EPI); }
     tc::mbar_init(&bars->dma_full, 1);
-    tc::mbar_init(&bars->dma_free, T_EPI);
+    tc::mbar_init(&bars->dma_free, T_SMX);
     tc::fence_barrier_init();
   }
-  if (warp == 4) { tc::tmem_alloc(&bars->tmem_base, 512); tc::tmem_relinquish(); }
+  if (warp == W_MMA) { tc::tmem_alloc(&bars->tmem_base, 512); tc::tmem_relinquish(); }
   tc::tcgen05_fence_before();
   __syncthreads();
   tc::tcgen05_fence_after();
   const uint32_t tmem = bars->tmem_base;
 
-  if (warp < 4) {
-    // ------------------------------------------------------------------ gathers
+  if (warp < W_G2) {
+    // ------------------------------------------------------------------ gathers of the (E, TW) ring: thread = one 16-byte chunk of rows
+    //        r0 + G1_STEP jj
     const int t = threadIdx.x;
-    const int chunk = t & 7, r0 = t >> 3;                    // 16-byte chunk of the 128-byte block row; rows r0 + 16 jj
+    const int chunk = t & 7, r0 = t >> 3;
     const uint32_t row_bytes = static_cast<uint32_t>(D) * 2;
     const char* table_b = reinterpret_cast<const char*>(args.table);
     const char* tw_b = reinterpret_cast<const char*>(args.tw);
-    uint32_t dst_off[8];
-#pragma unroll
-    for (int jj = 0; jj < 8; ++jj) dst_off[jj] = tc::sw128_offset(r0 + 16 * jj, chunk);
-    int32_t ids_pre[8];
+    const uint32_t dst0 = tc::sw128_offset(r0, chunk);       // row r0 + G1_STEP jj sits jj * G1_STEP / 8 KB further
+    RawId ids_pre[G1_ROWS];                                  // raw ids of the next tile (see RawId)
     auto fetch_ids = [&](int lt) {
       const int tile = static_cast<int>(blockIdx.x) + lt * static_cast<int>(gridDim.x);
 #pragma unroll
-      for (int jj = 0; jj < 8; ++jj) {
-        const int r = r0 + 16 * jj;
+      for (int jj = 0; jj < G1_ROWS; ++jj) {
+        const int r = r0 + G1_STEP * jj;
         const int64_t imp = static_cast<int64_t>(tile) * IPT + r / HP;
         const int h = r % HP;
         const bool ok = h < H && imp < args.B;
-        const int64_t id = load_id(args.his_ids, ok ? imp * H + h : 0, args.id_dtype);
-        ids_pre[jj] = (ok && id >= 0 && id < args.n_rows) ? static_cast<int32_t>(id) : -1;
+        ids_pre[jj] = load_id_raw(args.his_ids, ok ? imp * H + h : 0, args.id_dtype);
       }
     };
     uint32_t g = 0;
     PROF_DECL;
-    if (n_local > 0) fetch_ids(0);
+    int64_t cs = 0, ce = 0;
+    if (n_local > 0) { fetch_ids(0); tile_range(args, static_cast<int>(blockIdx.x), cs, ce); }
     for (int lt = 0; lt < n_local; ++lt) {
       const int tile = static_cast<int>(blockIdx.x) + lt * static_cast<int>(gridDim.x);
-      uint32_t eoff[8];                                      // byte offset of this thread's 16-byte chunk in its rows (table < 4 GB, checked by the launcher)
+      uint32_t eoff[G1_ROWS];                                // byte offset of this thread's 16-byte chunk in its rows (table < 4 GB, checked by the launcher)
       uint32_t emask = 0;
 #pragma unroll
-      for (int jj = 0; jj < 8; ++jj) {
-        const bool ok = ids_pre[jj] >= 0;
-        eoff[jj] = static_cast<uint32_t>(ok ? ids_pre[jj] : 0) * row_bytes + chunk * 16;
+      for (int jj = 0; jj < G1_ROWS; ++jj) {
+        const int r = r0 + G1_STEP * jj;
+        const int64_t id = id_of(ids_pre[jj], args.id_dtype);
+        const bool ok = r % HP < H && static_cast<int64_t>(tile) * IPT + r / HP < args.B && id >= 0 && id < args.n_rows;
+        eoff[jj] = static_cast<uint32_t>(ok ? id : 0) * row_bytes + chunk * 16;
         emask |= ok ? (1u << jj) : 0u;
       }
-      if (lt + 1 < n_local) fetch_ids(lt + 1);
-      int64_t cs, ce;
-      int npass;
-      tile_cands(args, tile, cs, ce, npass);
+      if (args.dbg & 1) emask = 0;
+      const int npass = passes_of(cs, ce);
+      if (lt + 1 < n_local) {                                // the next tile's ids and candidate range are fetched a tile ahead
+        fetch_ids(lt + 1);
+        tile_range(args, static_cast<int>(blockIdx.x) + (lt + 1) * static_cast<int>(gridDim.x), cs, ce);
+      }
       for (int p = 0; p < npass; ++p) {
-        const int64_t pc0 = cs + static_cast<int64_t>(p) * NC_MAX;
-        const int nc = static_cast<int>(ce - pc0 < NC_MAX ? ce - pc0 : NC_MAX);
-        const int nc16 = nc <= 16 ? 16 : (nc + 15) & ~15;
-        uint32_t coff[6];
-        uint32_t cmask = 0;
-#pragma unroll
-        for (int jj = 0; jj < 6; ++jj) {
-          const int c = r0 + 16 * jj;
-          int64_t id = -1;
-          if (c < nc) id = load_id(args.cand_ids, pc0 + c, args.id_dtype);
-          const bool ok = id >= 0 && id < args.n_rows;
-          coff[jj] = static_cast<uint32_t>(ok ? id : 0) * row_bytes + chunk * 16;
-          cmask |= ok ? (1u << jj) : 0u;
-        }
         for (int j = 0; j < KB; ++j, ++g) {
-          {
-            const uint32_t s = g % S1, ph = (g / S1) & 1;
-            PROF_ADD(0);
-            tc::mbar_wait_relaxed(&bars->empty1[s], ph ^ 1);
-            PROF_ADD(1);
-            const uint32_t base = tc::smem_u32(st1 + s * ST1_BYTES);
-            const uint32_t jb = static_cast<uint32_t>(j) * (FB * 2);
+          const uint32_t s = g % S1, ph = (g / S1) & 1;
+          PROF_ADD(0);
+          tc::mbar_wait(&bars->empty1[s], ph ^ 1);
+          PROF_ADD(1);
+          const uint32_t base = tc::smem_u32(st1 + s * ST1_BYTES) + dst0;
+          const uint32_t jb = static_cast<uint32_t>(j) * (FB * 2);
 #pragma unroll
-            for (int jj = 0; jj < 8; ++jj) {
-              const uint32_t o = eoff[jj] + jb, sz = ((emask >> jj) & 1u) ? 16u : 0u;
-              tc::cp_async_16(base + dst_off[jj], table_b + o, sz);
-              tc::cp_async_16(base + E_BYTES + dst_off[jj], tw_b + o, sz);
-            }
-            tc::cp_async_mbar_arrive_noinc(&bars->full1[s]);
+          for (int jj = 0; jj < G1_ROWS; ++jj) {
+            const uint32_t o = eoff[jj] + jb, sz = ((emask >> jj) & 1u) ? 16u : 0u;
+            tc::cp_async_16(base + jj * (G1_STEP * 128), table_b + o, sz);
+            tc::cp_async_16(base + E_BYTES + jj * (G1_STEP * 128), tw_b + o, (args.dbg & 2) ? 0u : sz);
           }
-          {
-            const uint32_t s = g % S2, ph = (g / S2) & 1;
-            PROF_ADD(2);
-            tc::mbar_wait_relaxed(&bars->empty2[s], ph ^ 1);
-            PROF_ADD(3);
-            const uint32_t base = tc::smem_u32(st2 + s * C_BYTES);
-#pragma unroll
-            for (int jj = 0; jj < 6; ++jj)
-              if (r0 + 16 * jj < nc16)
-                tc::cp_async_16(base + dst_off[jj], table_b + (coff[jj] + static_cast<uint32_t>(j) * (FB * 2)), ((cmask >> jj) & 1u) ? 16u : 0u);
-            tc::cp_async_mbar_arrive_noinc(&bars->full2[s]);
+#ifdef MINER_TS_PROF
+          if (lane == 0) *reinterpret_cast<volatile long long*>(&bars->issue_clk[s][warp]) = clock64();
+#ifdef MINER_TS_PROF_LAT
+          if (warp == 0) {                                   // experiment: how long do this warp's own copies of the stage take to land?
+            const long long l0 = clock64();
+            tc::cp_async_wait_all();
+            prof_c[8] += clock64() - l0; prof_c[9] += 1;
           }
+#endif
+#endif
+          tc::cp_async_mbar_arrive_noinc(&bars->full1[s]);
+          PROF_ADD(2);
         }
       }
     }
     tc::cp_async_wait_all();
     if (threadIdx.x == 0) PROF_STORE(2);
-  } else if (warp == 4) {
+  } else if (warp < W_MMA) {
+    // ------------------------------------------------------------------ gathers of the candidate ring: thread = one 16-byte chunk of
+    //        rows r0 + G2_STEP jj.  Own warps: the candidate stages are released two blocks later than the (E, TW) stages and
+    //        must not hold those back.  The candidate ids of the next unit are fetched one unit ahead.
+    const int t = threadIdx.x - T_G1;
+    const int chunk = t & 7, r0 = t >> 3;
+    const uint32_t row_bytes = static_cast<uint32_t>(D) * 2;
+    const char* table_b = reinterpret_cast<const char*>(args.table);
+    const uint32_t dst0 = tc::sw128_offset(r0, chunk);
+    RawId cid_pre[G2_ROWS];                                  // raw candidate ids of the next unit (see RawId)
+    auto fetch_cands = [&](int64_t pc0, int nc) {
+#pragma unroll
+      for (int jj = 0; jj < G2_ROWS; ++jj) {
+        const int c = r0 + G2_STEP * jj;
+        cid_pre[jj] = RawId{0u, 0u};
+        if (c < nc) cid_pre[jj] = load_id_raw(args.cand_ids, pc0 + c, args.id_dtype);
+      }
+    };
+    uint32_t g = 0;
+    const int tile0 = static_cast<int>(blockIdx.x), tstep = static_cast<int>(gridDim.x);
+    int64_t cs = 0, ce = 0, ncs = 0, nce = 0, n2cs = 0, n2ce = 0;      // candidate ranges of this tile, the next one, the one after
+    if (n_local > 0) {
+      tile_range(args, tile0, cs, ce);
+      if (n_local > 1) tile_range(args, tile0 + tstep, ncs, nce);
+      fetch_cands(cs, static_cast<int>(ce - cs < NC_MAX ? ce - cs : NC_MAX));
+    }
+    for (int lt = 0; lt < n_local; ++lt) {
+      const int npass = passes_of(cs, ce);
+      if (lt + 2 < n_local) tile_range(args, tile0 + (lt + 2) * tstep, n2cs, n2ce);
+      for (int p = 0; p < npass; ++p) {
+        const int64_t pc0 = cs + static_cast<int64_t>(p) * NC_MAX;
+        const int nc = static_cast<int>(ce - pc0 < NC_MAX ? ce - pc0 : NC_MAX);
+        const int nc16 = nc <= 16 ? 16 : (nc + 15) & ~15;
+        uint32_t coff[G2_ROWS];
+        uint32_t cmask = 0;
+#pragma unroll
+        for (int jj = 0; jj < G2_ROWS; ++jj) {
+          const int64_t id = id_of(cid_pre[jj], args.id_dtype);
+          const bool ok = r0 + G2_STEP * jj < nc && id >= 0 && id < args.n_rows;
+          coff[jj] = static_cast<uint32_t>(ok ? id : 0) * row_bytes + chunk * 16;
+          cmask |= ok ? (1u << jj) : 0u;
+        }
+        if (args.dbg & 5) cmask = 0;
+        // ids of the next unit: next pass of this tile, else first pass of the next tile (its range was loaded a tile ago)
+        if (p + 1 < npass) {
+          const int64_t q0 = pc0 + NC_MAX;
+          fetch_cands(q0, static_cast<int>(ce - q0 < NC_MAX ? ce - q0 : NC_MAX));
+        } else if (lt + 1 < n_local) {
+          fetch_cands(ncs, static_cast<int>(nce - ncs < NC_MAX ? nce - ncs : NC_MAX));
+        }
+        for (int j = 0; j < KB; ++j, ++g) {
+          const uint32_t s = g % S2, ph = (g / S2) & 1;
+          tc::mbar_wait(&bars->empty2[s], ph ^ 1);
+          const uint32_t base = tc::smem_u32(st2 + s * C_BYTES) + dst0;
+          const uint32_t jb = static_cast<uint32_t>(j) * (FB * 2);
+#pragma unroll
+          for (int jj = 0; jj < G2_ROWS; ++jj)
+            if (G2_STEP * jj < nc16)
+              tc::cp_async_16(base + jj * (G2_STEP * 128), table_b + (coff[jj] + jb), ((cmask >> jj) & 1u) ? 16u : 0u);
+          tc::cp_async_mbar_arrive_noinc(&bars->full2[s]);
+        }
+      }
+      cs = ncs; ce = nce; ncs = n2cs; nce = n2ce;
+    }
+    tc::cp_async_wait_all();
+  } else if (warp == W_MMA) {
     // ------------------------------------------------------------------ MMA issuer
     const uint32_t idesc1 = tc::make_idesc_bf16_f32_major(TM, FB, false, true);        // B = gathered tile, MN-major
+    const uint32_t idesc1w = tc::make_idesc_bf16_f32_major(TM, 2 * FB, false, true);
+    (void)idesc1w;
     uint32_t g1 = 0, g2 = 0, u = 0;
     bool pending = false;
     int pend_j = 0, pend_nc16 = 16;
@@ -272,11 +351,13 @@ tscore_kernel(const TScoreArgs args, int n_tiles) {
       ++g2;
       PROF_ADD(7);
     };
+    int64_t t_cs = 0, t_ce = 0;
+    if (n_local > 0) tile_range(args, static_cast<int>(blockIdx.x), t_cs, t_ce);
     for (int lt = 0; lt < n_local; ++lt) {
       const int tile = static_cast<int>(blockIdx.x) + lt * static_cast<int>(gridDim.x);
-      int64_t cs, ce;
-      int npass;
-      tile_cands(args, tile, cs, ce, npass);
+      const int64_t cs = t_cs, ce = t_ce;
+      const int npass = passes_of(cs, ce);
+      if (lt + 1 < n_local) tile_range(args, tile + static_cast<int>(gridDim.x), t_cs, t_ce);      // a tile ahead: off the critical path
       for (int p = 0; p < npass; ++p, ++u) {
         const int64_t pc0 = cs + static_cast<int64_t>(p) * NC_MAX;
         const int nc = static_cast<int>(ce - pc0 < NC_MAX ? ce - pc0 : NC_MAX);
@@ -288,18 +369,41 @@ tscore_kernel(const TScoreArgs args, int n_tiles) {
         for (int j = 0; j < KB; ++j) {
           const uint32_t s = g1 % S1, ph = (g1 / S1) & 1, b = g1 & 1;
           PROF_ADD(0);
+#ifdef MINER_TS_PROF
+          const long long lat_a = clock64();
+#endif
           tc::mbar_wait(&bars->full1[s], ph);
+#ifdef MINER_TS_PROF
+          {
+            const long long lat_b = clock64();
+            long long lat_c = 0;
+            for (int w_ = 0; w_ < 4; ++w_) {
+              const long long c_ = *reinterpret_cast<volatile long long*>(&bars->issue_clk[s][w_]);
+              lat_c = c_ > lat_c ? c_ : lat_c;
+            }
+            if (lat_b - lat_a > 400) { prof_c[8] += lat_b - lat_c; prof_c[9] += 1; prof_c[12] += lat_b - lat_a; prof_c[14] += (j == 0) ? 1 : ((j == 1) ? 1000000 : 0); } else { prof_c[10] += lat_a - lat_c; prof_c[11] += 1; prof_c[13] += lat_b - lat_a; }
+          }
+#endif
           PROF_ADD(2);
           tc::tcgen05_fence_after();
           const uint64_t e_desc = tc::make_smem_desc_sw128_mn(tc::smem_u32(st1 + s * ST1_BYTES));
           const uint64_t t_desc = tc::make_smem_desc_sw128_mn(tc::smem_u32(st1 + s * ST1_BYTES + E_BYTES));
           const uint32_t d_i = tmem + IP_COL + b * 128, d_p = d_i + 64;
           if (tc::elect_one()) {
+#ifdef MINER_TS_N128
+            // one N = 128 MMA per k-step: B = [E_j | TW_j], two 64-feature atoms E_BYTES apart, D = [D_I | D_P]
+            const uint64_t et_desc = tc::make_smem_desc_sw128_mn_wide(tc::smem_u32(st1 + s * ST1_BYTES), E_BYTES);
+#pragma unroll
+            for (int ks = 0; ks < TM / 16; ++ks)
+              tc::umma_bf16_ts(d_i, tmem + AW_COL + 8 * ks, et_desc + ks * (2048 >> 4), idesc1w, ks != 0 ? 1u : 0u);
+            (void)e_desc; (void)t_desc; (void)d_p;
+#else
 #pragma unroll
             for (int ks = 0; ks < TM / 16; ++ks) {
               tc::umma_bf16_ts(d_i, tmem + AW_COL + 8 * ks, e_desc + ks * (2048 >> 4), idesc1, ks != 0 ? 1u : 0u);
               tc::umma_bf16_ts(d_p, tmem + AW_COL + 8 * ks, t_desc + ks * (2048 >> 4), idesc1, ks != 0 ? 1u : 0u);
             }
+#endif
             tc::umma_commit(&bars->empty1[s]);
             tc::umma_commit(&bars->ip_full[b]);
             if (j == KB - 1) tc::umma_commit(&bars->w_free);
@@ -315,35 +419,28 @@ tscore_kernel(const TScoreArgs args, int n_tiles) {
     if (pending) stage2();
     if (lane == 0) PROF_STORE(0);
   } else if (warp < W_SMX0) {
-    // ------------------------------------------------------------------ epilogue warps 5..12
+    // ------------------------------------------------------------------ epilogue warps
     const int ew = warp - W_EPI0;
     const int q = warp & 3;                                    // TMEM lane quarter
-    const int half = ew >> 2;                                  // per block: 16-lane group of the quarter; per pass: 0 = D_m, 1 = D_a
+    const int half = ew >> 2;                                  // 16-lane group of the quarter
     const int et = ew * 32 + lane;
-    const int tl = q * 32 + lane;                              // TMEM lane = (i, k, hl), see lane_of()
-    const int li = tl / LPI, lk = ((tl % LPI) >> 4) * 8 + (tl & 7);
-    const bool lo_part = (tl & 8) != 0;
-    const bool row_ok = lk < K;
-    const uint32_t lane_addr = static_cast<uint32_t>(q * 32) << 16;
-    // block epilogue: this warp owns lanes [16 half, 16 half + 16) of its quarter; thread t meets the (hi, lo) rows of code bk
+    const int li = q >> 1;                                     // impression of this quarter's lanes
+    // this warp owns lanes [16 half, 16 half + 16) of its quarter; thread t meets the (hi, lo) rows of code bk
     const uint32_t grp_addr = static_cast<uint32_t>(q * 32 + half * 16) << 16;
     const int bk = ((q & 1) * 2 + half) * 8 + (lane >> 2);      // context code of this thread's row pair
     const int bf = 2 * (lane & 3);                              // its features inside an 8-feature group
-    uint32_t g = 0, u = 0;
+    uint32_t g = 0;
     PROF_DECL;
+    int64_t t_cs = 0, t_ce = 0;
+    if (n_local > 0) tile_range(args, static_cast<int>(blockIdx.x), t_cs, t_ce);
     for (int lt = 0; lt < n_local; ++lt) {
       const int tile = static_cast<int>(blockIdx.x) + lt * static_cast<int>(gridDim.x);
-      int64_t cs, ce;
-      int npass;
-      tile_cands(args, tile, cs, ce, npass);
+      const int64_t cs = t_cs, ce = t_ce;
+      const int npass = passes_of(cs, ce);
+      if (lt + 1 < n_local) tile_range(args, tile + static_cast<int>(gridDim.x), t_cs, t_ce);      // a tile ahead: off the critical path
       const int64_t i0 = static_cast<int64_t>(tile) * IPT;
       const int64_t my_imp = i0 + li;
-      // candidate range of this lane's impression
-      const int64_t my_cs = my_imp < args.B ? cand_off(args, my_imp) : ce;
-      const int64_t my_ce = my_imp < args.B ? cand_off(args, my_imp + 1) : ce;
-      for (int p = 0; p < npass; ++p, ++u) {
-        const int64_t pc0 = cs + static_cast<int64_t>(p) * NC_MAX;
-        const int nc = static_cast<int>(ce - pc0 < NC_MAX ? ce - pc0 : NC_MAX);
+      for (int p = 0; p < npass; ++p) {
         const bool want_i = args.out_interests != nullptr && p == 0 && bk < K && my_imp < args.B;
         for (int j = 0; j < KB; ++j, ++g) {
           const uint32_t b = g & 1;
@@ -390,72 +487,87 @@ tscore_kernel(const TScoreArgs args, int n_tiles) {
           tc::mbar_arrive(&bars->a_ready[b]);
           PROF_ADD(2);
         }
-        // ---- scores of this pass (model.py:127-136,213-214)
-        tc::mbar_wait(&bars->dma_full, u & 1);
-        PROF_ADD(3);
-        tc::tcgen05_fence_after();
-        tc::named_bar_sync(1, T_EPI);                                          // the previous pass's score threads are done with Sm / Sa
-        {
-          // columns of this lane's impression inside the pass (warp-uniform: a warp's 32 lanes belong to one impression)
-          const int64_t r_lo = my_cs - pc0, r_hi = my_ce - pc0;
-          const int c_lo = static_cast<int>(r_lo < 0 ? 0 : (r_lo > nc ? nc : r_lo));
-          int c_hi = static_cast<int>(r_hi < 0 ? 0 : (r_hi > nc ? nc : r_hi));
-          if (c_hi < c_lo) c_hi = c_lo;
-          float* S = half == 0 ? Sm : Sa;
-          const uint32_t dcol = tmem + lane_addr + (half == 0 ? DM_COL : DA_COL);
-          for (int c0 = c_lo & ~15; c0 < c_hi; c0 += 16) {
-            uint32_t v[16];
-            tc::tmem_ld_32x16(dcol + c0, v);
-            tc::tmem_ld_wait();
-#pragma unroll
-            for (int c = 0; c < 16; ++c) {
-              const float x = __uint_as_float(v[c]);
-              const float sum = x + __shfl_xor_sync(0xffffffffu, x, 8);       // A_hi . cand + A_lo . cand
-              const int col = c0 + c;
-              if (!lo_part && row_ok && col >= c_lo && col < c_hi) S[col * SS + lk] = sum;
-            }
-          }
-        }
-        tc::tcgen05_fence_before();
-        tc::mbar_arrive(&bars->dma_free);
-        tc::named_bar_sync(1, T_EPI);
-        if (et < nc) {
-          const float* m = Sm + et * SS;
-          const float* a = Sa + et * SS;
-          float score;
-          if (args.score_type == MINER_SCORE_WEIGHTED) {
-            float mx = -INFINITY;
-            for (int k = 0; k < K; ++k) mx = fmaxf(mx, a[k]);
-            float den = 0.f, num = 0.f;
-            for (int k = 0; k < K; ++k) {
-              const float e = __expf(a[k] - mx);
-              den += e;
-              num = fmaf(e, m[k], num);
-            }
-            score = num / den;
-          } else if (args.score_type == MINER_SCORE_MAX) {
-            score = -INFINITY;
-            for (int k = 0; k < K; ++k) score = fmaxf(score, m[k]);
-          } else {
-            score = 0.f;
-            for (int k = 0; k < K; ++k) score += m[k];
-            score /= static_cast<float>(K);
-          }
-          args.out_scores[pc0 + et] = score;
-        }
-        PROF_ADD(4);
       }
     }
     if (et == 0) PROF_STORE(1);
     if (et == 128) PROF_STORE(4);
   } else {
-    // ------------------------------------------------------------------ softmax warps 13..16
+    // ------------------------------------------------------------------ softmax / score warps
     const int sw = warp - W_SMX0;
     const int q = warp & 3;
     const int li = q >> 1;                                     // impression of this quarter's lanes
     const uint32_t lane_addr = static_cast<uint32_t>(q * 32) << 16;
+    const int st = sw * 32 + lane;                             // 0..127
+    const int tl = q * 32 + lane;                              // TMEM lane = (i, k, hl) for the 32-lane reads of the score stage
+    const int lk = ((tl % LPI) >> 4) * 8 + (tl & 7);
+    const bool lo_part = (tl & 8) != 0;
     uint32_t u = 0;
     PROF_DECL;
+    // ---- scores of a finished unit (model.py:127-136,213-214).  These warps have the slack: while they do this the epilogue
+    //      warps are already converting the blocks of the next unit.
+    int64_t f_pc0 = 0, f_cs = 0, f_ce = 0;
+    int f_nc = 0;
+    auto score_stage = [&](uint32_t fu) {
+      const int64_t pc0 = f_pc0, my_cs = f_cs, my_ce = f_ce;
+      const int nc = f_nc;
+      const bool row_ok = lk < K;
+      tc::mbar_wait(&bars->dma_full, fu & 1);
+      PROF_ADD(5);
+      tc::tcgen05_fence_after();
+      tc::named_bar_sync(1, T_SMX);                                            // the previous unit's score threads are done with Sm / Sa
+      {
+        // columns of this lane's impression inside the pass (warp-uniform: a warp's 32 lanes belong to one impression)
+        const int64_t r_lo = my_cs - pc0, r_hi = my_ce - pc0;
+        const int c_lo = static_cast<int>(r_lo < 0 ? 0 : (r_lo > nc ? nc : r_lo));
+        int c_hi = static_cast<int>(r_hi < 0 ? 0 : (r_hi > nc ? nc : r_hi));
+        if (c_hi < c_lo) c_hi = c_lo;
+        for (int c0 = c_lo & ~15; c0 < c_hi; c0 += 16) {
+          uint32_t vm[16], va[16];
+          tc::tmem_ld_32x16(tmem + lane_addr + DM_COL + c0, vm);
+          tc::tmem_ld_32x16(tmem + lane_addr + DA_COL + c0, va);
+          tc::tmem_ld_wait();
+#pragma unroll
+          for (int c = 0; c < 16; ++c) {
+            const float xm = __uint_as_float(vm[c]), xa = __uint_as_float(va[c]);
+            const float sm_ = xm + __shfl_xor_sync(0xffffffffu, xm, 8);       // A_hi . cand + A_lo . cand
+            const float sa_ = xa + __shfl_xor_sync(0xffffffffu, xa, 8);
+            const int col = c0 + c;
+            if (!lo_part && row_ok && col >= c_lo && col < c_hi) {
+              Sm[col * SS + lk] = sm_;
+              Sa[col * SS + lk] = sa_;
+            }
+          }
+        }
+      }
+      tc::tcgen05_fence_before();
+      tc::mbar_arrive(&bars->dma_free);
+      tc::named_bar_sync(1, T_SMX);
+      if (st < nc) {
+        const float* m = Sm + st * SS;
+        const float* a = Sa + st * SS;
+        float score;
+        if (args.score_type == MINER_SCORE_WEIGHTED) {
+          float mx = -INFINITY;
+          for (int k = 0; k < K; ++k) mx = fmaxf(mx, a[k]);
+          float den = 0.f, num = 0.f;
+          for (int k = 0; k < K; ++k) {
+            const float e = __expf(a[k] - mx);
+            den += e;
+            num = fmaf(e, m[k], num);
+          }
+          score = num / den;
+        } else if (args.score_type == MINER_SCORE_MAX) {
+          score = -INFINITY;
+          for (int k = 0; k < K; ++k) score = fmaxf(score, m[k]);
+        } else {
+          score = 0.f;
+          for (int k = 0; k < K; ++k) score += m[k];
+          score /= static_cast<float>(K);
+        }
+        args.out_scores[pc0 + st] = score;
+      }
+      PROF_ADD(6);
+    };
     {
       // the off-diagonal half of A_w (slots of the other impression) stays zero for the whole kernel
       uint32_t z[16];
@@ -465,45 +577,49 @@ tscore_kernel(const TScoreArgs args, int n_tiles) {
       for (int cc = 0; cc < 4; ++cc) tc::tmem_st_32x16(tmem + lane_addr + AW_COL + cc * 16, z);
       tc::tmem_st_wait();
     }
+    int64_t t_cs = 0, t_ce = 0;
+    if (n_local > 0) tile_range(args, static_cast<int>(blockIdx.x), t_cs, t_ce);
     for (int lt = 0; lt < n_local; ++lt) {
       const int tile = static_cast<int>(blockIdx.x) + lt * static_cast<int>(gridDim.x);
-      int64_t cs, ce;
-      int npass;
-      tile_cands(args, tile, cs, ce, npass);
+      const int64_t cs = t_cs, ce = t_ce;
+      const int npass = passes_of(cs, ce);
+      if (lt + 1 < n_local) tile_range(args, tile + static_cast<int>(gridDim.x), t_cs, t_ce);      // a tile ahead: off the critical path
       for (int p = 0; p < npass; ++p, ++u) {
         PROF_ADD(0);
         tc::named_bar_sync(2, T_SMX);                                          // previous unit's reads of L are done
         {
-          // logits of 32 slots per warp: lg rows are K consecutive floats (model.py:174 hoisted to the table)
+          // logits of 32 slots per warp: lg rows are K consecutive floats (model.py:174 hoisted to the table).  Stored scaled by
+          // log2(e): the softmax below runs on ex2.
           const int slot = sw * 32 + lane;
           const int64_t imp = static_cast<int64_t>(tile) * IPT + slot / HP;
           const int h = slot % HP;
           const bool valid = h < H && imp < args.B;
-          int64_t id = -1;
-          bool keep = false;
+          uint32_t info = 0;                                                   // id | code << 30; code 0 padding, 1 masked, 2 kept, 3 kept with a bad id
           float bias = 0.f;
           if (valid) {
-            id = load_id(args.his_ids, imp * H + h, args.id_dtype);
-            keep = args.mask[imp * H + h] != 0;
+            const int64_t id = load_id(args.his_ids, imp * H + h, args.id_dtype);
+            const bool keep = args.mask[imp * H + h] != 0;
             if (args.bias_mean) bias = args.bias_mean[imp * H + h];
-            if (id < 0 || id >= args.n_rows) id = -1;
+            const bool id_ok = id >= 0 && id < args.n_rows;
+            info = (id_ok ? static_cast<uint32_t>(id) : 0u) | ((keep ? (id_ok ? 2u : 3u) : 1u) << 30);
           }
-          const int code = valid ? ((keep && id >= 0) ? 2 : (keep ? 3 : 1)) : 0;
+          const float* lgp = args.lg + lane;
+          const uint32_t Ku = static_cast<uint32_t>(K);
           float v[32];
 #pragma unroll
           for (int ss = 0; ss < 32; ++ss) {                                    // 32 independent 128-byte row loads in flight
-            const long long id_s = __shfl_sync(0xffffffffu, static_cast<long long>(id), ss);
-            const int code_s = __shfl_sync(0xffffffffu, code, ss);
-            v[ss] = (code_s == 2 && lane < K) ? args.lg[id_s * K + lane] : 0.f;
+            const uint32_t info_s = __shfl_sync(0xffffffffu, info, ss);
+            v[ss] = ((info_s >> 30) == 2u && lane < K) ? lgp[(info_s & 0x3fffffffu) * Ku] : 0.f;
           }
+          const bool has_bias = args.bias_mean != nullptr;
 #pragma unroll
           for (int ss = 0; ss < 32; ++ss) {
-            const int code_s = __shfl_sync(0xffffffffu, code, ss);
-            const float bias_s = __shfl_sync(0xffffffffu, bias, ss);
-            float x = v[ss] + bias_s;                                          // model.py:174-177
-            if (code_s == 1) x = kMaskFill;                                    // model.py:180 (1e-30, not -inf)
-            if (code_s == 0) x = -INFINITY;                                    // tile padding: not part of the history
-            L[(sw * 32 + ss) * LS + lane] = x;
+            const uint32_t code_s = __shfl_sync(0xffffffffu, info, ss) >> 30;
+            float x = v[ss];
+            if (has_bias) x += __shfl_sync(0xffffffffu, bias, ss);             // model.py:174-177
+            if (code_s == 1u) x = kMaskFill;                                   // model.py:180 (1e-30, not -inf)
+            if (code_s == 0u) x = -INFINITY;                                   // tile padding: not part of the history
+            L[(sw * 32 + ss) * LS + lane] = x * 1.4426950408889634f;
           }
         }
         tc::named_bar_sync(2, T_SMX);
@@ -531,12 +647,12 @@ tscore_kernel(const TScoreArgs args, int n_tiles) {
           float sum = 0.f;
 #pragma unroll
           for (int n = 0; n < 16; ++n) {
-            e[n] = dead ? 0.f : __expf(e[n] - mx);
+            e[n] = dead ? 0.f : ex2_approx(e[n] - mx);
             sum += e[n];
           }
           sum += __shfl_xor_sync(0xffffffffu, sum, 1);
           sum += __shfl_xor_sync(0xffffffffu, sum, 2);
-          const float inv = dead ? 0.f : 1.0f / sum;
+          const float inv = dead ? 0.f : __fdividef(1.0f, sum);
 #pragma unroll
           for (int n = 0; n < 8; ++n) {
             const float w0 = e[2 * n] * inv, w1 = e[2 * n + 1] * inv;
@@ -556,14 +672,23 @@ tscore_kernel(const TScoreArgs args, int n_tiles) {
         tc::tcgen05_fence_before();
         tc::mbar_arrive(&bars->w_ready);
         PROF_ADD(4);
+        if (u > 0) score_stage(u - 1);
+        {
+          const int64_t my_imp = static_cast<int64_t>(tile) * IPT + li;
+          f_pc0 = cs + static_cast<int64_t>(p) * NC_MAX;
+          f_nc = static_cast<int>(ce - f_pc0 < NC_MAX ? ce - f_pc0 : NC_MAX);
+          f_cs = my_imp < args.B ? cand_off(args, my_imp) : ce;
+          f_ce = my_imp < args.B ? cand_off(args, my_imp + 1) : ce;
+        }
       }
     }
+    if (u > 0) score_stage(u - 1);
     if (threadIdx.x == W_SMX0 * 32) PROF_STORE(3);
   }
 
   tc::tcgen05_fence_before();
   __syncthreads();
-  if (warp == 4) tc::tmem_dealloc(tmem, 512);
+  if (warp == W_MMA) tc::tmem_dealloc(tmem, 512);
 }
 
 constexpr int T_SMEM = 1024 + S1 * ST1_BYTES + S2 * C_BYTES + TM * LS * 4 + 2 * NC_MAX * SS * 4 + 256;
@@ -584,7 +709,8 @@ int launch_tscore_kernel(const void* table, const void* tw, const float* lg, int
               (long long)D);
     return MINER_ERR_UNSUPPORTED;
   }
-  if (static_cast<uint64_t>(n_rows) * static_cast<uint64_t>(D) * 2 > 0xffffffffull) {
+  if (static_cast<uint64_t>(n_rows) * static_cast<uint64_t>(D) * 2 > 0xffffffffull || n_rows >= (1ll << 30) ||
+      static_cast<uint64_t>(n_rows) * static_cast<uint64_t>(K) > 0xffffffffull) {
     set_error("table-level scoring: table of %lld x %lld bf16 exceeds the 4 GB the kernel addresses with 32-bit offsets", (long long)n_rows,
               (long long)D);
     return MINER_ERR_UNSUPPORTED;
@@ -595,6 +721,10 @@ int launch_tscore_kernel(const void* table, const void* tw, const float* lg, int
   a.cand_offsets = cand_offsets; a.B = B; a.H = static_cast<int>(H); a.K = static_cast<int>(K); a.D = static_cast<int>(D);
   a.C = static_cast<int>(C); a.score_type = score_type; a.out_scores = out_scores; a.out_interests = out_interests;
   a.prof = hist_prof_buffer();
+  {
+    static const char* env_dbg = getenv("MINER_TS_DBG");
+    a.dbg = env_dbg ? atoi(env_dbg) : 0;
+  }
   const int64_t n_tiles = (B + IPT - 1) / IPT;
   const int grid = static_cast<int>(n_tiles < sm_count() ? n_tiles : sm_count());
   MINER_CUDA_OK(cudaFuncSetAttribute(tscore_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, T_SMEM));

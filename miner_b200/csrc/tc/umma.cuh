@@ -54,6 +54,9 @@ __device__ __forceinline__ bool mbar_try_wait(uint64_t* bar, uint32_t parity) {
 }
 __device__ __forceinline__ void mbar_wait(uint64_t* bar, uint32_t parity) {
   while (!mbar_try_wait(bar, parity)) {
+#ifdef MINER_MBAR_SLEEP_NS
+    __nanosleep(MINER_MBAR_SLEEP_NS);
+#endif
   }
 }
 // for warps that are far ahead of their consumer (producers waiting for a free stage): back off between probes so the
@@ -193,6 +196,17 @@ __device__ __forceinline__ uint64_t make_smem_desc_sw128_mn(uint32_t smem_addr) 
   d |= static_cast<uint64_t>((smem_addr & 0x3FFFFu) >> 4);
   d |= static_cast<uint64_t>(1) << 16;                          // LBO (unused: one atom along MN)
   d |= static_cast<uint64_t>(1024 >> 4) << 32;                  // SBO: next group of 8 K-rows
+  d |= static_cast<uint64_t>(1) << 46;
+  d |= static_cast<uint64_t>(2) << 61;
+  return d;
+}
+// MN-major operand that is several 64-element swizzle atoms wide along MN: atom a of the operand starts lbo_bytes after atom a-1
+// (LBO = distance between MN atoms, SBO = distance between groups of 8 K-rows).
+__device__ __forceinline__ uint64_t make_smem_desc_sw128_mn_wide(uint32_t smem_addr, uint32_t lbo_bytes) {
+  uint64_t d = 0;
+  d |= static_cast<uint64_t>((smem_addr & 0x3FFFFu) >> 4);
+  d |= static_cast<uint64_t>((lbo_bytes >> 4) & 0x3FFFu) << 16;
+  d |= static_cast<uint64_t>(1024 >> 4) << 32;
   d |= static_cast<uint64_t>(1) << 46;
   d |= static_cast<uint64_t>(2) << 61;
   return d;

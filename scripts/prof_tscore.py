@@ -35,11 +35,22 @@ print(f'{ms:.2f} ms  {B / ms / 1e3:.2f} M impressions/s', sys.argv[1:])
 p = prof.cpu().view(148, 5, 16).double()
 names = {0: ('MMA issuer', ['other', 'wait w_ready', 'wait full1 (E,TW)', 'issue S1', 'wait a_ready', 'wait full2 (cand)', 'wait dma_free', 'issue S2']),
          1: ('epilogue (interest half)', ['other', 'wait ip_full', 'fence+arrive', 'wait dma_full', 'scores', 'tmem ld+wait', 'shuffle/gelu/pack', 'tmem st issue', 'tmem st wait']),
-         2: ('gather', ['issue/other', 'wait empty1', 'issue E,TW', 'wait empty2']),
+         2: ('gather (E, TW ring)', ['other', 'wait empty1', 'issue E,TW']),
          4: ('epilogue (gelu half)', ['other', 'wait ip_full', 'fence+arrive', 'wait dma_full', 'scores', 'tmem ld+wait', 'shuffle/gelu/pack', 'tmem st issue', 'tmem st wait']),
-         3: ('softmax', ['other', 'load lg', 'softmax', 'wait w_free', 'store'])}
+         3: ('softmax + scores', ['other', 'load lg', 'softmax', 'wait w_free', 'store', 'wait dma_full', 'score stage'])}
 for role, (rn, cn) in names.items():
     tot = p[:, role, 15].mean()
     print(f'{rn}: total {tot:.0f} cycles')
     for i, n in enumerate(cn):
         print(f'    {n:24s} {p[:, role, i].mean() / tot * 100:5.1f} %')
+
+m = p[:, 0, :]
+print(f'(E, TW) stages the MMA warp waited > 400 cycles for: {m[:, 9].sum():.0f}, mean wait {m[:, 12].sum() / max(m[:, 9].sum(), 1):.0f}, mean issue->full {m[:, 8].sum() / max(m[:, 9].sum(), 1):.0f} cycles; '
+      f'others: {m[:, 11].sum():.0f}, mean wait {m[:, 13].sum() / max(m[:, 11].sum(), 1):.0f}, mean age at use {m[:, 10].sum() / max(m[:, 11].sum(), 1):.0f} cycles')
+
+c14 = m[:, 14].sum()
+print(f'   of the long waits: block 0 of a tile {c14 % 1000000:.0f}, block 1 {c14 // 1000000:.0f}')
+
+gm = p[:, 2, :]
+if gm[:, 9].sum() > 0:
+    print(f'   gather warp 0: cp.async.wait_all right after issuing a stage took {gm[:, 8].sum() / gm[:, 9].sum():.0f} cycles on average (-DMINER_TS_PROF_LAT)')
