@@ -20,6 +20,7 @@ namespace miner {
 constexpr int MT = 256;            // threads per block (8 warps)
 constexpr int MCAP = 1024;         // candidates per impression staged in shared memory per warp
 constexpr int MAXK = 8;            // cut-offs
+constexpr int LOG2_TAB = 256;      // ranks below this take log2 from a shared-memory table
 constexpr int MAXM = 2 + 2 * MAXK;
 
 struct MetricKs { int n_k; int k[MAXK]; };
@@ -37,6 +38,9 @@ __global__ void __launch_bounds__(MT) rank_metrics_kernel(const float* __restric
   __shared__ float p_s[MT / 32][MCAP];
   __shared__ int8_t y_s[MT / 32][MCAP];
   __shared__ double red[MT / 32][2 * MAXM];
+  __shared__ double log2_tab[LOG2_TAB];          // log2(r) of the small ranks: an fp64 log2 costs ~100x an fp64 shared-memory load here
+  for (int i = threadIdx.x; i < LOG2_TAB; i += MT) log2_tab[i] = i > 0 ? log2(static_cast<double>(i)) : 0.0;
+  __syncthreads();
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const int M = 2 + 2 * ks.n_k;
   float* ps = p_s[warp];
@@ -92,21 +96,26 @@ __global__ void __launch_bounds__(MT) rank_metrics_kernel(const float* __restric
       const int rank_np = gt + eq_after;
       const int rank_py = gt + eq_before;
       const int rank_ideal = y_gt + y_eq_before;
-      const double gain = exp2(static_cast<double>(yi)) - 1.0;          // 2 ** y_true - 1, evaluation.py:210
       if (yi > 0) {
         n_pos += 1.0;
         auc_wins += static_cast<double>(neg_lt) + 0.5 * static_cast<double>(neg_eq);
       } else {
         n_neg += 1.0;
       }
-      rr += static_cast<double>(yi) / static_cast<double>(rank_np + 1);  // evaluation.py:190
+      if (yi != 0) {                                                      // a zero label adds exactly 0 to rr, dcg and idcg
+        // 2 ** y_true - 1 (evaluation.py:210); small non-negative labels are exact powers of two
+        const double gain = (yi > 0 && yi < 31) ? static_cast<double>((1 << yi) - 1) : exp2(static_cast<double>(yi)) - 1.0;
+        rr += static_cast<double>(yi) / static_cast<double>(rank_np + 1);  // evaluation.py:190
+        const double l_np = rank_np + 2 < LOG2_TAB ? log2_tab[rank_np + 2] : log2(static_cast<double>(rank_np + 2));
+        const double l_id = rank_ideal + 2 < LOG2_TAB ? log2_tab[rank_ideal + 2] : log2(static_cast<double>(rank_ideal + 2));
 #pragma unroll
-      for (int q = 0; q < MAXK; ++q) {
-        if (q < ks.n_k) {
-          const int kk = ks.k[q] < n ? ks.k[q] : n;                      // k = min(len, k), evaluation.py:207
-          if (rank_np < kk) dcg[q] += gain / log2(static_cast<double>(rank_np + 2));
-          if (rank_ideal < kk) idcg[q] += gain / log2(static_cast<double>(rank_ideal + 2));
-          if (rank_py < ks.k[q] && yi > 0) hit[q] = 1.0;                 // evaluation.py:247-249
+        for (int q = 0; q < MAXK; ++q) {
+          if (q < ks.n_k) {
+            const int kk = ks.k[q] < n ? ks.k[q] : n;                      // k = min(len, k), evaluation.py:207
+            if (rank_np < kk) dcg[q] += gain / l_np;
+            if (rank_ideal < kk) idcg[q] += gain / l_id;
+            if (rank_py < ks.k[q] && yi > 0) hit[q] = 1.0;                 // evaluation.py:247-249
+          }
         }
       }
     }

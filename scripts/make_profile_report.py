@@ -16,17 +16,20 @@ subprocess.run([sys.executable, os.path.join(ROOT, 'scripts', 'ncu_summary.py'),
                stdout=subprocess.DEVNULL, check=True)
 lib = os.path.join(ROOT, 'miner_b200', 'libminer_b200.so')
 with open(out, 'a') as f:
-    for kre, stem in (('hist_kernel2', 'hist_kernel2'), ('cand_kernel', 'cand_kernel')):
+    for kre, stem in (('tscore_kernel', 'tscore_kernel'), ('hist_kernel2', 'hist_kernel2'), ('cand_kernel', 'cand_kernel')):
         r = subprocess.run([sys.executable, os.path.join(ROOT, 'scripts', 'ncu_hot.py'), rep, kre, lib, stem, '14'], capture_output=True, text=True)
-        f.write(f'\n== hot source lines, warp-stall samples ({kre}) ==\n' + r.stdout)
+        if r.returncode == 0 and r.stdout.strip():
+            f.write(f'\n== hot source lines, warp-stall samples ({kre}) ==\n' + r.stdout)
 # traffic
 r = subprocess.run(['ncu', '-i', rep, '--page', 'raw', '--csv'], capture_output=True, text=True)
 rows = list(csv.reader(r.stdout.splitlines()))
 hdr, units = rows[0], rows[1]
+tpath = os.path.join(ROOT, 'profiles', 'traffic.json')
+old = json.load(open(tpath)) if os.path.exists(tpath) else {}
 traffic = {}
 for row in rows[2:]:
     name = row[hdr.index('Kernel Name')]
-    key = 'hist_kernel' if 'hist_kernel' in name else 'cand_kernel' if 'cand_kernel' in name else None
+    key = 'tscore_kernel' if 'tscore_kernel' in name else 'hist_kernel' if 'hist_kernel' in name else 'cand_kernel' if 'cand_kernel' in name else None
     if not key:
         continue
     tot = 0.0
@@ -40,6 +43,8 @@ for k, t in traffic.items():
     t['dram_bytes_per_impression'] = sum(t['samples']) / len(t['samples'])
     t['source'] = f'profiles/{tag}_ncu_summary.txt (ncu --set full, {per_launch} impressions per launch)'
     del t['samples']
-json.dump(traffic, open(os.path.join(ROOT, 'profiles', 'traffic.json'), 'w'), indent=1)
+old.update(traffic)          # kernels not in this capture keep their earlier figures
+traffic = old
+json.dump(traffic, open(tpath, 'w'), indent=1)
 print(open(out).read()[:3000])
 print(json.dumps(traffic, indent=1))
