@@ -44,13 +44,20 @@ constexpr int TM = 128;                      // TMEM lanes = history slots per t
 constexpr int FB = 64;                       // feature block (128 bytes of bf16)
 constexpr int IPT = 2, HP = TM / IPT, LPI = TM / IPT;
 constexpr int KMAX = 32;
-constexpr int S1 = 4, S2 = 4;                // ring depths: (E, TW) blocks / candidate blocks
+#ifndef MINER_TS_S1
+#define MINER_TS_S1 5
+#endif
+#ifndef MINER_TS_S2
+#define MINER_TS_S2 3
+#endif
+constexpr int S1 = MINER_TS_S1, S2 = MINER_TS_S2;   // ring depths: (E, TW) blocks / candidate blocks
 constexpr int E_BYTES = TM * FB * 2;         // 16 KB
 constexpr int ST1_BYTES = 2 * E_BYTES;
 constexpr int NC_MAX = 96;                   // candidate columns per pass
 constexpr int C_BYTES = NC_MAX * FB * 2;     // 12 KB
 constexpr int LS = KMAX;                     // logits scratch row stride (floats)
 constexpr int SS = KMAX + 1;                 // score scratch row stride (floats)
+constexpr int SCRATCH_FLOATS = (TM * LS > 2 * NC_MAX * SS ? TM * LS : 2 * NC_MAX * SS + 2) & ~1;
 constexpr int T_EPI = 256, T_SMX = 128;                // 8 epilogue warps, 4 softmax / score warps
 constexpr int T_G1 = 128, T_G2 = 64;                   // gather threads of the (E, TW) ring / of the candidate ring
 constexpr int G1_ROWS = TM * 8 / T_G1, G2_ROWS = NC_MAX * 8 / T_G2;  // rows per thread (a thread moves one 16-byte chunk per row)
@@ -148,10 +155,12 @@ tscore_kernel(const TScoreArgs args, int n_tiles) {
   uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~static_cast<uintptr_t>(1023));
   uint8_t* st1 = smem;                                         // [S1][E 16 KB | TW 16 KB]
   uint8_t* st2 = st1 + S1 * ST1_BYTES;                         // [S2][12 KB] candidate rows
+  // scratch of the softmax / score warps: the logits L of the unit being prepared and the score transposes Sm / Sa of the unit
+  // being finished are never live at the same time (named barriers 1 and 2 separate the phases), so they share the bytes
   float* L = reinterpret_cast<float*>(st2 + S2 * C_BYTES);     // [128 slots][LS] logits
-  float* Sm = L + TM * LS;                                     // [NC_MAX][SS] matching scores, transposed
+  float* Sm = L;                                               // [NC_MAX][SS] matching scores, transposed
   float* Sa = Sm + NC_MAX * SS;                                // [NC_MAX][SS] attention logits, transposed
-  TBarriers* bars = reinterpret_cast<TBarriers*>(Sa + NC_MAX * SS);
+  TBarriers* bars = reinterpret_cast<TBarriers*>(L + SCRATCH_FLOATS);
 
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const int H = args.H, K = args.K, D = args.D;
@@ -691,7 +700,7 @@ tscore_kernel(const TScoreArgs args, int n_tiles) {
   if (warp == W_MMA) tc::tmem_dealloc(tmem, 512);
 }
 
-constexpr int T_SMEM = 1024 + S1 * ST1_BYTES + S2 * C_BYTES + TM * LS * 4 + 2 * NC_MAX * SS * 4 + 256;
+constexpr int T_SMEM = 1024 + S1 * ST1_BYTES + S2 * C_BYTES + SCRATCH_FLOATS * 4 + 512;
 
 }  // namespace
 
