@@ -192,6 +192,29 @@ int miner_loss_fwd(const float* interests, const float* logits, const float* lab
                    int64_t B, int64_t C, int64_t K, int64_t D, int mode,
                    float* out, void* workspace, size_t workspace_bytes, void* stream);
 
+/* ---- Train variant: Miner.forward with the intermediates its backward needs, the backward of
+ *      Loss.compute (loss.py:27-44) and the backward of Miner.forward (model.py:61-138, score_type 'weighted', category bias
+ *      off) down to the three weight matrices.  fp32, reference operation order, deterministic reductions.  Dense layout:
+ *      cand_ids (B,C).  The news table is a frozen buffer: no gradient flows into its rows.
+ *      miner_train_fwd writes interests (B,K,D), scores (B,C) and saves T = tanh(E Wp^T) (B*H,Dc), the softmax weights
+ *      (B,K,H) and Z = I Wt^T (B*K,D).  miner_loss_bwd: d loss / d interests and d loss / d logits, scaled by *grad_out
+ *      (device float, NULL = 1).  miner_train_bwd: grad_w_proj (Dc,D), grad_codes (K,Dc), grad_w_target (D,D) from d_scores
+ *      (B,C) and d_interests (B,K,D, nullable).  The same workspace size serves fwd and bwd. */
+size_t miner_train_workspace_bytes(int64_t B, int64_t H, int64_t K, int64_t Dc, int64_t D);
+int miner_train_fwd(const void* table, int64_t n_rows, int table_dtype, const void* his_ids, const uint8_t* his_mask,
+                    const void* cand_ids, int id_dtype, const float* w_proj, const float* codes, const float* w_target,
+                    int64_t B, int64_t H, int64_t C, int64_t K, int64_t Dc, int64_t D, float* out_interests, float* out_scores,
+                    float* save_t, float* save_w, float* save_z, void* workspace, size_t workspace_bytes, void* stream);
+int miner_loss_bwd(const float* interests, const float* logits, const float* labels, const float* grad_out,
+                   int64_t B, int64_t C, int64_t K, int64_t D, float* d_interests, float* d_logits, void* stream);
+int miner_train_bwd(const void* table, int64_t n_rows, int table_dtype, const void* his_ids, const uint8_t* his_mask,
+                    const void* cand_ids, int id_dtype, const float* w_proj, const float* codes, const float* w_target,
+                    const float* save_t, const float* save_w, const float* interests, const float* save_z,
+                    const float* d_scores, const float* d_interests,
+                    int64_t B, int64_t H, int64_t C, int64_t K, int64_t Dc, int64_t D,
+                    float* grad_w_proj, float* grad_codes, float* grad_w_target,
+                    void* workspace, size_t workspace_bytes, void* stream);
+
 #ifdef __cplusplus
 }
 #endif

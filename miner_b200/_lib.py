@@ -31,6 +31,7 @@ EXPORTS = [
     'miner_tc_gemm', 'miner_rank_metrics_workspace_bytes', 'miner_rank_metrics', 'miner_loss_workspace_bytes',
     'miner_loss_fwd', 'miner_hist_interests_workspace_bytes', 'miner_hist_interests_fwd', 'miner_cand_score_fwd',
     'miner_table_project_workspace_bytes', 'miner_table_project', 'miner_score_table_supported', 'miner_score_table_fwd',
+    'miner_train_workspace_bytes', 'miner_train_fwd', 'miner_loss_bwd', 'miner_train_bwd',
 ]
 
 
@@ -90,6 +91,12 @@ def _declare(lib: C.CDLL) -> None:
     lib.miner_table_project_workspace_bytes.restype = sz
     lib.miner_table_project.argtypes = [vp, i64, i64, vp, vp, vp, i64, i64, vp, vp, vp, sz, vp]
     lib.miner_score_table_supported.argtypes = [i64, i64, i64]
+    lib.miner_train_workspace_bytes.argtypes = [i64] * 5
+    lib.miner_train_workspace_bytes.restype = sz
+    lib.miner_train_fwd.argtypes = [vp, i64, i32, vp, vp, vp, i32, vp, vp, vp, i64, i64, i64, i64, i64, i64, vp, vp, vp, vp, vp, vp, sz, vp]
+    lib.miner_loss_bwd.argtypes = [vp, vp, vp, vp, i64, i64, i64, i64, vp, vp, vp]
+    lib.miner_train_bwd.argtypes = [vp, i64, i32, vp, vp, vp, i32, vp, vp, vp, vp, vp, vp, vp, vp, vp, i64, i64, i64, i64, i64, i64, vp, vp, vp,
+                                    vp, sz, vp]
     lib.miner_score_table_fwd.argtypes = [vp, vp, vp, i64, vp, vp, vp, vp, i32, vp, i64, i64, i64, i64, i64, i32, vp, vp, vp]
 
 

@@ -1,0 +1,502 @@
+// Train variant of the scoring path: forward with the intermediates the backward needs, the
+// backward of Loss.compute (reference src/loss.py:27-44) and the backward of Miner.forward (src/model/model.py:61-138,
+// score_type 'weighted', category bias off) down to the three weight matrices.  fp32 CUDA-core kernels in the reference's
+// operation order; every reduction over the batch goes through per-CTA partials summed in a fixed order (deterministic).
+// The news table is a frozen buffer (TableNewsEncoder): no gradient flows into its rows.
+//
+//   forward   E = table[his]; T = tanh(E Wp^T); logits = T codes^T, masked := 1e-30; w = softmax_H; I = w E        (model.py:159-185)
+//             Z = I Wt^T; G = gelu(Z); m = Cd I^T; a = Cd G^T; ws = softmax_K(a); s = sum_k ws m                     (model.py:127,200-216)
+//   loss      mean_{b,k!=l} cos(I_k, I_l) + CE_mean(s, argmax labels)                                                 (loss.py:39-42)
+//   backward  ds, dI(loss) -> dm = ds ws, dws = ds m, da = ws (dws - sum ws dws) -> dI += dm^T Cd, dG = da^T Cd, dZ = dG gelu'(Z)
+//             dI += dZ Wt, dWt = dZ^T I -> dw = dI E^T -> dlogits = w (dw - sum w dw), 0 on masked slots
+//             dT = dlogits^T codes, dcodes = sum_b dlogits T, dZ1 = dT (1 - T^2), dWp = dZ1^T E
+#include "common.cuh"
+
+namespace miner {
+
+namespace {
+
+constexpr int TT = 256;
+
+__device__ __forceinline__ float table_elem(const void* table, int dtype, int64_t idx) {
+  return dtype == MINER_F32 ? reinterpret_cast<const float*>(table)[idx]
+                            : bf16_bits_to_float(reinterpret_cast<const uint16_t*>(table)[idx]);
+}
+// d/dz of the exact erf gelu (model.py:212)
+__device__ __forceinline__ float gelu_erf_grad(float z) {
+  return 0.5f * (1.0f + erff(z * 0.70710678118654752440f)) + z * 0.3989422804014327f * expf(-0.5f * z * z);
+}
+
+__global__ void gelu_kernel(const float* __restrict__ z, float* __restrict__ g, int64_t n) {
+  for (int64_t i = static_cast<int64_t>(blockIdx.x) * blockDim.x + threadIdx.x; i < n; i += static_cast<int64_t>(gridDim.x) * blockDim.x)
+    g[i] = gelu_erf(z[i]);
+}
+
+__global__ void transpose_kernel(const float* __restrict__ src, float* __restrict__ dst, int rows, int cols) {
+  __shared__ float tile[32][33];
+  const int c0 = blockIdx.x * 32, r0 = blockIdx.y * 32;
+  for (int i = threadIdx.y; i < 32; i += blockDim.y)
+    if (r0 + i < rows && c0 + threadIdx.x < cols) tile[i][threadIdx.x] = src[static_cast<int64_t>(r0 + i) * cols + c0 + threadIdx.x];
+  __syncthreads();
+  for (int i = threadIdx.y; i < 32; i += blockDim.y)
+    if (c0 + i < cols && r0 + threadIdx.x < rows) dst[static_cast<int64_t>(c0 + i) * rows + r0 + threadIdx.x] = tile[threadIdx.x][i];
+}
+
+// ---- backward of Loss.compute: one CTA per impression
+//      d_logits = g (softmax(s) - onehot(argmax labels)) / B                                   (CrossEntropyLoss, reduction 'mean')
+//      d_I[k]   = g 2 / (B K K) * (S_k - (u_k . S_k) u_k) / |I_k|,  u = I / |I|, S_k = sum_{l != k} u_l   (utils.py:21-27, loss.py:39)
+__global__ void __launch_bounds__(TT) loss_bwd_kernel(const float* __restrict__ interests, const float* __restrict__ logits,
+                                                      const float* __restrict__ labels, const float* __restrict__ grad_out, int64_t B, int C,
+                                                      int K, int D, float* __restrict__ d_interests, float* __restrict__ d_logits) {
+  extern __shared__ __align__(16) float smem[];
+  const int DP = D + 1;
+  float* U = smem;                       // [K][D+1] normalised interests
+  float* Usum = U + K * DP;              // [D]
+  float* nrm = Usum + D;                 // [K]
+  float* dotU = nrm + K;                 // [K]   u_k . sum_l u_l
+  const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+  const int64_t b = blockIdx.x;
+  const float g = grad_out ? grad_out[0] : 1.0f;
+  const float* Ib = interests + b * static_cast<int64_t>(K) * D;
+  for (int k = warp; k < K; k += TT / 32) {
+    float ss = 0.f;
+    for (int d = lane; d < D; d += 32) { const float v = Ib[static_cast<int64_t>(k) * D + d]; ss = fmaf(v, v, ss); }
+    const float n = sqrtf(warp_sum(ss));
+    if (lane == 0) nrm[k] = n;
+    for (int d = lane; d < D; d += 32) U[k * DP + d] = Ib[static_cast<int64_t>(k) * D + d] / n;
+  }
+  __syncthreads();
+  for (int d = tid; d < D; d += TT) {
+    float s = 0.f;
+    for (int k = 0; k < K; ++k) s += U[k * DP + d];
+    Usum[d] = s;
+  }
+  __syncthreads();
+  for (int k = warp; k < K; k += TT / 32) {
+    float s = 0.f;
+    for (int d = lane; d < D; d += 32) s = fmaf(U[k * DP + d], Usum[d], s);
+    s = warp_sum(s);
+    if (lane == 0) dotU[k] = s;
+  }
+  __syncthreads();
+  const float scale = g * 2.0f / (static_cast<float>(B) * K * K);
+  float* dIb = d_interests + b * static_cast<int64_t>(K) * D;
+  for (int i = tid; i < K * D; i += TT) {
+    const int k = i / D, d = i - k * D;
+    const float u = U[k * DP + d];
+    // S_k = Usum - u_k ;  u_k . S_k = u_k . Usum - |u_k|^2 with |u_k|^2 = 1
+    dIb[i] = scale * ((Usum[d] - u) - (dotU[k] - 1.0f) * u) / nrm[k];
+  }
+  if (warp == 0) {
+    const float* lg = logits + b * C;
+    const float* lb = labels + b * C;
+    float best = -INFINITY; int arg = 0;
+    for (int c = 0; c < C; ++c) { const float v = lb[c]; if (v > best) { best = v; arg = c; } }     // argmax, first maximum
+    float mx = -INFINITY;
+    for (int c = lane; c < C; c += 32) mx = fmaxf(mx, lg[c]);
+    mx = warp_max(mx);
+    float se = 0.f;
+    for (int c = lane; c < C; c += 32) se += expf(lg[c] - mx);
+    se = warp_sum(se);
+    for (int c = lane; c < C; c += 32)
+      d_logits[b * C + c] = g * (expf(lg[c] - mx) / se - (c == arg ? 1.0f : 0.0f)) / static_cast<float>(B);
+  }
+}
+
+// ---- backward through the target-aware attention of one impression (model.py:127,200-216): one CTA per impression
+__global__ void __launch_bounds__(TT) target_bwd_kernel(const void* __restrict__ table, int table_dtype, int64_t n_rows,
+                                                        const void* __restrict__ cand_ids, int id_dtype, const float* __restrict__ interests,
+                                                        const float* __restrict__ Z, const float* __restrict__ d_scores,
+                                                        const float* __restrict__ d_interests_in, int C, int K, int D,
+                                                        float* __restrict__ d_interests, float* __restrict__ dZ) {
+  extern __shared__ __align__(16) float smem[];
+  float* Cd = smem;                      // [C][D] candidate vectors
+  float* m = Cd + C * D;                 // [C][K] matching scores
+  float* a = m + C * K;                  // [C][K] attention logits -> softmax weights
+  float* dm = a + C * K;                 // [C][K]
+  float* da = dm + C * K;                // [C][K]
+  const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+  const int64_t b = blockIdx.x;
+  for (int c = 0; c < C; ++c) {
+    const int64_t id = load_id(cand_ids, b * C + c, id_dtype);
+    const bool ok = id >= 0 && id < n_rows;
+    for (int d = tid; d < D; d += TT) Cd[c * D + d] = ok ? table_elem(table, table_dtype, id * D + d) : 0.f;
+  }
+  __syncthreads();
+  const float* Ib = interests + b * static_cast<int64_t>(K) * D;
+  const float* Zb = Z + b * static_cast<int64_t>(K) * D;
+  for (int p = warp; p < C * K; p += TT / 32) {
+    const int c = p / K, k = p - c * K;
+    float sm_ = 0.f, sa_ = 0.f;
+    for (int d = lane; d < D; d += 32) {
+      const float cd = Cd[c * D + d];
+      sm_ = fmaf(cd, Ib[static_cast<int64_t>(k) * D + d], sm_);                       // model.py:127
+      sa_ = fmaf(cd, gelu_erf(Zb[static_cast<int64_t>(k) * D + d]), sa_);             // model.py:212-213
+    }
+    sm_ = warp_sum(sm_); sa_ = warp_sum(sa_);
+    if (lane == 0) { m[p] = sm_; a[p] = sa_; }
+  }
+  __syncthreads();
+  if (tid < C) {
+    const int c = tid;
+    const float ds = d_scores[b * C + c];
+    float mx = -INFINITY;
+    for (int k = 0; k < K; ++k) mx = fmaxf(mx, a[c * K + k]);
+    float se = 0.f;
+    for (int k = 0; k < K; ++k) se += expf(a[c * K + k] - mx);
+    float inner = 0.f;
+    for (int k = 0; k < K; ++k) {
+      const float w = expf(a[c * K + k] - mx) / se;                                   // model.py:213
+      a[c * K + k] = w;
+      inner = fmaf(w, ds * m[c * K + k], inner);
+    }
+    for (int k = 0; k < K; ++k) {
+      const float w = a[c * K + k];
+      dm[c * K + k] = ds * w;                                                         // d score / d m   (model.py:214)
+      da[c * K + k] = w * (ds * m[c * K + k] - inner);                                // softmax backward
+    }
+  }
+  __syncthreads();
+  const float* dIin = d_interests_in ? d_interests_in + b * static_cast<int64_t>(K) * D : nullptr;
+  float* dIb = d_interests + b * static_cast<int64_t>(K) * D;
+  float* dZb = dZ + b * static_cast<int64_t>(K) * D;
+  for (int i = tid; i < K * D; i += TT) {
+    const int k = i / D, d = i - k * D;
+    float gi = dIin ? dIin[i] : 0.f, gg = 0.f;
+    for (int c = 0; c < C; ++c) {
+      const float cd = Cd[c * D + d];
+      gi = fmaf(dm[c * K + k], cd, gi);
+      gg = fmaf(da[c * K + k], cd, gg);
+    }
+    dIb[i] = gi;
+    dZb[i] = gg * gelu_erf_grad(Zb[i]);
+  }
+}
+
+// ---- backward through the poly attention (model.py:159-185): CTAs stride over impressions and keep their share of dcodes in
+//      shared memory; dZ1 = dT (1 - T^2) goes to global memory for the dWp contraction
+__global__ void __launch_bounds__(TT) poly_bwd_kernel(const void* __restrict__ table, int table_dtype, int64_t n_rows,
+                                                      const void* __restrict__ his_ids, int id_dtype, const uint8_t* __restrict__ mask,
+                                                      const float* __restrict__ codes, const float* __restrict__ T,
+                                                      const float* __restrict__ W, const float* __restrict__ dI_a,
+                                                      const float* __restrict__ dI_b, int64_t B, int H, int K, int Dc, int D,
+                                                      float* __restrict__ dZ1, float* __restrict__ dcodes_partial) {
+  extern __shared__ __align__(16) float smem[];
+  constexpr int DK = 64;                 // feature chunk
+  float* codes_s = smem;                 // [K][Dc]
+  float* dcodes_s = codes_s + K * Dc;    // [K][Dc]
+  float* dIc = dcodes_s + K * Dc;        // [K][DK+1]
+  float* Ec = dIc + K * (DK + 1);        // [H][DK+1]
+  float* dw = Ec + H * (DK + 1);         // [K][H]  dw -> dlogits
+  int* ids_s = reinterpret_cast<int*>(dw + K * H);   // [H] table row of each history slot, -1 = zero row
+  const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+  for (int i = tid; i < K * Dc; i += TT) { codes_s[i] = codes[i]; dcodes_s[i] = 0.f; }
+  __syncthreads();
+  const int npairs = K * H;
+  for (int64_t b = blockIdx.x; b < B; b += gridDim.x) {
+    for (int h = tid; h < H; h += TT) {
+      const int64_t id = load_id(his_ids, b * H + h, id_dtype);
+      ids_s[h] = (id >= 0 && id < n_rows) ? static_cast<int>(id) : -1;
+    }
+    for (int i = tid; i < npairs; i += TT) dw[i] = 0.f;
+    __syncthreads();
+    // dw[k,h] = sum_d dI[k,d] E[h,d]                                                   (model.py:182)
+    for (int d0 = 0; d0 < D; d0 += DK) {
+      const int dn = D - d0 < DK ? D - d0 : DK;
+      for (int i = tid; i < K * DK; i += TT) {
+        const int k = i / DK, d = i - k * DK;
+        const int64_t o = (b * K + k) * D + d0 + d;
+        dIc[k * (DK + 1) + d] = d < dn ? dI_a[o] + (dI_b ? dI_b[o] : 0.f) : 0.f;
+      }
+      for (int i = tid; i < H * DK; i += TT) {
+        const int h = i / DK, d = i - h * DK;
+        const int id = ids_s[h];
+        Ec[h * (DK + 1) + d] = (d < dn && id >= 0) ? table_elem(table, table_dtype, static_cast<int64_t>(id) * D + d0 + d) : 0.f;
+      }
+      __syncthreads();
+      for (int p = tid; p < npairs; p += TT) {
+        const int k = p / H, h = p - k * H;
+        const float* x = dIc + k * (DK + 1);
+        const float* y = Ec + h * (DK + 1);
+        float s = 0.f;
+#pragma unroll 8
+        for (int d = 0; d < DK; ++d) s = fmaf(x[d], y[d], s);
+        dw[p] += s;
+      }
+      __syncthreads();
+    }
+    // softmax backward over the history; masked slots were overwritten by a constant (model.py:180): no gradient
+    for (int k = warp; k < K; k += TT / 32) {
+      const float* wk = W + (b * K + k) * H;
+      float inner = 0.f;
+      for (int h = lane; h < H; h += 32) inner = fmaf(wk[h], dw[k * H + h], inner);
+      inner = warp_sum(inner);
+      for (int h = lane; h < H; h += 32) {
+        const float gl = wk[h] * (dw[k * H + h] - inner);
+        dw[k * H + h] = mask[b * H + h] ? gl : 0.f;
+      }
+    }
+    __syncthreads();
+    // dT = dlogits^T codes, dZ1 = dT (1 - T^2)                                          (model.py:171,174)
+    for (int i = tid; i < H * Dc; i += TT) {
+      const int h = i / Dc, dc = i - h * Dc;
+      float s = 0.f;
+      for (int k = 0; k < K; ++k) s = fmaf(dw[k * H + h], codes_s[k * Dc + dc], s);
+      const float t = T[(b * H + h) * Dc + dc];
+      dZ1[(b * H + h) * Dc + dc] = s * (1.0f - t * t);
+    }
+    // dcodes += dlogits T                                                              (model.py:174)
+    for (int i = tid; i < K * Dc; i += TT) {
+      const int k = i / Dc, dc = i - k * Dc;
+      float s = 0.f;
+      for (int h = 0; h < H; ++h) s = fmaf(dw[k * H + h], T[(b * H + h) * Dc + dc], s);
+      dcodes_s[i] += s;
+    }
+    __syncthreads();
+  }
+  for (int i = tid; i < K * Dc; i += TT) dcodes_partial[static_cast<int64_t>(blockIdx.x) * K * Dc + i] = dcodes_s[i];
+}
+
+// ---- out_partial[s][m][n] = sum over the rows r of split s of A[r][m] * Bm[r][n]   (A^T B over a row range);  Bm rows are
+//      dense fp32 or gathered from the table.  64 x 64 output tile per CTA, 4 x 4 per thread, 16 rows per step.
+__global__ void __launch_bounds__(TT) atb_kernel(const float* __restrict__ A, int lda, int M, const float* __restrict__ Bd,
+                                                 const void* __restrict__ table, int table_dtype, int64_t n_rows, const void* __restrict__ ids,
+                                                 int id_dtype, int ldb, int N, int64_t R, int64_t rows_per_split,
+                                                 float* __restrict__ out_partial) {
+  __shared__ float As[16][64 + 4];
+  __shared__ float Bs[16][64 + 4];
+  __shared__ int64_t rid[16];
+  const int tid = threadIdx.x, tx = tid & 15, ty = tid >> 4;
+  const int n0 = blockIdx.x * 64, m0 = blockIdx.y * 64;
+  const int64_t r_begin = static_cast<int64_t>(blockIdx.z) * rows_per_split;
+  const int64_t r_end = r_begin + rows_per_split < R ? r_begin + rows_per_split : R;
+  float acc[4][4];
+#pragma unroll
+  for (int i = 0; i < 4; ++i)
+#pragma unroll
+    for (int j = 0; j < 4; ++j) acc[i][j] = 0.f;
+  for (int64_t r0 = r_begin; r0 < r_end; r0 += 16) {
+    if (ids && tid < 16) {
+      int64_t id = -1;
+      if (r0 + tid < r_end) { id = load_id(ids, r0 + tid, id_dtype); if (id < 0 || id >= n_rows) id = -1; }
+      rid[tid] = id;
+    }
+    __syncthreads();
+#pragma unroll
+    for (int q = 0; q < 4; ++q) {
+      const int e = tid + q * TT, rr = e >> 6, cc = e & 63;
+      const int64_t r = r0 + rr;
+      const bool rok = r < r_end;
+      As[rr][cc] = (rok && m0 + cc < M) ? A[r * lda + m0 + cc] : 0.f;
+      float bv = 0.f;
+      if (rok && n0 + cc < N) {
+        if (ids) { const int64_t id = rid[rr]; bv = id >= 0 ? table_elem(table, table_dtype, id * ldb + n0 + cc) : 0.f; }
+        else bv = Bd[r * ldb + n0 + cc];
+      }
+      Bs[rr][cc] = bv;
+    }
+    __syncthreads();
+#pragma unroll
+    for (int rr = 0; rr < 16; ++rr) {
+      float av[4], bv[4];
+#pragma unroll
+      for (int i = 0; i < 4; ++i) av[i] = As[rr][ty * 4 + i];
+#pragma unroll
+      for (int j = 0; j < 4; ++j) bv[j] = Bs[rr][tx * 4 + j];
+#pragma unroll
+      for (int i = 0; i < 4; ++i)
+#pragma unroll
+        for (int j = 0; j < 4; ++j) acc[i][j] = fmaf(av[i], bv[j], acc[i][j]);
+    }
+    __syncthreads();
+  }
+  float* outp = out_partial + static_cast<int64_t>(blockIdx.z) * M * N;
+#pragma unroll
+  for (int i = 0; i < 4; ++i)
+#pragma unroll
+    for (int j = 0; j < 4; ++j) {
+      const int mm = m0 + ty * 4 + i, nn = n0 + tx * 4 + j;
+      if (mm < M && nn < N) outp[static_cast<int64_t>(mm) * N + nn] = acc[i][j];
+    }
+}
+
+// out[i] = sum_s partial[s][i] in split order
+__global__ void sum_partials_kernel(const float* __restrict__ partial, int n_splits, int64_t n, float* __restrict__ out) {
+  for (int64_t i = static_cast<int64_t>(blockIdx.x) * blockDim.x + threadIdx.x; i < n; i += static_cast<int64_t>(gridDim.x) * blockDim.x) {
+    float s = 0.f;
+    for (int p = 0; p < n_splits; ++p) s += partial[static_cast<int64_t>(p) * n + i];
+    out[i] = s;
+  }
+}
+
+int atb_splits(int64_t R, int tiles) {
+  int s = (8 * sm_count() + tiles - 1) / tiles;
+  if (s < 1) s = 1;
+  const int64_t max_s = (R + 255) / 256;
+  if (s > max_s) s = static_cast<int>(max_s);
+  if (s < 1) s = 1;
+  return s;
+}
+
+struct TrainWs {
+  size_t g, di, di2, dz, dz1, wt_t, part_wp, part_wt, part_codes, total;
+  int s_wp, s_wt, g_poly;
+};
+TrainWs train_ws(int64_t B, int64_t H, int64_t K, int64_t Dc, int64_t D) {
+  TrainWs w{};
+  size_t off = 0;
+  auto take = [&](size_t bytes) { size_t o = off; off += align_up(bytes, 256); return o; };
+  const size_t f = sizeof(float);
+  w.g = take(f * B * K * D);           // gelu(Z) in the forward; dI (Wt path) in the backward
+  w.di = take(f * B * K * D);
+  w.dz = take(f * B * K * D);
+  w.dz1 = take(f * B * H * Dc);
+  w.wt_t = take(f * D * D);
+  w.s_wp = atb_splits(B * H, static_cast<int>(((Dc + 63) / 64) * ((D + 63) / 64)));
+  w.s_wt = atb_splits(B * K, static_cast<int>(((D + 63) / 64) * ((D + 63) / 64)));
+  w.g_poly = static_cast<int>(B < 4 * sm_count() ? B : 4 * sm_count());
+  w.part_wp = take(f * w.s_wp * Dc * D);
+  w.part_wt = take(f * w.s_wt * D * D);
+  w.part_codes = take(f * w.g_poly * K * Dc);
+  w.di2 = w.g;
+  w.total = off;
+  return w;
+}
+
+}  // namespace
+}  // namespace miner
+
+using namespace miner;
+
+extern "C" size_t miner_train_workspace_bytes(int64_t B, int64_t H, int64_t K, int64_t Dc, int64_t D) {
+  if (B <= 0) return 256;
+  return train_ws(B, H, K, Dc, D).total;
+}
+
+extern "C" int miner_train_fwd(const void* table, int64_t n_rows, int table_dtype, const void* his_ids, const uint8_t* his_mask,
+                               const void* cand_ids, int id_dtype, const float* w_proj, const float* codes, const float* w_target,
+                               int64_t B, int64_t H, int64_t C, int64_t K, int64_t Dc, int64_t D, float* out_interests, float* out_scores,
+                               float* save_t, float* save_w, float* save_z, void* workspace, size_t workspace_bytes, void* stream) {
+  MINER_CHECK_ARG(B >= 0 && H > 0 && C > 0 && K > 0 && Dc > 0 && D > 0 && n_rows > 0, "train_fwd: bad sizes");
+  if (B == 0) return MINER_OK;
+  MINER_CHECK_ARG(table && his_ids && his_mask && cand_ids && w_proj && codes && w_target && out_interests && out_scores && save_t &&
+                      save_w && save_z,
+                  "train_fwd: null pointer");
+  MINER_CHECK_ARG(table_dtype == MINER_F32 || table_dtype == MINER_BF16, "train_fwd: table dtype must be fp32 or bf16");
+  MINER_CHECK_ARG(id_dtype == MINER_I32 || id_dtype == MINER_I64, "train_fwd: id dtype must be int32 or int64");
+  const TrainWs w = train_ws(B, H, K, Dc, D);
+  if (!workspace || workspace_bytes < w.total) {
+    set_error("train_fwd: workspace too small (%zu bytes needed)", w.total);
+    return MINER_ERR_WORKSPACE;
+  }
+  auto st = static_cast<cudaStream_t>(stream);
+  float* G = reinterpret_cast<float*>(static_cast<char*>(workspace) + w.g);
+  int rc = launch_sgemm_nt(table, table_dtype, his_ids, id_dtype, n_rows, w_proj, save_t, B * H, Dc, D, EPI_TANH, st);      // model.py:171
+  if (rc) return rc;
+  rc = launch_poly_softmax_wsum(save_t, codes, his_mask, nullptr, nullptr, table, table_dtype, his_ids, id_dtype, n_rows, B, H, K, Dc, D,
+                                out_interests, save_w, nullptr, st);                                                          // model.py:174-182
+  if (rc) return rc;
+  rc = launch_sgemm_nt(out_interests, MINER_F32, nullptr, id_dtype, 0, w_target, save_z, B * K, D, D, EPI_NONE, st);         // model.py:212
+  if (rc) return rc;
+  const int64_t n = B * K * D;
+  gelu_kernel<<<static_cast<int>((n + 1023) / 1024 < 8 * sm_count() ? (n + 1023) / 1024 : 8 * sm_count()), 256, 0, st>>>(save_z, G, n);
+  MINER_LAUNCH_OK("gelu");
+  return launch_target_score(out_interests, G, nullptr, nullptr, table, table_dtype, cand_ids, id_dtype, n_rows, nullptr, B, C, K, D,
+                             MINER_SCORE_WEIGHTED, out_scores, st);                                                           // model.py:127,213-214
+}
+
+extern "C" int miner_loss_bwd(const float* interests, const float* logits, const float* labels, const float* grad_out, int64_t B,
+                              int64_t C, int64_t K, int64_t D, float* d_interests, float* d_logits, void* stream) {
+  MINER_CHECK_ARG(B > 0 && C > 0 && K > 0 && D > 0, "loss_bwd: bad sizes");
+  MINER_CHECK_ARG(interests && logits && labels && d_interests && d_logits, "loss_bwd: null pointer");
+  const size_t smem = sizeof(float) * (static_cast<size_t>(K) * (D + 1) + D + 2 * K);
+  if (smem > 220 * 1024) {
+    set_error("loss_bwd: K=%lld D=%lld needs %zu bytes of shared memory", (long long)K, (long long)D, smem);
+    return MINER_ERR_UNSUPPORTED;
+  }
+  MINER_CUDA_OK(cudaFuncSetAttribute(loss_bwd_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, static_cast<int>(smem)));
+  loss_bwd_kernel<<<static_cast<unsigned>(B), TT, smem, static_cast<cudaStream_t>(stream)>>>(interests, logits, labels, grad_out, B, (int)C,
+                                                                                             (int)K, (int)D, d_interests, d_logits);
+  MINER_LAUNCH_OK("loss_bwd");
+  return MINER_OK;
+}
+
+extern "C" int miner_train_bwd(const void* table, int64_t n_rows, int table_dtype, const void* his_ids, const uint8_t* his_mask,
+                               const void* cand_ids, int id_dtype, const float* w_proj, const float* codes, const float* w_target,
+                               const float* save_t, const float* save_w, const float* interests, const float* save_z,
+                               const float* d_scores, const float* d_interests, int64_t B, int64_t H, int64_t C, int64_t K, int64_t Dc,
+                               int64_t D, float* grad_w_proj, float* grad_codes, float* grad_w_target, void* workspace,
+                               size_t workspace_bytes, void* stream) {
+  (void)w_proj;
+  MINER_CHECK_ARG(B > 0 && H > 0 && C > 0 && K > 0 && Dc > 0 && D > 0 && n_rows > 0, "train_bwd: bad sizes");
+  MINER_CHECK_ARG(table && his_ids && his_mask && cand_ids && codes && w_target && save_t && save_w && interests && save_z && d_scores &&
+                      grad_w_proj && grad_codes && grad_w_target,
+                  "train_bwd: null pointer");
+  const TrainWs w = train_ws(B, H, K, Dc, D);
+  if (!workspace || workspace_bytes < w.total) {
+    set_error("train_bwd: workspace too small (%zu bytes needed)", w.total);
+    return MINER_ERR_WORKSPACE;
+  }
+  auto st = static_cast<cudaStream_t>(stream);
+  char* ws = static_cast<char*>(workspace);
+  float* dI = reinterpret_cast<float*>(ws + w.di);
+  float* dI2 = reinterpret_cast<float*>(ws + w.di2);
+  float* dZ = reinterpret_cast<float*>(ws + w.dz);
+  float* dZ1 = reinterpret_cast<float*>(ws + w.dz1);
+  float* WtT = reinterpret_cast<float*>(ws + w.wt_t);
+  float* pWp = reinterpret_cast<float*>(ws + w.part_wp);
+  float* pWt = reinterpret_cast<float*>(ws + w.part_wt);
+  float* pCodes = reinterpret_cast<float*>(ws + w.part_codes);
+  // 1. target-aware attention: dI (direct paths), dZ
+  {
+    const size_t smem = sizeof(float) * (static_cast<size_t>(C) * D + 4 * C * K);
+    if (smem > 200 * 1024 || C > TT) {
+      set_error("train_bwd: C=%lld D=%lld needs %zu bytes of shared memory", (long long)C, (long long)D, smem);
+      return MINER_ERR_UNSUPPORTED;
+    }
+    MINER_CUDA_OK(cudaFuncSetAttribute(target_bwd_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, static_cast<int>(smem)));
+    target_bwd_kernel<<<static_cast<unsigned>(B), TT, smem, st>>>(table, table_dtype, n_rows, cand_ids, id_dtype, interests, save_z, d_scores,
+                                                                 d_interests, (int)C, (int)K, (int)D, dI, dZ);
+    MINER_LAUNCH_OK("target_bwd");
+  }
+  // 2. Z = I Wt^T:  dI2 = dZ Wt  (as dZ (Wt^T)^T with the NT GEMM),  dWt = dZ^T I
+  {
+    dim3 tb(32, 8), tg(static_cast<unsigned>((D + 31) / 32), static_cast<unsigned>((D + 31) / 32));
+    transpose_kernel<<<tg, tb, 0, st>>>(w_target, WtT, (int)D, (int)D);
+    MINER_LAUNCH_OK("transpose");
+    int rc = launch_sgemm_nt(dZ, MINER_F32, nullptr, id_dtype, 0, WtT, dI2, B * K, D, D, EPI_NONE, st);
+    if (rc) return rc;
+    const int64_t R = B * K;
+    const int64_t rps = ((R + w.s_wt - 1) / w.s_wt + 15) / 16 * 16;
+    dim3 grid(static_cast<unsigned>((D + 63) / 64), static_cast<unsigned>((D + 63) / 64), static_cast<unsigned>(w.s_wt));
+    atb_kernel<<<grid, TT, 0, st>>>(dZ, (int)D, (int)D, interests, nullptr, MINER_F32, 0, nullptr, id_dtype, (int)D, (int)D, R, rps, pWt);
+    MINER_LAUNCH_OK("atb(dWt)");
+    sum_partials_kernel<<<static_cast<int>((D * D + 255) / 256), 256, 0, st>>>(pWt, w.s_wt, D * D, grad_w_target);
+    MINER_LAUNCH_OK("sum_partials(dWt)");
+  }
+  // 3. poly attention: dZ1, dcodes
+  {
+    const size_t smem = sizeof(float) * (2 * static_cast<size_t>(K) * Dc + K * 65 + H * 65 + K * H) + sizeof(int) * H;
+    if (smem > 220 * 1024) {
+      set_error("train_bwd: H=%lld K=%lld Dc=%lld need %zu bytes of shared memory", (long long)H, (long long)K, (long long)Dc, smem);
+      return MINER_ERR_UNSUPPORTED;
+    }
+    MINER_CUDA_OK(cudaFuncSetAttribute(poly_bwd_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, static_cast<int>(smem)));
+    poly_bwd_kernel<<<w.g_poly, TT, smem, st>>>(table, table_dtype, n_rows, his_ids, id_dtype, his_mask, codes, save_t, save_w, dI, dI2, B,
+                                                (int)H, (int)K, (int)Dc, (int)D, dZ1, pCodes);
+    MINER_LAUNCH_OK("poly_bwd");
+    sum_partials_kernel<<<static_cast<int>((K * Dc + 255) / 256), 256, 0, st>>>(pCodes, w.g_poly, K * Dc, grad_codes);
+    MINER_LAUNCH_OK("sum_partials(dcodes)");
+  }
+  // 4. Z1 = E Wp^T:  dWp = dZ1^T E  (E gathered from the table)
+  {
+    const int64_t R = B * H;
+    const int64_t rps = ((R + w.s_wp - 1) / w.s_wp + 15) / 16 * 16;
+    dim3 grid(static_cast<unsigned>((D + 63) / 64), static_cast<unsigned>((Dc + 63) / 64), static_cast<unsigned>(w.s_wp));
+    atb_kernel<<<grid, TT, 0, st>>>(dZ1, (int)Dc, (int)Dc, nullptr, table, table_dtype, n_rows, his_ids, id_dtype, (int)D, (int)D, R, rps, pWp);
+    MINER_LAUNCH_OK("atb(dWp)");
+    sum_partials_kernel<<<static_cast<int>((Dc * D + 255) / 256), 256, 0, st>>>(pWp, w.s_wp, Dc * D, grad_w_proj);
+    MINER_LAUNCH_OK("sum_partials(dWp)");
+  }
+  return MINER_OK;
+}

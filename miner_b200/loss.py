@@ -5,7 +5,22 @@ import torch
 from torch import Tensor
 
 from . import ops
-from .model import _attach
+
+
+class _LossFn(torch.autograd.Function):
+    """Loss.compute with its backward kernel (``miner_loss_fwd`` / ``miner_loss_bwd``)."""
+
+    @staticmethod
+    def forward(ctx, poly_attn: Tensor, logits: Tensor, labels: Tensor):
+        out = ops.loss_forward(poly_attn, logits, labels, eval_mode=False)
+        ctx.save_for_backward(poly_attn, logits, labels)
+        return out[0].clone()
+
+    @staticmethod
+    def backward(ctx, grad_out):
+        poly_attn, logits, labels = ctx.saved_tensors
+        d_i, d_l = ops.loss_backward(poly_attn, logits, labels, grad_out)
+        return d_i, d_l, None
 
 
 class Loss:
@@ -24,8 +39,10 @@ class Loss:
 
         poly_attn ``(B, K, D)``, logits ``(B, npratio+1)``, labels one-hot ``(B, npratio+1)``.  Returns a 0-dim tensor.
         """
-        out = ops.loss_forward(poly_attn, logits, labels.to(torch.float32), eval_mode=False)
-        return _attach(out[0], poly_attn, logits)
+        labels = labels.to(torch.float32)
+        if torch.is_grad_enabled() and (poly_attn.requires_grad or logits.requires_grad):
+            return _LossFn.apply(poly_attn, logits, labels)
+        return ops.loss_forward(poly_attn, logits, labels, eval_mode=False)[0]
 
     @staticmethod
     def compute_eval_loss(poly_attn: Tensor, logits: Tensor, labels: Tensor) -> float:

@@ -17,8 +17,9 @@ State-dict keys match the reference (``poly_attn.linear.weight``, ``poly_attn.co
 ``target_aware_attn.linear.weight``, ``category_embedding.weight``), so reference checkpoints load.
 
 All arithmetic runs in the sm_100a kernels of libminer_b200.so through ``miner_b200.ops``; there is no
-PyTorch fallback -- CPU tensors raise.  The backward of the train variant is SURVEY.md section 8 row f1 and is not
-built yet: a forward under autograd works, calling ``.backward()`` through it raises NotImplementedError.
+PyTorch fallback -- CPU tensors raise.  The train variant has real backward kernels for the
+table-based forward with ``score_type='weighted'`` and no category bias (``miner_train_fwd`` / ``miner_train_bwd``); every other
+forward under autograd still works, and calling ``.backward()`` through it raises NotImplementedError.
 """
 from __future__ import annotations
 
@@ -41,7 +42,23 @@ class _NoBackward(torch.autograd.Function):
 
     @staticmethod
     def backward(ctx, *grads):
-        raise NotImplementedError('miner_b200: the backward kernels of the train variant (SURVEY.md section 8 f1) are not built yet')
+        raise NotImplementedError('miner_b200: backward kernels exist for the table-based forward with score_type="weighted" and no '
+                                  'category bias (SURVEY.md section 8 f1); this path has none')
+
+
+class _MinerTrainFn(torch.autograd.Function):
+    """Train variant of the table-based forward: ``miner_train_fwd`` / ``miner_train_bwd``."""
+
+    @staticmethod
+    def forward(ctx, w_proj: Tensor, codes: Tensor, w_target: Tensor, table: Tensor, his_ids: Tensor, his_mask: Tensor, cand_ids: Tensor):
+        interests, scores, saved = ops.train_forward(table, his_ids, his_mask, cand_ids, w_proj, codes, w_target)
+        ctx.saved = saved
+        return interests, scores
+
+    @staticmethod
+    def backward(ctx, d_interests, d_scores):
+        gwp, gc, gwt = ops.train_backward(ctx.saved, d_scores, d_interests)
+        return gwp, gc, gwt, None, None, None, None
 
 
 def _attach(out: Tensor, *params: Tensor) -> Tensor:
@@ -209,6 +226,11 @@ class Miner(nn.Module):
             w = self._weights(with_bf16=(math == L.MATH_TENSOR))
             cand_ids = title.reshape(batch_size, num_candidates, -1)[..., 0]
             his_ids = his_title.reshape(batch_size, his_length, -1)[..., 0]
+            if (torch.is_grad_enabled() and self.score_type == 'weighted' and not self.use_category_bias
+                    and any(p.requires_grad for p in self.parameters())):
+                # train variant (reference trainer.py:246-261): forward that keeps its intermediates + real backward kernels
+                return _MinerTrainFn.apply(self.poly_attn.linear.weight, self.poly_attn.context_codes,
+                                           self.target_aware_attn.linear.weight, table, his_ids, his_mask, cand_ids)
             if self.table_level and table.dtype == torch.bfloat16 and ops.score_table_supported(his_length, self.poly_attn.context_codes.shape[0],
                                                                                                table.shape[1]):
                 interests, scores = ops.score_table(self.table_projections(), his_ids, his_mask, cand_ids, self.score_type,

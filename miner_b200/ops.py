@@ -453,3 +453,76 @@ def loss_forward(interests: torch.Tensor, logits: torch.Tensor, labels: torch.Te
         L.check(lib.miner_loss_fwd(_ptr(I), _ptr(lg), _ptr(lb), B, Cn, K, D, 1 if eval_mode else 0, _ptr(out), _ptr(ws), ws_bytes,
                                    _stream()))
     return out
+
+
+# ------------------------------------------------------------------------------------------------ train variant (section 8 f1)
+class TrainSaved:
+    """Intermediates of :func:`train_forward` that :func:`train_backward` reads."""
+
+    def __init__(self, **kw):
+        self.__dict__.update(kw)
+
+
+def train_forward(table: torch.Tensor, his_ids: torch.Tensor, his_mask: torch.Tensor, cand_ids: torch.Tensor,
+                  w_proj: torch.Tensor, codes: torch.Tensor, w_target: torch.Tensor):
+    """Miner.forward (reference model.py:61-138, 'weighted', no category bias) keeping what the backward needs.
+
+    Dense layout, ``cand_ids`` (B,C).  Returns ``(interests (B,K,D), scores (B,C), saved)``.
+    """
+    dev = _need_cuda(table, his_ids, his_mask, cand_ids, w_proj, codes, w_target)
+    lib = L.load()
+    table = table.detach().contiguous()
+    B, H = his_ids.shape
+    Cn = cand_ids.shape[1]
+    D = table.shape[1]
+    K, Dc = codes.shape
+    hid, it = _ids(his_ids)
+    cid, it2 = _ids(cand_ids)
+    if it != it2:
+        cid, it2 = _ids(cand_ids.to(his_ids.dtype))
+    m = _mask_u8(his_mask)
+    wp, cd, wt = _f32(w_proj), _f32(codes), _f32(w_target)
+    f = dict(dtype=torch.float32, device=dev)
+    interests, scores = torch.empty(B, K, D, **f), torch.empty(B, Cn, **f)
+    t, w, z = torch.empty(B * H, Dc, **f), torch.empty(B, K, H, **f), torch.empty(B * K, D, **f)
+    ws_bytes = lib.miner_train_workspace_bytes(B, H, K, Dc, D)
+    ws = torch.empty(max(ws_bytes, 1), dtype=torch.uint8, device=dev)
+    with torch.cuda.device(dev):
+        L.check(lib.miner_train_fwd(_ptr(table), table.shape[0], _table_dtype(table), _ptr(hid), _ptr(m), _ptr(cid), it, _ptr(wp), _ptr(cd),
+                                    _ptr(wt), B, H, Cn, K, Dc, D, _ptr(interests), _ptr(scores), _ptr(t), _ptr(w), _ptr(z), _ptr(ws),
+                                    ws.numel(), _stream()))
+    saved = TrainSaved(table=table, his_ids=hid, his_mask=m, cand_ids=cid, id_dtype=it, w_proj=wp, codes=cd, w_target=wt, t=t, w=w, z=z,
+                       interests=interests, ws=ws, dims=(B, H, Cn, K, Dc, D))
+    return interests, scores, saved
+
+
+def train_backward(saved: TrainSaved, d_scores: Optional[torch.Tensor], d_interests: Optional[torch.Tensor]):
+    """Gradients of the three weight matrices: ``(grad_w_proj (Dc,D), grad_codes (K,Dc), grad_w_target (D,D))``."""
+    lib = L.load()
+    B, H, Cn, K, Dc, D = saved.dims
+    dev = saved.table.device
+    f = dict(dtype=torch.float32, device=dev)
+    ds = _f32(d_scores) if d_scores is not None else torch.zeros(B, Cn, **f)
+    di = _f32(d_interests) if d_interests is not None else None
+    gwp, gc, gwt = torch.empty(Dc, D, **f), torch.empty(K, Dc, **f), torch.empty(D, D, **f)
+    with torch.cuda.device(dev):
+        L.check(lib.miner_train_bwd(_ptr(saved.table), saved.table.shape[0], _table_dtype(saved.table), _ptr(saved.his_ids),
+                                    _ptr(saved.his_mask), _ptr(saved.cand_ids), saved.id_dtype, _ptr(saved.w_proj), _ptr(saved.codes),
+                                    _ptr(saved.w_target), _ptr(saved.t), _ptr(saved.w), _ptr(saved.interests), _ptr(saved.z), _ptr(ds),
+                                    _ptr(di), B, H, Cn, K, Dc, D, _ptr(gwp), _ptr(gc), _ptr(gwt), _ptr(saved.ws), saved.ws.numel(), _stream()))
+    return gwp, gc, gwt
+
+
+def loss_backward(interests: torch.Tensor, logits: torch.Tensor, labels: torch.Tensor, grad_out: Optional[torch.Tensor] = None):
+    """Backward of Loss.compute (reference loss.py:27-44): ``(d_interests (B,K,D), d_logits (B,C))``."""
+    dev = _need_cuda(interests, logits, labels, grad_out)
+    lib = L.load()
+    B, K, D = interests.shape
+    Cn = logits.shape[1]
+    I, lg, lb = _f32(interests), _f32(logits), _f32(labels)
+    go = _f32(grad_out).reshape(1) if grad_out is not None else None
+    di = torch.empty(B, K, D, dtype=torch.float32, device=dev)
+    dl = torch.empty(B, Cn, dtype=torch.float32, device=dev)
+    with torch.cuda.device(dev):
+        L.check(lib.miner_loss_bwd(_ptr(I), _ptr(lg), _ptr(lb), _ptr(go), B, Cn, K, D, _ptr(di), _ptr(dl), _stream()))
+    return di, dl
