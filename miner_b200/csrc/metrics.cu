@@ -31,7 +31,8 @@ __device__ __forceinline__ float transform_score(float s, int transform, float m
   return s;
 }
 
-__global__ void __launch_bounds__(MT) rank_metrics_kernel(const float* __restrict__ scores, const int8_t* __restrict__ labels,
+template <int NK>
+__global__ void __launch_bounds__(MT, 2) rank_metrics_kernel(const float* __restrict__ scores, const int8_t* __restrict__ labels,
                                                           const int64_t* __restrict__ offsets, int64_t B, int transform,
                                                           MetricKs ks, double* __restrict__ block_partials,
                                                           double* __restrict__ per_impression) {
@@ -42,12 +43,12 @@ __global__ void __launch_bounds__(MT) rank_metrics_kernel(const float* __restric
   for (int i = threadIdx.x; i < LOG2_TAB; i += MT) log2_tab[i] = i > 0 ? log2(static_cast<double>(i)) : 0.0;
   __syncthreads();
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-  const int M = 2 + 2 * ks.n_k;
+  constexpr int M = 2 + 2 * NK;
   float* ps = p_s[warp];
   int8_t* ys = y_s[warp];
-  double acc_sum[MAXM], acc_cnt[MAXM];
+  double acc_sum[M], acc_cnt[M];
 #pragma unroll
-  for (int m = 0; m < MAXM; ++m) acc_sum[m] = 0.0, acc_cnt[m] = 0.0;
+  for (int m = 0; m < M; ++m) acc_sum[m] = 0.0, acc_cnt[m] = 0.0;
 
   const int64_t warps_total = static_cast<int64_t>(gridDim.x) * (MT / 32);
   for (int64_t b = static_cast<int64_t>(blockIdx.x) * (MT / 32) + warp; b < B; b += warps_total) {
@@ -72,10 +73,13 @@ __global__ void __launch_bounds__(MT) rank_metrics_kernel(const float* __restric
       }
     }
     __syncwarp();
-    double auc_wins = 0.0, rr = 0.0, n_pos = 0.0, n_neg = 0.0;
-    double dcg[MAXK], idcg[MAXK], hit[MAXK];
+    // integer tallies are reduced exactly with redux.sync; only rr / dcg / idcg need fp64 sums
+    int wins2 = 0, n_pos = 0, n_neg = 0, sum_y = 0;                    // wins2 = 2 * (#neg below + 0.5 #neg tied), summed over positives
+    double rr = 0.0;
+    double dcg[NK > 0 ? NK : 1], idcg[NK > 0 ? NK : 1];
+    unsigned hit = 0;                                                   // bit q: a positive inside the top ks[q]
 #pragma unroll
-    for (int q = 0; q < MAXK; ++q) dcg[q] = idcg[q] = hit[q] = 0.0;
+    for (int q = 0; q < NK; ++q) dcg[q] = idcg[q] = 0.0;
     for (int i = lane; i < n; i += 32) {
       const float pi = staged ? ps[i] : transform_score(sb[i], transform, mx, sum);
       const int yi = staged ? ys[i] : yb[i];
@@ -96,11 +100,12 @@ __global__ void __launch_bounds__(MT) rank_metrics_kernel(const float* __restric
       const int rank_np = gt + eq_after;
       const int rank_py = gt + eq_before;
       const int rank_ideal = y_gt + y_eq_before;
+      sum_y += yi;
       if (yi > 0) {
-        n_pos += 1.0;
-        auc_wins += static_cast<double>(neg_lt) + 0.5 * static_cast<double>(neg_eq);
+        n_pos += 1;
+        wins2 += 2 * neg_lt + neg_eq;
       } else {
-        n_neg += 1.0;
+        n_neg += 1;
       }
       if (yi != 0) {                                                      // a zero label adds exactly 0 to rr, dcg and idcg
         // 2 ** y_true - 1 (evaluation.py:210); small non-negative labels are exact powers of two
@@ -109,33 +114,29 @@ __global__ void __launch_bounds__(MT) rank_metrics_kernel(const float* __restric
         const double l_np = rank_np + 2 < LOG2_TAB ? log2_tab[rank_np + 2] : log2(static_cast<double>(rank_np + 2));
         const double l_id = rank_ideal + 2 < LOG2_TAB ? log2_tab[rank_ideal + 2] : log2(static_cast<double>(rank_ideal + 2));
 #pragma unroll
-        for (int q = 0; q < MAXK; ++q) {
-          if (q < ks.n_k) {
-            const int kk = ks.k[q] < n ? ks.k[q] : n;                      // k = min(len, k), evaluation.py:207
-            if (rank_np < kk) dcg[q] += gain / l_np;
-            if (rank_ideal < kk) idcg[q] += gain / l_id;
-            if (rank_py < ks.k[q] && yi > 0) hit[q] = 1.0;                 // evaluation.py:247-249
-          }
+        for (int q = 0; q < NK; ++q) {
+          const int kk = ks.k[q] < n ? ks.k[q] : n;                      // k = min(len, k), evaluation.py:207
+          if (rank_np < kk) dcg[q] += gain / l_np;
+          if (rank_ideal < kk) idcg[q] += gain / l_id;
+          if (rank_py < ks.k[q] && yi > 0) hit |= 1u << q;               // evaluation.py:247-249
         }
       }
     }
-    auc_wins = warp_sum(auc_wins); rr = warp_sum(rr); n_pos = warp_sum(n_pos); n_neg = warp_sum(n_neg);
-    double sum_y = 0.0;
-    for (int i = lane; i < n; i += 32) sum_y += static_cast<double>(staged ? ys[i] : yb[i]);
-    sum_y = warp_sum(sum_y);
-    double vals[MAXM];
-    vals[0] = (n_pos > 0.0 && n_neg > 0.0) ? auc_wins / (n_pos * n_neg) : NAN;   // one class: sklearn raises -> NaN here
-    vals[1] = rr / sum_y;                                                          // 0/0 -> NaN (no positives)
+    wins2 = __reduce_add_sync(0xffffffffu, wins2);
+    n_pos = __reduce_add_sync(0xffffffffu, n_pos);
+    n_neg = __reduce_add_sync(0xffffffffu, n_neg);
+    sum_y = __reduce_add_sync(0xffffffffu, sum_y);
+    hit = __reduce_or_sync(0xffffffffu, hit);
+    rr = warp_sum(rr);
+    double vals[M];
+    vals[0] = (n_pos > 0 && n_neg > 0) ? (0.5 * static_cast<double>(wins2)) / (static_cast<double>(n_pos) * static_cast<double>(n_neg))
+                                       : NAN;                             // one class: sklearn raises -> NaN here
+    vals[1] = rr / static_cast<double>(sum_y);                            // 0/0 -> NaN (no positives)
 #pragma unroll
-    for (int q = 0; q < MAXK; ++q) {
-      if (q < ks.n_k) {
-        const double d = warp_sum(dcg[q]), id = warp_sum(idcg[q]);
-        double h = hit[q];
-#pragma unroll
-        for (int o = 16; o > 0; o >>= 1) h = fmax(h, __shfl_xor_sync(0xffffffffu, h, o));
-        vals[2 + q] = d / id;                                                      // evaluation.py:231
-        vals[2 + ks.n_k + q] = h;
-      }
+    for (int q = 0; q < NK; ++q) {
+      const double d = warp_sum(dcg[q]), id = warp_sum(idcg[q]);
+      vals[2 + q] = d / id;                                               // evaluation.py:231
+      vals[2 + NK + q] = (hit >> q) & 1u ? 1.0 : 0.0;
     }
     if (lane == 0) {
       for (int m = 0; m < M; ++m) {
@@ -197,7 +198,13 @@ extern "C" int miner_rank_metrics(const float* scores, const int8_t* labels, con
   mk.n_k = n_k;
   for (int i = 0; i < MAXK; ++i) mk.k[i] = i < n_k ? ks[i] : 0;
   auto st = static_cast<cudaStream_t>(stream);
-  rank_metrics_kernel<<<grid, MT, 0, st>>>(scores, labels, offsets, B, transform, mk, static_cast<double*>(workspace), out_per_impression);
+  double* parts = static_cast<double*>(workspace);
+#define MINER_RM_CASE(NKV) case NKV: rank_metrics_kernel<NKV><<<grid, MT, 0, st>>>(scores, labels, offsets, B, transform, mk, parts, out_per_impression); break;
+  switch (n_k) {       // the cut-off count is a template parameter: fixed-size register arrays, no predicated fp64 reductions
+    MINER_RM_CASE(0) MINER_RM_CASE(1) MINER_RM_CASE(2) MINER_RM_CASE(3) MINER_RM_CASE(4)
+    MINER_RM_CASE(5) MINER_RM_CASE(6) MINER_RM_CASE(7) MINER_RM_CASE(8)
+  }
+#undef MINER_RM_CASE
   MINER_LAUNCH_OK("rank_metrics");
   rank_metrics_finalize<<<1, 64, 0, st>>>(static_cast<const double*>(workspace), grid, 2 + 2 * n_k, out_partials);
   MINER_LAUNCH_OK("rank_metrics_finalize");

@@ -50,6 +50,24 @@ def allreduce_partials(partials: torch.Tensor, group=None) -> torch.Tensor:
     return partials
 
 
+def allreduce_gradients(params, group=None) -> None:
+    """Train variant: average the gradients of ``params`` over ranks with ONE flat all-reduce (the path has ~0.75 M weights:
+    a single bucket, latency-bound).  With equal local batches the result is the gradient of the loss over the GLOBAL batch,
+    which is what the reference's single-process ``CrossEntropyLoss(reduction='mean')`` / ``.mean()`` compute (loss.py:39-41)."""
+    if not (dist.is_available() and dist.is_initialized()) or dist.get_world_size(group) == 1:
+        return
+    grads = [p.grad for p in params if p.grad is not None]
+    if not grads:
+        return
+    flat = torch.cat([g.reshape(-1) for g in grads])
+    dist.all_reduce(flat, op=dist.ReduceOp.SUM, group=group)
+    flat /= dist.get_world_size(group)
+    off = 0
+    for g in grads:
+        g.copy_(flat[off:off + g.numel()].view_as(g))
+        off += g.numel()
+
+
 def finalize_metrics(partials: torch.Tensor, names: Sequence[str]) -> Dict[str, float]:
     p = partials.detach().to('cpu', torch.float64).view(-1, 2)
     return {n: (float(p[i, 0] / p[i, 1]) if p[i, 1] > 0 else float('nan')) for i, n in enumerate(names)}

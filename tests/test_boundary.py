@@ -144,3 +144,47 @@ def test_two_rank_metric_reduction_gloo(tmp_path):
     outs = [p.communicate(timeout=240)[0] for p in procs]
     assert all(p.returncode == 0 for p in procs), outs
     assert 'OK' in outs[0]
+
+
+GRAD_WORKER = r'''
+import os, sys, torch, torch.distributed as dist
+sys.path.insert(0, sys.argv[1])
+from miner_b200.parallel import allreduce_gradients
+from miner_b200 import synth
+from oracle import miner_oracle as O
+rank, world = int(os.environ['RANK']), int(os.environ['WORLD_SIZE'])
+dist.init_process_group('gloo', rank=rank, world_size=world)
+B, H, N, D, K, Dc = 8, 6, 40, 16, 4, 8
+table = synth.make_table(N, D, 3)
+w = synth.make_weights(D, K, Dc, 3)
+his, mask, _, cand, _, labels = synth.make_train_batch(B, H, N, 4, 3)
+
+def grads(sl):
+    ps = [t.clone().requires_grad_(True) for t in (w.w_proj, w.context_codes, w.w_target)]
+    I, S = O.miner_forward(table, his[sl], mask[sl], cand[sl], ps[0], ps[1], ps[2], 'weighted')
+    O.loss_compute(I, S, labels[sl].float()).backward()
+    return ps
+
+half = B // world
+local = grads(slice(rank * half, (rank + 1) * half))        # CPU stand-in for the per-rank CUDA backward
+allreduce_gradients(local)
+full = grads(slice(0, B))
+for a, b in zip(local, full):
+    assert torch.allclose(a.grad, b.grad, rtol=1e-4, atol=1e-6), float((a.grad - b.grad).abs().max())
+if rank == 0:
+    print('OK')
+dist.destroy_process_group()
+'''
+
+
+def test_two_rank_gradient_averaging_gloo(tmp_path):
+    """world_size 2 over gloo: per-rank gradients of equal local batches, averaged with one flat all-reduce, equal the gradient
+    of the loss over the global batch (SURVEY.md section 8e caveat)."""
+    script = tmp_path / 'grad_worker.py'
+    script.write_text(GRAD_WORKER)
+    env = dict(os.environ, MASTER_ADDR='127.0.0.1', MASTER_PORT='29613', WORLD_SIZE='2')
+    procs = [subprocess.Popen([sys.executable, str(script), ROOT], env=dict(env, RANK=str(r)), stdout=subprocess.PIPE,
+                              stderr=subprocess.STDOUT, text=True) for r in range(2)]
+    outs = [p.communicate(timeout=240)[0] for p in procs]
+    assert all(p.returncode == 0 for p in procs), outs
+    assert 'OK' in outs[0]
