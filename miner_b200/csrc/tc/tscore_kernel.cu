@@ -11,7 +11,8 @@
 // which turns the 2HDDc + 2KD^2 FLOP of the reference order into two more gathered rows per history slot: the kernel is
 // bound by the gather (HBM / L2 ingest), not by the tensor pipe.
 //
-// One persistent CTA per SM; a tile is IPT = 2 impressions = 128 history slots (64 per impression, H <= 64).  TMEM lanes are
+// One persistent CTA per SM; a tile is IPT = 2 impressions = 128 history slots (64 per impression, H <= 64; IPT = 1 with 128
+// slots for 64 < H <= 128: the same code, a template parameter).  TMEM lanes are
 // (impression i, context code k, part hl): lane 64 i + 16 (k / 8) + 8 hl + k % 8, where hl selects the bf16 hi / lo part of the
 // softmax weight -- the two lanes of a pair accumulate  w_hi . E  and  w_lo . E  and are summed in the epilogue (fp32-level
 // weights).  Keeping a pair 8 lanes apart lets the 16-lane tcgen05.ld / st shapes (16x256b / 16x128b) hand both rows of a pair
@@ -42,7 +43,7 @@ namespace {
 
 constexpr int TM = 128;                      // TMEM lanes = history slots per tile
 constexpr int FB = 64;                       // feature block (128 bytes of bf16)
-constexpr int IPT = 2, HP = TM / IPT, LPI = TM / IPT;
+// IPT impressions share a tile: 2 for H <= 64 (64 slots and 64 lanes each), 1 for H <= 128; template parameter of the kernel
 constexpr int KMAX = 32;
 #ifndef MINER_TS_S1
 #define MINER_TS_S1 5
@@ -124,6 +125,7 @@ __device__ __forceinline__ int64_t id_of(RawId r, int id_dtype) {
 
 // candidate range of a tile (two loads, nothing else: callers issue them a tile ahead and only look at the values a tile later,
 // so their latency never sits on a role's critical path) and its number of passes
+template <int IPT>
 __device__ __forceinline__ void tile_range(const TScoreArgs& a, int tile, int64_t& cs, int64_t& ce) {
   const int64_t i0 = static_cast<int64_t>(tile) * IPT;
   const int64_t i1 = i0 + IPT < a.B ? i0 + IPT : a.B;
@@ -149,8 +151,10 @@ __device__ __forceinline__ uint32_t pack2(float a, float b) {
   __nv_bfloat162 v = __floats2bfloat162_rn(a, b);
   return *reinterpret_cast<uint32_t*>(&v);
 }
+template <int IPT>
 __global__ void __launch_bounds__(T_THREADS, 1)
 tscore_kernel(const TScoreArgs args, int n_tiles) {
+  constexpr int HP = TM / IPT, LPI = TM / IPT;          // history slots / TMEM lanes per impression
   extern __shared__ uint8_t smem_raw[];
   uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~static_cast<uintptr_t>(1023));
   uint8_t* st1 = smem;                                         // [S1][E 16 KB | TW 16 KB]
@@ -207,7 +211,7 @@ tscore_kernel(const TScoreArgs args, int n_tiles) {
     uint32_t g = 0;
     PROF_DECL;
     int64_t cs = 0, ce = 0;
-    if (n_local > 0) { fetch_ids(0); tile_range(args, static_cast<int>(blockIdx.x), cs, ce); }
+    if (n_local > 0) { fetch_ids(0); tile_range<IPT>(args, static_cast<int>(blockIdx.x), cs, ce); }
     for (int lt = 0; lt < n_local; ++lt) {
       const int tile = static_cast<int>(blockIdx.x) + lt * static_cast<int>(gridDim.x);
       uint32_t eoff[G1_ROWS];                                // byte offset of this thread's 16-byte chunk in its rows (table < 4 GB, checked by the launcher)
@@ -224,7 +228,7 @@ tscore_kernel(const TScoreArgs args, int n_tiles) {
       const int npass = passes_of(cs, ce);
       if (lt + 1 < n_local) {                                // the next tile's ids and candidate range are fetched a tile ahead
         fetch_ids(lt + 1);
-        tile_range(args, static_cast<int>(blockIdx.x) + (lt + 1) * static_cast<int>(gridDim.x), cs, ce);
+        tile_range<IPT>(args, static_cast<int>(blockIdx.x) + (lt + 1) * static_cast<int>(gridDim.x), cs, ce);
       }
       for (int p = 0; p < npass; ++p) {
         for (int j = 0; j < KB; ++j, ++g) {
@@ -279,13 +283,13 @@ tscore_kernel(const TScoreArgs args, int n_tiles) {
     const int tile0 = static_cast<int>(blockIdx.x), tstep = static_cast<int>(gridDim.x);
     int64_t cs = 0, ce = 0, ncs = 0, nce = 0, n2cs = 0, n2ce = 0;      // candidate ranges of this tile, the next one, the one after
     if (n_local > 0) {
-      tile_range(args, tile0, cs, ce);
-      if (n_local > 1) tile_range(args, tile0 + tstep, ncs, nce);
+      tile_range<IPT>(args, tile0, cs, ce);
+      if (n_local > 1) tile_range<IPT>(args, tile0 + tstep, ncs, nce);
       fetch_cands(cs, static_cast<int>(ce - cs < NC_MAX ? ce - cs : NC_MAX));
     }
     for (int lt = 0; lt < n_local; ++lt) {
       const int npass = passes_of(cs, ce);
-      if (lt + 2 < n_local) tile_range(args, tile0 + (lt + 2) * tstep, n2cs, n2ce);
+      if (lt + 2 < n_local) tile_range<IPT>(args, tile0 + (lt + 2) * tstep, n2cs, n2ce);
       for (int p = 0; p < npass; ++p) {
         const int64_t pc0 = cs + static_cast<int64_t>(p) * NC_MAX;
         const int nc = static_cast<int>(ce - pc0 < NC_MAX ? ce - pc0 : NC_MAX);
@@ -361,12 +365,12 @@ tscore_kernel(const TScoreArgs args, int n_tiles) {
       PROF_ADD(7);
     };
     int64_t t_cs = 0, t_ce = 0;
-    if (n_local > 0) tile_range(args, static_cast<int>(blockIdx.x), t_cs, t_ce);
+    if (n_local > 0) tile_range<IPT>(args, static_cast<int>(blockIdx.x), t_cs, t_ce);
     for (int lt = 0; lt < n_local; ++lt) {
       const int tile = static_cast<int>(blockIdx.x) + lt * static_cast<int>(gridDim.x);
       const int64_t cs = t_cs, ce = t_ce;
       const int npass = passes_of(cs, ce);
-      if (lt + 1 < n_local) tile_range(args, tile + static_cast<int>(gridDim.x), t_cs, t_ce);      // a tile ahead: off the critical path
+      if (lt + 1 < n_local) tile_range<IPT>(args, tile + static_cast<int>(gridDim.x), t_cs, t_ce);      // a tile ahead: off the critical path
       for (int p = 0; p < npass; ++p, ++u) {
         const int64_t pc0 = cs + static_cast<int64_t>(p) * NC_MAX;
         const int nc = static_cast<int>(ce - pc0 < NC_MAX ? ce - pc0 : NC_MAX);
@@ -433,20 +437,20 @@ tscore_kernel(const TScoreArgs args, int n_tiles) {
     const int q = warp & 3;                                    // TMEM lane quarter
     const int half = ew >> 2;                                  // 16-lane group of the quarter
     const int et = ew * 32 + lane;
-    const int li = q >> 1;                                     // impression of this quarter's lanes
+    const int li = (q * 32) / LPI;                             // impression of this quarter's lanes
     // this warp owns lanes [16 half, 16 half + 16) of its quarter; thread t meets the (hi, lo) rows of code bk
     const uint32_t grp_addr = static_cast<uint32_t>(q * 32 + half * 16) << 16;
-    const int bk = ((q & 1) * 2 + half) * 8 + (lane >> 2);      // context code of this thread's row pair
+    const int bk = (((q * 32) % LPI) / 16 + half) * 8 + (lane >> 2);   // context code of this thread's row pair
     const int bf = 2 * (lane & 3);                              // its features inside an 8-feature group
     uint32_t g = 0;
     PROF_DECL;
     int64_t t_cs = 0, t_ce = 0;
-    if (n_local > 0) tile_range(args, static_cast<int>(blockIdx.x), t_cs, t_ce);
+    if (n_local > 0) tile_range<IPT>(args, static_cast<int>(blockIdx.x), t_cs, t_ce);
     for (int lt = 0; lt < n_local; ++lt) {
       const int tile = static_cast<int>(blockIdx.x) + lt * static_cast<int>(gridDim.x);
       const int64_t cs = t_cs, ce = t_ce;
       const int npass = passes_of(cs, ce);
-      if (lt + 1 < n_local) tile_range(args, tile + static_cast<int>(gridDim.x), t_cs, t_ce);      // a tile ahead: off the critical path
+      if (lt + 1 < n_local) tile_range<IPT>(args, tile + static_cast<int>(gridDim.x), t_cs, t_ce);      // a tile ahead: off the critical path
       const int64_t i0 = static_cast<int64_t>(tile) * IPT;
       const int64_t my_imp = i0 + li;
       for (int p = 0; p < npass; ++p) {
@@ -504,7 +508,7 @@ tscore_kernel(const TScoreArgs args, int n_tiles) {
     // ------------------------------------------------------------------ softmax / score warps
     const int sw = warp - W_SMX0;
     const int q = warp & 3;
-    const int li = q >> 1;                                     // impression of this quarter's lanes
+    const int li = (q * 32) / LPI;                             // impression of this quarter's lanes
     const uint32_t lane_addr = static_cast<uint32_t>(q * 32) << 16;
     const int st = sw * 32 + lane;                             // 0..127
     const int tl = q * 32 + lane;                              // TMEM lane = (i, k, hl) for the 32-lane reads of the score stage
@@ -587,12 +591,12 @@ tscore_kernel(const TScoreArgs args, int n_tiles) {
       tc::tmem_st_wait();
     }
     int64_t t_cs = 0, t_ce = 0;
-    if (n_local > 0) tile_range(args, static_cast<int>(blockIdx.x), t_cs, t_ce);
+    if (n_local > 0) tile_range<IPT>(args, static_cast<int>(blockIdx.x), t_cs, t_ce);
     for (int lt = 0; lt < n_local; ++lt) {
       const int tile = static_cast<int>(blockIdx.x) + lt * static_cast<int>(gridDim.x);
       const int64_t cs = t_cs, ce = t_ce;
       const int npass = passes_of(cs, ce);
-      if (lt + 1 < n_local) tile_range(args, tile + static_cast<int>(gridDim.x), t_cs, t_ce);      // a tile ahead: off the critical path
+      if (lt + 1 < n_local) tile_range<IPT>(args, tile + static_cast<int>(gridDim.x), t_cs, t_ce);      // a tile ahead: off the critical path
       for (int p = 0; p < npass; ++p, ++u) {
         PROF_ADD(0);
         tc::named_bar_sync(2, T_SMX);                                          // previous unit's reads of L are done
@@ -635,16 +639,18 @@ tscore_kernel(const TScoreArgs args, int n_tiles) {
         PROF_ADD(1);
         // softmax over the history (model.py:181): per 16-lane group, thread t owns code k = 8 group + t/4 and the 16 slots
         // {2c, 2c+1 : c = t%4 + 4n}; the (hi, lo) rows of the pair leave through one 16x128b store
-        uint32_t pk[2][16];
+        constexpr int NC8 = HP / 8;                                            // packed columns per thread: c = t%4 + 4n, n < NC8
+        uint32_t pk[2][2 * NC8];
+        if (IPT == 1 && u > 0) tc::mbar_wait(&bars->w_free, (u - 1) & 1);      // 128-slot rows: too many registers to hold across the wait
 #pragma unroll
         for (int hf = 0; hf < 2; ++hf) {
-          const int k = ((q & 1) * 2 + hf) * 8 + (lane >> 2);
+          const int k = (((q * 32) % LPI) / 16 + hf) * 8 + (lane >> 2);
           const bool row_ok = k < K;
           const float* col = L + (li * HP) * LS + (row_ok ? k : 0);
-          float e[16];
+          float e[2 * NC8];
           float mx = -INFINITY;
 #pragma unroll
-          for (int n = 0; n < 8; ++n) {
+          for (int n = 0; n < NC8; ++n) {
             const int c = (lane & 3) + 4 * n;
             e[2 * n] = col[(2 * c) * LS];
             e[2 * n + 1] = col[(2 * c + 1) * LS];
@@ -655,7 +661,7 @@ tscore_kernel(const TScoreArgs args, int n_tiles) {
           const bool dead = mx == -INFINITY || !row_ok;                        // impression past the end of the batch / unused row
           float sum = 0.f;
 #pragma unroll
-          for (int n = 0; n < 16; ++n) {
+          for (int n = 0; n < 2 * NC8; ++n) {
             e[n] = dead ? 0.f : ex2_approx(e[n] - mx);
             sum += e[n];
           }
@@ -663,7 +669,7 @@ tscore_kernel(const TScoreArgs args, int n_tiles) {
           sum += __shfl_xor_sync(0xffffffffu, sum, 2);
           const float inv = dead ? 0.f : __fdividef(1.0f, sum);
 #pragma unroll
-          for (int n = 0; n < 8; ++n) {
+          for (int n = 0; n < NC8; ++n) {
             const float w0 = e[2 * n] * inv, w1 = e[2 * n + 1] * inv;
             const uint32_t hi = pack2(w0, w1);
             pk[hf][2 * n] = hi;
@@ -671,12 +677,18 @@ tscore_kernel(const TScoreArgs args, int n_tiles) {
           }
         }
         PROF_ADD(2);
-        if (u > 0) tc::mbar_wait(&bars->w_free, (u - 1) & 1);                  // S1 of the previous unit no longer reads A_w
+        if (IPT != 1 && u > 0) tc::mbar_wait(&bars->w_free, (u - 1) & 1);      // S1 of the previous unit no longer reads A_w
         PROF_ADD(3);
         tc::tcgen05_fence_after();
 #pragma unroll
         for (int hf = 0; hf < 2; ++hf)
-          tc::tmem_st_16x128b_x8(tmem + (static_cast<uint32_t>(q * 32 + hf * 16) << 16) + AW_COL + li * (HP / 2), pk[hf]);
+#pragma unroll
+          for (int part = 0; part < NC8 / 8; ++part) {
+            uint32_t o[16];
+#pragma unroll
+            for (int c = 0; c < 16; ++c) o[c] = pk[hf][16 * part + c];
+            tc::tmem_st_16x128b_x8(tmem + (static_cast<uint32_t>(q * 32 + hf * 16) << 16) + AW_COL + li * (HP / 2) + part * 32, o);
+          }
         tc::tmem_st_wait();
         tc::tcgen05_fence_before();
         tc::mbar_arrive(&bars->w_ready);
@@ -705,7 +717,7 @@ constexpr int T_SMEM = 1024 + S1 * ST1_BYTES + S2 * C_BYTES + SCRATCH_FLOATS * 4
 }  // namespace
 
 bool tscore_kernel_supported(int64_t H, int64_t K, int64_t D) {
-  return H >= 1 && H <= HP && K >= 1 && K <= KMAX && D >= FB && D % FB == 0 && D <= 8192;
+  return H >= 1 && H <= TM && K >= 1 && K <= KMAX && D >= FB && D % FB == 0 && D <= 8192;
 }
 
 int launch_tscore_kernel(const void* table, const void* tw, const float* lg, int64_t n_rows, const void* his_ids, int id_dtype,
@@ -714,7 +726,7 @@ int launch_tscore_kernel(const void* table, const void* tw, const float* lg, int
                          cudaStream_t stream) {
   if (B == 0) return MINER_OK;
   if (!tscore_kernel_supported(H, K, D)) {
-    set_error("table-level scoring: unsupported shape H=%lld K=%lld D=%lld (need H <= 64, K <= 32, D %% 64 == 0)", (long long)H, (long long)K,
+    set_error("table-level scoring: unsupported shape H=%lld K=%lld D=%lld (need H <= 128, K <= 32, D %% 64 == 0)", (long long)H, (long long)K,
               (long long)D);
     return MINER_ERR_UNSUPPORTED;
   }
@@ -734,10 +746,16 @@ int launch_tscore_kernel(const void* table, const void* tw, const float* lg, int
     static const char* env_dbg = getenv("MINER_TS_DBG");
     a.dbg = env_dbg ? atoi(env_dbg) : 0;
   }
-  const int64_t n_tiles = (B + IPT - 1) / IPT;
+  const int ipt = H <= TM / 2 ? 2 : 1;
+  const int64_t n_tiles = (B + ipt - 1) / ipt;
   const int grid = static_cast<int>(n_tiles < sm_count() ? n_tiles : sm_count());
-  MINER_CUDA_OK(cudaFuncSetAttribute(tscore_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, T_SMEM));
-  tscore_kernel<<<grid, T_THREADS, T_SMEM, stream>>>(a, static_cast<int>(n_tiles));
+  if (ipt == 2) {
+    MINER_CUDA_OK(cudaFuncSetAttribute(tscore_kernel<2>, cudaFuncAttributeMaxDynamicSharedMemorySize, T_SMEM));
+    tscore_kernel<2><<<grid, T_THREADS, T_SMEM, stream>>>(a, static_cast<int>(n_tiles));
+  } else {
+    MINER_CUDA_OK(cudaFuncSetAttribute(tscore_kernel<1>, cudaFuncAttributeMaxDynamicSharedMemorySize, T_SMEM));
+    tscore_kernel<1><<<grid, T_THREADS, T_SMEM, stream>>>(a, static_cast<int>(n_tiles));
+  }
   MINER_LAUNCH_OK("tscore_kernel");
   return MINER_OK;
 }
