@@ -44,21 +44,26 @@ namespace {
 constexpr int TM = 128;                      // TMEM lanes = history slots per tile
 constexpr int FB = 64;                       // feature block (128 bytes of bf16)
 // IPT impressions share a tile: 2 for H <= 64 (64 slots and 64 lanes each), 1 for H <= 128; template parameter of the kernel
-constexpr int KMAX = 32;
+constexpr int KMAX = 64;                     // largest number of context codes (template parameter KM = 32 or 64 picks the scratch sizes)
 #ifndef MINER_TS_S1
 #define MINER_TS_S1 5
 #endif
 #ifndef MINER_TS_S2
 #define MINER_TS_S2 3
 #endif
-constexpr int S1 = MINER_TS_S1, S2 = MINER_TS_S2;   // ring depths: (E, TW) blocks / candidate blocks
+constexpr int S1_MAX = MINER_TS_S1, S2 = MINER_TS_S2;   // ring depths: (E, TW) blocks (one less when K > 32 needs the bytes) / candidate blocks
 constexpr int E_BYTES = TM * FB * 2;         // 16 KB
 constexpr int ST1_BYTES = 2 * E_BYTES;
 constexpr int NC_MAX = 96;                   // candidate columns per pass
 constexpr int C_BYTES = NC_MAX * FB * 2;     // 12 KB
-constexpr int LS = KMAX;                     // logits scratch row stride (floats)
-constexpr int SS = KMAX + 1;                 // score scratch row stride (floats)
-constexpr int SCRATCH_FLOATS = (TM * LS > 2 * NC_MAX * SS ? TM * LS : 2 * NC_MAX * SS + 2) & ~1;
+template <int KM>
+struct Shape {
+  static constexpr int LS = KM;              // logits scratch row stride (floats)
+  static constexpr int SS = KM + 1;          // score scratch row stride (floats)
+  static constexpr int SCRATCH_FLOATS = (TM * LS > 2 * NC_MAX * SS ? TM * LS : 2 * NC_MAX * SS + 2) & ~1;
+  static constexpr int S1 = KM > 32 ? S1_MAX - 1 : S1_MAX;
+  static constexpr int SMEM = 1024 + S1 * ST1_BYTES + S2 * C_BYTES + SCRATCH_FLOATS * 4 + 512;
+};
 constexpr int T_EPI = 256, T_SMX = 128;                // 8 epilogue warps, 4 softmax / score warps
 constexpr int T_G1 = 128, T_G2 = 64;                   // gather threads of the (E, TW) ring / of the candidate ring
 constexpr int G1_ROWS = TM * 8 / T_G1, G2_ROWS = NC_MAX * 8 / T_G2;  // rows per thread (a thread moves one 16-byte chunk per row)
@@ -84,11 +89,11 @@ constexpr int DA_COL = DM_COL + NC_MAX;      // attention logits a[(i,k,hl), c]
 #endif
 
 struct TBarriers {
-  uint64_t full1[S1], empty1[S1], full2[S2], empty2[S2];
+  uint64_t full1[S1_MAX], empty1[S1_MAX], full2[S2], empty2[S2];
   uint64_t w_ready, w_free, ip_full[2], a_ready[2], dma_full, dma_free;
   uint32_t tmem_base;
 #ifdef MINER_TS_PROF
-  long long issue_clk[S1][4];   // when lane 0 of each (E, TW) gather warp finished issuing a stage (latency accounting)
+  long long issue_clk[S1_MAX][4];   // when lane 0 of each (E, TW) gather warp finished issuing a stage (latency accounting)
 #endif
 };
 
@@ -151,10 +156,11 @@ __device__ __forceinline__ uint32_t pack2(float a, float b) {
   __nv_bfloat162 v = __floats2bfloat162_rn(a, b);
   return *reinterpret_cast<uint32_t*>(&v);
 }
-template <int IPT>
+template <int IPT, int KM>
 __global__ void __launch_bounds__(T_THREADS, 1)
 tscore_kernel(const TScoreArgs args, int n_tiles) {
   constexpr int HP = TM / IPT, LPI = TM / IPT;          // history slots / TMEM lanes per impression
+  constexpr int LS = Shape<KM>::LS, SS = Shape<KM>::SS, SCRATCH_FLOATS = Shape<KM>::SCRATCH_FLOATS, S1 = Shape<KM>::S1;
   extern __shared__ uint8_t smem_raw[];
   uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~static_cast<uintptr_t>(1023));
   uint8_t* st1 = smem;                                         // [S1][E 16 KB | TW 16 KB]
@@ -616,23 +622,27 @@ tscore_kernel(const TScoreArgs args, int n_tiles) {
             const bool id_ok = id >= 0 && id < args.n_rows;
             info = (id_ok ? static_cast<uint32_t>(id) : 0u) | ((keep ? (id_ok ? 2u : 3u) : 1u) << 30);
           }
-          const float* lgp = args.lg + lane;
           const uint32_t Ku = static_cast<uint32_t>(K);
-          float v[32];
-#pragma unroll
-          for (int ss = 0; ss < 32; ++ss) {                                    // 32 independent 128-byte row loads in flight
-            const uint32_t info_s = __shfl_sync(0xffffffffu, info, ss);
-            v[ss] = ((info_s >> 30) == 2u && lane < K) ? lgp[(info_s & 0x3fffffffu) * Ku] : 0.f;
-          }
           const bool has_bias = args.bias_mean != nullptr;
 #pragma unroll
-          for (int ss = 0; ss < 32; ++ss) {
-            const uint32_t code_s = __shfl_sync(0xffffffffu, info, ss) >> 30;
-            float x = v[ss];
-            if (has_bias) x += __shfl_sync(0xffffffffu, bias, ss);             // model.py:174-177
-            if (code_s == 1u) x = kMaskFill;                                   // model.py:180 (1e-30, not -inf)
-            if (code_s == 0u) x = -INFINITY;                                   // tile padding: not part of the history
-            L[(sw * 32 + ss) * LS + lane] = x * 1.4426950408889634f;
+          for (int kk = 0; kk < KM / 32; ++kk) {                               // 32 codes per pass
+            const int kcol = lane + 32 * kk;
+            const float* lgp = args.lg + kcol;
+            float v[32];
+#pragma unroll
+            for (int ss = 0; ss < 32; ++ss) {                                  // 32 independent 128-byte row loads in flight
+              const uint32_t info_s = __shfl_sync(0xffffffffu, info, ss);
+              v[ss] = ((info_s >> 30) == 2u && kcol < K) ? lgp[(info_s & 0x3fffffffu) * Ku] : 0.f;
+            }
+#pragma unroll
+            for (int ss = 0; ss < 32; ++ss) {
+              const uint32_t code_s = __shfl_sync(0xffffffffu, info, ss) >> 30;
+              float x = v[ss];
+              if (has_bias) x += __shfl_sync(0xffffffffu, bias, ss);           // model.py:174-177
+              if (code_s == 1u) x = kMaskFill;                                 // model.py:180 (1e-30, not -inf)
+              if (code_s == 0u) x = -INFINITY;                                 // tile padding: not part of the history
+              L[(sw * 32 + ss) * LS + kcol] = x * 1.4426950408889634f;
+            }
           }
         }
         tc::named_bar_sync(2, T_SMX);
@@ -712,7 +722,6 @@ tscore_kernel(const TScoreArgs args, int n_tiles) {
   if (warp == W_MMA) tc::tmem_dealloc(tmem, 512);
 }
 
-constexpr int T_SMEM = 1024 + S1 * ST1_BYTES + S2 * C_BYTES + SCRATCH_FLOATS * 4 + 512;
 
 }  // namespace
 
@@ -726,7 +735,7 @@ int launch_tscore_kernel(const void* table, const void* tw, const float* lg, int
                          cudaStream_t stream) {
   if (B == 0) return MINER_OK;
   if (!tscore_kernel_supported(H, K, D)) {
-    set_error("table-level scoring: unsupported shape H=%lld K=%lld D=%lld (need H <= 128, K <= 32, D %% 64 == 0)", (long long)H, (long long)K,
+    set_error("table-level scoring: unsupported shape H=%lld K=%lld D=%lld (need H <= 128, K <= 64, D %% 64 == 0)", (long long)H, (long long)K,
               (long long)D);
     return MINER_ERR_UNSUPPORTED;
   }
@@ -746,16 +755,19 @@ int launch_tscore_kernel(const void* table, const void* tw, const float* lg, int
     static const char* env_dbg = getenv("MINER_TS_DBG");
     a.dbg = env_dbg ? atoi(env_dbg) : 0;
   }
-  const int ipt = H <= TM / 2 ? 2 : 1;
+  // lanes per impression: 2 K (hi / lo rows of every code) -> two impressions share a tile only if K <= 32 and H <= 64
+  const int ipt = (H <= TM / 2 && K <= 32) ? 2 : 1;
   const int64_t n_tiles = (B + ipt - 1) / ipt;
   const int grid = static_cast<int>(n_tiles < sm_count() ? n_tiles : sm_count());
-  if (ipt == 2) {
-    MINER_CUDA_OK(cudaFuncSetAttribute(tscore_kernel<2>, cudaFuncAttributeMaxDynamicSharedMemorySize, T_SMEM));
-    tscore_kernel<2><<<grid, T_THREADS, T_SMEM, stream>>>(a, static_cast<int>(n_tiles));
-  } else {
-    MINER_CUDA_OK(cudaFuncSetAttribute(tscore_kernel<1>, cudaFuncAttributeMaxDynamicSharedMemorySize, T_SMEM));
-    tscore_kernel<1><<<grid, T_THREADS, T_SMEM, stream>>>(a, static_cast<int>(n_tiles));
-  }
+#define MINER_TS_LAUNCH(I, KMV)                                                                                                   \
+  do {                                                                                                                            \
+    MINER_CUDA_OK(cudaFuncSetAttribute(tscore_kernel<I, KMV>, cudaFuncAttributeMaxDynamicSharedMemorySize, Shape<KMV>::SMEM));   \
+    tscore_kernel<I, KMV><<<grid, T_THREADS, Shape<KMV>::SMEM, stream>>>(a, static_cast<int>(n_tiles));                          \
+  } while (0)
+  if (K > 32) MINER_TS_LAUNCH(1, 64);
+  else if (ipt == 2) MINER_TS_LAUNCH(2, 32);
+  else MINER_TS_LAUNCH(1, 32);
+#undef MINER_TS_LAUNCH
   MINER_LAUNCH_OK("tscore_kernel");
   return MINER_OK;
 }
