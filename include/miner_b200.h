@@ -200,12 +200,16 @@ int miner_loss_fwd(const float* interests, const float* logits, const float* lab
  *      miner_train_fwd writes interests (B,K,D), scores (B,C) and saves T = tanh(E Wp^T) (B*H,Dc), the softmax weights
  *      (B,K,H) and Z = I Wt^T (B*K,D).  miner_loss_bwd: d loss / d interests and d loss / d logits, scaled by *grad_out
  *      (device float, NULL = 1).  miner_train_bwd: grad_w_proj (Dc,D), grad_codes (K,Dc), grad_w_target (D,D) from d_scores
- *      (B,C) and d_interests (B,K,D, nullable).  The same workspace size serves fwd and bwd. */
-size_t miner_train_workspace_bytes(int64_t B, int64_t H, int64_t K, int64_t Dc, int64_t D);
+ *      (B,C) and d_interests (B,K,D, nullable).  The same workspace size serves fwd and bwd.
+ *      math = MINER_MATH_FP32, or MINER_MATH_TENSOR: the five projection-sized GEMMs of the step (E Wp^T, I Wt^T, dZ Wt,
+ *      dZ^T I, dZ1^T E) on tcgen05 with bf16 operands and fp32 accumulation (bf16 table, D % 64 == 0, bf16 weight copies). */
+size_t miner_train_workspace_bytes(int64_t B, int64_t H, int64_t K, int64_t Dc, int64_t D, int math);
 int miner_train_fwd(const void* table, int64_t n_rows, int table_dtype, const void* his_ids, const uint8_t* his_mask,
                     const void* cand_ids, int id_dtype, const float* w_proj, const float* codes, const float* w_target,
                     int64_t B, int64_t H, int64_t C, int64_t K, int64_t Dc, int64_t D, float* out_interests, float* out_scores,
-                    float* save_t, float* save_w, float* save_z, void* workspace, size_t workspace_bytes, void* stream);
+                    float* save_t, float* save_w, float* save_z,
+                    int math, const void* w_proj_bf16, const void* w_target_bf16,
+                    void* workspace, size_t workspace_bytes, void* stream);
 int miner_loss_bwd(const float* interests, const float* logits, const float* labels, const float* grad_out,
                    int64_t B, int64_t C, int64_t K, int64_t D, float* d_interests, float* d_logits, void* stream);
 int miner_train_bwd(const void* table, int64_t n_rows, int table_dtype, const void* his_ids, const uint8_t* his_mask,
@@ -214,6 +218,7 @@ int miner_train_bwd(const void* table, int64_t n_rows, int table_dtype, const vo
                     const float* d_scores, const float* d_interests,
                     int64_t B, int64_t H, int64_t C, int64_t K, int64_t Dc, int64_t D,
                     float* grad_w_proj, float* grad_codes, float* grad_w_target,
+                    int math, const void* w_proj_bf16, const void* w_target_bf16,
                     void* workspace, size_t workspace_bytes, void* stream);
 
 #ifdef __cplusplus

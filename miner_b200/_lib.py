@@ -91,12 +91,13 @@ def _declare(lib: C.CDLL) -> None:
     lib.miner_table_project_workspace_bytes.restype = sz
     lib.miner_table_project.argtypes = [vp, i64, i64, vp, vp, vp, i64, i64, vp, vp, vp, sz, vp]
     lib.miner_score_table_supported.argtypes = [i64, i64, i64]
-    lib.miner_train_workspace_bytes.argtypes = [i64] * 5
+    lib.miner_train_workspace_bytes.argtypes = [i64, i64, i64, i64, i64, i32]
     lib.miner_train_workspace_bytes.restype = sz
-    lib.miner_train_fwd.argtypes = [vp, i64, i32, vp, vp, vp, i32, vp, vp, vp, i64, i64, i64, i64, i64, i64, vp, vp, vp, vp, vp, vp, sz, vp]
+    lib.miner_train_fwd.argtypes = [vp, i64, i32, vp, vp, vp, i32, vp, vp, vp, i64, i64, i64, i64, i64, i64, vp, vp, vp, vp, vp, i32, vp, vp,
+                                    vp, sz, vp]
     lib.miner_loss_bwd.argtypes = [vp, vp, vp, vp, i64, i64, i64, i64, vp, vp, vp]
     lib.miner_train_bwd.argtypes = [vp, i64, i32, vp, vp, vp, i32, vp, vp, vp, vp, vp, vp, vp, vp, vp, i64, i64, i64, i64, i64, i64, vp, vp, vp,
-                                    vp, sz, vp]
+                                    i32, vp, vp, vp, sz, vp]
     lib.miner_score_table_fwd.argtypes = [vp, vp, vp, i64, vp, vp, vp, vp, i32, vp, i64, i64, i64, i64, i64, i32, vp, vp, vp]
 
 

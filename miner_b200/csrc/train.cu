@@ -11,6 +11,7 @@
 //             dI += dZ Wt, dWt = dZ^T I -> dw = dI E^T -> dlogits = w (dw - sum w dw), 0 on masked slots
 //             dT = dlogits^T codes, dcodes = sum_b dlogits T, dZ1 = dT (1 - T^2), dWp = dZ1^T E
 #include "common.cuh"
+#include "tc/tc_gemm.cuh"
 
 namespace miner {
 
@@ -40,6 +41,36 @@ __global__ void transpose_kernel(const float* __restrict__ src, float* __restric
   __syncthreads();
   for (int i = threadIdx.y; i < 32; i += blockDim.y)
     if (c0 + i < cols && r0 + threadIdx.x < rows) dst[static_cast<int64_t>(c0 + i) * rows + r0 + threadIdx.x] = tile[threadIdx.x][i];
+}
+
+// dst (cols x rpad, bf16) = src (rows x cols, fp32) transposed; columns rows..rpad-1 of dst are zero (K padding of the tensor-core GEMMs)
+__global__ void transpose_cast_kernel(const float* __restrict__ src, __nv_bfloat16* __restrict__ dst, int64_t rows, int cols, int64_t rpad) {
+  __shared__ float tile[32][33];
+  const int64_t r0 = static_cast<int64_t>(blockIdx.x) * 32;
+  const int c0 = blockIdx.y * 32;
+  for (int i = threadIdx.y; i < 32; i += blockDim.y)
+    tile[i][threadIdx.x] = (r0 + i < rows && c0 + threadIdx.x < cols) ? src[(r0 + i) * cols + c0 + threadIdx.x] : 0.f;
+  __syncthreads();
+  for (int i = threadIdx.y; i < 32; i += blockDim.y)
+    if (c0 + i < cols && r0 + threadIdx.x < rpad) dst[static_cast<int64_t>(c0 + i) * rpad + r0 + threadIdx.x] = __float2bfloat16_rn(tile[threadIdx.x][i]);
+}
+// dst (D x rpad, bf16): dst[d][r] = table[ids[r]][d]  (bf16 table; invalid ids and r >= rows give zeros)
+__global__ void gather_transpose_kernel(const uint16_t* __restrict__ table, int64_t n_rows, const void* __restrict__ ids, int id_dtype,
+                                        int64_t rows, int D, int64_t rpad, uint16_t* __restrict__ dst) {
+  __shared__ uint16_t tile[32][34];
+  const int64_t r0 = static_cast<int64_t>(blockIdx.x) * 32;
+  const int c0 = blockIdx.y * 32;
+  for (int i = threadIdx.y; i < 32; i += blockDim.y) {
+    uint16_t v = 0;
+    if (r0 + i < rows && c0 + threadIdx.x < D) {
+      const int64_t id = load_id(ids, r0 + i, id_dtype);
+      if (id >= 0 && id < n_rows) v = table[id * D + c0 + threadIdx.x];
+    }
+    tile[i][threadIdx.x] = v;
+  }
+  __syncthreads();
+  for (int i = threadIdx.y; i < 32; i += blockDim.y)
+    if (c0 + i < D && r0 + threadIdx.x < rpad) dst[static_cast<int64_t>(c0 + i) * rpad + r0 + threadIdx.x] = tile[threadIdx.x][i];
 }
 
 // ---- backward of Loss.compute: one CTA per impression
@@ -341,8 +372,11 @@ int atb_splits(int64_t R, int tiles) {
 struct TrainWs {
   size_t g, di, di2, dz, dz1, wt_t, part_wp, part_wt, part_codes, total;
   int s_wp, s_wt, g_poly;
+  // tensor-core family: bf16 operands of the five projection-sized GEMMs
+  size_t i_bf16, dz_bf16, wtt_bf16, dzt, it, dz1t, et;
+  int64_t bk_pad, bh_pad;
 };
-TrainWs train_ws(int64_t B, int64_t H, int64_t K, int64_t Dc, int64_t D) {
+TrainWs train_ws(int64_t B, int64_t H, int64_t K, int64_t Dc, int64_t D, int math) {
   TrainWs w{};
   size_t off = 0;
   auto take = [&](size_t bytes) { size_t o = off; off += align_up(bytes, 256); return o; };
@@ -355,12 +389,34 @@ TrainWs train_ws(int64_t B, int64_t H, int64_t K, int64_t Dc, int64_t D) {
   w.s_wp = atb_splits(B * H, static_cast<int>(((Dc + 63) / 64) * ((D + 63) / 64)));
   w.s_wt = atb_splits(B * K, static_cast<int>(((D + 63) / 64) * ((D + 63) / 64)));
   w.g_poly = static_cast<int>(B < 4 * sm_count() ? B : 4 * sm_count());
-  w.part_wp = take(f * w.s_wp * Dc * D);
-  w.part_wt = take(f * w.s_wt * D * D);
+  w.part_wp = take(math == MINER_MATH_TENSOR ? 0 : f * w.s_wp * Dc * D);
+  w.part_wt = take(math == MINER_MATH_TENSOR ? 0 : f * w.s_wt * D * D);
   w.part_codes = take(f * w.g_poly * K * Dc);
   w.di2 = w.g;
+  w.bk_pad = (B * K + 63) / 64 * 64;
+  w.bh_pad = (B * H + 63) / 64 * 64;
+  if (math == MINER_MATH_TENSOR) {
+    w.i_bf16 = take(2 * static_cast<size_t>(B) * K * D);
+    w.dz_bf16 = w.i_bf16;              // forward / backward never need both
+    w.wtt_bf16 = take(2 * static_cast<size_t>(D) * D);
+    w.dzt = take(2 * static_cast<size_t>(D) * w.bk_pad);
+    w.it = take(2 * static_cast<size_t>(D) * w.bk_pad);
+    w.dz1t = take(2 * static_cast<size_t>(Dc) * w.bh_pad);
+    w.et = take(2 * static_cast<size_t>(D) * w.bh_pad);
+  }
   w.total = off;
   return w;
+}
+
+int check_train_math(int math, int table_dtype, int64_t D, int64_t Dc, const void* w_proj_bf16, const void* w_target_bf16) {
+  if (math == MINER_MATH_FP32) return MINER_OK;
+  MINER_CHECK_ARG(math == MINER_MATH_TENSOR, "train: math must be MINER_MATH_FP32 or MINER_MATH_TENSOR");
+  MINER_CHECK_ARG(table_dtype == MINER_BF16 && w_proj_bf16 && w_target_bf16, "train: the tensor-core family needs a bf16 table and bf16 weight copies");
+  if (!tc_gemm_supported(D, Dc) || !tc_gemm_supported(D, D)) {
+    set_error("train: the tensor-core family needs D %% 64 == 0 and Dc >= 16 (D=%lld Dc=%lld)", (long long)D, (long long)Dc);
+    return MINER_ERR_UNSUPPORTED;
+  }
+  return MINER_OK;
 }
 
 }  // namespace
@@ -368,15 +424,16 @@ TrainWs train_ws(int64_t B, int64_t H, int64_t K, int64_t Dc, int64_t D) {
 
 using namespace miner;
 
-extern "C" size_t miner_train_workspace_bytes(int64_t B, int64_t H, int64_t K, int64_t Dc, int64_t D) {
+extern "C" size_t miner_train_workspace_bytes(int64_t B, int64_t H, int64_t K, int64_t Dc, int64_t D, int math) {
   if (B <= 0) return 256;
-  return train_ws(B, H, K, Dc, D).total;
+  return train_ws(B, H, K, Dc, D, math).total;
 }
 
 extern "C" int miner_train_fwd(const void* table, int64_t n_rows, int table_dtype, const void* his_ids, const uint8_t* his_mask,
                                const void* cand_ids, int id_dtype, const float* w_proj, const float* codes, const float* w_target,
                                int64_t B, int64_t H, int64_t C, int64_t K, int64_t Dc, int64_t D, float* out_interests, float* out_scores,
-                               float* save_t, float* save_w, float* save_z, void* workspace, size_t workspace_bytes, void* stream) {
+                               float* save_t, float* save_w, float* save_z, int math, const void* w_proj_bf16, const void* w_target_bf16,
+                               void* workspace, size_t workspace_bytes, void* stream) {
   MINER_CHECK_ARG(B >= 0 && H > 0 && C > 0 && K > 0 && Dc > 0 && D > 0 && n_rows > 0, "train_fwd: bad sizes");
   if (B == 0) return MINER_OK;
   MINER_CHECK_ARG(table && his_ids && his_mask && cand_ids && w_proj && codes && w_target && out_interests && out_scores && save_t &&
@@ -384,20 +441,34 @@ extern "C" int miner_train_fwd(const void* table, int64_t n_rows, int table_dtyp
                   "train_fwd: null pointer");
   MINER_CHECK_ARG(table_dtype == MINER_F32 || table_dtype == MINER_BF16, "train_fwd: table dtype must be fp32 or bf16");
   MINER_CHECK_ARG(id_dtype == MINER_I32 || id_dtype == MINER_I64, "train_fwd: id dtype must be int32 or int64");
-  const TrainWs w = train_ws(B, H, K, Dc, D);
+  int rc = check_train_math(math, table_dtype, D, Dc, w_proj_bf16, w_target_bf16);
+  if (rc) return rc;
+  const TrainWs w = train_ws(B, H, K, Dc, D, math);
   if (!workspace || workspace_bytes < w.total) {
     set_error("train_fwd: workspace too small (%zu bytes needed)", w.total);
     return MINER_ERR_WORKSPACE;
   }
   auto st = static_cast<cudaStream_t>(stream);
-  float* G = reinterpret_cast<float*>(static_cast<char*>(workspace) + w.g);
-  int rc = launch_sgemm_nt(table, table_dtype, his_ids, id_dtype, n_rows, w_proj, save_t, B * H, Dc, D, EPI_TANH, st);      // model.py:171
-  if (rc) return rc;
-  rc = launch_poly_softmax_wsum(save_t, codes, his_mask, nullptr, nullptr, table, table_dtype, his_ids, id_dtype, n_rows, B, H, K, Dc, D,
-                                out_interests, save_w, nullptr, st);                                                          // model.py:174-182
-  if (rc) return rc;
-  rc = launch_sgemm_nt(out_interests, MINER_F32, nullptr, id_dtype, 0, w_target, save_z, B * K, D, D, EPI_NONE, st);         // model.py:212
-  if (rc) return rc;
+  char* wsb = static_cast<char*>(workspace);
+  float* G = reinterpret_cast<float*>(wsb + w.g);
+  if (math == MINER_MATH_TENSOR) {
+    // the two projection GEMMs on tcgen05 (bf16 operands, fp32 accumulation), everything else as in the fp32 family
+    rc = launch_tc_gemm(table, his_ids, id_dtype, n_rows, w_proj_bf16, save_t, nullptr, B * H, Dc, D, EPI_TANH, st);          // model.py:171
+    if (rc) return rc;
+    rc = launch_poly_softmax_wsum(save_t, codes, his_mask, nullptr, nullptr, table, table_dtype, his_ids, id_dtype, n_rows, B, H, K, Dc, D,
+                                  out_interests, save_w, wsb + w.i_bf16, st);                                                  // model.py:174-182
+    if (rc) return rc;
+    rc = launch_tc_gemm(wsb + w.i_bf16, nullptr, id_dtype, 0, w_target_bf16, save_z, nullptr, B * K, D, D, EPI_NONE, st);     // model.py:212
+    if (rc) return rc;
+  } else {
+    rc = launch_sgemm_nt(table, table_dtype, his_ids, id_dtype, n_rows, w_proj, save_t, B * H, Dc, D, EPI_TANH, st);          // model.py:171
+    if (rc) return rc;
+    rc = launch_poly_softmax_wsum(save_t, codes, his_mask, nullptr, nullptr, table, table_dtype, his_ids, id_dtype, n_rows, B, H, K, Dc, D,
+                                  out_interests, save_w, nullptr, st);                                                          // model.py:174-182
+    if (rc) return rc;
+    rc = launch_sgemm_nt(out_interests, MINER_F32, nullptr, id_dtype, 0, w_target, save_z, B * K, D, D, EPI_NONE, st);         // model.py:212
+    if (rc) return rc;
+  }
   const int64_t n = B * K * D;
   gelu_kernel<<<static_cast<int>((n + 1023) / 1024 < 8 * sm_count() ? (n + 1023) / 1024 : 8 * sm_count()), 256, 0, st>>>(save_z, G, n);
   MINER_LAUNCH_OK("gelu");
@@ -425,14 +496,19 @@ extern "C" int miner_train_bwd(const void* table, int64_t n_rows, int table_dtyp
                                const void* cand_ids, int id_dtype, const float* w_proj, const float* codes, const float* w_target,
                                const float* save_t, const float* save_w, const float* interests, const float* save_z,
                                const float* d_scores, const float* d_interests, int64_t B, int64_t H, int64_t C, int64_t K, int64_t Dc,
-                               int64_t D, float* grad_w_proj, float* grad_codes, float* grad_w_target, void* workspace,
-                               size_t workspace_bytes, void* stream) {
+                               int64_t D, float* grad_w_proj, float* grad_codes, float* grad_w_target, int math, const void* w_proj_bf16,
+                               const void* w_target_bf16, void* workspace, size_t workspace_bytes, void* stream) {
   (void)w_proj;
   MINER_CHECK_ARG(B > 0 && H > 0 && C > 0 && K > 0 && Dc > 0 && D > 0 && n_rows > 0, "train_bwd: bad sizes");
   MINER_CHECK_ARG(table && his_ids && his_mask && cand_ids && codes && w_target && save_t && save_w && interests && save_z && d_scores &&
                       grad_w_proj && grad_codes && grad_w_target,
                   "train_bwd: null pointer");
-  const TrainWs w = train_ws(B, H, K, Dc, D);
+  {
+    const int rc0 = check_train_math(math, table_dtype, D, Dc, w_proj_bf16, w_target_bf16);
+    if (rc0) return rc0;
+  }
+  const bool tensor = math == MINER_MATH_TENSOR;
+  const TrainWs w = train_ws(B, H, K, Dc, D, math);
   if (!workspace || workspace_bytes < w.total) {
     set_error("train_bwd: workspace too small (%zu bytes needed)", w.total);
     return MINER_ERR_WORKSPACE;
@@ -460,7 +536,27 @@ extern "C" int miner_train_bwd(const void* table, int64_t n_rows, int table_dtyp
     MINER_LAUNCH_OK("target_bwd");
   }
   // 2. Z = I Wt^T:  dI2 = dZ Wt  (as dZ (Wt^T)^T with the NT GEMM),  dWt = dZ^T I
-  {
+  if (tensor) {
+    dim3 tb(32, 8);
+    const int64_t R = B * K;
+    __nv_bfloat16* dz16 = reinterpret_cast<__nv_bfloat16*>(ws + w.dz_bf16);
+    __nv_bfloat16* wtt16 = reinterpret_cast<__nv_bfloat16*>(ws + w.wtt_bf16);
+    __nv_bfloat16* dzt = reinterpret_cast<__nv_bfloat16*>(ws + w.dzt);
+    __nv_bfloat16* it = reinterpret_cast<__nv_bfloat16*>(ws + w.it);
+    int rc = launch_cast_f32_to_bf16(dZ, dz16, R * D, st);
+    if (rc) return rc;
+    transpose_cast_kernel<<<dim3(static_cast<unsigned>((D + 31) / 32), static_cast<unsigned>((D + 31) / 32)), tb, 0, st>>>(w_target, wtt16, D, (int)D, D);
+    MINER_LAUNCH_OK("transpose_cast(Wt)");
+    rc = launch_tc_gemm(dz16, nullptr, id_dtype, 0, wtt16, dI2, nullptr, R, D, D, EPI_NONE, st);
+    if (rc) return rc;
+    const dim3 tg(static_cast<unsigned>((w.bk_pad + 31) / 32), static_cast<unsigned>((D + 31) / 32));
+    transpose_cast_kernel<<<tg, tb, 0, st>>>(dZ, dzt, R, (int)D, w.bk_pad);
+    MINER_LAUNCH_OK("transpose_cast(dZ)");
+    transpose_cast_kernel<<<tg, tb, 0, st>>>(interests, it, R, (int)D, w.bk_pad);
+    MINER_LAUNCH_OK("transpose_cast(I)");
+    rc = launch_tc_gemm(dzt, nullptr, id_dtype, 0, it, grad_w_target, nullptr, D, D, w.bk_pad, EPI_NONE, st);      // dWt[o,i] = sum_r dZ[r,o] I[r,i]
+    if (rc) return rc;
+  } else {
     dim3 tb(32, 8), tg(static_cast<unsigned>((D + 31) / 32), static_cast<unsigned>((D + 31) / 32));
     transpose_kernel<<<tg, tb, 0, st>>>(w_target, WtT, (int)D, (int)D);
     MINER_LAUNCH_OK("transpose");
@@ -489,7 +585,20 @@ extern "C" int miner_train_bwd(const void* table, int64_t n_rows, int table_dtyp
     MINER_LAUNCH_OK("sum_partials(dcodes)");
   }
   // 4. Z1 = E Wp^T:  dWp = dZ1^T E  (E gathered from the table)
-  {
+  if (tensor) {
+    dim3 tb(32, 8);
+    const int64_t R = B * H;
+    __nv_bfloat16* dz1t = reinterpret_cast<__nv_bfloat16*>(ws + w.dz1t);
+    uint16_t* et = reinterpret_cast<uint16_t*>(ws + w.et);
+    transpose_cast_kernel<<<dim3(static_cast<unsigned>((w.bh_pad + 31) / 32), static_cast<unsigned>((Dc + 31) / 32)), tb, 0, st>>>(dZ1, dz1t, R, (int)Dc,
+                                                                                                                              w.bh_pad);
+    MINER_LAUNCH_OK("transpose_cast(dZ1)");
+    gather_transpose_kernel<<<dim3(static_cast<unsigned>((w.bh_pad + 31) / 32), static_cast<unsigned>((D + 31) / 32)), tb, 0, st>>>(
+        static_cast<const uint16_t*>(table), n_rows, his_ids, id_dtype, R, (int)D, w.bh_pad, et);
+    MINER_LAUNCH_OK("gather_transpose(E)");
+    const int rc = launch_tc_gemm(dz1t, nullptr, id_dtype, 0, et, grad_w_proj, nullptr, Dc, D, w.bh_pad, EPI_NONE, st);     // dWp[c,d] = sum_r dZ1[r,c] E[r,d]
+    if (rc) return rc;
+  } else {
     const int64_t R = B * H;
     const int64_t rps = ((R + w.s_wp - 1) / w.s_wp + 15) / 16 * 16;
     dim3 grid(static_cast<unsigned>((D + 63) / 64), static_cast<unsigned>((Dc + 63) / 64), static_cast<unsigned>(w.s_wp));

@@ -50,15 +50,16 @@ class _MinerTrainFn(torch.autograd.Function):
     """Train variant of the table-based forward: ``miner_train_fwd`` / ``miner_train_bwd``."""
 
     @staticmethod
-    def forward(ctx, w_proj: Tensor, codes: Tensor, w_target: Tensor, table: Tensor, his_ids: Tensor, his_mask: Tensor, cand_ids: Tensor):
-        interests, scores, saved = ops.train_forward(table, his_ids, his_mask, cand_ids, w_proj, codes, w_target)
+    def forward(ctx, w_proj: Tensor, codes: Tensor, w_target: Tensor, table: Tensor, his_ids: Tensor, his_mask: Tensor, cand_ids: Tensor,
+                math: int):
+        interests, scores, saved = ops.train_forward(table, his_ids, his_mask, cand_ids, w_proj, codes, w_target, math)
         ctx.saved = saved
         return interests, scores
 
     @staticmethod
     def backward(ctx, d_interests, d_scores):
         gwp, gc, gwt = ops.train_backward(ctx.saved, d_scores, d_interests)
-        return gwp, gc, gwt, None, None, None, None
+        return gwp, gc, gwt, None, None, None, None, None
 
 
 def _attach(out: Tensor, *params: Tensor) -> Tensor:
@@ -176,6 +177,7 @@ class Miner(nn.Module):
         self._prepared = None                        # (version key, ops.ScoreWeights)
         self._table_proj = None                      # (version key, ops.TableProjections)
         self.table_level = False                     # forward(): opt into the table-level mode (score_impressions uses it by default)
+        self.train_math = 'fp32'                     # train variant: 'fp32' (reference arithmetic) or 'tensor' (bf16 tcgen05 GEMMs, as autocast)
 
     # -- parameter staging -------------------------------------------------------------------------------------
     def _weights(self, with_bf16: bool) -> ops.ScoreWeights:
@@ -230,7 +232,9 @@ class Miner(nn.Module):
                     and any(p.requires_grad for p in self.parameters())):
                 # train variant (reference trainer.py:246-261): forward that keeps its intermediates + real backward kernels
                 return _MinerTrainFn.apply(self.poly_attn.linear.weight, self.poly_attn.context_codes,
-                                           self.target_aware_attn.linear.weight, table, his_ids, his_mask, cand_ids)
+                                           self.target_aware_attn.linear.weight, table, his_ids, his_mask, cand_ids,
+                                           L.MATH_TENSOR if (self.train_math == 'tensor' and table.dtype == torch.bfloat16
+                                                             and table.shape[1] % 64 == 0) else L.MATH_FP32)
             if self.table_level and table.dtype == torch.bfloat16 and ops.score_table_supported(his_length, self.poly_attn.context_codes.shape[0],
                                                                                                table.shape[1]):
                 interests, scores = ops.score_table(self.table_projections(), his_ids, his_mask, cand_ids, self.score_type,

@@ -464,10 +464,11 @@ class TrainSaved:
 
 
 def train_forward(table: torch.Tensor, his_ids: torch.Tensor, his_mask: torch.Tensor, cand_ids: torch.Tensor,
-                  w_proj: torch.Tensor, codes: torch.Tensor, w_target: torch.Tensor):
+                  w_proj: torch.Tensor, codes: torch.Tensor, w_target: torch.Tensor, math: int = L.MATH_FP32):
     """Miner.forward (reference model.py:61-138, 'weighted', no category bias) keeping what the backward needs.
 
-    Dense layout, ``cand_ids`` (B,C).  Returns ``(interests (B,K,D), scores (B,C), saved)``.
+    Dense layout, ``cand_ids`` (B,C).  Returns ``(interests (B,K,D), scores (B,C), saved)``.  ``math=MATH_TENSOR`` runs the
+    projection-sized GEMMs of the step on tcgen05 with bf16 operands (bf16 table, D % 64 == 0).
     """
     dev = _need_cuda(table, his_ids, his_mask, cand_ids, w_proj, codes, w_target)
     lib = L.load()
@@ -485,14 +486,16 @@ def train_forward(table: torch.Tensor, his_ids: torch.Tensor, his_mask: torch.Te
     f = dict(dtype=torch.float32, device=dev)
     interests, scores = torch.empty(B, K, D, **f), torch.empty(B, Cn, **f)
     t, w, z = torch.empty(B * H, Dc, **f), torch.empty(B, K, H, **f), torch.empty(B * K, D, **f)
-    ws_bytes = lib.miner_train_workspace_bytes(B, H, K, Dc, D)
+    wp16 = cast_bf16(wp) if math == L.MATH_TENSOR else None
+    wt16 = cast_bf16(wt) if math == L.MATH_TENSOR else None
+    ws_bytes = lib.miner_train_workspace_bytes(B, H, K, Dc, D, math)
     ws = torch.empty(max(ws_bytes, 1), dtype=torch.uint8, device=dev)
     with torch.cuda.device(dev):
         L.check(lib.miner_train_fwd(_ptr(table), table.shape[0], _table_dtype(table), _ptr(hid), _ptr(m), _ptr(cid), it, _ptr(wp), _ptr(cd),
-                                    _ptr(wt), B, H, Cn, K, Dc, D, _ptr(interests), _ptr(scores), _ptr(t), _ptr(w), _ptr(z), _ptr(ws),
-                                    ws.numel(), _stream()))
+                                    _ptr(wt), B, H, Cn, K, Dc, D, _ptr(interests), _ptr(scores), _ptr(t), _ptr(w), _ptr(z), math,
+                                    _ptr(wp16), _ptr(wt16), _ptr(ws), ws.numel(), _stream()))
     saved = TrainSaved(table=table, his_ids=hid, his_mask=m, cand_ids=cid, id_dtype=it, w_proj=wp, codes=cd, w_target=wt, t=t, w=w, z=z,
-                       interests=interests, ws=ws, dims=(B, H, Cn, K, Dc, D))
+                       interests=interests, ws=ws, dims=(B, H, Cn, K, Dc, D), math=math, w_proj_bf16=wp16, w_target_bf16=wt16)
     return interests, scores, saved
 
 
@@ -509,7 +512,8 @@ def train_backward(saved: TrainSaved, d_scores: Optional[torch.Tensor], d_intere
         L.check(lib.miner_train_bwd(_ptr(saved.table), saved.table.shape[0], _table_dtype(saved.table), _ptr(saved.his_ids),
                                     _ptr(saved.his_mask), _ptr(saved.cand_ids), saved.id_dtype, _ptr(saved.w_proj), _ptr(saved.codes),
                                     _ptr(saved.w_target), _ptr(saved.t), _ptr(saved.w), _ptr(saved.interests), _ptr(saved.z), _ptr(ds),
-                                    _ptr(di), B, H, Cn, K, Dc, D, _ptr(gwp), _ptr(gc), _ptr(gwt), _ptr(saved.ws), saved.ws.numel(), _stream()))
+                                    _ptr(di), B, H, Cn, K, Dc, D, _ptr(gwp), _ptr(gc), _ptr(gwt), saved.math, _ptr(saved.w_proj_bf16),
+                                    _ptr(saved.w_target_bf16), _ptr(saved.ws), saved.ws.numel(), _stream()))
     return gwp, gc, gwt
 
 
