@@ -156,16 +156,28 @@ __global__ void __launch_bounds__(TT) target_bwd_kernel(const void* __restrict__
   __syncthreads();
   const float* Ib = interests + b * static_cast<int64_t>(K) * D;
   const float* Zb = Z + b * static_cast<int64_t>(K) * D;
-  for (int p = warp; p < C * K; p += TT / 32) {
-    const int c = p / K, k = p - c * K;
-    float sm_ = 0.f, sa_ = 0.f;
-    for (int d = lane; d < D; d += 32) {
-      const float cd = Cd[c * D + d];
-      sm_ = fmaf(cd, Ib[static_cast<int64_t>(k) * D + d], sm_);                       // model.py:127
-      sa_ = fmaf(cd, gelu_erf(Zb[static_cast<int64_t>(k) * D + d]), sa_);             // model.py:212-213
+  constexpr int CB = 8;                                     // candidates per sweep over an interest row: gelu(Z) is evaluated once per sweep
+  for (int k = warp; k < K; k += TT / 32) {
+    for (int c0 = 0; c0 < C; c0 += CB) {
+      float sm_[CB], sa_[CB];
+#pragma unroll
+      for (int j = 0; j < CB; ++j) sm_[j] = sa_[j] = 0.f;
+      for (int d = lane; d < D; d += 32) {
+        const float iv = Ib[static_cast<int64_t>(k) * D + d];
+        const float gv = gelu_erf(Zb[static_cast<int64_t>(k) * D + d]);                // model.py:212
+#pragma unroll
+        for (int j = 0; j < CB; ++j) {
+          const float cd = c0 + j < C ? Cd[(c0 + j) * D + d] : 0.f;
+          sm_[j] = fmaf(cd, iv, sm_[j]);                                               // model.py:127
+          sa_[j] = fmaf(cd, gv, sa_[j]);                                               // model.py:213
+        }
+      }
+#pragma unroll
+      for (int j = 0; j < CB; ++j) {
+        const float vm = warp_sum(sm_[j]), va = warp_sum(sa_[j]);
+        if (lane == 0 && c0 + j < C) { m[(c0 + j) * K + k] = vm; a[(c0 + j) * K + k] = va; }
+      }
     }
-    sm_ = warp_sum(sm_); sa_ = warp_sum(sa_);
-    if (lane == 0) { m[p] = sm_; a[p] = sa_; }
   }
   __syncthreads();
   if (tid < C) {
@@ -245,14 +257,33 @@ __global__ void __launch_bounds__(TT) poly_bwd_kernel(const void* __restrict__ t
         Ec[h * (DK + 1) + d] = (d < dn && id >= 0) ? table_elem(table, table_dtype, static_cast<int64_t>(id) * D + d0 + d) : 0.f;
       }
       __syncthreads();
-      for (int p = tid; p < npairs; p += TT) {
-        const int k = p / H, h = p - k * H;
-        const float* x = dIc + k * (DK + 1);
-        const float* y = Ec + h * (DK + 1);
-        float s = 0.f;
+      // 4 (codes) x 2 (slots) register tiles: 6 shared-memory loads per 8 FMAs
+      const int th_n = (H + 1) / 2, tk_n = (K + 3) / 4;
+      for (int t = tid; t < th_n * tk_n; t += TT) {
+        const int tk = t / th_n, th = t - tk * th_n;
+        const int k0 = tk * 4, h0 = th * 2;
+        const float* x[4];
+        const float* y[2];
+#pragma unroll
+        for (int i = 0; i < 4; ++i) x[i] = dIc + (k0 + i < K ? k0 + i : K - 1) * (DK + 1);
+#pragma unroll
+        for (int j = 0; j < 2; ++j) y[j] = Ec + (h0 + j < H ? h0 + j : H - 1) * (DK + 1);
+        float acc[4][2] = {{0.f, 0.f}, {0.f, 0.f}, {0.f, 0.f}, {0.f, 0.f}};
 #pragma unroll 8
-        for (int d = 0; d < DK; ++d) s = fmaf(x[d], y[d], s);
-        dw[p] += s;
+        for (int d = 0; d < DK; ++d) {
+          const float y0 = y[0][d], y1 = y[1][d];
+#pragma unroll
+          for (int i = 0; i < 4; ++i) {
+            const float xv = x[i][d];
+            acc[i][0] = fmaf(xv, y0, acc[i][0]);
+            acc[i][1] = fmaf(xv, y1, acc[i][1]);
+          }
+        }
+#pragma unroll
+        for (int i = 0; i < 4; ++i)
+#pragma unroll
+          for (int j = 0; j < 2; ++j)
+            if (k0 + i < K && h0 + j < H) dw[(k0 + i) * H + h0 + j] += acc[i][j];
       }
       __syncthreads();
     }
@@ -277,11 +308,18 @@ __global__ void __launch_bounds__(TT) poly_bwd_kernel(const void* __restrict__ t
       dZ1[(b * H + h) * Dc + dc] = s * (1.0f - t * t);
     }
     // dcodes += dlogits T                                                              (model.py:174)
-    for (int i = tid; i < K * Dc; i += TT) {
-      const int k = i / Dc, dc = i - k * Dc;
-      float s = 0.f;
-      for (int h = 0; h < H; ++h) s = fmaf(dw[k * H + h], T[(b * H + h) * Dc + dc], s);
-      dcodes_s[i] += s;
+    for (int i = tid; i < ((K + 3) / 4) * Dc; i += TT) {                               // 4 codes per thread: one T load feeds 4 FMAs
+      const int k4 = i / Dc, dc = i - k4 * Dc;
+      const int k0 = k4 * 4;
+      float s[4] = {0.f, 0.f, 0.f, 0.f};
+      for (int h = 0; h < H; ++h) {
+        const float tv = T[(b * H + h) * Dc + dc];
+#pragma unroll
+        for (int j = 0; j < 4; ++j) s[j] = fmaf(dw[(k0 + j < K ? k0 + j : K - 1) * H + h], tv, s[j]);
+      }
+#pragma unroll
+      for (int j = 0; j < 4; ++j)
+        if (k0 + j < K) dcodes_s[(k0 + j) * Dc + dc] += s[j];
     }
     __syncthreads();
   }
