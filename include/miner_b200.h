@@ -160,7 +160,7 @@ int miner_cand_score_fwd(const void* i_hi, const void* i_lo, const void* w_targe
  *      miner_table_project computes them (once per weight version / table; bench.py does it inside every timed step);
  *      miner_score_table_fwd is Miner.forward (model.py:61-138) for B impressions from table, lg, tw in one kernel:
  *      masked softmax over the history (1e-30 fill, model.py:180), interests, gelu, matching scores, softmax over K, score.
- *      Needs a bf16 table, H <= 128, K <= 64, D % 64 == 0 (two impressions share a tile when H <= 64 and K <= 32).
+ *      Needs a bf16 table, H <= 128 with K <= 64 or H <= 256 with K <= 32, D % 64 == 0 (two impressions share a tile when H <= 64 and K <= 32).
  *      out_interests (B,K,D) fp32 or NULL. */
 size_t miner_table_project_workspace_bytes(int64_t n_rows, int64_t Dc);
 int miner_table_project(const void* table_bf16, int64_t n_rows, int64_t D, const void* w_proj_bf16, const float* codes,

@@ -56,12 +56,12 @@ constexpr int E_BYTES = TM * FB * 2;         // 16 KB
 constexpr int ST1_BYTES = 2 * E_BYTES;
 constexpr int NC_MAX = 96;                   // candidate columns per pass
 constexpr int C_BYTES = NC_MAX * FB * 2;     // 12 KB
-template <int KM>
+template <int KM, int NH>
 struct Shape {
   static constexpr int LS = KM;              // logits scratch row stride (floats)
   static constexpr int SS = KM + 1;          // score scratch row stride (floats)
-  static constexpr int SCRATCH_FLOATS = (TM * LS > 2 * NC_MAX * SS ? TM * LS : 2 * NC_MAX * SS + 2) & ~1;
-  static constexpr int S1 = KM > 32 ? S1_MAX - 1 : S1_MAX;
+  static constexpr int SCRATCH_FLOATS = (TM * NH * LS > 2 * NC_MAX * SS ? TM * NH * LS : 2 * NC_MAX * SS + 2) & ~1;
+  static constexpr int S1 = (KM > 32 || NH > 1) ? S1_MAX - 1 : S1_MAX;
   static constexpr int SMEM = 1024 + S1 * ST1_BYTES + S2 * C_BYTES + SCRATCH_FLOATS * 4 + 512;
 };
 constexpr int T_EPI = 256, T_SMX = 128;                // 8 epilogue warps, 4 softmax / score warps
@@ -71,10 +71,10 @@ constexpr int G1_STEP = T_G1 / 8, G2_STEP = T_G2 / 8;
 constexpr int W_G2 = T_G1 / 32, W_MMA = W_G2 + T_G2 / 32, W_EPI0 = W_MMA + 1, W_SMX0 = W_EPI0 + T_EPI / 32;
 constexpr int T_THREADS = (W_SMX0 + T_SMX / 32) * 32;
 // TMEM map (512 columns)
-constexpr int AW_COL = 0;                    // softmax weights, packed bf16: 128 slots -> 64 columns
-constexpr int IP_COL = 64;                   // 2 buffers x (I 64 | P 64) fp32; their first 32 columns become the packed A operands
-constexpr int DM_COL = IP_COL + 2 * 128;     // matching scores  m[(i,k,hl), c]
-constexpr int DA_COL = DM_COL + NC_MAX;      // attention logits a[(i,k,hl), c]
+// (NH = 128-slot halves of a tile's history: 1, or 2 for 128 < H <= 256)
+constexpr int AW_COL = 0;                    // softmax weights, packed bf16: 128 NH slots -> 64 NH columns
+// then IP_COL = 64 NH: 2 buffers x (I 64 | P 64) fp32, their first 32 columns become the packed A operands;
+// DM_COL = IP_COL + 256: matching scores m[(i,k,hl), c];  DA_COL = DM_COL + NCM: attention logits;  NCM = 96 (NH = 1) or 64
 
 // Optional cycle accounting (build with -DMINER_TS_PROF): per CTA, 16 counters for one thread of each role (0 MMA issuer,
 // 1 epilogue (interest half), 2 gather, 3 softmax, 4 epilogue (gelu half)), written to args.prof at the end (scripts/prof_tscore.py prints them).
@@ -137,9 +137,10 @@ __device__ __forceinline__ void tile_range(const TScoreArgs& a, int tile, int64_
   cs = cand_off(a, i0);
   ce = cand_off(a, i1);
 }
+template <int NCM>
 __device__ __forceinline__ int passes_of(int64_t cs, int64_t ce) {
   const int64_t n = ce - cs;
-  return n <= NC_MAX ? 1 : static_cast<int>((n + NC_MAX - 1) / NC_MAX);
+  return n <= NCM ? 1 : static_cast<int>((n + NCM - 1) / NCM);
 }
 
 __device__ __forceinline__ float gelu_fast(float x) {               // tanh form, hardware tanh (see cand_kernel.cu)
@@ -156,11 +157,13 @@ __device__ __forceinline__ uint32_t pack2(float a, float b) {
   __nv_bfloat162 v = __floats2bfloat162_rn(a, b);
   return *reinterpret_cast<uint32_t*>(&v);
 }
-template <int IPT, int KM>
+template <int IPT, int KM, int NH>
 __global__ void __launch_bounds__(T_THREADS, 1)
 tscore_kernel(const TScoreArgs args, int n_tiles) {
-  constexpr int HP = TM / IPT, LPI = TM / IPT;          // history slots / TMEM lanes per impression
-  constexpr int LS = Shape<KM>::LS, SS = Shape<KM>::SS, SCRATCH_FLOATS = Shape<KM>::SCRATCH_FLOATS, S1 = Shape<KM>::S1;
+  constexpr int HP = TM * NH / IPT, LPI = TM / IPT;     // history slots / TMEM lanes per impression
+  constexpr int LS = Shape<KM, NH>::LS, SS = Shape<KM, NH>::SS, SCRATCH_FLOATS = Shape<KM, NH>::SCRATCH_FLOATS, S1 = Shape<KM, NH>::S1;
+  constexpr int NCM = NH == 1 ? NC_MAX : 64;            // candidate columns per pass
+  constexpr int IP_COL = 64 * NH, DM_COL = IP_COL + 256, DA_COL = DM_COL + NCM;
   extern __shared__ uint8_t smem_raw[];
   uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~static_cast<uintptr_t>(1023));
   uint8_t* st1 = smem;                                         // [S1][E 16 KB | TW 16 KB]
@@ -202,14 +205,14 @@ tscore_kernel(const TScoreArgs args, int n_tiles) {
     const char* table_b = reinterpret_cast<const char*>(args.table);
     const char* tw_b = reinterpret_cast<const char*>(args.tw);
     const uint32_t dst0 = tc::sw128_offset(r0, chunk);       // row r0 + G1_STEP jj sits jj * G1_STEP / 8 KB further
-    RawId ids_pre[G1_ROWS];                                  // raw ids of the next tile (see RawId)
+    RawId ids_pre[G1_ROWS * NH];                             // raw ids of the next tile (see RawId)
     auto fetch_ids = [&](int lt) {
       const int tile = static_cast<int>(blockIdx.x) + lt * static_cast<int>(gridDim.x);
 #pragma unroll
-      for (int jj = 0; jj < G1_ROWS; ++jj) {
-        const int r = r0 + G1_STEP * jj;
-        const int64_t imp = static_cast<int64_t>(tile) * IPT + r / HP;
-        const int h = r % HP;
+      for (int jj = 0; jj < G1_ROWS * NH; ++jj) {
+        const int slot = (jj / G1_ROWS) * TM + r0 + G1_STEP * (jj % G1_ROWS);      // half * 128 + row of the stage
+        const int64_t imp = static_cast<int64_t>(tile) * IPT + slot / HP;
+        const int h = slot % HP;
         const bool ok = h < H && imp < args.B;
         ids_pre[jj] = load_id_raw(args.his_ids, ok ? imp * H + h : 0, args.id_dtype);
       }
@@ -220,48 +223,44 @@ tscore_kernel(const TScoreArgs args, int n_tiles) {
     if (n_local > 0) { fetch_ids(0); tile_range<IPT>(args, static_cast<int>(blockIdx.x), cs, ce); }
     for (int lt = 0; lt < n_local; ++lt) {
       const int tile = static_cast<int>(blockIdx.x) + lt * static_cast<int>(gridDim.x);
-      uint32_t eoff[G1_ROWS];                                // byte offset of this thread's 16-byte chunk in its rows (table < 4 GB, checked by the launcher)
+      uint32_t eoff[G1_ROWS * NH];                           // byte offset of this thread's 16-byte chunk in its rows (table < 4 GB, checked by the launcher)
       uint32_t emask = 0;
 #pragma unroll
-      for (int jj = 0; jj < G1_ROWS; ++jj) {
-        const int r = r0 + G1_STEP * jj;
+      for (int jj = 0; jj < G1_ROWS * NH; ++jj) {
+        const int slot = (jj / G1_ROWS) * TM + r0 + G1_STEP * (jj % G1_ROWS);
         const int64_t id = id_of(ids_pre[jj], args.id_dtype);
-        const bool ok = r % HP < H && static_cast<int64_t>(tile) * IPT + r / HP < args.B && id >= 0 && id < args.n_rows;
+        const bool ok = slot % HP < H && static_cast<int64_t>(tile) * IPT + slot / HP < args.B && id >= 0 && id < args.n_rows;
         eoff[jj] = static_cast<uint32_t>(ok ? id : 0) * row_bytes + chunk * 16;
         emask |= ok ? (1u << jj) : 0u;
       }
       if (args.dbg & 1) emask = 0;
-      const int npass = passes_of(cs, ce);
+      const int npass = passes_of<NCM>(cs, ce);
       if (lt + 1 < n_local) {                                // the next tile's ids and candidate range are fetched a tile ahead
         fetch_ids(lt + 1);
         tile_range<IPT>(args, static_cast<int>(blockIdx.x) + (lt + 1) * static_cast<int>(gridDim.x), cs, ce);
       }
       for (int p = 0; p < npass; ++p) {
-        for (int j = 0; j < KB; ++j, ++g) {
-          const uint32_t s = g % S1, ph = (g / S1) & 1;
-          PROF_ADD(0);
-          tc::mbar_wait(&bars->empty1[s], ph ^ 1);
-          PROF_ADD(1);
-          const uint32_t base = tc::smem_u32(st1 + s * ST1_BYTES) + dst0;
-          const uint32_t jb = static_cast<uint32_t>(j) * (FB * 2);
+        for (int j = 0; j < KB; ++j) {
 #pragma unroll
-          for (int jj = 0; jj < G1_ROWS; ++jj) {
-            const uint32_t o = eoff[jj] + jb, sz = ((emask >> jj) & 1u) ? 16u : 0u;
-            tc::cp_async_16(base + jj * (G1_STEP * 128), table_b + o, sz);
-            tc::cp_async_16(base + E_BYTES + jj * (G1_STEP * 128), tw_b + o, (args.dbg & 2) ? 0u : sz);
-          }
+          for (int half = 0; half < NH; ++half, ++g) {             // one ring stage per 128-slot half
+            const uint32_t s = g % S1, ph = (g / S1) & 1;
+            PROF_ADD(0);
+            tc::mbar_wait(&bars->empty1[s], ph ^ 1);
+            PROF_ADD(1);
+            const uint32_t base = tc::smem_u32(st1 + s * ST1_BYTES) + dst0;
+            const uint32_t jb = static_cast<uint32_t>(j) * (FB * 2);
+#pragma unroll
+            for (int jj = 0; jj < G1_ROWS; ++jj) {
+              const uint32_t o = eoff[half * G1_ROWS + jj] + jb, sz = ((emask >> (half * G1_ROWS + jj)) & 1u) ? 16u : 0u;
+              tc::cp_async_16(base + jj * (G1_STEP * 128), table_b + o, sz);
+              tc::cp_async_16(base + E_BYTES + jj * (G1_STEP * 128), tw_b + o, (args.dbg & 2) ? 0u : sz);
+            }
 #ifdef MINER_TS_PROF
-          if (lane == 0) *reinterpret_cast<volatile long long*>(&bars->issue_clk[s][warp]) = clock64();
-#ifdef MINER_TS_PROF_LAT
-          if (warp == 0) {                                   // experiment: how long do this warp's own copies of the stage take to land?
-            const long long l0 = clock64();
-            tc::cp_async_wait_all();
-            prof_c[8] += clock64() - l0; prof_c[9] += 1;
+            if (lane == 0) *reinterpret_cast<volatile long long*>(&bars->issue_clk[s][warp]) = clock64();
+#endif
+            tc::cp_async_mbar_arrive_noinc(&bars->full1[s]);
+            PROF_ADD(2);
           }
-#endif
-#endif
-          tc::cp_async_mbar_arrive_noinc(&bars->full1[s]);
-          PROF_ADD(2);
         }
       }
     }
@@ -291,14 +290,14 @@ tscore_kernel(const TScoreArgs args, int n_tiles) {
     if (n_local > 0) {
       tile_range<IPT>(args, tile0, cs, ce);
       if (n_local > 1) tile_range<IPT>(args, tile0 + tstep, ncs, nce);
-      fetch_cands(cs, static_cast<int>(ce - cs < NC_MAX ? ce - cs : NC_MAX));
+      fetch_cands(cs, static_cast<int>(ce - cs < NCM ? ce - cs : NCM));
     }
     for (int lt = 0; lt < n_local; ++lt) {
-      const int npass = passes_of(cs, ce);
+      const int npass = passes_of<NCM>(cs, ce);
       if (lt + 2 < n_local) tile_range<IPT>(args, tile0 + (lt + 2) * tstep, n2cs, n2ce);
       for (int p = 0; p < npass; ++p) {
-        const int64_t pc0 = cs + static_cast<int64_t>(p) * NC_MAX;
-        const int nc = static_cast<int>(ce - pc0 < NC_MAX ? ce - pc0 : NC_MAX);
+        const int64_t pc0 = cs + static_cast<int64_t>(p) * NCM;
+        const int nc = static_cast<int>(ce - pc0 < NCM ? ce - pc0 : NCM);
         const int nc16 = nc <= 16 ? 16 : (nc + 15) & ~15;
         uint32_t coff[G2_ROWS];
         uint32_t cmask = 0;
@@ -312,10 +311,10 @@ tscore_kernel(const TScoreArgs args, int n_tiles) {
         if (args.dbg & 5) cmask = 0;
         // ids of the next unit: next pass of this tile, else first pass of the next tile (its range was loaded a tile ago)
         if (p + 1 < npass) {
-          const int64_t q0 = pc0 + NC_MAX;
-          fetch_cands(q0, static_cast<int>(ce - q0 < NC_MAX ? ce - q0 : NC_MAX));
+          const int64_t q0 = pc0 + NCM;
+          fetch_cands(q0, static_cast<int>(ce - q0 < NCM ? ce - q0 : NCM));
         } else if (lt + 1 < n_local) {
-          fetch_cands(ncs, static_cast<int>(nce - ncs < NC_MAX ? nce - ncs : NC_MAX));
+          fetch_cands(ncs, static_cast<int>(nce - ncs < NCM ? nce - ncs : NCM));
         }
         for (int j = 0; j < KB; ++j, ++g) {
           const uint32_t s = g % S2, ph = (g / S2) & 1;
@@ -337,7 +336,7 @@ tscore_kernel(const TScoreArgs args, int n_tiles) {
     const uint32_t idesc1 = tc::make_idesc_bf16_f32_major(TM, FB, false, true);        // B = gathered tile, MN-major
     const uint32_t idesc1w = tc::make_idesc_bf16_f32_major(TM, 2 * FB, false, true);
     (void)idesc1w;
-    uint32_t g1 = 0, g2 = 0, u = 0;
+    uint32_t g1 = 0, g2 = 0, u = 0, sg = 0;                      // blocks issued (S1 / S2), units, ring stages consumed
     bool pending = false;
     int pend_j = 0, pend_nc16 = 16;
     uint32_t pend_u = 0;
@@ -375,59 +374,43 @@ tscore_kernel(const TScoreArgs args, int n_tiles) {
     for (int lt = 0; lt < n_local; ++lt) {
       const int tile = static_cast<int>(blockIdx.x) + lt * static_cast<int>(gridDim.x);
       const int64_t cs = t_cs, ce = t_ce;
-      const int npass = passes_of(cs, ce);
+      const int npass = passes_of<NCM>(cs, ce);
       if (lt + 1 < n_local) tile_range<IPT>(args, tile + static_cast<int>(gridDim.x), t_cs, t_ce);      // a tile ahead: off the critical path
       for (int p = 0; p < npass; ++p, ++u) {
-        const int64_t pc0 = cs + static_cast<int64_t>(p) * NC_MAX;
-        const int nc = static_cast<int>(ce - pc0 < NC_MAX ? ce - pc0 : NC_MAX);
+        const int64_t pc0 = cs + static_cast<int64_t>(p) * NCM;
+        const int nc = static_cast<int>(ce - pc0 < NCM ? ce - pc0 : NCM);
         const int nc16 = nc <= 16 ? 16 : (nc + 15) & ~15;
         PROF_ADD(0);
         tc::mbar_wait(&bars->w_ready, u & 1);
         PROF_ADD(1);
         tc::tcgen05_fence_after();
         for (int j = 0; j < KB; ++j) {
-          const uint32_t s = g1 % S1, ph = (g1 / S1) & 1, b = g1 & 1;
-          PROF_ADD(0);
-#ifdef MINER_TS_PROF
-          const long long lat_a = clock64();
-#endif
-          tc::mbar_wait(&bars->full1[s], ph);
-#ifdef MINER_TS_PROF
-          {
-            const long long lat_b = clock64();
-            long long lat_c = 0;
-            for (int w_ = 0; w_ < 4; ++w_) {
-              const long long c_ = *reinterpret_cast<volatile long long*>(&bars->issue_clk[s][w_]);
-              lat_c = c_ > lat_c ? c_ : lat_c;
-            }
-            if (lat_b - lat_a > 400) { prof_c[8] += lat_b - lat_c; prof_c[9] += 1; prof_c[12] += lat_b - lat_a; prof_c[14] += (j == 0) ? 1 : ((j == 1) ? 1000000 : 0); } else { prof_c[10] += lat_a - lat_c; prof_c[11] += 1; prof_c[13] += lat_b - lat_a; }
-          }
-#endif
-          PROF_ADD(2);
-          tc::tcgen05_fence_after();
-          const uint64_t e_desc = tc::make_smem_desc_sw128_mn(tc::smem_u32(st1 + s * ST1_BYTES));
-          const uint64_t t_desc = tc::make_smem_desc_sw128_mn(tc::smem_u32(st1 + s * ST1_BYTES + E_BYTES));
+          const uint32_t b = g1 & 1;
           const uint32_t d_i = tmem + IP_COL + b * 128, d_p = d_i + 64;
-          if (tc::elect_one()) {
-#ifdef MINER_TS_N128
-            // one N = 128 MMA per k-step: B = [E_j | TW_j], two 64-feature atoms E_BYTES apart, D = [D_I | D_P]
-            const uint64_t et_desc = tc::make_smem_desc_sw128_mn_wide(tc::smem_u32(st1 + s * ST1_BYTES), E_BYTES);
 #pragma unroll
-            for (int ks = 0; ks < TM / 16; ++ks)
-              tc::umma_bf16_ts(d_i, tmem + AW_COL + 8 * ks, et_desc + ks * (2048 >> 4), idesc1w, ks != 0 ? 1u : 0u);
-            (void)e_desc; (void)t_desc; (void)d_p;
-#else
+          for (int half = 0; half < NH; ++half, ++sg) {
+            const uint32_t s = sg % S1, ph = (sg / S1) & 1;
+            PROF_ADD(0);
+            tc::mbar_wait(&bars->full1[s], ph);
+            PROF_ADD(2);
+            tc::tcgen05_fence_after();
+            const uint64_t e_desc = tc::make_smem_desc_sw128_mn(tc::smem_u32(st1 + s * ST1_BYTES));
+            const uint64_t t_desc = tc::make_smem_desc_sw128_mn(tc::smem_u32(st1 + s * ST1_BYTES + E_BYTES));
+            if (tc::elect_one()) {
 #pragma unroll
-            for (int ks = 0; ks < TM / 16; ++ks) {
-              tc::umma_bf16_ts(d_i, tmem + AW_COL + 8 * ks, e_desc + ks * (2048 >> 4), idesc1, ks != 0 ? 1u : 0u);
-              tc::umma_bf16_ts(d_p, tmem + AW_COL + 8 * ks, t_desc + ks * (2048 >> 4), idesc1, ks != 0 ? 1u : 0u);
+              for (int ks = 0; ks < TM / 16; ++ks) {
+                const uint32_t acc = (half | ks) != 0 ? 1u : 0u;
+                tc::umma_bf16_ts(d_i, tmem + AW_COL + half * 64 + 8 * ks, e_desc + ks * (2048 >> 4), idesc1, acc);
+                tc::umma_bf16_ts(d_p, tmem + AW_COL + half * 64 + 8 * ks, t_desc + ks * (2048 >> 4), idesc1, acc);
+              }
+              tc::umma_commit(&bars->empty1[s]);
+              if (half == NH - 1) {
+                tc::umma_commit(&bars->ip_full[b]);
+                if (j == KB - 1) tc::umma_commit(&bars->w_free);
+              }
             }
-#endif
-            tc::umma_commit(&bars->empty1[s]);
-            tc::umma_commit(&bars->ip_full[b]);
-            if (j == KB - 1) tc::umma_commit(&bars->w_free);
+            __syncwarp();
           }
-          __syncwarp();
           ++g1;
           PROF_ADD(3);
           if (pending) stage2();
@@ -455,7 +438,7 @@ tscore_kernel(const TScoreArgs args, int n_tiles) {
     for (int lt = 0; lt < n_local; ++lt) {
       const int tile = static_cast<int>(blockIdx.x) + lt * static_cast<int>(gridDim.x);
       const int64_t cs = t_cs, ce = t_ce;
-      const int npass = passes_of(cs, ce);
+      const int npass = passes_of<NCM>(cs, ce);
       if (lt + 1 < n_local) tile_range<IPT>(args, tile + static_cast<int>(gridDim.x), t_cs, t_ce);      // a tile ahead: off the critical path
       const int64_t i0 = static_cast<int64_t>(tile) * IPT;
       const int64_t my_imp = i0 + li;
@@ -593,7 +576,7 @@ tscore_kernel(const TScoreArgs args, int n_tiles) {
 #pragma unroll
       for (int c = 0; c < 16; ++c) z[c] = 0u;
 #pragma unroll
-      for (int cc = 0; cc < 4; ++cc) tc::tmem_st_32x16(tmem + lane_addr + AW_COL + cc * 16, z);
+      for (int cc = 0; cc < 4 * NH; ++cc) tc::tmem_st_32x16(tmem + lane_addr + AW_COL + cc * 16, z);
       tc::tmem_st_wait();
     }
     int64_t t_cs = 0, t_ce = 0;
@@ -601,7 +584,7 @@ tscore_kernel(const TScoreArgs args, int n_tiles) {
     for (int lt = 0; lt < n_local; ++lt) {
       const int tile = static_cast<int>(blockIdx.x) + lt * static_cast<int>(gridDim.x);
       const int64_t cs = t_cs, ce = t_ce;
-      const int npass = passes_of(cs, ce);
+      const int npass = passes_of<NCM>(cs, ce);
       if (lt + 1 < n_local) tile_range<IPT>(args, tile + static_cast<int>(gridDim.x), t_cs, t_ce);      // a tile ahead: off the critical path
       for (int p = 0; p < npass; ++p, ++u) {
         PROF_ADD(0);
@@ -609,39 +592,42 @@ tscore_kernel(const TScoreArgs args, int n_tiles) {
         {
           // logits of 32 slots per warp: lg rows are K consecutive floats (model.py:174 hoisted to the table).  Stored scaled by
           // log2(e): the softmax below runs on ex2.
-          const int slot = sw * 32 + lane;
-          const int64_t imp = static_cast<int64_t>(tile) * IPT + slot / HP;
-          const int h = slot % HP;
-          const bool valid = h < H && imp < args.B;
-          uint32_t info = 0;                                                   // id | code << 30; code 0 padding, 1 masked, 2 kept, 3 kept with a bad id
-          float bias = 0.f;
-          if (valid) {
-            const int64_t id = load_id(args.his_ids, imp * H + h, args.id_dtype);
-            const bool keep = args.mask[imp * H + h] != 0;
-            if (args.bias_mean) bias = args.bias_mean[imp * H + h];
-            const bool id_ok = id >= 0 && id < args.n_rows;
-            info = (id_ok ? static_cast<uint32_t>(id) : 0u) | ((keep ? (id_ok ? 2u : 3u) : 1u) << 30);
-          }
           const uint32_t Ku = static_cast<uint32_t>(K);
           const bool has_bias = args.bias_mean != nullptr;
 #pragma unroll
-          for (int kk = 0; kk < KM / 32; ++kk) {                               // 32 codes per pass
-            const int kcol = lane + 32 * kk;
-            const float* lgp = args.lg + kcol;
-            float v[32];
-#pragma unroll
-            for (int ss = 0; ss < 32; ++ss) {                                  // 32 independent 128-byte row loads in flight
-              const uint32_t info_s = __shfl_sync(0xffffffffu, info, ss);
-              v[ss] = ((info_s >> 30) == 2u && kcol < K) ? lgp[(info_s & 0x3fffffffu) * Ku] : 0.f;
+          for (int hh = 0; hh < NH; ++hh) {                                    // 128 slots per pass, 32 per warp
+            const int slot = hh * TM + sw * 32 + lane;
+            const int64_t imp = static_cast<int64_t>(tile) * IPT + slot / HP;
+            const int h = slot % HP;
+            const bool valid = h < H && imp < args.B;
+            uint32_t info = 0;                                                 // id | code << 30; code 0 padding, 1 masked, 2 kept, 3 kept with a bad id
+            float bias = 0.f;
+            if (valid) {
+              const int64_t id = load_id(args.his_ids, imp * H + h, args.id_dtype);
+              const bool keep = args.mask[imp * H + h] != 0;
+              if (args.bias_mean) bias = args.bias_mean[imp * H + h];
+              const bool id_ok = id >= 0 && id < args.n_rows;
+              info = (id_ok ? static_cast<uint32_t>(id) : 0u) | ((keep ? (id_ok ? 2u : 3u) : 1u) << 30);
             }
 #pragma unroll
-            for (int ss = 0; ss < 32; ++ss) {
-              const uint32_t code_s = __shfl_sync(0xffffffffu, info, ss) >> 30;
-              float x = v[ss];
-              if (has_bias) x += __shfl_sync(0xffffffffu, bias, ss);           // model.py:174-177
-              if (code_s == 1u) x = kMaskFill;                                 // model.py:180 (1e-30, not -inf)
-              if (code_s == 0u) x = -INFINITY;                                 // tile padding: not part of the history
-              L[(sw * 32 + ss) * LS + kcol] = x * 1.4426950408889634f;
+            for (int kk = 0; kk < KM / 32; ++kk) {                             // 32 codes per pass
+              const int kcol = lane + 32 * kk;
+              const float* lgp = args.lg + kcol;
+              float v[32];
+#pragma unroll
+              for (int ss = 0; ss < 32; ++ss) {                                // 32 independent 128-byte row loads in flight
+                const uint32_t info_s = __shfl_sync(0xffffffffu, info, ss);
+                v[ss] = ((info_s >> 30) == 2u && kcol < K) ? lgp[(info_s & 0x3fffffffu) * Ku] : 0.f;
+              }
+#pragma unroll
+              for (int ss = 0; ss < 32; ++ss) {
+                const uint32_t code_s = __shfl_sync(0xffffffffu, info, ss) >> 30;
+                float x = v[ss];
+                if (has_bias) x += __shfl_sync(0xffffffffu, bias, ss);         // model.py:174-177
+                if (code_s == 1u) x = kMaskFill;                               // model.py:180 (1e-30, not -inf)
+                if (code_s == 0u) x = -INFINITY;                               // tile padding: not part of the history
+                L[(hh * TM + sw * 32 + ss) * LS + kcol] = x * 1.4426950408889634f;
+              }
             }
           }
         }
@@ -649,9 +635,53 @@ tscore_kernel(const TScoreArgs args, int n_tiles) {
         PROF_ADD(1);
         // softmax over the history (model.py:181): per 16-lane group, thread t owns code k = 8 group + t/4 and the 16 slots
         // {2c, 2c+1 : c = t%4 + 4n}; the (hi, lo) rows of the pair leave through one 16x128b store
+        if constexpr (IPT == 1) {
+          // one impression per tile (up to 128 NH slots): too many weights to hold in registers across the wait, so wait first,
+          // take max and sum in two passes over the logits, then recompute, pack and store 32 packed columns at a time
+          if (u > 0) tc::mbar_wait(&bars->w_free, (u - 1) & 1);                // S1 of the previous unit no longer reads A_w
+          PROF_ADD(3);
+          tc::tcgen05_fence_after();
+          constexpr int NCT = HP / 8;                                          // packed columns per thread: c = t%4 + 4n, n < NCT
+#pragma unroll
+          for (int hf = 0; hf < 2; ++hf) {
+            const int k = (((q * 32) % LPI) / 16 + hf) * 8 + (lane >> 2);
+            const bool row_ok = k < K;
+            const float* col = L + (row_ok ? k : 0);
+            float mx = -INFINITY;
+            for (int n = 0; n < NCT; ++n) {
+              const int c = (lane & 3) + 4 * n;
+              mx = fmaxf(mx, fmaxf(col[(2 * c) * LS], col[(2 * c + 1) * LS]));
+            }
+            mx = fmaxf(mx, __shfl_xor_sync(0xffffffffu, mx, 1));
+            mx = fmaxf(mx, __shfl_xor_sync(0xffffffffu, mx, 2));
+            const bool dead = mx == -INFINITY || !row_ok;                      // impression past the end of the batch / unused row
+            float sum = 0.f;
+            for (int n = 0; n < NCT; ++n) {
+              const int c = (lane & 3) + 4 * n;
+              sum += dead ? 0.f : ex2_approx(col[(2 * c) * LS] - mx) + ex2_approx(col[(2 * c + 1) * LS] - mx);
+            }
+            sum += __shfl_xor_sync(0xffffffffu, sum, 1);
+            sum += __shfl_xor_sync(0xffffffffu, sum, 2);
+            const float inv = dead ? 0.f : __fdividef(1.0f, sum);
+#pragma unroll
+            for (int part = 0; part < NCT / 8; ++part) {
+              uint32_t o[16];
+#pragma unroll
+              for (int n = 0; n < 8; ++n) {
+                const int c = (lane & 3) + 4 * (8 * part + n);
+                const float w0 = dead ? 0.f : ex2_approx(col[(2 * c) * LS] - mx) * inv;          // model.py:181
+                const float w1 = dead ? 0.f : ex2_approx(col[(2 * c + 1) * LS] - mx) * inv;
+                const uint32_t hi = pack2(w0, w1);
+                o[2 * n] = hi;
+                o[2 * n + 1] = pack2(w0 - __uint_as_float(hi << 16), w1 - __uint_as_float(hi & 0xffff0000u));
+              }
+              tc::tmem_st_16x128b_x8(tmem + (static_cast<uint32_t>(q * 32 + hf * 16) << 16) + AW_COL + part * 32, o);
+            }
+          }
+          PROF_ADD(2);
+        } else {
         constexpr int NC8 = HP / 8;                                            // packed columns per thread: c = t%4 + 4n, n < NC8
         uint32_t pk[2][2 * NC8];
-        if (IPT == 1 && u > 0) tc::mbar_wait(&bars->w_free, (u - 1) & 1);      // 128-slot rows: too many registers to hold across the wait
 #pragma unroll
         for (int hf = 0; hf < 2; ++hf) {
           const int k = (((q * 32) % LPI) / 16 + hf) * 8 + (lane >> 2);
@@ -687,18 +717,13 @@ tscore_kernel(const TScoreArgs args, int n_tiles) {
           }
         }
         PROF_ADD(2);
-        if (IPT != 1 && u > 0) tc::mbar_wait(&bars->w_free, (u - 1) & 1);      // S1 of the previous unit no longer reads A_w
+        if (u > 0) tc::mbar_wait(&bars->w_free, (u - 1) & 1);                  // S1 of the previous unit no longer reads A_w
         PROF_ADD(3);
         tc::tcgen05_fence_after();
 #pragma unroll
         for (int hf = 0; hf < 2; ++hf)
-#pragma unroll
-          for (int part = 0; part < NC8 / 8; ++part) {
-            uint32_t o[16];
-#pragma unroll
-            for (int c = 0; c < 16; ++c) o[c] = pk[hf][16 * part + c];
-            tc::tmem_st_16x128b_x8(tmem + (static_cast<uint32_t>(q * 32 + hf * 16) << 16) + AW_COL + li * (HP / 2) + part * 32, o);
-          }
+          tc::tmem_st_16x128b_x8(tmem + (static_cast<uint32_t>(q * 32 + hf * 16) << 16) + AW_COL + li * (HP / 2), pk[hf]);
+        }
         tc::tmem_st_wait();
         tc::tcgen05_fence_before();
         tc::mbar_arrive(&bars->w_ready);
@@ -706,8 +731,8 @@ tscore_kernel(const TScoreArgs args, int n_tiles) {
         if (u > 0) score_stage(u - 1);
         {
           const int64_t my_imp = static_cast<int64_t>(tile) * IPT + li;
-          f_pc0 = cs + static_cast<int64_t>(p) * NC_MAX;
-          f_nc = static_cast<int>(ce - f_pc0 < NC_MAX ? ce - f_pc0 : NC_MAX);
+          f_pc0 = cs + static_cast<int64_t>(p) * NCM;
+          f_nc = static_cast<int>(ce - f_pc0 < NCM ? ce - f_pc0 : NCM);
           f_cs = my_imp < args.B ? cand_off(args, my_imp) : ce;
           f_ce = my_imp < args.B ? cand_off(args, my_imp + 1) : ce;
         }
@@ -726,7 +751,7 @@ tscore_kernel(const TScoreArgs args, int n_tiles) {
 }  // namespace
 
 bool tscore_kernel_supported(int64_t H, int64_t K, int64_t D) {
-  return H >= 1 && H <= TM && K >= 1 && K <= KMAX && D >= FB && D % FB == 0 && D <= 8192;
+  return H >= 1 && (H <= TM || (H <= 2 * TM && K <= 32)) && K >= 1 && K <= KMAX && D >= FB && D % FB == 0 && D <= 8192;
 }
 
 int launch_tscore_kernel(const void* table, const void* tw, const float* lg, int64_t n_rows, const void* his_ids, int id_dtype,
@@ -735,7 +760,7 @@ int launch_tscore_kernel(const void* table, const void* tw, const float* lg, int
                          cudaStream_t stream) {
   if (B == 0) return MINER_OK;
   if (!tscore_kernel_supported(H, K, D)) {
-    set_error("table-level scoring: unsupported shape H=%lld K=%lld D=%lld (need H <= 128, K <= 64, D %% 64 == 0)", (long long)H, (long long)K,
+    set_error("table-level scoring: unsupported shape H=%lld K=%lld D=%lld (need H <= 128 and K <= 64, or H <= 256 and K <= 32; D %% 64 == 0)", (long long)H, (long long)K,
               (long long)D);
     return MINER_ERR_UNSUPPORTED;
   }
@@ -759,14 +784,15 @@ int launch_tscore_kernel(const void* table, const void* tw, const float* lg, int
   const int ipt = (H <= TM / 2 && K <= 32) ? 2 : 1;
   const int64_t n_tiles = (B + ipt - 1) / ipt;
   const int grid = static_cast<int>(n_tiles < sm_count() ? n_tiles : sm_count());
-#define MINER_TS_LAUNCH(I, KMV)                                                                                                   \
-  do {                                                                                                                            \
-    MINER_CUDA_OK(cudaFuncSetAttribute(tscore_kernel<I, KMV>, cudaFuncAttributeMaxDynamicSharedMemorySize, Shape<KMV>::SMEM));   \
-    tscore_kernel<I, KMV><<<grid, T_THREADS, Shape<KMV>::SMEM, stream>>>(a, static_cast<int>(n_tiles));                          \
+#define MINER_TS_LAUNCH(I, KMV, NHV)                                                                                                    \
+  do {                                                                                                                                  \
+    MINER_CUDA_OK(cudaFuncSetAttribute(tscore_kernel<I, KMV, NHV>, cudaFuncAttributeMaxDynamicSharedMemorySize, Shape<KMV, NHV>::SMEM)); \
+    tscore_kernel<I, KMV, NHV><<<grid, T_THREADS, Shape<KMV, NHV>::SMEM, stream>>>(a, static_cast<int>(n_tiles));                      \
   } while (0)
-  if (K > 32) MINER_TS_LAUNCH(1, 64);
-  else if (ipt == 2) MINER_TS_LAUNCH(2, 32);
-  else MINER_TS_LAUNCH(1, 32);
+  if (H > TM) MINER_TS_LAUNCH(1, 32, 2);                    // 128 < H <= 256: two 128-slot halves accumulate into one D_I | D_P pair
+  else if (K > 32) MINER_TS_LAUNCH(1, 64, 1);
+  else if (ipt == 2) MINER_TS_LAUNCH(2, 32, 1);
+  else MINER_TS_LAUNCH(1, 32, 1);
 #undef MINER_TS_LAUNCH
   MINER_LAUNCH_OK("tscore_kernel");
   return MINER_OK;

@@ -815,12 +815,14 @@ def test_table_project(N, D, K, Dc):
                                                       (301, 50, 256, 32, 48, 12.0, 70), (33, 64, 128, 16, 40, 20.0, 300),
                                                       (9, 50, 768, 32, 200, 150.0, 300), (1, 1, 64, 1, 16, 2.0, 2), (5, 7, 192, 5, 16, 40.0, 100),
                                                       (33, 100, 256, 32, 48, 20.0, 300), (7, 128, 128, 16, 40, 20.0, 120), (10, 65, 64, 8, 24, 5.0, 10),
-                                                      (33, 50, 256, 64, 48, 20.0, 300), (5, 100, 128, 64, 40, 12.0, 120), (4, 20, 64, 40, 24, 5.0, 10)])
+                                                      (33, 50, 256, 64, 48, 20.0, 300), (5, 100, 128, 64, 40, 12.0, 120), (4, 20, 64, 40, 24, 5.0, 10),
+                                                      (21, 200, 256, 32, 48, 20.0, 300), (3, 256, 64, 8, 24, 5.0, 10), (6, 129, 128, 16, 40, 70.0, 200)])
 @pytest.mark.parametrize('score_type', ['weighted', 'max', 'mean'])
 def test_table_level_scores(B, H, D, K, Dc, mean_c, max_c, score_type):
     """Table-level mode (miner_table_project + miner_score_table_fwd) against the oracle in the reference's operation order on the
     same bf16-valued weights: CSR impressions of 2..300 candidates (several 96-candidate passes), ragged histories with left
-    padding, both tile shapes (two impressions per tile for H <= 64 and K <= 32, one for H <= 128 or K <= 64), with and without the category-bias scalar.  Interests 3e-5, scores 3e-4 normwise (tolerance north_star: 1e-3)."""
+    padding, every tile shape (two impressions per tile for H <= 64 and K <= 32, one for H <= 128 or K <= 64, one over two 128-slot halves
+    for H <= 256), with and without the category-bias scalar.  Interests 3e-5, scores 3e-4 normwise (tolerance north_star: 1e-3)."""
     from miner_b200 import ops, synth
     N = 900
     table = synth.make_table(N, D, 5, torch.bfloat16)
@@ -872,7 +874,8 @@ def test_table_level_dense_layout_and_invariance():
     # empty batch / unsupported shapes
     _, s0 = ops.score_table(tp, his[:0].to(DEV), mask[:0].to(DEV), cd[:0].to(DEV))
     assert s0.shape == (0, Cd)
-    assert ops.score_table_supported(100, 32, 256) and not ops.score_table_supported(129, 32, 256)
+    assert ops.score_table_supported(100, 32, 256) and ops.score_table_supported(200, 32, 256) and not ops.score_table_supported(257, 32, 256)
+    assert not ops.score_table_supported(200, 64, 256)
     assert ops.score_table_supported(50, 64, 256) and not ops.score_table_supported(50, 65, 256) and not ops.score_table_supported(50, 32, 100)
     with pytest.raises(ValueError, match='Invalid method of aggregating matching score'):
         ops.score_table(tp, his.to(DEV), mask.to(DEV), cd.to(DEV), 'median')
