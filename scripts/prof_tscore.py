@@ -44,13 +44,3 @@ for role, (rn, cn) in names.items():
     for i, n in enumerate(cn):
         print(f'    {n:24s} {p[:, role, i].mean() / tot * 100:5.1f} %')
 
-m = p[:, 0, :]
-print(f'(E, TW) stages the MMA warp waited > 400 cycles for: {m[:, 9].sum():.0f}, mean wait {m[:, 12].sum() / max(m[:, 9].sum(), 1):.0f}, mean issue->full {m[:, 8].sum() / max(m[:, 9].sum(), 1):.0f} cycles; '
-      f'others: {m[:, 11].sum():.0f}, mean wait {m[:, 13].sum() / max(m[:, 11].sum(), 1):.0f}, mean age at use {m[:, 10].sum() / max(m[:, 11].sum(), 1):.0f} cycles')
-
-c14 = m[:, 14].sum()
-print(f'   of the long waits: block 0 of a tile {c14 % 1000000:.0f}, block 1 {c14 // 1000000:.0f}')
-
-gm = p[:, 2, :]
-if gm[:, 9].sum() > 0:
-    print(f'   gather warp 0: cp.async.wait_all right after issuing a stage took {gm[:, 8].sum() / gm[:, 9].sum():.0f} cycles on average (-DMINER_TS_PROF_LAT)')
