@@ -61,7 +61,7 @@ struct Shape {
   static constexpr int LS = KM;              // logits scratch row stride (floats)
   static constexpr int SS = KM + 1;          // score scratch row stride (floats)
   static constexpr int SCRATCH_FLOATS = (TM * NH * LS > 2 * NC_MAX * SS ? TM * NH * LS : 2 * NC_MAX * SS + 2) & ~1;
-  static constexpr int S1 = (KM > 32 || NH > 1) ? S1_MAX - 1 : S1_MAX;
+  static constexpr int S1 = S1_MAX - (KM > 32 ? 1 : 0) - (NH > 1 ? 1 : 0);      // wider scratch takes ring stages
   static constexpr int SMEM = 1024 + S1 * ST1_BYTES + S2 * C_BYTES + SCRATCH_FLOATS * 4 + 512;
 };
 constexpr int T_EPI = 256, T_SMX = 128;                // 8 epilogue warps, 4 softmax / score warps
@@ -751,7 +751,7 @@ tscore_kernel(const TScoreArgs args, int n_tiles) {
 }  // namespace
 
 bool tscore_kernel_supported(int64_t H, int64_t K, int64_t D) {
-  return H >= 1 && (H <= TM || (H <= 2 * TM && K <= 32)) && K >= 1 && K <= KMAX && D >= FB && D % FB == 0 && D <= 8192;
+  return H >= 1 && H <= 2 * TM && K >= 1 && K <= KMAX && D >= FB && D % FB == 0 && D <= 8192;
 }
 
 int launch_tscore_kernel(const void* table, const void* tw, const float* lg, int64_t n_rows, const void* his_ids, int id_dtype,
@@ -760,7 +760,7 @@ int launch_tscore_kernel(const void* table, const void* tw, const float* lg, int
                          cudaStream_t stream) {
   if (B == 0) return MINER_OK;
   if (!tscore_kernel_supported(H, K, D)) {
-    set_error("table-level scoring: unsupported shape H=%lld K=%lld D=%lld (need H <= 128 and K <= 64, or H <= 256 and K <= 32; D %% 64 == 0)", (long long)H, (long long)K,
+    set_error("table-level scoring: unsupported shape H=%lld K=%lld D=%lld (need H <= 256, K <= 64, D %% 64 == 0)", (long long)H, (long long)K,
               (long long)D);
     return MINER_ERR_UNSUPPORTED;
   }
@@ -789,7 +789,8 @@ int launch_tscore_kernel(const void* table, const void* tw, const float* lg, int
     MINER_CUDA_OK(cudaFuncSetAttribute(tscore_kernel<I, KMV, NHV>, cudaFuncAttributeMaxDynamicSharedMemorySize, Shape<KMV, NHV>::SMEM)); \
     tscore_kernel<I, KMV, NHV><<<grid, T_THREADS, Shape<KMV, NHV>::SMEM, stream>>>(a, static_cast<int>(n_tiles));                      \
   } while (0)
-  if (H > TM) MINER_TS_LAUNCH(1, 32, 2);                    // 128 < H <= 256: two 128-slot halves accumulate into one D_I | D_P pair
+  if (H > TM && K > 32) MINER_TS_LAUNCH(1, 64, 2);          // 128 < H <= 256: two 128-slot halves accumulate into one D_I | D_P pair
+  else if (H > TM) MINER_TS_LAUNCH(1, 32, 2);
   else if (K > 32) MINER_TS_LAUNCH(1, 64, 1);
   else if (ipt == 2) MINER_TS_LAUNCH(2, 32, 1);
   else MINER_TS_LAUNCH(1, 32, 1);

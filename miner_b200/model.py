@@ -270,7 +270,7 @@ class Miner(nn.Module):
                           chunk: int = 16384, math: Optional[int] = None) -> Tensor:
         """Scores of every candidate of every impression, CSR layout (``cand_offsets`` (B+1,) into flat ``cand_ids``).
 
-        ``math``: ``MATH_TABLE`` (default when the shape allows: bf16 table, H <= 128 with K <= 64 or H <= 256 with K <= 32, D % 64 == 0) applies the two linear
+        ``math``: ``MATH_TABLE`` (default when the shape allows: bf16 table, H <= 256, K <= 64, D % 64 == 0) applies the two linear
         layers once per table row and scores in one kernel; ``MATH_TENSOR`` / ``MATH_FP32`` keep the reference operation order.
 
         Equals the reference's per-candidate eval rows (src/reader.py:376-379: one sample per candidate, interests

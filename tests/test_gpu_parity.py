@@ -816,7 +816,8 @@ def test_table_project(N, D, K, Dc):
                                                       (9, 50, 768, 32, 200, 150.0, 300), (1, 1, 64, 1, 16, 2.0, 2), (5, 7, 192, 5, 16, 40.0, 100),
                                                       (33, 100, 256, 32, 48, 20.0, 300), (7, 128, 128, 16, 40, 20.0, 120), (10, 65, 64, 8, 24, 5.0, 10),
                                                       (33, 50, 256, 64, 48, 20.0, 300), (5, 100, 128, 64, 40, 12.0, 120), (4, 20, 64, 40, 24, 5.0, 10),
-                                                      (21, 200, 256, 32, 48, 20.0, 300), (3, 256, 64, 8, 24, 5.0, 10), (6, 129, 128, 16, 40, 70.0, 200)])
+                                                      (21, 200, 256, 32, 48, 20.0, 300), (3, 256, 64, 8, 24, 5.0, 10), (6, 129, 128, 16, 40, 70.0, 200),
+                                                      (9, 200, 128, 64, 40, 20.0, 300)])
 @pytest.mark.parametrize('score_type', ['weighted', 'max', 'mean'])
 def test_table_level_scores(B, H, D, K, Dc, mean_c, max_c, score_type):
     """Table-level mode (miner_table_project + miner_score_table_fwd) against the oracle in the reference's operation order on the
@@ -875,7 +876,7 @@ def test_table_level_dense_layout_and_invariance():
     _, s0 = ops.score_table(tp, his[:0].to(DEV), mask[:0].to(DEV), cd[:0].to(DEV))
     assert s0.shape == (0, Cd)
     assert ops.score_table_supported(100, 32, 256) and ops.score_table_supported(200, 32, 256) and not ops.score_table_supported(257, 32, 256)
-    assert not ops.score_table_supported(200, 64, 256)
+    assert ops.score_table_supported(200, 64, 256) and not ops.score_table_supported(50, 65, 256)
     assert ops.score_table_supported(50, 64, 256) and not ops.score_table_supported(50, 65, 256) and not ops.score_table_supported(50, 32, 100)
     with pytest.raises(ValueError, match='Invalid method of aggregating matching score'):
         ops.score_table(tp, his.to(DEV), mask.to(DEV), cd.to(DEV), 'median')
