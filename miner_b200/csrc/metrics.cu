@@ -73,41 +73,52 @@ __global__ void __launch_bounds__(MT, 2) rank_metrics_kernel(const float* __rest
       }
     }
     __syncwarp();
-    // integer tallies are reduced exactly with redux.sync; only rr / dcg / idcg need fp64 sums
-    int wins2 = 0, n_pos = 0, n_neg = 0, sum_y = 0;                    // wins2 = 2 * (#neg below + 0.5 #neg tied), summed over positives
+    // Only candidates with a non-zero label contribute to rr, dcg, idcg, hit and the AUC wins (a zero label adds exactly 0),
+    // so the pairwise counting runs once per such candidate -- about 2.4 per impression -- with all 32 lanes comparing one
+    // chunk of the others against it (ballot + popc): every tally is warp-uniform and exact, the fp64 sums run in candidate
+    // order in every lane, and nothing is reduced by shuffles.
+    long long wins2 = 0;                                                // 2 * (#neg below + 0.5 #neg tied), summed over positives
+    int n_pos = 0, n_neg = 0, sum_y = 0;
     double rr = 0.0;
     double dcg[NK > 0 ? NK : 1], idcg[NK > 0 ? NK : 1];
     unsigned hit = 0;                                                   // bit q: a positive inside the top ks[q]
 #pragma unroll
     for (int q = 0; q < NK; ++q) dcg[q] = idcg[q] = 0.0;
-    for (int i = lane; i < n; i += 32) {
-      const float pi = staged ? ps[i] : transform_score(sb[i], transform, mx, sum);
-      const int yi = staged ? ys[i] : yb[i];
-      int gt = 0, eq_before = 0, eq_after = 0, neg_lt = 0, neg_eq = 0, y_gt = 0, y_eq_before = 0;
-      for (int j = 0; j < n; ++j) {
-        const float pj = staged ? ps[j] : transform_score(sb[j], transform, mx, sum);
-        const int yj = staged ? ys[j] : yb[j];
-        gt += pj > pi;
-        const bool eq = pj == pi;
-        eq_before += eq && (j < i);
-        eq_after += eq && (j > i);
-        const bool negj = yj <= 0;
-        neg_lt += negj && (pj < pi);
-        neg_eq += negj && eq;
-        y_gt += yj > yi;
-        y_eq_before += (yj == yi) && (j < i);
-      }
-      const int rank_np = gt + eq_after;
-      const int rank_py = gt + eq_before;
-      const int rank_ideal = y_gt + y_eq_before;
-      sum_y += yi;
-      if (yi > 0) {
-        n_pos += 1;
-        wins2 += 2 * neg_lt + neg_eq;
-      } else {
-        n_neg += 1;
-      }
-      if (yi != 0) {                                                      // a zero label adds exactly 0 to rr, dcg and idcg
+    for (int base = 0; base < n; base += 32) {
+      const int i_l = base + lane;
+      const bool in_l = i_l < n;
+      const float p_l = in_l ? (staged ? ps[i_l] : transform_score(sb[i_l], transform, mx, sum)) : 0.f;
+      const int y_l = in_l ? (staged ? ys[i_l] : yb[i_l]) : 0;
+      n_pos += __popc(__ballot_sync(0xffffffffu, in_l && y_l > 0));
+      n_neg += __popc(__ballot_sync(0xffffffffu, in_l && y_l <= 0));
+      sum_y += __reduce_add_sync(0xffffffffu, y_l);
+      unsigned nz = __ballot_sync(0xffffffffu, in_l && y_l != 0);
+      while (nz) {
+        const int src = __ffs(nz) - 1;
+        nz &= nz - 1;
+        const float pi = __shfl_sync(0xffffffffu, p_l, src);
+        const int yi = __shfl_sync(0xffffffffu, y_l, src);
+        const int i = base + src;
+        int gt = 0, eq_before = 0, eq_after = 0, neg_lt = 0, neg_eq = 0, y_gt = 0, y_eq_before = 0;
+        for (int jb = 0; jb < n; jb += 32) {
+          const int j = jb + lane;
+          const bool vj = j < n;
+          const float pj = vj ? (staged ? ps[j] : transform_score(sb[j], transform, mx, sum)) : 0.f;
+          const int yj = vj ? (staged ? ys[j] : yb[j]) : 0;
+          const bool eq = vj && pj == pi;
+          const bool negj = vj && yj <= 0;
+          gt += __popc(__ballot_sync(0xffffffffu, vj && pj > pi));
+          eq_before += __popc(__ballot_sync(0xffffffffu, eq && j < i));
+          eq_after += __popc(__ballot_sync(0xffffffffu, eq && j > i));
+          neg_lt += __popc(__ballot_sync(0xffffffffu, negj && pj < pi));
+          neg_eq += __popc(__ballot_sync(0xffffffffu, negj && eq));
+          y_gt += __popc(__ballot_sync(0xffffffffu, vj && yj > yi));
+          y_eq_before += __popc(__ballot_sync(0xffffffffu, vj && yj == yi && j < i));
+        }
+        const int rank_np = gt + eq_after;                               // position under np.argsort(p)[::-1] (evaluation.py:188,208)
+        const int rank_py = gt + eq_before;                              // position under python's stable sorted(reverse=True) (:247)
+        const int rank_ideal = y_gt + y_eq_before;
+        if (yi > 0) wins2 += 2 * neg_lt + neg_eq;
         // 2 ** y_true - 1 (evaluation.py:210); small non-negative labels are exact powers of two
         const double gain = (yi > 0 && yi < 31) ? static_cast<double>((1 << yi) - 1) : exp2(static_cast<double>(yi)) - 1.0;
         rr += static_cast<double>(yi) / static_cast<double>(rank_np + 1);  // evaluation.py:190
@@ -122,20 +133,13 @@ __global__ void __launch_bounds__(MT, 2) rank_metrics_kernel(const float* __rest
         }
       }
     }
-    wins2 = __reduce_add_sync(0xffffffffu, wins2);
-    n_pos = __reduce_add_sync(0xffffffffu, n_pos);
-    n_neg = __reduce_add_sync(0xffffffffu, n_neg);
-    sum_y = __reduce_add_sync(0xffffffffu, sum_y);
-    hit = __reduce_or_sync(0xffffffffu, hit);
-    rr = warp_sum(rr);
     double vals[M];
     vals[0] = (n_pos > 0 && n_neg > 0) ? (0.5 * static_cast<double>(wins2)) / (static_cast<double>(n_pos) * static_cast<double>(n_neg))
                                        : NAN;                             // one class: sklearn raises -> NaN here
     vals[1] = rr / static_cast<double>(sum_y);                            // 0/0 -> NaN (no positives)
 #pragma unroll
     for (int q = 0; q < NK; ++q) {
-      const double d = warp_sum(dcg[q]), id = warp_sum(idcg[q]);
-      vals[2 + q] = d / id;                                               // evaluation.py:231
+      vals[2 + q] = dcg[q] / idcg[q];                                     // evaluation.py:231
       vals[2 + NK + q] = (hit >> q) & 1u ? 1.0 : 0.0;
     }
     if (lane == 0) {
