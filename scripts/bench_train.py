@@ -1,7 +1,7 @@
 #!/usr/bin/env python
 """Train-step timing of the MINER path (BASELINE.json configs[2]: npratio 4, batch 4096 per GPU, history 50, K=32, Dc=200, D=768).
 
-    python scripts/bench_train.py [--batch 4096] [--steps 10] [--warmup 3]
+    python scripts/bench_train.py [--batch 4096] [--steps 10] [--warmup 40]
     python -m torch.distributed.run --nproc-per-node N ... scripts/bench_train.py --gpus N
 
 One step = Miner.forward (train variant) + Loss.compute + backward (CUDA kernels of libminer_b200.so) + one flat NCCL
@@ -21,7 +21,7 @@ def main():
     ap.add_argument('--gpus', type=int, default=1)
     ap.add_argument('--batch', type=int, default=4096)
     ap.add_argument('--steps', type=int, default=10)
-    ap.add_argument('--warmup', type=int, default=3)
+    ap.add_argument('--warmup', type=int, default=40, help='untimed steps; with several ranks the first ~20 steps (NCCL channel setup, allocator growth) run at half speed')
     ap.add_argument('--table', default='bf16', choices=['bf16', 'f32'])
     ap.add_argument('--math', default='tensor', choices=['tensor', 'fp32'], help='tensor: projection-sized GEMMs on tcgen05 (bf16 operands)')
     args = ap.parse_args()
