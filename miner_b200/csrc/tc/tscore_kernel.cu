@@ -11,8 +11,9 @@
 // which turns the 2HDDc + 2KD^2 FLOP of the reference order into two more gathered rows per history slot: the kernel is
 // bound by the gather (HBM / L2 ingest), not by the tensor pipe.
 //
-// One persistent CTA per SM; a tile is IPT = 2 impressions = 128 history slots (64 per impression, H <= 64; IPT = 1 with 128
-// slots for 64 < H <= 128: the same code, a template parameter).  TMEM lanes are
+// One persistent CTA per SM.  A tile is 128 history slots: IPT = 2 impressions of 64 slots (H <= 64, K <= 32), or IPT = 1
+// impression (H <= 128, or K <= 64 which needs all 128 lanes), or, for 128 < H <= 256, one impression over NH = 2 halves of 128
+// slots whose products accumulate into the same D_I | D_P pair -- the same code, template parameters <IPT, KM, NH>.  TMEM lanes are
 // (impression i, context code k, part hl): lane 64 i + 16 (k / 8) + 8 hl + k % 8, where hl selects the bf16 hi / lo part of the
 // softmax weight -- the two lanes of a pair accumulate  w_hi . E  and  w_lo . E  and are summed in the epilogue (fp32-level
 // weights).  Keeping a pair 8 lanes apart lets the 16-lane tcgen05.ld / st shapes (16x256b / 16x128b) hand both rows of a pair
@@ -28,7 +29,7 @@
 //   warps 15-18 softmax over the history from the lg rows (L2-resident 128-byte rows), weights to tensor memory; and, per
 //               finished tile, the softmax over K and the weighted sum of the matching scores through a shared-memory
 //               transpose, one thread per candidate
-// Tiles with more than 96 candidates run several passes (the history side is recomputed; rare).
+// Tiles with more than 96 candidates (64 when NH = 2) run several passes (the history side is recomputed; rare).
 #include <cuda.h>
 #include <stdlib.h>
 
@@ -334,8 +335,6 @@ tscore_kernel(const TScoreArgs args, int n_tiles) {
   } else if (warp == W_MMA) {
     // ------------------------------------------------------------------ MMA issuer
     const uint32_t idesc1 = tc::make_idesc_bf16_f32_major(TM, FB, false, true);        // B = gathered tile, MN-major
-    const uint32_t idesc1w = tc::make_idesc_bf16_f32_major(TM, 2 * FB, false, true);
-    (void)idesc1w;
     uint32_t g1 = 0, g2 = 0, u = 0, sg = 0;                      // blocks issued (S1 / S2), units, ring stages consumed
     bool pending = false;
     int pend_j = 0, pend_nc16 = 16;

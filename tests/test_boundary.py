@@ -188,3 +188,13 @@ def test_two_rank_gradient_averaging_gloo(tmp_path):
     outs = [p.communicate(timeout=240)[0] for p in procs]
     assert all(p.returncode == 0 for p in procs), outs
     assert 'OK' in outs[0]
+
+
+def test_table_level_shape_query_is_host_only():
+    """`miner_score_table_supported` is a host-side shape query (no GPU): the table-level kernel covers H <= 256, K <= 64,
+    D a multiple of 64; everything else falls back to the reference-order families."""
+    from miner_b200 import _lib
+    lib = _lib.load()
+    ok = lambda h, k, d: bool(lib.miner_score_table_supported(h, k, d))
+    assert ok(50, 32, 768) and ok(1, 1, 64) and ok(128, 64, 256) and ok(200, 32, 768) and ok(256, 64, 64)
+    assert not ok(257, 32, 768) and not ok(50, 65, 768) and not ok(50, 32, 100) and not ok(0, 32, 768)
