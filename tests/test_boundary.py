@@ -198,3 +198,15 @@ def test_table_level_shape_query_is_host_only():
     ok = lambda h, k, d: bool(lib.miner_score_table_supported(h, k, d))
     assert ok(50, 32, 768) and ok(1, 1, 64) and ok(128, 64, 256) and ok(200, 32, 768) and ok(256, 64, 64)
     assert not ok(257, 32, 768) and not ok(50, 65, 768) and not ok(50, 32, 100) and not ok(0, 32, 768)
+
+
+def test_default_math_selection_is_host_logic():
+    """Which kernel family grouped evaluation picks depends only on dtype and shape (no GPU needed to decide)."""
+    from miner_b200 import ops, _lib
+    bf = torch.zeros(4, 768, dtype=torch.bfloat16)
+    assert ops.default_eval_math(bf, 50, 32) == _lib.MATH_TABLE
+    assert ops.default_eval_math(bf, 200, 64) == _lib.MATH_TABLE
+    assert ops.default_eval_math(bf, 300, 32) == _lib.MATH_TENSOR                     # history beyond the 256-slot tile: reference order on tcgen05
+    assert ops.default_eval_math(torch.zeros(4, 768), 50, 32) == _lib.MATH_FP32       # fp32 table: reference arithmetic
+    assert ops.default_eval_math(torch.zeros(4, 100, dtype=torch.bfloat16), 50, 32) == _lib.MATH_FP32   # D % 64 != 0
+    assert ops.default_math(bf, 768) == _lib.MATH_TENSOR                              # Miner.forward keeps the reference operation order
