@@ -204,10 +204,13 @@ def main():
     proj = ops.table_project(table, sw) if math == _lib.MATH_TABLE else None          # buffers; recomputed inside every step
     proj_ws = torch.empty(max(_lib.load().miner_table_project_workspace_bytes(table.shape[0], DC), 1), dtype=torch.uint8, device=dev)
 
+    tws = ops.score_table_workspace(B, H, K, dev) if math == _lib.MATH_TABLE else None   # packed tiles: rebuilt by every call
+
     def score_step(d, m):
         if m == _lib.MATH_TABLE:
             ops.table_project(table, sw, out=proj, workspace=proj_ws)       # part of the step: nothing is carried over between steps
-            ops.score_table(proj, d['his_ids'], d['his_mask'], d['cand_ids'], 'weighted', cand_offsets=d['offsets'], out_scores=scores_buf)
+            ops.score_table(proj, d['his_ids'], d['his_mask'], d['cand_ids'], 'weighted', cand_offsets=d['offsets'], out_scores=scores_buf,
+                            workspace=tws)
         else:
             ops.score(table, d['his_ids'], d['his_mask'], d['cand_ids'], sw, 'weighted', cand_offsets=d['offsets'], math=m,
                       chunk=chunk, out_scores=scores_buf)
@@ -293,7 +296,7 @@ def main():
                 fn = lambda: ops.table_project(table, sw, out=proj, workspace=proj_ws)
             elif mask == 'score':
                 fn = lambda: ops.score_table(proj, resident['his_ids'], resident['his_mask'], resident['cand_ids'], 'weighted',
-                                             cand_offsets=resident['offsets'], out_scores=scores_buf)
+                                             cand_offsets=resident['offsets'], out_scores=scores_buf, workspace=tws)
             else:
                 fn = lambda: ops.score(table, resident['his_ids'], resident['his_mask'], resident['cand_ids'], sw, 'weighted',
                                        cand_offsets=resident['offsets'], math=math, chunk=chunk, out_scores=scores_buf, stage_mask=mask)

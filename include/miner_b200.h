@@ -28,7 +28,7 @@
 extern "C" {
 #endif
 
-#define MINER_B200_ABI_VERSION 1
+#define MINER_B200_ABI_VERSION 2
 
 /* error codes */
 #define MINER_OK               0
@@ -160,17 +160,27 @@ int miner_cand_score_fwd(const void* i_hi, const void* i_lo, const void* w_targe
  *      miner_table_project computes them (once per weight version / table; bench.py does it inside every timed step);
  *      miner_score_table_fwd is Miner.forward (model.py:61-138) for B impressions from table, lg, tw in one kernel:
  *      masked softmax over the history (1e-30 fill, model.py:180), interests, gelu, matching scores, softmax over K, score.
- *      Needs a bf16 table, H <= 128 with K <= 64 or H <= 256 with K <= 32, D % 64 == 0 (two impressions share a tile when H <= 64 and K <= 32).
+ *      Needs a bf16 table, H <= 256, K <= 64, D % 64 == 0 (K <= 32: two impressions share a tile of 128 TMEM lanes; K <= 16 and
+ *      H <= 32: four).
  *      out_interests (B,K,D) fp32 or NULL. */
 size_t miner_table_project_workspace_bytes(int64_t n_rows, int64_t Dc);
 int miner_table_project(const void* table_bf16, int64_t n_rows, int64_t D, const void* w_proj_bf16, const float* codes,
                         const void* w_target_bf16, int64_t K, int64_t Dc, float* out_lg, void* out_tw,
                         void* workspace, size_t workspace_bytes, void* stream);
 int miner_score_table_supported(int64_t H, int64_t K, int64_t D);
+/*      Workspace of miner_score_table_fwd: the call first packs the histories into tiles (one launch, one warp per tile): masked
+ *      slots that point at the same news row -- the left padding, reader.py:368-369 -- all carry the logit 1e-30 (model.py:180)
+ *      and are merged into one slot of that multiplicity, so a short history costs as many gathered rows as it has clicks + 1.
+ *      The first 8 bytes of the workspace are two int32 counters the call ADDS to: history ids / candidate ids outside
+ *      [0, n_rows) (such rows read as zero; the reference's indexing raises IndexError).  Zero them before the first call and
+ *      read them back when convenient.  miner_score_table_tile_geometry reports the tiling of a shape (0 = unsupported). */
+size_t miner_score_table_workspace_bytes(int64_t B, int64_t H, int64_t K);
+int miner_score_table_tile_geometry(int64_t H, int64_t K, int* impressions_per_tile, int* halves);
 int miner_score_table_fwd(const void* table_bf16, const void* tw_bf16, const float* lg, int64_t n_rows,
                           const void* his_ids, const uint8_t* his_mask, const void* cand_ids, const int64_t* cand_offsets,
                           int id_dtype, const float* bias_mean, int64_t B, int64_t H, int64_t C, int64_t K, int64_t D,
-                          int score_type, float* out_scores, float* out_interests, void* stream);
+                          int score_type, float* out_scores, float* out_interests,
+                          void* workspace, size_t workspace_bytes, void* stream);
 
 /* ---- (a7..a12) segmented per-impression ranking metrics: replaces SlowEvaluator/FastEvaluator +
  *      compute_scores (evaluation.py:36-84,87-175) and compute_mrr/dcg/ndcg_score, is_hit (:177-249).

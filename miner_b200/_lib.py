@@ -20,7 +20,7 @@ I32, I64 = 0, 1
 SCORE_MAX, SCORE_MEAN, SCORE_WEIGHTED = 0, 1, 2
 MATH_FP32, MATH_TENSOR, MATH_TABLE = 0, 1, 2
 EPI_NONE, EPI_TANH, EPI_GELU = 0, 1, 2
-ABI_VERSION = 1
+ABI_VERSION = 2
 
 SCORE_TYPES = {'max': SCORE_MAX, 'mean': SCORE_MEAN, 'weighted': SCORE_WEIGHTED}
 
@@ -31,6 +31,7 @@ EXPORTS = [
     'miner_tc_gemm', 'miner_rank_metrics_workspace_bytes', 'miner_rank_metrics', 'miner_loss_workspace_bytes',
     'miner_loss_fwd', 'miner_hist_interests_workspace_bytes', 'miner_hist_interests_fwd', 'miner_cand_score_fwd',
     'miner_table_project_workspace_bytes', 'miner_table_project', 'miner_score_table_supported', 'miner_score_table_fwd',
+    'miner_score_table_workspace_bytes', 'miner_score_table_tile_geometry',
     'miner_train_workspace_bytes', 'miner_train_fwd', 'miner_loss_bwd', 'miner_train_bwd',
 ]
 
@@ -98,7 +99,10 @@ def _declare(lib: C.CDLL) -> None:
     lib.miner_loss_bwd.argtypes = [vp, vp, vp, vp, i64, i64, i64, i64, vp, vp, vp]
     lib.miner_train_bwd.argtypes = [vp, i64, i32, vp, vp, vp, i32, vp, vp, vp, vp, vp, vp, vp, vp, vp, i64, i64, i64, i64, i64, i64, vp, vp, vp,
                                     i32, vp, vp, vp, sz, vp]
-    lib.miner_score_table_fwd.argtypes = [vp, vp, vp, i64, vp, vp, vp, vp, i32, vp, i64, i64, i64, i64, i64, i32, vp, vp, vp]
+    lib.miner_score_table_fwd.argtypes = [vp, vp, vp, i64, vp, vp, vp, vp, i32, vp, i64, i64, i64, i64, i64, i32, vp, vp, vp, sz, vp]
+    lib.miner_score_table_workspace_bytes.argtypes = [i64, i64, i64]
+    lib.miner_score_table_workspace_bytes.restype = sz
+    lib.miner_score_table_tile_geometry.argtypes = [i64, i64, C.POINTER(i32), C.POINTER(i32)]
 
 
 def load(build_if_missing: bool = True) -> C.CDLL:

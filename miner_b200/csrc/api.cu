@@ -320,10 +320,16 @@ extern "C" int miner_table_project(const void* table, int64_t n_rows, int64_t D,
 
 extern "C" int miner_score_table_supported(int64_t H, int64_t K, int64_t D) { return tscore_kernel_supported(H, K, D) ? 1 : 0; }
 
+extern "C" size_t miner_score_table_workspace_bytes(int64_t B, int64_t H, int64_t K) { return tscore_ws_bytes(B, H, K); }
+
+extern "C" int miner_score_table_tile_geometry(int64_t H, int64_t K, int* impressions_per_tile, int* halves) {
+  return tscore_tile_geometry(H, K, impressions_per_tile, halves);
+}
+
 extern "C" int miner_score_table_fwd(const void* table, const void* tw, const float* lg, int64_t n_rows, const void* his_ids,
                                      const uint8_t* his_mask, const void* cand_ids, const int64_t* cand_offsets, int id_dtype,
                                      const float* bias_mean, int64_t B, int64_t H, int64_t C, int64_t K, int64_t D, int score_type,
-                                     float* out_scores, float* out_interests, void* stream) {
+                                     float* out_scores, float* out_interests, void* workspace, size_t workspace_bytes, void* stream) {
   MINER_CHECK_ARG(B >= 0 && n_rows > 0 && H > 0 && K > 0 && D > 0 && (cand_offsets || C > 0), "score_table: bad sizes");
   if (score_type != MINER_SCORE_MAX && score_type != MINER_SCORE_MEAN && score_type != MINER_SCORE_WEIGHTED) {
     set_error("Invalid method of aggregating matching score");
@@ -334,9 +340,11 @@ extern "C" int miner_score_table_fwd(const void* table, const void* tw, const fl
   MINER_CHECK_ARG(tw || score_type != MINER_SCORE_WEIGHTED, "score_table: 'weighted' needs the tw table");
   MINER_CHECK_ARG(id_dtype == MINER_I32 || id_dtype == MINER_I64, "score_table: id dtype must be int32 or int64");
   return launch_tscore_kernel(table, tw ? tw : table, lg, n_rows, his_ids, id_dtype, his_mask, bias_mean, cand_ids, cand_offsets, B, H, C, K,
-                              D, score_type, out_scores, out_interests, static_cast<cudaStream_t>(stream));
+                              D, score_type, out_scores, out_interests, workspace, workspace_bytes, static_cast<cudaStream_t>(stream));
 }
 
-// profiling hook (not part of the documented ABI): device buffer of 148*3*16 int64 for -DMINER_HIST_PROF builds
+#if defined(MINER_HIST_PROF) || defined(MINER_TS_PROF)
+// instrumented builds only (scripts/prof_hist.py, scripts/prof_tscore.py): device buffer of 148*5*16 int64 cycle counters.
+// The release library exports nothing outside include/miner_b200.h.
 extern "C" void miner_debug_set_hist_prof(void* p) { set_hist_prof_buffer(static_cast<long long*>(p)); }
-extern "C" void miner_debug_set_cand_pair(int on) { set_cand_pair(on); }
+#endif

@@ -361,13 +361,6 @@ cand_kernel(const __grid_constant__ CUtensorMap tmap_ihi, const __grid_constant_
 
 }  // namespace
 
-static int g_cand_pair = -1;
-bool cand_pair_enabled() {
-  if (g_cand_pair < 0) g_cand_pair = getenv("MINER_CAND_PAIR") != nullptr ? 1 : 0;
-  return g_cand_pair == 1;
-}
-void set_cand_pair(int on) { g_cand_pair = on ? 1 : 0; }
-
 bool cand_kernel_supported(int64_t K, int64_t D) { return (K == 8 || K == 16 || K == 32) && D >= 64 && D % 64 == 0 && D <= 4096; }
 
 int launch_cand_kernel(const void* i_hi, const void* i_lo, const void* wt_bf16, const void* table, int64_t n_rows,
@@ -378,10 +371,8 @@ int launch_cand_kernel(const void* i_hi, const void* i_lo, const void* wt_bf16, 
     set_error("cand_kernel: unsupported shape K=%lld D=%lld (need K in {8,16,32}, D %% 64 == 0)", (long long)K, (long long)D);
     return MINER_ERR_UNSUPPORTED;
   }
-  // The CTA-pair kernel (cand_kernel2.cu, cta_group::2) is correct but measured slightly slower than this one on the
-  // round-1 workload (19.6 vs 18.1 ms per 262 k impressions): it is opt-in (MINER_CAND_PAIR=1 or miner_debug_set_cand_pair).
-  if (cand_pair_enabled() && sm_count() >= 2)
-    return launch_cand_kernel2(i_hi, i_lo, wt_bf16, table, n_rows, cand_ids, id_dtype, cand_offsets, B, C, K, D, out_scores, stream);
+  // (A CTA-pair variant -- tcgen05 cta_group::2, Wt split across two SMs -- was built and verified in round 1 and measured slower,
+  // 19.6 vs 18.1 ms per 262 k impressions; it lives in the history, commit 2dddfec.)
   CUtensorMap m_hi, m_lo, m_wt;
   int rc = make_tmap_2d_bf16(&m_hi, i_hi, static_cast<uint64_t>(B * K), static_cast<uint64_t>(D), CM, CKB);
   if (rc) return rc;

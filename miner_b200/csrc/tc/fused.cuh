@@ -16,7 +16,7 @@ int launch_hist_kernel(const void* table, int64_t n_rows, const void* his_ids, i
                        const float* bias_mean, const void* w_proj_bf16, const float* codes, int64_t B, int64_t H, int64_t K,
                        int64_t Dc, int64_t D, void* i_hi, void* i_lo, float* out_interests, float* codes_t_ws, cudaStream_t stream);
 size_t hist_kernel_ws_bytes(int64_t Dc);
-// software-pipelined variant with tensor-core logits (hist_kernel2.cu), Dc <= 224; launch_hist_kernel dispatches to it
+// the kernel itself (hist_kernel2.cu: software-pipelined, tensor-core logits), Dc <= 208; launch_hist_kernel forwards to it
 bool hist_kernel2_supported(int64_t H, int64_t K, int64_t Dc, int64_t D);
 int launch_hist_kernel2(const void* table, int64_t n_rows, const void* his_ids, int id_dtype, const uint8_t* his_mask,
                         const float* bias_mean, const void* w_proj_bf16, const float* codes, int64_t B, int64_t H, int64_t K,
@@ -30,12 +30,6 @@ int launch_cand_kernel(const void* i_hi, const void* i_lo, const void* wt_bf16, 
                        const void* cand_ids, int id_dtype, const int64_t* cand_offsets, int64_t B, int64_t C, int64_t K, int64_t D,
                        float* out_scores, cudaStream_t stream);
 
-bool cand_pair_enabled();
-void set_cand_pair(int on);
-// CTA-pair variant (cand_kernel2.cu): tcgen05.mma.cta_group::2 projection with Wt split across two SMs; launch_cand_kernel dispatches to it
-int launch_cand_kernel2(const void* i_hi, const void* i_lo, const void* wt_bf16, const void* table, int64_t n_rows,
-                        const void* cand_ids, int id_dtype, const int64_t* cand_offsets, int64_t B, int64_t C, int64_t K, int64_t D,
-                        float* out_scores, cudaStream_t stream);
 
 // Table-level mode (table_project.cu, tscore_kernel.cu): projections hoisted to the news table, one scoring kernel.
 size_t table_project_ws_bytes(int64_t n_rows, int64_t Dc);
@@ -43,9 +37,11 @@ int launch_table_project(const void* table, int64_t n_rows, int64_t D, const voi
                          const void* w_target_bf16, int64_t K, int64_t Dc, float* out_lg, void* out_tw, float* proj_ws,
                          cudaStream_t stream);
 bool tscore_kernel_supported(int64_t H, int64_t K, int64_t D);
+size_t tscore_ws_bytes(int64_t B, int64_t H, int64_t K);                 // packed tiles (tpack_kernel) + the out-of-range id counters
+int tscore_tile_geometry(int64_t H, int64_t K, int* ipt, int* nh);      // impressions per tile / 128-slot halves for a shape (0 = unsupported)
 int launch_tscore_kernel(const void* table, const void* tw, const float* lg, int64_t n_rows, const void* his_ids, int id_dtype,
                          const uint8_t* his_mask, const float* bias_mean, const void* cand_ids, const int64_t* cand_offsets,
                          int64_t B, int64_t H, int64_t C, int64_t K, int64_t D, int score_type, float* out_scores, float* out_interests,
-                         cudaStream_t stream);
+                         void* workspace, size_t workspace_bytes, cudaStream_t stream);
 
 }  // namespace miner

@@ -527,7 +527,8 @@ hist_kernel2(const __grid_constant__ CUtensorMap tmap_wp, const Hist2Args args, 
 
 }  // namespace
 
-// debug buffer for -DMINER_HIST_PROF builds (148 CTAs x 3 roles x 16 counters), set through miner_debug_set_hist_prof
+// buffer for the cycle counters of -DMINER_HIST_PROF / -DMINER_TS_PROF builds (148 CTAs x 5 roles x 16 counters), set through
+// miner_debug_set_hist_prof -- an entry point only those builds export
 static long long* g_hist_prof = nullptr;
 long long* hist_prof_buffer() { return g_hist_prof; }
 void set_hist_prof_buffer(long long* p) { g_hist_prof = p; }
@@ -551,8 +552,11 @@ int launch_hist_kernel2(const void* table, int64_t n_rows, const void* his_ids, 
   a.b_bytes = N1 * HKB * 2;
   {
     const int kb = static_cast<int>(D / HKB);
-    static const char* env_first = getenv("MINER_HIST_FIRST");          // tuning knob; default keeps 2/3 of the blocks paired
-    a.first = env_first ? atoi(env_first) : (2 * kb) / 3;
+    a.first = (2 * kb) / 3;                                             // 2/3 of the blocks paired (measured best)
+#ifdef MINER_HIST_PROF
+    static const char* env_first = getenv("MINER_HIST_FIRST");          // tuning knob of the instrumented build only
+    if (env_first) a.first = atoi(env_first);
+#endif
     if (a.first < 0) a.first = 0;
     if (a.first > kb - 1) a.first = kb - 1;
   }
@@ -567,5 +571,22 @@ int launch_hist_kernel2(const void* table, int64_t n_rows, const void* his_ids, 
   MINER_LAUNCH_OK("hist_kernel2");
   return MINER_OK;
 }
+
+// public names of the history kernel (miner_hist_interests_fwd, miner_score_fwd's tensor family)
+bool hist_kernel_supported(int64_t H, int64_t K, int64_t Dc, int64_t D) { return hist_kernel2_supported(H, K, Dc, D); }
+size_t hist_kernel_ws_bytes(int64_t Dc) { (void)Dc; return 256; }      // the kernel stages the context codes itself; kept for the ABI
+int launch_hist_kernel(const void* table, int64_t n_rows, const void* his_ids, int id_dtype, const uint8_t* his_mask,
+                       const float* bias_mean, const void* w_proj_bf16, const float* codes, int64_t B, int64_t H, int64_t K,
+                       int64_t Dc, int64_t D, void* i_hi, void* i_lo, float* out_interests, float* codes_t_ws, cudaStream_t stream) {
+  (void)codes_t_ws;
+  if (B == 0) return MINER_OK;
+  if (!hist_kernel2_supported(H, K, Dc, D)) {
+    set_error("hist_kernel: unsupported shape H=%lld K=%lld Dc=%lld D=%lld", (long long)H, (long long)K, (long long)Dc, (long long)D);
+    return MINER_ERR_UNSUPPORTED;
+  }
+  return launch_hist_kernel2(table, n_rows, his_ids, id_dtype, his_mask, bias_mean, w_proj_bf16, codes, B, H, K, Dc, D, i_hi, i_lo,
+                             out_interests, stream);
+}
+
 
 }  // namespace miner

@@ -11,21 +11,30 @@
 // which turns the 2HDDc + 2KD^2 FLOP of the reference order into two more gathered rows per history slot: the kernel is
 // bound by the gather (HBM / L2 ingest), not by the tensor pipe.
 //
-// One persistent CTA per SM.  A tile is 128 history slots: IPT = 2 impressions of 64 slots (H <= 64, K <= 32), or IPT = 1
-// impression (H <= 128, or K <= 64 which needs all 128 lanes), or, for 128 < H <= 256, one impression over NH = 2 halves of 128
-// slots whose products accumulate into the same D_I | D_P pair -- the same code, template parameters <IPT, KM, NH>.  TMEM lanes are
-// (impression i, context code k, part hl): lane 64 i + 16 (k / 8) + 8 hl + k % 8, where hl selects the bf16 hi / lo part of the
-// softmax weight -- the two lanes of a pair accumulate  w_hi . E  and  w_lo . E  and are summed in the epilogue (fp32-level
-// weights).  Keeping a pair 8 lanes apart lets the 16-lane tcgen05.ld / st shapes (16x256b / 16x128b) hand both rows of a pair
-// to ONE thread: the pair sum, the gelu and the hi/lo split need no shuffles and no thread repeats another's work.
-//   warps 0-3   gather: per 64-feature block, table[his] and tw[his] rows (128 slots x 128 B each), 16-byte cp.async straight
-//               into the 128B-swizzled layout, completion through mbarriers;  warps 4-5: the tile's candidate rows, own ring
+// Two launches per call:
+//   tpack_kernel   (one warp per tile) turns his_ids / his_mask into PACKED TILES in the caller's workspace.  A tile holds IPT
+//       impressions; each impression's history becomes a compact list of slot records.  Every masked slot carries the SAME logit
+//       (the reference overwrites it with 1e-30 for every code, model.py:180), so masked slots that point at the same news row
+//       -- the left padding with the pad news, reader.py:368-369 -- have identical softmax weights and identical rows:
+//       sum_pads w E_pad = (n_pad w) E_pad.  They are merged into ONE record with multiplicity n_pad (its logit becomes
+//       1e-30 + ln n_pad, which is the same softmax term), so a 12-click history costs 13 gathered rows, not 50.  Same
+//       mathematics as the reference to fp32 rounding; nothing is dropped (masked slots with other ids stay separate records).
+//       The impressions of a tile are laid side by side (even start slots), so a tile is  sum(n_i) <= 128 NH  slots.
+//       Ids outside [0, n_rows) are counted into the workspace's oob counter (rows read as zero, as before).
+//   tscore_kernel  one persistent CTA per SM.  TMEM lanes are (impression i, context code k, part hl): lane
+//       LPI i + 16 (k / 8) + 8 hl + k % 8 with LPI = 128 / IPT, where hl selects the bf16 hi / lo part of the softmax weight --
+//       the two lanes of a pair accumulate  w_hi . E  and  w_lo . E  and are summed in the epilogue (fp32-level weights).
+//       Keeping a pair 8 lanes apart lets the 16-lane tcgen05.ld / st shapes (16x256b / 16x128b) hand both rows of a pair to ONE
+//       thread: the pair sum, the gelu and the hi/lo splits need no shuffles and no thread repeats another's work.
+//   warps 0-3   gather: per 64-feature block, table[id] and tw[id] rows of the tile's slots (only ceil(n / 16) 16-row groups),
+//               16-byte cp.async straight into the 128B-swizzled layout, completion through mbarriers;  warps 4-5: the
+//               tile's candidate rows, own ring
 //   warp 6      issues every tcgen05.mma:
-//               S1(j): D_I = A_w . E_j, D_P = A_w . TW_j   (A_w = softmax weights in tensor memory, TS form, block diagonal over
-//                      the two impressions; B = the gathered 128 x 64 tile read MN-major)
-//               S2(j): D_m += A_I . cand_j^T, D_a += A_G . cand_j^T  (A = bf16 hi|lo of I / gelu(P), written IN PLACE over the
-//                      fp32 accumulator by the epilogue warps; B = candidate rows, K-major)
-//   warps 7-14  epilogue: per block, pair sum, gelu, bf16 hi/lo split, tcgen05.st back in place (16-lane ld / st shapes)
+//               S1(j): D_I = A_w . E_j, D_P = A_w . TW_j   (A_w = softmax weights in tensor memory, TS form, block "staircase"
+//                      over the tile's impressions; B = the gathered tile read MN-major; ceil(n / 16) K-steps)
+//               S2(j): D_m += A_I . cand_j^T, D_a += A_G . cand_j^T  (A = bf16 hi|lo of I and of gelu(P), written IN PLACE over
+//                      the fp32 accumulators by the epilogue warps; B = candidate rows, K-major)
+//   warps 7-14  epilogue: per block, pair sum, gelu, bf16 hi/lo splits, tcgen05.st back in place (packed f32x2 arithmetic)
 //   warps 15-18 softmax over the history from the lg rows (L2-resident 128-byte rows), weights to tensor memory; and, per
 //               finished tile, the softmax over K and the weighted sum of the matching scores through a shared-memory
 //               transpose, one thread per candidate
@@ -42,9 +51,8 @@ long long* hist_prof_buffer();
 
 namespace {
 
-constexpr int TM = 128;                      // TMEM lanes = history slots per tile
+constexpr int TM = 128;                      // TMEM lanes; history slots per 128-slot half of a tile
 constexpr int FB = 64;                       // feature block (128 bytes of bf16)
-// IPT impressions share a tile: 2 for H <= 64 (64 slots and 64 lanes each), 1 for H <= 128; template parameter of the kernel
 constexpr int KMAX = 64;                     // largest number of context codes (template parameter KM = 32 or 64 picks the scratch sizes)
 #ifndef MINER_TS_S1
 #define MINER_TS_S1 5
@@ -59,7 +67,8 @@ constexpr int NC_MAX = 96;                   // candidate columns per pass
 constexpr int C_BYTES = NC_MAX * FB * 2;     // 12 KB
 template <int KM, int NH>
 struct Shape {
-  static constexpr int LS = KM;              // logits scratch row stride (floats)
+  static constexpr int LS = KM + 4;          // logits scratch row stride (floats): the softmax threads read column-wise (4 slots x 8 codes per
+                                             // request) and  8 c + k  then covers the 32 banks once
   static constexpr int SS = KM + 1;          // score scratch row stride (floats)
   static constexpr int SCRATCH_FLOATS = (TM * NH * LS > 2 * NC_MAX * SS ? TM * NH * LS : 2 * NC_MAX * SS + 2) & ~1;
   static constexpr int S1 = S1_MAX - (KM > 32 ? 1 : 0) - (NH > 1 ? 1 : 0);      // wider scratch takes ring stages
@@ -69,44 +78,55 @@ constexpr int T_EPI = 256, T_SMX = 128;                // 8 epilogue warps, 4 so
 constexpr int T_G1 = 128, T_G2 = 64;                   // gather threads of the (E, TW) ring / of the candidate ring
 constexpr int G1_ROWS = TM * 8 / T_G1, G2_ROWS = NC_MAX * 8 / T_G2;  // rows per thread (a thread moves one 16-byte chunk per row)
 constexpr int G1_STEP = T_G1 / 8, G2_STEP = T_G2 / 8;
+static_assert(G1_STEP == 16 && G1_ROWS == 8, "a gather thread's row jj is 16-row group jj: one K-step of S1");
 constexpr int W_G2 = T_G1 / 32, W_MMA = W_G2 + T_G2 / 32, W_EPI0 = W_MMA + 1, W_SMX0 = W_EPI0 + T_EPI / 32;
 constexpr int T_THREADS = (W_SMX0 + T_SMX / 32) * 32;
 // TMEM map (512 columns)
-// (NH = 128-slot halves of a tile's history: 1, or 2 for 128 < H <= 256)
+// (NH = 128-slot halves of a tile: 1, or 2 when IPT histories can exceed 128 slots)
 constexpr int AW_COL = 0;                    // softmax weights, packed bf16: 128 NH slots -> 64 NH columns
 // then IP_COL = 64 NH: 2 buffers x (I 64 | P 64) fp32, their first 32 columns become the packed A operands;
 // DM_COL = IP_COL + 256: matching scores m[(i,k,hl), c];  DA_COL = DM_COL + NCM: attention logits;  NCM = 96 (NH = 1) or 64
 
 // Optional cycle accounting (build with -DMINER_TS_PROF): per CTA, 16 counters for one thread of each role (0 MMA issuer,
-// 1 epilogue (interest half), 2 gather, 3 softmax, 4 epilogue (gelu half)), written to args.prof at the end (scripts/prof_tscore.py prints them).
+// 1 epilogue (first 16-lane group), 2 gather, 3 softmax, 4 epilogue (second group)), written to args.prof at the end
+// (scripts/prof_tscore.py prints them).  The same build reads the gather ablation bits from MINER_TS_DBG; the release library has neither.
 #ifdef MINER_TS_PROF
 #define PROF_DECL long long prof_c[16] = {0}; long long prof_t0 = clock64(), prof_start = prof_t0
 #define PROF_ADD(i) do { const long long prof_t1 = clock64(); prof_c[i] += prof_t1 - prof_t0; prof_t0 = prof_t1; } while (0)
 #define PROF_STORE(role) do { if (args.prof) { prof_c[15] = clock64() - prof_start; for (int i_ = 0; i_ < 16; ++i_) args.prof[(blockIdx.x * 5 + (role)) * 16 + i_] = prof_c[i_]; } } while (0)
+#define TS_DBG(bit) (args.dbg & (bit))
 #else
 #define PROF_DECL
 #define PROF_ADD(i)
 #define PROF_STORE(role)
+#define TS_DBG(bit) 0
 #endif
 
 struct TBarriers {
   uint64_t full1[S1_MAX], empty1[S1_MAX], full2[S2], empty2[S2];
   uint64_t w_ready, w_free, ip_full[2], a_ready[2], dma_full, dma_free;
   uint32_t tmem_base;
-#ifdef MINER_TS_PROF
-  long long issue_clk[S1_MAX][4];   // when lane 0 of each (E, TW) gather warp finished issuing a stage (latency accounting)
-#endif
 };
+
+// ---- packed tiles (written by tpack_kernel, read by tscore_kernel) ------------------------------------------------------------
+// record of one slot:  x = news id (30 bits) | masked << 30 | id-in-range << 31
+//                      y = multiplicity (16 bits; 0 = padding, not part of any history) | original slot h << 16 | impression-in-tile << 24
+// header of a tile:    end slot (exclusive) of impression i as 16-bit fields, x = end0 | end1 << 16, y = end2 | end3 << 16;
+//                      impression i starts at the even slot following end(i-1)
+constexpr uint32_t REC_MASKED = 1u << 30, REC_VALID = 1u << 31, REC_ID = 0x3fffffffu;
+__host__ __device__ __forceinline__ int hdr_end(uint2 h, int i) { return static_cast<int>(((i < 2 ? h.x : h.y) >> (16 * (i & 1))) & 0xffffu); }
+__host__ __device__ __forceinline__ int hdr_start(uint2 h, int i) { return i == 0 ? 0 : (hdr_end(h, i - 1) + 1) & ~1; }
 
 struct TScoreArgs {
   const uint16_t* table; const uint16_t* tw; const float* lg; int64_t n_rows;
-  const void* his_ids; const void* cand_ids; int id_dtype;
-  const uint8_t* mask; const float* bias_mean; const int64_t* cand_offsets;
+  const uint2* rec; const uint2* hdr; int* oob;
+  const void* cand_ids; int id_dtype;
+  const float* bias_mean; const int64_t* cand_offsets;
   int64_t B;
   int H, K, D, C, score_type;
   float* out_scores; float* out_interests;
   long long* prof;
-  int dbg;   // ablations (MINER_TS_DBG): bit 0 no global reads in the gathers (zero fill), bit 1 no tw reads, bit 2 no candidate reads
+  int dbg;   // -DMINER_TS_PROF builds only (MINER_TS_DBG): bit 0 no global reads in the gathers (zero fill), bit 1 no tw reads, bit 2 no candidate reads
 };
 
 __device__ __forceinline__ int64_t cand_off(const TScoreArgs& a, int64_t i) { return a.cand_offsets ? a.cand_offsets[i] : i * a.C; }
@@ -144,34 +164,166 @@ __device__ __forceinline__ int passes_of(int64_t cs, int64_t ce) {
   return n <= NCM ? 1 : static_cast<int>((n + NCM - 1) / NCM);
 }
 
-__device__ __forceinline__ float gelu_fast(float x) {               // tanh form, hardware tanh (see cand_kernel.cu)
-  const float u = x * fmaf(0.0356774081f, x * x, 0.7978845608f);
-  const float hx = 0.5f * x;
-  return fmaf(hx, tc::tanh_approx(u), hx);
+// ---- packed fp32x2 arithmetic (FADD2 / FMUL2 / FFMA2): the epilogue is issue-bound, two lanes per instruction
+__device__ __forceinline__ unsigned long long f2_pack(float a, float b) {
+  unsigned long long r;
+  asm("mov.b64 %0, {%1, %2};" : "=l"(r) : "f"(a), "f"(b));
+  return r;
+}
+__device__ __forceinline__ void f2_unpack(unsigned long long v, float& a, float& b) { asm("mov.b64 {%0, %1}, %2;" : "=f"(a), "=f"(b) : "l"(v)); }
+__device__ __forceinline__ unsigned long long f2_add(unsigned long long a, unsigned long long b) {
+  unsigned long long r;
+  asm("add.rn.f32x2 %0, %1, %2;" : "=l"(r) : "l"(a), "l"(b));
+  return r;
+}
+__device__ __forceinline__ unsigned long long f2_sub(unsigned long long a, unsigned long long b) {
+  unsigned long long r;
+  asm("sub.rn.f32x2 %0, %1, %2;" : "=l"(r) : "l"(a), "l"(b));
+  return r;
+}
+__device__ __forceinline__ unsigned long long f2_mul(unsigned long long a, unsigned long long b) {
+  unsigned long long r;
+  asm("mul.rn.f32x2 %0, %1, %2;" : "=l"(r) : "l"(a), "l"(b));
+  return r;
+}
+__device__ __forceinline__ unsigned long long f2_fma(unsigned long long a, unsigned long long b, unsigned long long c) {
+  unsigned long long r;
+  asm("fma.rn.f32x2 %0, %1, %2, %3;" : "=l"(r) : "l"(a), "l"(b), "l"(c));
+  return r;
+}
+__device__ __forceinline__ uint32_t pack2(float a, float b) {
+  __nv_bfloat162 v = __floats2bfloat162_rn(a, b);
+  return *reinterpret_cast<uint32_t*>(&v);
+}
+// (s0, s1) -> packed bf16 hi pair and packed bf16 lo pair with s = hi + lo to ~2^-17
+__device__ __forceinline__ void split_hi_lo(unsigned long long s, uint32_t& hi, uint32_t& lo) {
+  float s0, s1;
+  f2_unpack(s, s0, s1);
+  hi = pack2(s0, s1);
+  const unsigned long long hf = f2_pack(__uint_as_float(hi << 16), __uint_as_float(hi & 0xffff0000u));
+  float l0, l1;
+  f2_unpack(f2_sub(s, hf), l0, l1);
+  lo = pack2(l0, l1);
+}
+// gelu of two values, tanh form with the hardware tanh (model.py:212).  The erf and tanh forms differ by <= 5e-4 absolute; G only
+// feeds the softmax-over-K logits, where that is far below the bf16 rounding of tw (scripts/numerics_table_mode.py).
+__device__ __forceinline__ unsigned long long gelu2(unsigned long long x) {
+  const unsigned long long c1 = f2_pack(0.0356774081f, 0.0356774081f), c0 = f2_pack(0.7978845608f, 0.7978845608f), half = f2_pack(0.5f, 0.5f);
+  const unsigned long long u = f2_mul(x, f2_fma(f2_mul(x, x), c1, c0));
+  const unsigned long long hx = f2_mul(x, half);
+  float u0, u1;
+  f2_unpack(u, u0, u1);
+  return f2_fma(hx, f2_pack(tc::tanh_approx(u0), tc::tanh_approx(u1)), hx);
 }
 __device__ __forceinline__ float ex2_approx(float x) {
   float y;
   asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(y) : "f"(x));
   return y;
 }
-__device__ __forceinline__ uint32_t pack2(float a, float b) {
-  __nv_bfloat162 v = __floats2bfloat162_rn(a, b);
-  return *reinterpret_cast<uint32_t*>(&v);
+
+// -------------------------------------------------------------------------------------------------------------------- tpack_kernel
+__device__ __forceinline__ uint2 make_rec(int64_t id, bool masked, int64_t n_rows, int mult, int h, int il) {
+  const bool valid = id >= 0 && id < n_rows;
+  uint2 r;
+  r.x = (valid ? static_cast<uint32_t>(id) : 0u) | (masked ? REC_MASKED : 0u) | (valid ? REC_VALID : 0u);
+  r.y = static_cast<uint32_t>(mult) | (static_cast<uint32_t>(h) << 16) | (static_cast<uint32_t>(il) << 24);
+  return r;
 }
+
+// One warp per tile.  CH = ceil(H / 32) chunks of 32 slots per impression.
+template <int CH>
+__global__ void __launch_bounds__(256)
+tpack_kernel(const void* __restrict__ his_ids, int id_dtype, const uint8_t* __restrict__ mask, int64_t B, int H, int64_t n_rows, int ipt, int ts,
+             int64_t n_tiles, uint2* __restrict__ rec, uint2* __restrict__ hdr, int* __restrict__ oob) {
+  const int lane = threadIdx.x & 31;
+  const uint32_t lt_mask = (1u << lane) - 1u;
+  const int64_t w0 = (static_cast<int64_t>(blockIdx.x) * blockDim.x + threadIdx.x) >> 5, nw = (static_cast<int64_t>(gridDim.x) * blockDim.x) >> 5;
+  int bad = 0;
+  for (int64_t tile = w0; tile < n_tiles; tile += nw) {
+    uint2* out = rec + tile * ts;
+    int pos = 0;
+    uint32_t ends[4] = {0u, 0u, 0u, 0u};
+    for (int i = 0; i < 4; ++i) {
+      if (i < ipt) {
+        const int64_t imp = tile * ipt + i;
+        pos = (pos + 1) & ~1;
+        if (imp < B) {
+          int64_t id[CH];
+          bool in[CH], msk[CH];
+#pragma unroll
+          for (int c = 0; c < CH; ++c) {
+            const int h = c * 32 + lane;
+            in[c] = h < H;
+            id[c] = in[c] ? load_id(his_ids, imp * H + h, id_dtype) : -1;
+            msk[c] = in[c] && mask[imp * H + h] == 0;
+          }
+          // the first masked slot names the row every other masked slot with the same id is merged into
+          int64_t fm = 0;
+          bool have = false;
+          int fh = 0;
+#pragma unroll
+          for (int c = 0; c < CH; ++c) {
+            const unsigned b = __ballot_sync(0xffffffffu, msk[c]);
+            const int l = b ? __ffs(b) - 1 : 0;
+            const int64_t cand = __shfl_sync(0xffffffffu, id[c], l);
+            if (!have && b) { fm = cand; have = true; fh = c * 32 + l; }
+          }
+          bool mrg[CH];
+          int nm = 0;
+#pragma unroll
+          for (int c = 0; c < CH; ++c) {
+            mrg[c] = have && msk[c] && id[c] == fm;
+            nm += __popc(__ballot_sync(0xffffffffu, mrg[c]));
+          }
+          if (have) {
+            if (lane == 0) {
+              out[pos] = make_rec(fm, true, n_rows, nm, fh, i);
+              if (fm < 0 || fm >= n_rows) bad += nm;
+            }
+            pos += 1;
+          }
+#pragma unroll
+          for (int c = 0; c < CH; ++c) {
+            const bool keep = in[c] && !mrg[c];
+            const unsigned b = __ballot_sync(0xffffffffu, keep);
+            if (keep) {
+              out[pos + __popc(b & lt_mask)] = make_rec(id[c], msk[c], n_rows, 1, c * 32 + lane, i);
+              if (id[c] < 0 || id[c] >= n_rows) ++bad;
+            }
+            pos += __popc(b);
+          }
+        }
+      }
+      ends[i] = static_cast<uint32_t>(pos);
+    }
+    // padding records (multiplicity 0): the odd slot between two impressions and the tail up to the next 16-slot group
+    const int n_tot = pos, n16 = (n_tot + 15) & ~15;
+    if (lane < 3 && lane + 1 < ipt && (ends[lane] & 1u)) out[ends[lane]] = make_uint2(0u, 0u);
+    if (n_tot + lane < n16) out[n_tot + lane] = make_uint2(0u, 0u);
+    if (lane == 0) hdr[tile] = make_uint2(ends[0] | (ends[1] << 16), ends[2] | (ends[3] << 16));
+  }
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) bad += __shfl_xor_sync(0xffffffffu, bad, o);
+  if (lane == 0 && bad > 0 && oob) atomicAdd(oob, bad);
+}
+
+// -------------------------------------------------------------------------------------------------------------------- tscore_kernel
 template <int IPT, int KM, int NH>
 __global__ void __launch_bounds__(T_THREADS, 1)
 tscore_kernel(const TScoreArgs args, int n_tiles) {
-  constexpr int HP = TM * NH / IPT, LPI = TM / IPT;     // history slots / TMEM lanes per impression
+  constexpr int LPI = TM / IPT;                         // TMEM lanes per impression
+  constexpr int TS = TM * NH;                           // slot records per tile
   constexpr int LS = Shape<KM, NH>::LS, SS = Shape<KM, NH>::SS, SCRATCH_FLOATS = Shape<KM, NH>::SCRATCH_FLOATS, S1 = Shape<KM, NH>::S1;
   constexpr int NCM = NH == 1 ? NC_MAX : 64;            // candidate columns per pass
   constexpr int IP_COL = 64 * NH, DM_COL = IP_COL + 256, DA_COL = DM_COL + NCM;
+  static_assert(LPI >= 32, "a warp's 32 TMEM lanes belong to one impression");
   extern __shared__ uint8_t smem_raw[];
   uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~static_cast<uintptr_t>(1023));
   uint8_t* st1 = smem;                                         // [S1][E 16 KB | TW 16 KB]
   uint8_t* st2 = st1 + S1 * ST1_BYTES;                         // [S2][12 KB] candidate rows
   // scratch of the softmax / score warps: the logits L of the unit being prepared and the score transposes Sm / Sa of the unit
   // being finished are never live at the same time (named barriers 1 and 2 separate the phases), so they share the bytes
-  float* L = reinterpret_cast<float*>(st2 + S2 * C_BYTES);     // [128 slots][LS] logits
+  float* L = reinterpret_cast<float*>(st2 + S2 * C_BYTES);     // [128 NH slots][LS] logits, then exp2(logit - max) in place
   float* Sm = L;                                               // [NC_MAX][SS] matching scores, transposed
   float* Sa = Sm + NC_MAX * SS;                                // [NC_MAX][SS] attention logits, transposed
   TBarriers* bars = reinterpret_cast<TBarriers*>(L + SCRATCH_FLOATS);
@@ -199,52 +351,50 @@ tscore_kernel(const TScoreArgs args, int n_tiles) {
 
   if (warp < W_G2) {
     // ------------------------------------------------------------------ gathers of the (E, TW) ring: thread = one 16-byte chunk of rows
-    //        r0 + G1_STEP jj
+    //        r0 + 16 jj, i.e. one row of every 16-slot group (K-step) of the tile
     const int t = threadIdx.x;
     const int chunk = t & 7, r0 = t >> 3;
     const uint32_t row_bytes = static_cast<uint32_t>(D) * 2;
     const char* table_b = reinterpret_cast<const char*>(args.table);
     const char* tw_b = reinterpret_cast<const char*>(args.tw);
-    const uint32_t dst0 = tc::sw128_offset(r0, chunk);       // row r0 + G1_STEP jj sits jj * G1_STEP / 8 KB further
-    RawId ids_pre[G1_ROWS * NH];                             // raw ids of the next tile (see RawId)
-    auto fetch_ids = [&](int lt) {
+    const uint32_t dst0 = tc::sw128_offset(r0, chunk);       // row r0 + 16 jj sits 2 jj KB further
+    uint32_t rec_pre[G1_ROWS * NH];                          // raw slot records (x word) of the next tile (see RawId)
+    uint2 hdr_pre = make_uint2(0u, 0u);
+    auto fetch_recs = [&](int lt) {
       const int tile = static_cast<int>(blockIdx.x) + lt * static_cast<int>(gridDim.x);
+      const uint32_t* rt = reinterpret_cast<const uint32_t*>(args.rec + static_cast<int64_t>(tile) * TS);
 #pragma unroll
-      for (int jj = 0; jj < G1_ROWS * NH; ++jj) {
-        const int slot = (jj / G1_ROWS) * TM + r0 + G1_STEP * (jj % G1_ROWS);      // half * 128 + row of the stage
-        const int64_t imp = static_cast<int64_t>(tile) * IPT + slot / HP;
-        const int h = slot % HP;
-        const bool ok = h < H && imp < args.B;
-        ids_pre[jj] = load_id_raw(args.his_ids, ok ? imp * H + h : 0, args.id_dtype);
-      }
+      for (int jj = 0; jj < G1_ROWS * NH; ++jj) rec_pre[jj] = rt[2 * (r0 + G1_STEP * jj)];
+      hdr_pre = args.hdr[tile];
     };
     uint32_t g = 0;
     PROF_DECL;
     int64_t cs = 0, ce = 0;
-    if (n_local > 0) { fetch_ids(0); tile_range<IPT>(args, static_cast<int>(blockIdx.x), cs, ce); }
+    if (n_local > 0) { fetch_recs(0); tile_range<IPT>(args, static_cast<int>(blockIdx.x), cs, ce); }
     for (int lt = 0; lt < n_local; ++lt) {
-      const int tile = static_cast<int>(blockIdx.x) + lt * static_cast<int>(gridDim.x);
       uint32_t eoff[G1_ROWS * NH];                           // byte offset of this thread's 16-byte chunk in its rows (table < 4 GB, checked by the launcher)
       uint32_t emask = 0;
+      const int nks = (hdr_end(hdr_pre, IPT - 1) + 15) >> 4; // 16-slot groups of this tile
 #pragma unroll
       for (int jj = 0; jj < G1_ROWS * NH; ++jj) {
-        const int slot = (jj / G1_ROWS) * TM + r0 + G1_STEP * (jj % G1_ROWS);
-        const int64_t id = id_of(ids_pre[jj], args.id_dtype);
-        const bool ok = slot % HP < H && static_cast<int64_t>(tile) * IPT + slot / HP < args.B && id >= 0 && id < args.n_rows;
-        eoff[jj] = static_cast<uint32_t>(ok ? id : 0) * row_bytes + chunk * 16;
-        emask |= ok ? (1u << jj) : 0u;
+        const uint32_t rc = rec_pre[jj];
+        eoff[jj] = (rc & REC_ID) * row_bytes + chunk * 16;
+        emask |= (rc & REC_VALID) ? (1u << jj) : 0u;
       }
-      if (args.dbg & 1) emask = 0;
+      if (TS_DBG(1)) emask = 0;
       const int npass = passes_of<NCM>(cs, ce);
-      if (lt + 1 < n_local) {                                // the next tile's ids and candidate range are fetched a tile ahead
-        fetch_ids(lt + 1);
+      if (lt + 1 < n_local) {                                // the next tile's records and candidate range are fetched a tile ahead
+        fetch_recs(lt + 1);
         tile_range<IPT>(args, static_cast<int>(blockIdx.x) + (lt + 1) * static_cast<int>(gridDim.x), cs, ce);
       }
       for (int p = 0; p < npass; ++p) {
         for (int j = 0; j < KB; ++j) {
 #pragma unroll
-          for (int half = 0; half < NH; ++half, ++g) {             // one ring stage per 128-slot half
+          for (int half = 0; half < NH; ++half) {                  // one ring stage per 128-slot half in use
+            const int ng = nks - G1_ROWS * half;                   // 16-slot groups of this half
+            if (half > 0 && ng <= 0) break;
             const uint32_t s = g % S1, ph = (g / S1) & 1;
+            ++g;
             PROF_ADD(0);
             tc::mbar_wait(&bars->empty1[s], ph ^ 1);
             PROF_ADD(1);
@@ -252,13 +402,12 @@ tscore_kernel(const TScoreArgs args, int n_tiles) {
             const uint32_t jb = static_cast<uint32_t>(j) * (FB * 2);
 #pragma unroll
             for (int jj = 0; jj < G1_ROWS; ++jj) {
-              const uint32_t o = eoff[half * G1_ROWS + jj] + jb, sz = ((emask >> (half * G1_ROWS + jj)) & 1u) ? 16u : 0u;
-              tc::cp_async_16(base + jj * (G1_STEP * 128), table_b + o, sz);
-              tc::cp_async_16(base + E_BYTES + jj * (G1_STEP * 128), tw_b + o, (args.dbg & 2) ? 0u : sz);
+              if (jj < ng) {
+                const uint32_t o = eoff[half * G1_ROWS + jj] + jb, sz = ((emask >> (half * G1_ROWS + jj)) & 1u) ? 16u : 0u;
+                tc::cp_async_16(base + jj * (G1_STEP * 128), table_b + o, sz);
+                tc::cp_async_16(base + E_BYTES + jj * (G1_STEP * 128), tw_b + o, TS_DBG(2) ? 0u : sz);
+              }
             }
-#ifdef MINER_TS_PROF
-            if (lane == 0) *reinterpret_cast<volatile long long*>(&bars->issue_clk[s][warp]) = clock64();
-#endif
             tc::cp_async_mbar_arrive_noinc(&bars->full1[s]);
             PROF_ADD(2);
           }
@@ -286,6 +435,7 @@ tscore_kernel(const TScoreArgs args, int n_tiles) {
       }
     };
     uint32_t g = 0;
+    int bad = 0;
     const int tile0 = static_cast<int>(blockIdx.x), tstep = static_cast<int>(gridDim.x);
     int64_t cs = 0, ce = 0, ncs = 0, nce = 0, n2cs = 0, n2ce = 0;      // candidate ranges of this tile, the next one, the one after
     if (n_local > 0) {
@@ -305,11 +455,12 @@ tscore_kernel(const TScoreArgs args, int n_tiles) {
 #pragma unroll
         for (int jj = 0; jj < G2_ROWS; ++jj) {
           const int64_t id = id_of(cid_pre[jj], args.id_dtype);
-          const bool ok = r0 + G2_STEP * jj < nc && id >= 0 && id < args.n_rows;
+          const bool in = r0 + G2_STEP * jj < nc, ok = in && id >= 0 && id < args.n_rows;
           coff[jj] = static_cast<uint32_t>(ok ? id : 0) * row_bytes + chunk * 16;
           cmask |= ok ? (1u << jj) : 0u;
+          if (in && !ok && chunk == 0) ++bad;
         }
-        if (args.dbg & 5) cmask = 0;
+        if (TS_DBG(5)) cmask = 0;
         // ids of the next unit: next pass of this tile, else first pass of the next tile (its range was loaded a tile ago)
         if (p + 1 < npass) {
           const int64_t q0 = pc0 + NCM;
@@ -332,6 +483,7 @@ tscore_kernel(const TScoreArgs args, int n_tiles) {
       cs = ncs; ce = nce; ncs = n2cs; nce = n2ce;
     }
     tc::cp_async_wait_all();
+    if (bad > 0 && args.oob) atomicAdd(args.oob + 1, bad);   // candidate ids outside the table (their rows read as zero)
   } else if (warp == W_MMA) {
     // ------------------------------------------------------------------ MMA issuer
     const uint32_t idesc1 = tc::make_idesc_bf16_f32_major(TM, FB, false, true);        // B = gathered tile, MN-major
@@ -369,12 +521,17 @@ tscore_kernel(const TScoreArgs args, int n_tiles) {
       PROF_ADD(7);
     };
     int64_t t_cs = 0, t_ce = 0;
-    if (n_local > 0) tile_range<IPT>(args, static_cast<int>(blockIdx.x), t_cs, t_ce);
+    uint2 hdr_pre = make_uint2(0u, 0u);
+    if (n_local > 0) { tile_range<IPT>(args, static_cast<int>(blockIdx.x), t_cs, t_ce); hdr_pre = args.hdr[blockIdx.x]; }
     for (int lt = 0; lt < n_local; ++lt) {
       const int tile = static_cast<int>(blockIdx.x) + lt * static_cast<int>(gridDim.x);
       const int64_t cs = t_cs, ce = t_ce;
+      const int nks = (hdr_end(hdr_pre, IPT - 1) + 15) >> 4;
       const int npass = passes_of<NCM>(cs, ce);
-      if (lt + 1 < n_local) tile_range<IPT>(args, tile + static_cast<int>(gridDim.x), t_cs, t_ce);      // a tile ahead: off the critical path
+      if (lt + 1 < n_local) {                                  // a tile ahead: off the critical path
+        tile_range<IPT>(args, tile + static_cast<int>(gridDim.x), t_cs, t_ce);
+        hdr_pre = args.hdr[tile + static_cast<int>(gridDim.x)];
+      }
       for (int p = 0; p < npass; ++p, ++u) {
         const int64_t pc0 = cs + static_cast<int64_t>(p) * NCM;
         const int nc = static_cast<int>(ce - pc0 < NCM ? ce - pc0 : NCM);
@@ -387,8 +544,12 @@ tscore_kernel(const TScoreArgs args, int n_tiles) {
           const uint32_t b = g1 & 1;
           const uint32_t d_i = tmem + IP_COL + b * 128, d_p = d_i + 64;
 #pragma unroll
-          for (int half = 0; half < NH; ++half, ++sg) {
+          for (int half = 0; half < NH; ++half) {
+            const int ng = nks - 8 * half < 8 ? nks - 8 * half : 8;
+            if (half > 0 && ng <= 0) break;
+            const bool last_half = half == NH - 1 || nks <= 8 * (half + 1);
             const uint32_t s = sg % S1, ph = (sg / S1) & 1;
+            ++sg;
             PROF_ADD(0);
             tc::mbar_wait(&bars->full1[s], ph);
             PROF_ADD(2);
@@ -398,12 +559,14 @@ tscore_kernel(const TScoreArgs args, int n_tiles) {
             if (tc::elect_one()) {
 #pragma unroll
               for (int ks = 0; ks < TM / 16; ++ks) {
-                const uint32_t acc = (half | ks) != 0 ? 1u : 0u;
-                tc::umma_bf16_ts(d_i, tmem + AW_COL + half * 64 + 8 * ks, e_desc + ks * (2048 >> 4), idesc1, acc);
-                tc::umma_bf16_ts(d_p, tmem + AW_COL + half * 64 + 8 * ks, t_desc + ks * (2048 >> 4), idesc1, acc);
+                if (ks < ng) {
+                  const uint32_t acc = (half | ks) != 0 ? 1u : 0u;
+                  tc::umma_bf16_ts(d_i, tmem + AW_COL + half * 64 + 8 * ks, e_desc + ks * (2048 >> 4), idesc1, acc);
+                  tc::umma_bf16_ts(d_p, tmem + AW_COL + half * 64 + 8 * ks, t_desc + ks * (2048 >> 4), idesc1, acc);
+                }
               }
               tc::umma_commit(&bars->empty1[s]);
-              if (half == NH - 1) {
+              if (last_half) {
                 tc::umma_commit(&bars->ip_full[b]);
                 if (j == KB - 1) tc::umma_commit(&bars->w_free);
               }
@@ -425,10 +588,11 @@ tscore_kernel(const TScoreArgs args, int n_tiles) {
     const int q = warp & 3;                                    // TMEM lane quarter
     const int half = ew >> 2;                                  // 16-lane group of the quarter
     const int et = ew * 32 + lane;
-    const int li = (q * 32) / LPI;                             // impression of this quarter's lanes
-    // this warp owns lanes [16 half, 16 half + 16) of its quarter; thread t meets the (hi, lo) rows of code bk
-    const uint32_t grp_addr = static_cast<uint32_t>(q * 32 + half * 16) << 16;
-    const int bk = (((q * 32) % LPI) / 16 + half) * 8 + (lane >> 2);   // context code of this thread's row pair
+    const int g0 = q * 32 + half * 16;                         // first lane of this warp's group
+    const int li = g0 / LPI;                                   // its impression inside the tile
+    // this warp owns lanes [g0, g0 + 16); thread t meets the (hi, lo) rows of code bk
+    const uint32_t grp_addr = static_cast<uint32_t>(g0) << 16;
+    const int bk = ((g0 % LPI) / 16) * 8 + (lane >> 2);        // context code of this thread's row pair
     const int bf = 2 * (lane & 3);                              // its features inside an 8-feature group
     uint32_t g = 0;
     PROF_DECL;
@@ -439,8 +603,7 @@ tscore_kernel(const TScoreArgs args, int n_tiles) {
       const int64_t cs = t_cs, ce = t_ce;
       const int npass = passes_of<NCM>(cs, ce);
       if (lt + 1 < n_local) tile_range<IPT>(args, tile + static_cast<int>(gridDim.x), t_cs, t_ce);      // a tile ahead: off the critical path
-      const int64_t i0 = static_cast<int64_t>(tile) * IPT;
-      const int64_t my_imp = i0 + li;
+      const int64_t my_imp = static_cast<int64_t>(tile) * IPT + li;
       for (int p = 0; p < npass; ++p) {
         const bool want_i = args.out_interests != nullptr && p == 0 && bk < K && my_imp < args.B;
         for (int j = 0; j < KB; ++j, ++g) {
@@ -456,28 +619,25 @@ tscore_kernel(const TScoreArgs args, int n_tiles) {
           tc::tmem_ld_wait();
           PROF_ADD(5);
           uint32_t pk[16];
-          if (want_i) {                                                        // model.py:138 (interests are an output)
-            float* o = args.out_interests + (my_imp * K + bk) * D + j * FB + bf;
-#pragma unroll
-            for (int n = 0; n < 8; ++n)
-              *reinterpret_cast<float2*>(o + 8 * n) = make_float2(__uint_as_float(vi[4 * n]) + __uint_as_float(vi[4 * n + 2]),
-                                                                  __uint_as_float(vi[4 * n + 1]) + __uint_as_float(vi[4 * n + 3]));
-          }
 #pragma unroll
           for (int n = 0; n < 8; ++n) {
-            const float s0 = __uint_as_float(vi[4 * n]) + __uint_as_float(vi[4 * n + 2]);       // w_hi . E + w_lo . E
-            const float s1 = __uint_as_float(vi[4 * n + 1]) + __uint_as_float(vi[4 * n + 3]);
-            const uint32_t hi = pack2(s0, s1);
-            pk[2 * n] = hi;
-            pk[2 * n + 1] = pack2(s0 - __uint_as_float(hi << 16), s1 - __uint_as_float(hi & 0xffff0000u));
+            // w_hi . E + w_lo . E for two adjacent features, then the bf16 hi / lo images of the sum
+            const unsigned long long s = f2_add(f2_pack(__uint_as_float(vi[4 * n]), __uint_as_float(vi[4 * n + 1])),
+                                                f2_pack(__uint_as_float(vi[4 * n + 2]), __uint_as_float(vi[4 * n + 3])));
+            if (want_i) {                                                      // model.py:138 (interests are an output)
+              float s0, s1;
+              f2_unpack(s, s0, s1);
+              *reinterpret_cast<float2*>(args.out_interests + (my_imp * K + bk) * D + j * FB + bf + 8 * n) = make_float2(s0, s1);
+            }
+            split_hi_lo(s, pk[2 * n], pk[2 * n + 1]);
           }
           tc::tmem_st_16x128b_x8(acc, pk);                                     // in place: this thread group has read all 64 columns
 #pragma unroll
           for (int n = 0; n < 8; ++n) {
-            // gelu(P) only feeds the softmax-over-K logits: one bf16 (as cand_kernel.cu), the lo row of the pair stays zero
-            pk[2 * n] = pack2(gelu_fast(__uint_as_float(vp[4 * n]) + __uint_as_float(vp[4 * n + 2])),           // model.py:212
-                              gelu_fast(__uint_as_float(vp[4 * n + 1]) + __uint_as_float(vp[4 * n + 3])));
-            pk[2 * n + 1] = 0u;
+            // G = gelu(P) as hi + lo as well (model.py:212): a single bf16 G is the largest error of the path once |P| ~ 1
+            const unsigned long long s = f2_add(f2_pack(__uint_as_float(vp[4 * n]), __uint_as_float(vp[4 * n + 1])),
+                                                f2_pack(__uint_as_float(vp[4 * n + 2]), __uint_as_float(vp[4 * n + 3])));
+            split_hi_lo(gelu2(s), pk[2 * n], pk[2 * n + 1]);
           }
           PROF_ADD(6);
           tc::tmem_st_16x128b_x8(acc + 64, pk);
@@ -496,12 +656,13 @@ tscore_kernel(const TScoreArgs args, int n_tiles) {
     // ------------------------------------------------------------------ softmax / score warps
     const int sw = warp - W_SMX0;
     const int q = warp & 3;
-    const int li = (q * 32) / LPI;                             // impression of this quarter's lanes
+    const int li_q = (q * 32) / LPI;                           // impression of this quarter's lanes (LPI >= 32)
     const uint32_t lane_addr = static_cast<uint32_t>(q * 32) << 16;
     const int st = sw * 32 + lane;                             // 0..127
     const int tl = q * 32 + lane;                              // TMEM lane = (i, k, hl) for the 32-lane reads of the score stage
     const int lk = ((tl % LPI) >> 4) * 8 + (tl & 7);
     const bool lo_part = (tl & 8) != 0;
+    const int c4 = lane & 3;
     uint32_t u = 0;
     PROF_DECL;
     // ---- scores of a finished unit (model.py:127-136,213-214).  These warps have the slack: while they do this the epilogue
@@ -515,7 +676,7 @@ tscore_kernel(const TScoreArgs args, int n_tiles) {
       tc::mbar_wait(&bars->dma_full, fu & 1);
       PROF_ADD(5);
       tc::tcgen05_fence_after();
-      tc::named_bar_sync(1, T_SMX);                                            // the previous unit's score threads are done with Sm / Sa
+      tc::named_bar_sync(1, T_SMX);                                            // the softmax threads are done with L (= Sm / Sa); the previous unit's score threads with Sm / Sa
       {
         // columns of this lane's impression inside the pass (warp-uniform: a warp's 32 lanes belong to one impression)
         const int64_t r_lo = my_cs - pc0, r_hi = my_ce - pc0;
@@ -569,159 +730,145 @@ tscore_kernel(const TScoreArgs args, int n_tiles) {
       }
       PROF_ADD(6);
     };
-    {
-      // the off-diagonal half of A_w (slots of the other impression) stays zero for the whole kernel
-      uint32_t z[16];
+    // raw slot records of the next tile (see RawId): lane l of warp sw owns slot 4 l + sw of every 128-slot half
+    uint2 rec_pre[NH];
+    uint2 hdr_pre = make_uint2(0u, 0u);
+    auto fetch_recs = [&](int tile) {
+      const uint2* rt = args.rec + static_cast<int64_t>(tile) * TS;
 #pragma unroll
-      for (int c = 0; c < 16; ++c) z[c] = 0u;
-#pragma unroll
-      for (int cc = 0; cc < 4 * NH; ++cc) tc::tmem_st_32x16(tmem + lane_addr + AW_COL + cc * 16, z);
-      tc::tmem_st_wait();
-    }
+      for (int hh = 0; hh < NH; ++hh) rec_pre[hh] = rt[hh * TM + 4 * lane + sw];
+      hdr_pre = args.hdr[tile];
+    };
     int64_t t_cs = 0, t_ce = 0;
-    if (n_local > 0) tile_range<IPT>(args, static_cast<int>(blockIdx.x), t_cs, t_ce);
+    if (n_local > 0) { tile_range<IPT>(args, static_cast<int>(blockIdx.x), t_cs, t_ce); fetch_recs(static_cast<int>(blockIdx.x)); }
     for (int lt = 0; lt < n_local; ++lt) {
       const int tile = static_cast<int>(blockIdx.x) + lt * static_cast<int>(gridDim.x);
       const int64_t cs = t_cs, ce = t_ce;
       const int npass = passes_of<NCM>(cs, ce);
-      if (lt + 1 < n_local) tile_range<IPT>(args, tile + static_cast<int>(gridDim.x), t_cs, t_ce);      // a tile ahead: off the critical path
+      uint2 rec_cur[NH];
+#pragma unroll
+      for (int hh = 0; hh < NH; ++hh) rec_cur[hh] = rec_pre[hh];
+      const uint2 hd = hdr_pre;
+      if (lt + 1 < n_local) {                                  // a tile ahead: off the critical path
+        tile_range<IPT>(args, tile + static_cast<int>(gridDim.x), t_cs, t_ce);
+        fetch_recs(tile + static_cast<int>(gridDim.x));
+      }
+      const int n_tot = hdr_end(hd, IPT - 1);
+      const int nks = (n_tot + 15) >> 4;
       for (int p = 0; p < npass; ++p, ++u) {
         PROF_ADD(0);
-        tc::named_bar_sync(2, T_SMX);                                          // previous unit's reads of L are done
+        tc::named_bar_sync(2, T_SMX);                                          // previous unit's reads of Sm / Sa are done
         {
-          // logits of 32 slots per warp: lg rows are K consecutive floats (model.py:174 hoisted to the table).  Stored scaled by
-          // log2(e): the softmax below runs on ex2.
+          // logits of the tile's slots, interleaved over the four warps: lg rows are K consecutive floats (model.py:174 hoisted
+          // to the table).  Stored scaled by log2(e): the softmax below runs on ex2.
           const uint32_t Ku = static_cast<uint32_t>(K);
-          const bool has_bias = args.bias_mean != nullptr;
 #pragma unroll
-          for (int hh = 0; hh < NH; ++hh) {                                    // 128 slots per pass, 32 per warp
-            const int slot = hh * TM + sw * 32 + lane;
-            const int64_t imp = static_cast<int64_t>(tile) * IPT + slot / HP;
-            const int h = slot % HP;
-            const bool valid = h < H && imp < args.B;
-            uint32_t info = 0;                                                 // id | code << 30; code 0 padding, 1 masked, 2 kept, 3 kept with a bad id
-            float bias = 0.f;
-            if (valid) {
-              const int64_t id = load_id(args.his_ids, imp * H + h, args.id_dtype);
-              const bool keep = args.mask[imp * H + h] != 0;
-              if (args.bias_mean) bias = args.bias_mean[imp * H + h];
-              const bool id_ok = id >= 0 && id < args.n_rows;
-              info = (id_ok ? static_cast<uint32_t>(id) : 0u) | ((keep ? (id_ok ? 2u : 3u) : 1u) << 30);
-            }
+          for (int hh = 0; hh < NH; ++hh) {
+            const int base = hh * TM;
+            if (base >= n_tot) break;
+            const uint32_t info = rec_cur[hh].x, meta = rec_cur[hh].y;
+            const uint32_t mult = meta & 0xffffu;
+            const bool kept = mult != 0u && !(info & REC_MASKED);
+            // aux: the bias of a kept slot (model.py:176-177), else the slot's whole logit: -inf for padding, and for a masked record
+            // of multiplicity n  log2(e) 1e-30 + log2 n  (n slots filled with 1e-30, model.py:180, add up to n exp(1e-30))
+            float aux;
+            if (kept) aux = args.bias_mean ? args.bias_mean[(static_cast<int64_t>(tile) * IPT + ((meta >> 24) & 0xfu)) * H + ((meta >> 16) & 0xffu)] : 0.f;
+            else aux = mult == 0u ? -INFINITY : kMaskFill * 1.4426950408889634f + __log2f(static_cast<float>(mult));
+            const uint32_t word = (info & (REC_ID | REC_VALID)) | (kept ? REC_MASKED : 0u);     // bit 30 reused: 1 = kept
+            int cnt = (n_tot - base - sw + 3) >> 2;                            // this warp's slots base + sw + 4 ss < n_tot
+            cnt = cnt > 32 ? 32 : cnt;
 #pragma unroll
             for (int kk = 0; kk < KM / 32; ++kk) {                             // 32 codes per pass
               const int kcol = lane + 32 * kk;
               const float* lgp = args.lg + kcol;
-              float v[32];
+              for (int ss0 = 0; ss0 < cnt; ss0 += 16) {
+                float v[16];
 #pragma unroll
-              for (int ss = 0; ss < 32; ++ss) {                                // 32 independent 128-byte row loads in flight
-                const uint32_t info_s = __shfl_sync(0xffffffffu, info, ss);
-                v[ss] = ((info_s >> 30) == 2u && kcol < K) ? lgp[(info_s & 0x3fffffffu) * Ku] : 0.f;
-              }
+                for (int i = 0; i < 16; ++i) {                                 // 16 independent 128-byte row loads in flight
+                  const uint32_t w_s = __shfl_sync(0xffffffffu, word, (ss0 + i) & 31);
+                  v[i] = (ss0 + i < cnt && (w_s >> 30) == 3u && kcol < K) ? lgp[(w_s & REC_ID) * Ku] : 0.f;
+                }
 #pragma unroll
-              for (int ss = 0; ss < 32; ++ss) {
-                const uint32_t code_s = __shfl_sync(0xffffffffu, info, ss) >> 30;
-                float x = v[ss];
-                if (has_bias) x += __shfl_sync(0xffffffffu, bias, ss);         // model.py:174-177
-                if (code_s == 1u) x = kMaskFill;                               // model.py:180 (1e-30, not -inf)
-                if (code_s == 0u) x = -INFINITY;                               // tile padding: not part of the history
-                L[(hh * TM + sw * 32 + ss) * LS + kcol] = x * 1.4426950408889634f;
+                for (int i = 0; i < 16; ++i) {
+                  const uint32_t w_s = __shfl_sync(0xffffffffu, word, (ss0 + i) & 31);
+                  const float a_s = __shfl_sync(0xffffffffu, aux, (ss0 + i) & 31);
+                  if (ss0 + i < cnt)
+                    L[(base + sw + 4 * (ss0 + i)) * LS + kcol] = (w_s & REC_MASKED) ? (v[i] + a_s) * 1.4426950408889634f : a_s;
+                }
               }
             }
           }
         }
         tc::named_bar_sync(2, T_SMX);
         PROF_ADD(1);
-        // softmax over the history (model.py:181): per 16-lane group, thread t owns code k = 8 group + t/4 and the 16 slots
-        // {2c, 2c+1 : c = t%4 + 4n}; the (hi, lo) rows of the pair leave through one 16x128b store
-        if constexpr (IPT == 1) {
-          // one impression per tile (up to 128 NH slots): too many weights to hold in registers across the wait, so wait first,
-          // take max and sum in two passes over the logits, then recompute, pack and store 32 packed columns at a time
-          if (u > 0) tc::mbar_wait(&bars->w_free, (u - 1) & 1);                // S1 of the previous unit no longer reads A_w
-          PROF_ADD(3);
-          tc::tcgen05_fence_after();
-          constexpr int NCT = HP / 8;                                          // packed columns per thread: c = t%4 + 4n, n < NCT
-#pragma unroll
-          for (int hf = 0; hf < 2; ++hf) {
-            const int k = (((q * 32) % LPI) / 16 + hf) * 8 + (lane >> 2);
-            const bool row_ok = k < K;
-            const float* col = L + (row_ok ? k : 0);
-            float mx = -INFINITY;
-            for (int n = 0; n < NCT; ++n) {
-              const int c = (lane & 3) + 4 * n;
-              mx = fmaxf(mx, fmaxf(col[(2 * c) * LS], col[(2 * c + 1) * LS]));
-            }
-            mx = fmaxf(mx, __shfl_xor_sync(0xffffffffu, mx, 1));
-            mx = fmaxf(mx, __shfl_xor_sync(0xffffffffu, mx, 2));
-            const bool dead = mx == -INFINITY || !row_ok;                      // impression past the end of the batch / unused row
-            float sum = 0.f;
-            for (int n = 0; n < NCT; ++n) {
-              const int c = (lane & 3) + 4 * n;
-              sum += dead ? 0.f : ex2_approx(col[(2 * c) * LS] - mx) + ex2_approx(col[(2 * c + 1) * LS] - mx);
-            }
-            sum += __shfl_xor_sync(0xffffffffu, sum, 1);
-            sum += __shfl_xor_sync(0xffffffffu, sum, 2);
-            const float inv = dead ? 0.f : __fdividef(1.0f, sum);
-#pragma unroll
-            for (int part = 0; part < NCT / 8; ++part) {
-              uint32_t o[16];
-#pragma unroll
-              for (int n = 0; n < 8; ++n) {
-                const int c = (lane & 3) + 4 * (8 * part + n);
-                const float w0 = dead ? 0.f : ex2_approx(col[(2 * c) * LS] - mx) * inv;          // model.py:181
-                const float w1 = dead ? 0.f : ex2_approx(col[(2 * c + 1) * LS] - mx) * inv;
-                const uint32_t hi = pack2(w0, w1);
-                o[2 * n] = hi;
-                o[2 * n + 1] = pack2(w0 - __uint_as_float(hi << 16), w1 - __uint_as_float(hi & 0xffff0000u));
-              }
-              tc::tmem_st_16x128b_x8(tmem + (static_cast<uint32_t>(q * 32 + hf * 16) << 16) + AW_COL + part * 32, o);
-            }
-          }
-          PROF_ADD(2);
-        } else {
-        constexpr int NC8 = HP / 8;                                            // packed columns per thread: c = t%4 + 4n, n < NC8
-        uint32_t pk[2][2 * NC8];
+        // softmax over the history (model.py:181): per 16-lane group, thread t owns code k = 8 group + t/4 and the slots
+        // {2c, 2c+1 : c = t%4 + 4n} of its impression's range [s0, s1); the (hi, lo) rows of the pair leave through 16x128b stores
+        float inv[2];
+        int s0v[2], s1v[2];
+        bool deadv[2];
 #pragma unroll
         for (int hf = 0; hf < 2; ++hf) {
-          const int k = (((q * 32) % LPI) / 16 + hf) * 8 + (lane >> 2);
-          const bool row_ok = k < K;
-          const float* col = L + (li * HP) * LS + (row_ok ? k : 0);
-          float e[2 * NC8];
+          const int g0 = q * 32 + hf * 16;
+          const int li = g0 / LPI;
+          const int k = ((g0 % LPI) / 16) * 8 + (lane >> 2);
+          const int s0 = hdr_start(hd, li), s1 = hdr_end(hd, li);
+          const bool row_ok = k < K && s1 > s0;
+          float* col = L + (row_ok ? k : 0);
+          const int n_lo = s0 >> 3, n_hi = (s1 + 7) >> 3;
           float mx = -INFINITY;
-#pragma unroll
-          for (int n = 0; n < NC8; ++n) {
-            const int c = (lane & 3) + 4 * n;
-            e[2 * n] = col[(2 * c) * LS];
-            e[2 * n + 1] = col[(2 * c + 1) * LS];
-            mx = fmaxf(mx, fmaxf(e[2 * n], e[2 * n + 1]));
+          for (int n = n_lo; n < n_hi; ++n) {
+            const int sa = 2 * (c4 + 4 * n);
+            const float a = (sa >= s0 && sa < s1) ? col[sa * LS] : -INFINITY;
+            const float b = (sa + 1 < s1 && sa >= s0) ? col[(sa + 1) * LS] : -INFINITY;
+            mx = fmaxf(mx, fmaxf(a, b));
           }
           mx = fmaxf(mx, __shfl_xor_sync(0xffffffffu, mx, 1));
           mx = fmaxf(mx, __shfl_xor_sync(0xffffffffu, mx, 2));
           const bool dead = mx == -INFINITY || !row_ok;                        // impression past the end of the batch / unused row
           float sum = 0.f;
-#pragma unroll
-          for (int n = 0; n < 2 * NC8; ++n) {
-            e[n] = dead ? 0.f : ex2_approx(e[n] - mx);
-            sum += e[n];
+          for (int n = n_lo; n < n_hi; ++n) {
+            const int sa = 2 * (c4 + 4 * n);
+            if (!dead && sa >= s0 && sa < s1) {
+              const float e = ex2_approx(col[sa * LS] - mx);
+              col[sa * LS] = e;
+              sum += e;
+            }
+            if (!dead && sa >= s0 && sa + 1 < s1) {
+              const float e = ex2_approx(col[(sa + 1) * LS] - mx);
+              col[(sa + 1) * LS] = e;
+              sum += e;
+            }
           }
           sum += __shfl_xor_sync(0xffffffffu, sum, 1);
           sum += __shfl_xor_sync(0xffffffffu, sum, 2);
-          const float inv = dead ? 0.f : __fdividef(1.0f, sum);
-#pragma unroll
-          for (int n = 0; n < NC8; ++n) {
-            const float w0 = e[2 * n] * inv, w1 = e[2 * n + 1] * inv;
-            const uint32_t hi = pack2(w0, w1);
-            pk[hf][2 * n] = hi;
-            pk[hf][2 * n + 1] = pack2(w0 - __uint_as_float(hi << 16), w1 - __uint_as_float(hi & 0xffff0000u));
-          }
+          inv[hf] = dead ? 0.f : __fdividef(1.0f, sum);
+          s0v[hf] = s0; s1v[hf] = s1; deadv[hf] = dead;
         }
         PROF_ADD(2);
         if (u > 0) tc::mbar_wait(&bars->w_free, (u - 1) & 1);                  // S1 of the previous unit no longer reads A_w
         PROF_ADD(3);
         tc::tcgen05_fence_after();
+        // every column the MMAs of this tile read (8 per 16-slot group) is rewritten, zeros outside the impression's own range:
+        // the block "staircase" of A_w moves from tile to tile
+        const int nparts = (nks * 8 + 31) >> 5;
 #pragma unroll
-        for (int hf = 0; hf < 2; ++hf)
-          tc::tmem_st_16x128b_x8(tmem + (static_cast<uint32_t>(q * 32 + hf * 16) << 16) + AW_COL + li * (HP / 2), pk[hf]);
+        for (int hf = 0; hf < 2; ++hf) {
+          const int g0 = q * 32 + hf * 16;
+          const int k = ((g0 % LPI) / 16) * 8 + (lane >> 2);
+          const float* col = L + (deadv[hf] ? 0 : k);
+          const int s0 = s0v[hf], s1 = s1v[hf];
+          for (int part = 0; part < nparts; ++part) {
+            uint32_t o[16];
+#pragma unroll
+            for (int n = 0; n < 8; ++n) {
+              const int sa = 2 * (c4 + 4 * (8 * part + n));
+              const bool in0 = !deadv[hf] && sa >= s0 && sa < s1, in1 = !deadv[hf] && sa >= s0 && sa + 1 < s1;
+              const float w0 = in0 ? col[sa * LS] * inv[hf] : 0.f;               // model.py:181
+              const float w1 = in1 ? col[(sa + 1) * LS] * inv[hf] : 0.f;
+              split_hi_lo(f2_pack(w0, w1), o[2 * n], o[2 * n + 1]);
+            }
+            tc::tmem_st_16x128b_x8(tmem + (static_cast<uint32_t>(g0) << 16) + AW_COL + part * 32, o);
+          }
         }
         tc::tmem_st_wait();
         tc::tcgen05_fence_before();
@@ -729,7 +876,7 @@ tscore_kernel(const TScoreArgs args, int n_tiles) {
         PROF_ADD(4);
         if (u > 0) score_stage(u - 1);
         {
-          const int64_t my_imp = static_cast<int64_t>(tile) * IPT + li;
+          const int64_t my_imp = static_cast<int64_t>(tile) * IPT + li_q;
           f_pc0 = cs + static_cast<int64_t>(p) * NCM;
           f_nc = static_cast<int>(ce - f_pc0 < NCM ? ce - f_pc0 : NCM);
           f_cs = my_imp < args.B ? cand_off(args, my_imp) : ce;
@@ -746,19 +893,44 @@ tscore_kernel(const TScoreArgs args, int n_tiles) {
   if (warp == W_MMA) tc::tmem_dealloc(tmem, 512);
 }
 
+// tile geometry for a shape: impressions per tile and 128-slot halves.  An impression takes 2 K TMEM lanes (32 at least) and
+// up to (H + 1) & ~1 slots; four impressions share a tile only when their slots fit ONE half (two halves leave 64 candidate
+// columns per pass, too few for four impressions' candidates), two when they fit two halves.
+struct TileGeom { int ipt, nh, km; };
+bool tile_geom(int64_t H, int64_t K, TileGeom* g) {
+  if (H < 1 || H > 2 * TM || K < 1 || K > KMAX) return false;
+  const int ha = static_cast<int>((H + 1) & ~1ll);
+  int ipt = 1;
+  if (K <= 16 && 4 * ha <= TM) ipt = 4;
+  else if (K <= 32 && 2 * ha <= 2 * TM) ipt = 2;
+  g->ipt = ipt;
+  g->nh = ipt * ha > TM ? 2 : 1;
+  g->km = K > 32 ? 64 : 32;
+  return true;
+}
 
 }  // namespace
 
 bool tscore_kernel_supported(int64_t H, int64_t K, int64_t D) {
-  return H >= 1 && H <= 2 * TM && K >= 1 && K <= KMAX && D >= FB && D % FB == 0 && D <= 8192;
+  TileGeom g;
+  return tile_geom(H, K, &g) && D >= FB && D % FB == 0 && D <= 8192;
+}
+
+// workspace: [oob counters: 2 x int32, padded to 256 B][tile headers: n_tiles x uint2][slot records: n_tiles x 128 NH x uint2]
+size_t tscore_ws_bytes(int64_t B, int64_t H, int64_t K) {
+  TileGeom g;
+  if (B <= 0 || !tile_geom(H, K, &g)) return 256;
+  const size_t n_tiles = static_cast<size_t>((B + g.ipt - 1) / g.ipt);
+  return 256 + align_up(n_tiles * sizeof(uint2), 256) + n_tiles * static_cast<size_t>(TM * g.nh) * sizeof(uint2);
 }
 
 int launch_tscore_kernel(const void* table, const void* tw, const float* lg, int64_t n_rows, const void* his_ids, int id_dtype,
                          const uint8_t* his_mask, const float* bias_mean, const void* cand_ids, const int64_t* cand_offsets,
                          int64_t B, int64_t H, int64_t C, int64_t K, int64_t D, int score_type, float* out_scores, float* out_interests,
-                         cudaStream_t stream) {
+                         void* workspace, size_t workspace_bytes, cudaStream_t stream) {
   if (B == 0) return MINER_OK;
-  if (!tscore_kernel_supported(H, K, D)) {
+  TileGeom geo;
+  if (!tscore_kernel_supported(H, K, D) || !tile_geom(H, K, &geo)) {
     set_error("table-level scoring: unsupported shape H=%lld K=%lld D=%lld (need H <= 256, K <= 64, D %% 64 == 0)", (long long)H, (long long)K,
               (long long)D);
     return MINER_ERR_UNSUPPORTED;
@@ -769,33 +941,80 @@ int launch_tscore_kernel(const void* table, const void* tw, const float* lg, int
               (long long)D);
     return MINER_ERR_UNSUPPORTED;
   }
+  if (!workspace || workspace_bytes < tscore_ws_bytes(B, H, K)) {
+    set_error("table-level scoring: workspace too small (%zu bytes needed, %zu given)", tscore_ws_bytes(B, H, K), workspace_bytes);
+    return MINER_ERR_WORKSPACE;
+  }
+  const int64_t n_tiles = (B + geo.ipt - 1) / geo.ipt;
+  if (n_tiles > 0x7fffffffll) {
+    set_error("table-level scoring: %lld tiles in one call (split the batch)", (long long)n_tiles);
+    return MINER_ERR_UNSUPPORTED;
+  }
+  char* ws = static_cast<char*>(workspace);
+  int* oob = reinterpret_cast<int*>(ws);
+  uint2* hdr = reinterpret_cast<uint2*>(ws + 256);
+  uint2* rec = reinterpret_cast<uint2*>(ws + 256 + align_up(static_cast<size_t>(n_tiles) * sizeof(uint2), 256));
+  const int ts = TM * geo.nh;
+  {
+    // step 0: packed tiles (one warp per tile)
+    const int64_t blocks = (n_tiles + 7) / 8;
+    const int grid = static_cast<int>(blocks < 16ll * sm_count() ? blocks : 16ll * sm_count());
+    const int ch = static_cast<int>((H + 31) / 32);
+#define MINER_TP_LAUNCH(CHV)                                                                                                                \
+  tpack_kernel<CHV><<<grid, 256, 0, stream>>>(his_ids, id_dtype, his_mask, B, static_cast<int>(H), n_rows, geo.ipt, ts, n_tiles, rec, hdr, oob)
+    if (ch <= 1) MINER_TP_LAUNCH(1);
+    else if (ch <= 2) MINER_TP_LAUNCH(2);
+    else if (ch <= 4) MINER_TP_LAUNCH(4);
+    else MINER_TP_LAUNCH(8);
+#undef MINER_TP_LAUNCH
+    MINER_LAUNCH_OK("tpack_kernel");
+  }
   TScoreArgs a;
   a.table = static_cast<const uint16_t*>(table); a.tw = static_cast<const uint16_t*>(tw); a.lg = lg; a.n_rows = n_rows;
-  a.his_ids = his_ids; a.cand_ids = cand_ids; a.id_dtype = id_dtype; a.mask = his_mask; a.bias_mean = bias_mean;
+  a.rec = rec; a.hdr = hdr; a.oob = oob;
+  a.cand_ids = cand_ids; a.id_dtype = id_dtype; a.bias_mean = bias_mean;
   a.cand_offsets = cand_offsets; a.B = B; a.H = static_cast<int>(H); a.K = static_cast<int>(K); a.D = static_cast<int>(D);
   a.C = static_cast<int>(C); a.score_type = score_type; a.out_scores = out_scores; a.out_interests = out_interests;
+  a.prof = nullptr;
+  a.dbg = 0;
+#ifdef MINER_TS_PROF
   a.prof = hist_prof_buffer();
   {
     static const char* env_dbg = getenv("MINER_TS_DBG");
     a.dbg = env_dbg ? atoi(env_dbg) : 0;
   }
-  // lanes per impression: 2 K (hi / lo rows of every code) -> two impressions share a tile only if K <= 32 and H <= 64
-  const int ipt = (H <= TM / 2 && K <= 32) ? 2 : 1;
-  const int64_t n_tiles = (B + ipt - 1) / ipt;
+#endif
   const int grid = static_cast<int>(n_tiles < sm_count() ? n_tiles : sm_count());
 #define MINER_TS_LAUNCH(I, KMV, NHV)                                                                                                    \
   do {                                                                                                                                  \
     MINER_CUDA_OK(cudaFuncSetAttribute(tscore_kernel<I, KMV, NHV>, cudaFuncAttributeMaxDynamicSharedMemorySize, Shape<KMV, NHV>::SMEM)); \
     tscore_kernel<I, KMV, NHV><<<grid, T_THREADS, Shape<KMV, NHV>::SMEM, stream>>>(a, static_cast<int>(n_tiles));                      \
   } while (0)
-  if (H > TM && K > 32) MINER_TS_LAUNCH(1, 64, 2);          // 128 < H <= 256: two 128-slot halves accumulate into one D_I | D_P pair
-  else if (H > TM) MINER_TS_LAUNCH(1, 32, 2);
-  else if (K > 32) MINER_TS_LAUNCH(1, 64, 1);
-  else if (ipt == 2) MINER_TS_LAUNCH(2, 32, 1);
-  else MINER_TS_LAUNCH(1, 32, 1);
+  const int key = geo.ipt * 100 + geo.km + geo.nh;
+  switch (key) {
+    case 4 * 100 + 32 + 1: MINER_TS_LAUNCH(4, 32, 1); break;
+    case 2 * 100 + 32 + 1: MINER_TS_LAUNCH(2, 32, 1); break;
+    case 2 * 100 + 32 + 2: MINER_TS_LAUNCH(2, 32, 2); break;
+    case 1 * 100 + 32 + 1: MINER_TS_LAUNCH(1, 32, 1); break;
+    case 1 * 100 + 32 + 2: MINER_TS_LAUNCH(1, 32, 2); break;
+    case 1 * 100 + 64 + 1: MINER_TS_LAUNCH(1, 64, 1); break;
+    case 1 * 100 + 64 + 2: MINER_TS_LAUNCH(1, 64, 2); break;
+    default:
+      set_error("table-level scoring: no kernel variant for ipt=%d km=%d nh=%d", geo.ipt, geo.km, geo.nh);
+      return MINER_ERR_UNSUPPORTED;
+  }
 #undef MINER_TS_LAUNCH
   MINER_LAUNCH_OK("tscore_kernel");
   return MINER_OK;
+}
+
+// what a caller needs to know about the tiling of a shape (tests, bench): impressions per tile, 128-slot halves
+int tscore_tile_geometry(int64_t H, int64_t K, int* ipt, int* nh) {
+  TileGeom g;
+  if (!tile_geom(H, K, &g)) return 0;
+  if (ipt) *ipt = g.ipt;
+  if (nh) *nh = g.nh;
+  return 1;
 }
 
 }  // namespace miner

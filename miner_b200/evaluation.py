@@ -70,6 +70,7 @@ class BaseEvaluator:
 
     def compute_scores(self, metrics: List[str], save_result: bool = False, path: Optional[str] = None) -> Dict[str, float]:
         ks = _parse_metrics(metrics)
+        ops.check_oob_all()            # an id outside the news table raises IndexError, as the reference's table indexing does
         scores_flat, labels_flat, offsets = self._csr()
         partials, per = ops.rank_metrics_raw(scores_flat, labels_flat, offsets, self.transform, ks, per_impression=save_result)
         p = partials.cpu().view(-1, 2)

@@ -200,6 +200,28 @@ class Miner(nn.Module):
             self._table_proj = (key, ops.table_project(table, w, weighted=self.score_type == 'weighted'))
         return self._table_proj[1]
 
+    def _table_ws(self, B: int, H: int) -> Tensor:
+        """Workspace of the table-level kernel, kept across calls (its out-of-range id counters accumulate; ``check_bounds``)."""
+        K = self.poly_attn.context_codes.shape[0]
+        need = L.load().miner_score_table_workspace_bytes(B, H, K)
+        ws = getattr(self, '_tws', None)
+        if ws is None or ws.numel() < need or ws.device != self.news_encoder.table.device:
+            if ws is not None:
+                ops.check_oob(ws)
+            self._tws = ws = ops.score_table_workspace(B, H, K, self.news_encoder.table.device)
+        return ws
+
+    def check_bounds(self) -> None:
+        """Raise IndexError if any table-level call so far saw a news id outside the table (the reference's indexing would have)."""
+        if getattr(self, '_tws', None) is not None:
+            ops.check_oob(self._tws)
+
+    def invalidate(self) -> None:
+        """Drop the staged weight copies and table projections.  They are keyed on ``(data_ptr, _version)`` of the parameters and
+        the table; an update through ``p.data.*`` does not bump ``_version`` -- call this after one."""
+        self._prepared = None
+        self._table_proj = None
+
     def _bias_mean(self, his_category: Tensor, category: Tensor) -> Tensor:
         if self.training and self.category_dropout.p > 0:
             raise NotImplementedError('miner_b200: category dropout in train mode belongs to the train variant (section 8 f1)')
@@ -238,7 +260,8 @@ class Miner(nn.Module):
             if self.table_level and table.dtype == torch.bfloat16 and ops.score_table_supported(his_length, self.poly_attn.context_codes.shape[0],
                                                                                                table.shape[1]):
                 interests, scores = ops.score_table(self.table_projections(), his_ids, his_mask, cand_ids, self.score_type,
-                                                    bias_mean=bias_mean, want_interests=True)
+                                                    bias_mean=bias_mean, want_interests=True,
+                                                    workspace=self._table_ws(batch_size, his_length))
                 params = [p for p in self.parameters()]
                 return _attach(interests, *params), _attach(scores, *params)
             interests, scores = ops.score(table, his_ids, his_mask, cand_ids, w, self.score_type, bias_mean=bias_mean,
@@ -285,7 +308,8 @@ class Miner(nn.Module):
         if math is None:
             math = ops.default_eval_math(table, his_ids.shape[1], self.poly_attn.context_codes.shape[0])
         if math == L.MATH_TABLE:
-            _, scores = ops.score_table(self.table_projections(), his_ids, his_mask, cand_ids, self.score_type, cand_offsets=cand_offsets)
+            _, scores = ops.score_table(self.table_projections(), his_ids, his_mask, cand_ids, self.score_type, cand_offsets=cand_offsets,
+                                        workspace=self._table_ws(his_ids.shape[0], his_ids.shape[1]))
             return scores
         w = self._weights(with_bf16=(math == L.MATH_TENSOR))
         _, scores = ops.score(table, his_ids, his_mask, cand_ids, w, self.score_type, cand_offsets=cand_offsets, math=math,

@@ -6,6 +6,7 @@ sm_100a kernels of libminer_b200.so.  Every function requires CUDA tensors -- th
 from __future__ import annotations
 
 import ctypes as C
+import weakref
 from typing import Dict, Optional, Sequence, Tuple
 
 import torch
@@ -190,8 +191,10 @@ def default_math(table: torch.Tensor, D: int) -> int:
 
 def default_eval_math(table: torch.Tensor, H: int, K: int) -> int:
     """Grouped (CSR) evaluation: the table-level mode whenever its kernel covers the shape, else :func:`default_math`."""
-    D = table.shape[1]
-    if table.dtype == torch.bfloat16 and score_table_supported(H, K, D):
+    N, D = table.shape[0], table.shape[1]
+    # the table-level kernel addresses rows with 32-bit byte offsets: tables of 4 GB and more run the reference-order family
+    fits = N * D * 2 <= 0xffffffff and N < (1 << 30) and N * K <= 0xffffffff
+    if table.dtype == torch.bfloat16 and fits and score_table_supported(H, K, D):
         return L.MATH_TABLE
     return default_math(table, D)
 
@@ -296,12 +299,54 @@ def score_table_supported(H: int, K: int, D: int) -> bool:
     return bool(L.load().miner_score_table_supported(H, K, D))
 
 
+def score_table_geometry(H: int, K: int) -> Tuple[int, int]:
+    """``(impressions per tile, 128-slot halves)`` of the table-level kernel for a shape (``miner_score_table_tile_geometry``)."""
+    ipt, nh = C.c_int(), C.c_int()
+    if not L.load().miner_score_table_tile_geometry(H, K, C.byref(ipt), C.byref(nh)):
+        raise L.MinerError(f'table-level scoring does not cover H={H} K={K}')
+    return ipt.value, nh.value
+
+
+_WORKSPACES = weakref.WeakSet()      # live score_table workspaces: their out-of-range counters are checked by check_oob_all()
+
+
+def score_table_workspace(B: int, H: int, K: int, device) -> torch.Tensor:
+    """Workspace of :func:`score_table` (packed history tiles + the two out-of-range id counters, zeroed here)."""
+    n = int(L.load().miner_score_table_workspace_bytes(B, H, K))
+    ws = torch.empty(max(n, 256), dtype=torch.uint8, device=device)
+    ws[:8].zero_()
+    _WORKSPACES.add(ws)
+    return ws
+
+
+def oob_counts(workspace: torch.Tensor) -> torch.Tensor:
+    """``(2,) int32`` view of a :func:`score_table` workspace: history ids / candidate ids outside the table seen so far."""
+    return workspace[:8].view(torch.int32)
+
+
+def check_oob(workspace: torch.Tensor) -> None:
+    """Raise what the reference's table indexing raises (IndexError) if any call that used ``workspace`` saw an id outside the table."""
+    n = oob_counts(workspace).tolist()
+    if n[0] or n[1]:
+        raise IndexError(f'index out of range in embedding table ({n[0]} history ids, {n[1]} candidate ids)')
+
+
+def check_oob_all() -> None:
+    """:func:`check_oob` over every live workspace (what the evaluators call once per ``compute_scores`` / ``evaluate``)."""
+    for ws in list(_WORKSPACES):
+        check_oob(ws)
+
+
 def score_table(proj: TableProjections, his_ids: torch.Tensor, his_mask: torch.Tensor, cand_ids: torch.Tensor,
                 score_type: str = 'weighted', cand_offsets: Optional[torch.Tensor] = None, bias_mean: Optional[torch.Tensor] = None,
-                want_interests: bool = False, out_scores: Optional[torch.Tensor] = None):
-    """Miner.forward (reference model.py:61-138) for a block of impressions in one kernel from the table-level projections.
+                want_interests: bool = False, out_scores: Optional[torch.Tensor] = None, workspace: Optional[torch.Tensor] = None,
+                check_bounds: bool = False):
+    """Miner.forward (reference model.py:61-138) for a block of impressions from the table-level projections: one launch packs the
+    histories into tiles (masked slots of the same news row merged), one fused kernel scores them.
 
     Dense layout: ``cand_ids`` (B,C).  CSR layout: ``cand_ids`` (T,) + ``cand_offsets`` (B+1,) int64.
+    ``workspace`` (from :func:`score_table_workspace`) can be reused across calls; its out-of-range counters accumulate
+    (:func:`check_oob`); ``check_bounds=True`` checks them here (one device sync).
     Returns ``(interests (B,K,D) or None, scores)``.
     """
     dev = _need_cuda(proj.table, his_ids, his_mask, cand_ids, cand_offsets, bias_mean)
@@ -328,9 +373,13 @@ def score_table(proj: TableProjections, his_ids: torch.Tensor, his_mask: torch.T
     bm = _f32(bias_mean) if bias_mean is not None else None
     scores = out_scores if out_scores is not None else torch.empty(out_shape, dtype=torch.float32, device=dev)
     interests = torch.empty(B, K, D, dtype=torch.float32, device=dev) if want_interests else None
+    ws_bytes = int(lib.miner_score_table_workspace_bytes(B, H, K))
+    ws = workspace if (workspace is not None and workspace.numel() >= ws_bytes) else score_table_workspace(B, H, K, dev)
     with torch.cuda.device(dev):
         L.check(lib.miner_score_table_fwd(_ptr(proj.table), _ptr(proj.tw), _ptr(proj.lg), N, _ptr(hid), _ptr(m), _ptr(cid), _ptr(offs), it,
-                                          _ptr(bm), B, H, Cn, K, D, st, _ptr(scores), _ptr(interests), _stream()))
+                                          _ptr(bm), B, H, Cn, K, D, st, _ptr(scores), _ptr(interests), _ptr(ws), ws.numel(), _stream()))
+    if check_bounds:
+        check_oob(ws)
     return interests, scores
 
 

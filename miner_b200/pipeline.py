@@ -18,7 +18,7 @@ from . import _lib as L
 
 class HostEvaluator:
     def __init__(self, model, wave: int = 65536, chunk: int = 32768, ks: Sequence[int] = (5, 10), transform: str = 'sigmoid',
-                 math: Optional[int] = None):
+                 math: Optional[int] = None, check_bounds: bool = True):
         from .model import TableNewsEncoder
         if not isinstance(model.news_encoder, TableNewsEncoder):
             raise L.MinerError('HostEvaluator needs a Miner with a TableNewsEncoder')
@@ -30,6 +30,7 @@ class HostEvaluator:
         self._math_arg = math
         self.math = math
         self.copy_stream = torch.cuda.Stream(device=self.dev)
+        self.check_bounds = check_bounds
 
     def _proj_ws(self) -> torch.Tensor:
         n = L.load().miner_table_project_workspace_bytes(self.table.shape[0], self.model.poly_attn.context_codes.shape[1])
@@ -57,6 +58,7 @@ class HostEvaluator:
         """host: pinned CPU tensors his_ids (B,H), his_mask (B,H), cand_ids (T,), labels (T,), offsets (B+1,).
         Returns (partials (2*M,) float64 on the device: [sum, count] per metric of ops.metric_names(ks), scores (T,) or None)."""
         B = host['his_ids'].shape[0]
+        Hh, Kk = host['his_ids'].shape[1], self.model.poly_attn.context_codes.shape[0]
         if self._math_arg is None:
             self.math = ops.default_eval_math(self.table, host['his_ids'].shape[1], self.model.poly_attn.context_codes.shape[0])
         w = self.model._weights(with_bf16=(self.math != L.MATH_FP32))
@@ -75,7 +77,11 @@ class HostEvaluator:
             compute.wait_event(ev)
             offs = d['offsets'] - d['c0']
             if self.math == L.MATH_TABLE:
-                _, s = ops.score_table(self._proj, d['his_ids'], d['his_mask'], d['cand_ids'], self.model.score_type, cand_offsets=offs)
+                nb = d['his_ids'].shape[0]
+                if getattr(self, '_tws', None) is None or self._tws.numel() < L.load().miner_score_table_workspace_bytes(nb, Hh, Kk):
+                    self._tws = ops.score_table_workspace(max(nb, self.wave), Hh, Kk, self.dev)
+                _, s = ops.score_table(self._proj, d['his_ids'], d['his_mask'], d['cand_ids'], self.model.score_type, cand_offsets=offs,
+                                       workspace=self._tws)
             else:
                 _, s = ops.score(self.table, d['his_ids'], d['his_mask'], d['cand_ids'], w, self.model.score_type, cand_offsets=offs,
                                  math=self.math, chunk=self.chunk)
@@ -88,4 +94,10 @@ class HostEvaluator:
                     t.record_stream(compute)
         if total is None:
             total = torch.zeros(2 * (2 + 2 * len(self.ks)), dtype=torch.float64, device=self.dev)
+        if self.check_bounds and getattr(self, '_tws', None) is not None:
+            # ids outside the table raise what the reference's indexing raises (one 8-byte read at the end of the call)
+            try:
+                ops.check_oob(self._tws)
+            finally:
+                self._tws[:8].zero_()
         return total, scores_all

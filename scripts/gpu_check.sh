@@ -3,7 +3,7 @@
 # own timeout so a hang cannot hide the other results), then a short bench.  Logs land in gpurun_out/.
 mkdir -p gpurun_out
 nvidia-smi --query-gpu=name,clocks.sm,clocks.max.sm,memory.total --format=csv > gpurun_out/gpu.txt 2>&1
-TC='tc_gemm or tensor or test_score_impressions_csr or properties_at_scale or table or hist_kernel or cand_kernel or fused or sweep or host_evaluator or fastformer or cand_pair'
+TC='tc_gemm or tensor or test_score_impressions_csr or properties_at_scale or table or hist_kernel or cand_kernel or fused or sweep or host_evaluator or fastformer'
 timeout -k 10 900 python -m pytest tests -m gpu -q -x --timeout 300 -k "not ($TC)" > gpurun_out/t1.log 2>&1
 echo "t1 exit $?" >> gpurun_out/t1.log
 tail -5 gpurun_out/t1.log

@@ -198,6 +198,14 @@ def test_table_level_shape_query_is_host_only():
     ok = lambda h, k, d: bool(lib.miner_score_table_supported(h, k, d))
     assert ok(50, 32, 768) and ok(1, 1, 64) and ok(128, 64, 256) and ok(200, 32, 768) and ok(256, 64, 64)
     assert not ok(257, 32, 768) and not ok(50, 65, 768) and not ok(50, 32, 100) and not ok(0, 32, 768)
+    # tiling of a shape: impressions per tile (2 K TMEM lanes each) and 128-slot halves; workspace = 256 B of counters + headers + records
+    from miner_b200 import ops
+    assert ops.score_table_geometry(50, 32) == (2, 1) and ops.score_table_geometry(50, 8) == (2, 1) and ops.score_table_geometry(32, 16) == (4, 1)
+    assert ops.score_table_geometry(100, 32) == (2, 2) and ops.score_table_geometry(200, 32) == (1, 2) and ops.score_table_geometry(50, 64) == (1, 1)
+    assert ops.score_table_geometry(128, 64) == (1, 1) and ops.score_table_geometry(129, 64) == (1, 2) and ops.score_table_geometry(64, 32) == (2, 1)
+    assert ops.score_table_geometry(65, 32) == (2, 2)
+    ws = lib.miner_score_table_workspace_bytes
+    assert ws(1000, 50, 32) == 256 + 4096 + 500 * 128 * 8 and ws(3, 200, 32) == 256 + 256 + 3 * 256 * 8 and ws(0, 50, 32) == 256
 
 
 def test_default_math_selection_is_host_logic():
@@ -210,3 +218,6 @@ def test_default_math_selection_is_host_logic():
     assert ops.default_eval_math(torch.zeros(4, 768), 50, 32) == _lib.MATH_FP32       # fp32 table: reference arithmetic
     assert ops.default_eval_math(torch.zeros(4, 100, dtype=torch.bfloat16), 50, 32) == _lib.MATH_FP32   # D % 64 != 0
     assert ops.default_math(bf, 768) == _lib.MATH_TENSOR                              # Miner.forward keeps the reference operation order
+    class _Shape:                                                                     # a 3M-row table (4.6 GB) without allocating it
+        dtype, shape = torch.bfloat16, (3_000_000, 768)
+    assert ops.default_eval_math(_Shape, 50, 32) == _lib.MATH_TENSOR                  # beyond the kernel's 32-bit row offsets: reference order
