@@ -14,11 +14,14 @@ import torch
 import torch.distributed as dist
 
 
-def shard_bounds(offsets: torch.Tensor, world_size: int, his_len: int = 0) -> List[Tuple[int, int]]:
+def shard_bounds(offsets: torch.Tensor, world_size: int, his_len: int = 0, align: int = 4) -> List[Tuple[int, int]]:
     """Split impressions ``[0, B)`` into ``world_size`` contiguous ranges of near-equal cost.
 
     cost(impression) = his_len + n_candidates (rows gathered), taken from the CSR ``offsets`` (B+1,).
     Returns ``[(start, end), ...]``; ranges are contiguous, cover every impression once and may be empty.
+    Interior boundaries are multiples of ``align`` (4 = the most impressions the table-level kernel puts in one tile): an
+    impression then shares its tile with the same neighbours whatever the number of ranks, so every score -- and with it every
+    metric -- is bit-identical at 1, 2, 4 and 8 ranks.
     """
     offs = offsets.detach().to('cpu', torch.int64)
     B = offs.numel() - 1
@@ -31,6 +34,7 @@ def shard_bounds(offsets: torch.Tensor, world_size: int, his_len: int = 0) -> Li
     for r in range(1, world_size):
         target = total * r // world_size
         idx = int(torch.searchsorted(csum, torch.tensor(target, dtype=torch.int64), right=False))
+        idx = (idx + align // 2) // align * align if align > 1 else idx
         bounds.append(min(max(idx, bounds[-1]), B))
     bounds.append(B)
     return [(bounds[i], bounds[i + 1]) for i in range(world_size)]
@@ -66,6 +70,34 @@ def allreduce_gradients(params, group=None) -> None:
     for g in grads:
         g.copy_(flat[off:off + g.numel()].view_as(g))
         off += g.numel()
+
+
+class FlatGradients:
+    """The gradients of ``params`` as views of ONE flat fp32 buffer, so that the data-parallel exchange of a train step is a
+    single in-place all-reduce (no concatenate / split copies around a 3 MB collective).  ``zero()`` replaces
+    ``optimizer.zero_grad()`` (which would drop the views); autograd accumulates into the views in place."""
+
+    def __init__(self, params: Sequence[torch.nn.Parameter]):
+        self.params = [p for p in params if p.requires_grad]
+        n = sum(p.numel() for p in self.params)
+        self.flat = torch.zeros(n, dtype=torch.float32, device=self.params[0].device)
+        off = 0
+        for p in self.params:
+            p.grad = self.flat[off:off + p.numel()].view_as(p)
+            off += p.numel()
+
+    def zero(self) -> None:
+        self.flat.zero_()
+
+    def allreduce(self, group=None) -> None:
+        """Average over ranks: with equal local batches this is the gradient of the loss over the GLOBAL batch (loss.py:39-41)."""
+        if not (dist.is_available() and dist.is_initialized()) or dist.get_world_size(group) == 1:
+            return
+        if dist.get_backend(group) == 'nccl':
+            dist.all_reduce(self.flat, op=dist.ReduceOp.AVG, group=group)
+        else:                                        # gloo (CPU tests) has no AVG
+            dist.all_reduce(self.flat, op=dist.ReduceOp.SUM, group=group)
+            self.flat /= dist.get_world_size(group)
 
 
 def finalize_metrics(partials: torch.Tensor, names: Sequence[str]) -> Dict[str, float]:

@@ -101,7 +101,9 @@ def test_shard_bounds_balance_and_cover():
         assert b[0][0] == 0 and b[-1][1] == 1000
         assert all(b[i][1] == b[i + 1][0] for i in range(ws - 1))
         cost = [int(offs[e] - offs[s]) + 50 * (e - s) for s, e in b]
-        assert max(cost) - min(cost) <= 350 + 50, cost
+        assert max(cost) - min(cost) <= 4 * (350 + 50), cost
+        assert all(s % 4 == 0 for s, _ in b)                  # shards start on a tile boundary of the table-level kernel
+        assert shard_bounds(offs, ws, his_len=50, align=1)[0][0] == 0
     s, e, loc = local_shard(offs, 1, 4, 50)
     assert loc[0] == 0 and loc.numel() == e - s + 1 and int(loc[-1]) == int(offs[e] - offs[s])
     assert shard_bounds(torch.zeros(1, dtype=torch.int64), 4) == [(0, 0)] * 4
@@ -149,7 +151,7 @@ def test_two_rank_metric_reduction_gloo(tmp_path):
 GRAD_WORKER = r'''
 import os, sys, torch, torch.distributed as dist
 sys.path.insert(0, sys.argv[1])
-from miner_b200.parallel import allreduce_gradients
+from miner_b200.parallel import allreduce_gradients, FlatGradients
 from miner_b200 import synth
 from oracle import miner_oracle as O
 rank, world = int(os.environ['RANK']), int(os.environ['WORLD_SIZE'])
@@ -171,6 +173,18 @@ allreduce_gradients(local)
 full = grads(slice(0, B))
 for a, b in zip(local, full):
     assert torch.allclose(a.grad, b.grad, rtol=1e-4, atol=1e-6), float((a.grad - b.grad).abs().max())
+# the same through FlatGradients: the three gradients are views of one buffer, one in-place all-reduce
+ps = [torch.nn.Parameter(t.clone()) for t in (w.w_proj, w.context_codes, w.w_target)]
+fg = FlatGradients(ps)
+for _ in range(2):                                           # second round: zero() keeps the views, autograd accumulates in place
+    fg.zero()
+    sl = slice(rank * half, (rank + 1) * half)
+    I, S = O.miner_forward(table, his[sl], mask[sl], cand[sl], ps[0], ps[1], ps[2], 'weighted')
+    O.loss_compute(I, S, labels[sl].float()).backward()
+    assert all(p.grad.data_ptr() >= fg.flat.data_ptr() and p.grad.data_ptr() < fg.flat.data_ptr() + 4 * fg.flat.numel() for p in ps)
+    fg.allreduce()
+    for a, b in zip(ps, full):
+        assert torch.allclose(a.grad, b.grad, rtol=1e-4, atol=1e-6), float((a.grad - b.grad).abs().max())
 if rank == 0:
     print('OK')
 dist.destroy_process_group()

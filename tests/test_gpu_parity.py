@@ -955,3 +955,56 @@ def test_miner_forward_table_level_matches_reference(name):
     B, C = x['cand'].shape
     s_csr = m.score_impressions(x['his_ids'].to(DEV), x['his_mask'].to(DEV), x['cand'].reshape(-1).to(DEV), (torch.arange(B + 1) * C).to(DEV))
     assert torch.equal(s_csr.view(B, C), S.detach())
+
+
+# ------------------------------------------------------------------------------------------------ rank-count invariance
+def test_rank_count_invariance_single_gpu():
+    """SURVEY section 4 tier 4: the same impressions at 1 / 2 / 4 / 8 ranks give identical metrics.  Here the ranks are emulated
+    one after the other on one GPU through the real path (parallel.shard_bounds -> score_impressions -> rank_metrics partials ->
+    sum of partials): shards start on tile boundaries, so every score is bit-identical, and the [sum, count] partials add up to
+    the single-shard metrics to 1e-12 (np.nanmean of evaluation.py:59-80)."""
+    import miner_b200 as mb
+    from miner_b200 import ops, synth, parallel
+    B, H, N, D, K, Dc = 3001, 50, 3000, 256, 32, 48
+    table = synth.make_table(N, D, 11, torch.bfloat16).to(DEV)
+    w = synth.make_weights(D, K, Dc, 11)
+    eb = synth.make_eval_batch(B, H, N, 11)
+    m = mb.Miner(mb.TableNewsEncoder(table), False, K, Dc, 'weighted', 0.2).to(DEV).eval()
+    with torch.no_grad():
+        m.poly_attn.linear.weight.copy_(w.w_proj.to(DEV)); m.poly_attn.context_codes.copy_(w.context_codes.to(DEV))
+        m.target_aware_attn.linear.weight.copy_(w.w_target.to(DEV))
+    names = ops.metric_names((5, 10))
+    results, all_scores = {}, {}
+    for ws in (1, 2, 4, 8):
+        total, scores = None, []
+        for s, e in parallel.shard_bounds(eb.offsets, ws, H):
+            c0, c1 = int(eb.offsets[s]), int(eb.offsets[e])
+            offs = (eb.offsets[s:e + 1] - c0).to(DEV)
+            sc = m.score_impressions(eb.his_ids[s:e].to(DEV), eb.his_mask[s:e].to(DEV), eb.cand_ids[c0:c1].to(DEV), offs)
+            p, _ = ops.rank_metrics_raw(sc, eb.labels[c0:c1].to(DEV), offs, 'sigmoid', (5, 10))
+            total = p if total is None else total + p
+            scores.append(sc)
+        results[ws] = parallel.finalize_metrics(total, names)
+        all_scores[ws] = torch.cat(scores)
+    for ws in (2, 4, 8):
+        assert torch.equal(all_scores[ws], all_scores[1])
+        for n in names:
+            assert abs(results[ws][n] - results[1][n]) <= 1e-12, (ws, n, results[ws][n], results[1][n])
+
+
+@pytest.mark.skipif(torch.cuda.device_count() < 2, reason='needs two GPUs')
+def test_strong_scaling_rank_invariance_torchrun(tmp_path):
+    """bench.py --scaling strong at 1 and at 2 ranks (torchrun, NCCL): one global batch, the six metrics agree to 1e-12."""
+    import json, subprocess, sys as _sys
+    root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    common = ['bench.py', '--scaling', 'strong', '--impressions', '20000', '--steps', '1', '--warmup', '3', '--no-cpu-baseline',
+              '--no-reference-order', '--no-breakdown', '--no-extras']
+    one = subprocess.run([_sys.executable] + common, cwd=root, capture_output=True, text=True, timeout=600)
+    assert one.returncode == 0, one.stderr[-2000:]
+    two = subprocess.run([_sys.executable, '-m', 'torch.distributed.run', '--nnodes=1', '--nproc-per-node', '2', '--master-addr', '127.0.0.1',
+                          '--master-port', '29655'] + common + ['--gpus', '2'], cwd=root, capture_output=True, text=True, timeout=600)
+    assert two.returncode == 0, two.stderr[-2000:]
+    m1 = json.loads(one.stdout.strip().splitlines()[-1])['metrics']
+    m2 = json.loads(two.stdout.strip().splitlines()[-1])['metrics']
+    for k in m1:
+        assert abs(m1[k] - m2[k]) <= 1e-12, (k, m1[k], m2[k])
