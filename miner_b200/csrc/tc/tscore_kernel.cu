@@ -35,9 +35,9 @@
 //               S2(j): D_m += A_I . cand_j^T, D_a += A_G . cand_j^T  (A = bf16 hi|lo of I and of gelu(P), written IN PLACE over
 //                      the fp32 accumulators by the epilogue warps; B = candidate rows, K-major)
 //   warps 7-14  epilogue: per block, pair sum, gelu, bf16 hi/lo splits, tcgen05.st back in place (packed f32x2 arithmetic)
-//   warps 15-18 softmax over the history from the lg rows (L2-resident 128-byte rows), weights to tensor memory; and, per
-//               finished tile, the softmax over K and the weighted sum of the matching scores through a shared-memory
-//               transpose, one thread per candidate
+//   warps 15-18 softmax over the history from the lg rows (L2-resident 128-byte rows, one slot per lane), weights to tensor memory
+//   warps 19-22 per finished tile, the softmax over K and the weighted sum of the matching scores through a shared-memory
+//               transpose, 1 / 2 / 4 threads per candidate
 // Tiles with more than 96 candidates (64 when NH = 2) run several passes (the history side is recomputed; rare).
 #include <cuda.h>
 #include <stdlib.h>
@@ -69,18 +69,19 @@ template <int KM, int NH>
 struct Shape {
   static constexpr int LS = KM + 4;          // logits scratch row stride (floats): the softmax threads read column-wise (4 slots x 8 codes per
                                              // request) and  8 c + k  then covers the 32 banks once
-  static constexpr int SS = KM + 1;          // score scratch row stride (floats)
-  static constexpr int SCRATCH_FLOATS = (TM * NH * LS > 2 * NC_MAX * SS ? TM * NH * LS : 2 * NC_MAX * SS + 2) & ~1;
-  static constexpr int S1 = S1_MAX - (KM > 32 ? 1 : 0) - (NH > 1 ? 1 : 0);      // wider scratch takes ring stages
+  static constexpr int SS = KM + 2;          // score scratch row stride (floats): 1, 2 or 4 threads per candidate read it with at most 2-way conflicts
+  static constexpr int L_FLOATS = TM * NH * LS, S_FLOATS = 2 * NC_MAX * SS;
+  static constexpr int SCRATCH_FLOATS = L_FLOATS + S_FLOATS;                    // the softmax warps' logits and the score warps' transposes are live together
+  static constexpr int S1 = S1_MAX - 1 - (KM > 32 ? 1 : 0) - (NH > 1 ? 1 : 0);  // wider scratch takes ring stages
   static constexpr int SMEM = 1024 + S1 * ST1_BYTES + S2 * C_BYTES + SCRATCH_FLOATS * 4 + 512;
 };
-constexpr int T_EPI = 256, T_SMX = 128;                // 8 epilogue warps, 4 softmax / score warps
+constexpr int T_EPI = 256, T_SMX = 128, T_SCR = 128;   // 8 epilogue warps, 4 softmax warps, 4 score warps
 constexpr int T_G1 = 128, T_G2 = 64;                   // gather threads of the (E, TW) ring / of the candidate ring
 constexpr int G1_ROWS = TM * 8 / T_G1, G2_ROWS = NC_MAX * 8 / T_G2;  // rows per thread (a thread moves one 16-byte chunk per row)
 constexpr int G1_STEP = T_G1 / 8, G2_STEP = T_G2 / 8;
 static_assert(G1_STEP == 16 && G1_ROWS == 8, "a gather thread's row jj is 16-row group jj: one K-step of S1");
-constexpr int W_G2 = T_G1 / 32, W_MMA = W_G2 + T_G2 / 32, W_EPI0 = W_MMA + 1, W_SMX0 = W_EPI0 + T_EPI / 32;
-constexpr int T_THREADS = (W_SMX0 + T_SMX / 32) * 32;
+constexpr int W_G2 = T_G1 / 32, W_MMA = W_G2 + T_G2 / 32, W_EPI0 = W_MMA + 1, W_SMX0 = W_EPI0 + T_EPI / 32, W_SCR0 = W_SMX0 + T_SMX / 32;
+constexpr int T_THREADS = (W_SCR0 + T_SCR / 32) * 32;
 // TMEM map (512 columns)
 // (NH = 128-slot halves of a tile: 1, or 2 when IPT histories can exceed 128 slots)
 constexpr int AW_COL = 0;                    // softmax weights, packed bf16: 128 NH slots -> 64 NH columns
@@ -321,10 +322,9 @@ tscore_kernel(const TScoreArgs args, int n_tiles) {
   uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~static_cast<uintptr_t>(1023));
   uint8_t* st1 = smem;                                         // [S1][E 16 KB | TW 16 KB]
   uint8_t* st2 = st1 + S1 * ST1_BYTES;                         // [S2][12 KB] candidate rows
-  // scratch of the softmax / score warps: the logits L of the unit being prepared and the score transposes Sm / Sa of the unit
-  // being finished are never live at the same time (named barriers 1 and 2 separate the phases), so they share the bytes
+  // scratch: the logits L of the unit the softmax warps prepare, and the score transposes Sm / Sa of the unit the score warps finish
   float* L = reinterpret_cast<float*>(st2 + S2 * C_BYTES);     // [128 NH slots][LS] logits, then exp2(logit - max) in place
-  float* Sm = L;                                               // [NC_MAX][SS] matching scores, transposed
+  float* Sm = L + Shape<KM, NH>::L_FLOATS;                     // [NC_MAX][SS] matching scores, transposed
   float* Sa = Sm + NC_MAX * SS;                                // [NC_MAX][SS] attention logits, transposed
   TBarriers* bars = reinterpret_cast<TBarriers*>(L + SCRATCH_FLOATS);
 
@@ -340,7 +340,7 @@ tscore_kernel(const TScoreArgs args, int n_tiles) {
     tc::mbar_init(&bars->w_free, 1);
     for (int b = 0; b < 2; ++b) { tc::mbar_init(&bars->ip_full[b], 1); tc::mbar_init(&bars->a_ready[b], T_EPI); }
     tc::mbar_init(&bars->dma_full, 1);
-    tc::mbar_init(&bars->dma_free, T_SMX);
+    tc::mbar_init(&bars->dma_free, T_SCR);
     tc::fence_barrier_init();
   }
   if (warp == W_MMA) { tc::tmem_alloc(&bars->tmem_base, 512); tc::tmem_relinquish(); }
@@ -652,84 +652,14 @@ tscore_kernel(const TScoreArgs args, int n_tiles) {
     }
     if (et == 0) PROF_STORE(1);
     if (et == 128) PROF_STORE(4);
-  } else {
-    // ------------------------------------------------------------------ softmax / score warps
+  } else if (warp < W_SCR0) {
+    // ------------------------------------------------------------------ softmax warps: logits of the tile's slots -> softmax over the
+    //        history -> A_w in tensor memory
     const int sw = warp - W_SMX0;
     const int q = warp & 3;
-    const int li_q = (q * 32) / LPI;                           // impression of this quarter's lanes (LPI >= 32)
-    const uint32_t lane_addr = static_cast<uint32_t>(q * 32) << 16;
-    const int st = sw * 32 + lane;                             // 0..127
-    const int tl = q * 32 + lane;                              // TMEM lane = (i, k, hl) for the 32-lane reads of the score stage
-    const int lk = ((tl % LPI) >> 4) * 8 + (tl & 7);
-    const bool lo_part = (tl & 8) != 0;
     const int c4 = lane & 3;
     uint32_t u = 0;
     PROF_DECL;
-    // ---- scores of a finished unit (model.py:127-136,213-214).  These warps have the slack: while they do this the epilogue
-    //      warps are already converting the blocks of the next unit.
-    int64_t f_pc0 = 0, f_cs = 0, f_ce = 0;
-    int f_nc = 0;
-    auto score_stage = [&](uint32_t fu) {
-      const int64_t pc0 = f_pc0, my_cs = f_cs, my_ce = f_ce;
-      const int nc = f_nc;
-      const bool row_ok = lk < K;
-      tc::mbar_wait(&bars->dma_full, fu & 1);
-      PROF_ADD(5);
-      tc::tcgen05_fence_after();
-      tc::named_bar_sync(1, T_SMX);                                            // the softmax threads are done with L (= Sm / Sa); the previous unit's score threads with Sm / Sa
-      {
-        // columns of this lane's impression inside the pass (warp-uniform: a warp's 32 lanes belong to one impression)
-        const int64_t r_lo = my_cs - pc0, r_hi = my_ce - pc0;
-        const int c_lo = static_cast<int>(r_lo < 0 ? 0 : (r_lo > nc ? nc : r_lo));
-        int c_hi = static_cast<int>(r_hi < 0 ? 0 : (r_hi > nc ? nc : r_hi));
-        if (c_hi < c_lo) c_hi = c_lo;
-        for (int c0 = c_lo & ~15; c0 < c_hi; c0 += 16) {
-          uint32_t vm[16], va[16];
-          tc::tmem_ld_32x16(tmem + lane_addr + DM_COL + c0, vm);
-          tc::tmem_ld_32x16(tmem + lane_addr + DA_COL + c0, va);
-          tc::tmem_ld_wait();
-#pragma unroll
-          for (int c = 0; c < 16; ++c) {
-            const float xm = __uint_as_float(vm[c]), xa = __uint_as_float(va[c]);
-            const float sm_ = xm + __shfl_xor_sync(0xffffffffu, xm, 8);       // A_hi . cand + A_lo . cand
-            const float sa_ = xa + __shfl_xor_sync(0xffffffffu, xa, 8);
-            const int col = c0 + c;
-            if (!lo_part && row_ok && col >= c_lo && col < c_hi) {
-              Sm[col * SS + lk] = sm_;
-              Sa[col * SS + lk] = sa_;
-            }
-          }
-        }
-      }
-      tc::tcgen05_fence_before();
-      tc::mbar_arrive(&bars->dma_free);
-      tc::named_bar_sync(1, T_SMX);
-      if (st < nc) {
-        const float* m = Sm + st * SS;
-        const float* a = Sa + st * SS;
-        float score;
-        if (args.score_type == MINER_SCORE_WEIGHTED) {
-          float mx = -INFINITY;
-          for (int k = 0; k < K; ++k) mx = fmaxf(mx, a[k]);
-          float den = 0.f, num = 0.f;
-          for (int k = 0; k < K; ++k) {
-            const float e = __expf(a[k] - mx);
-            den += e;
-            num = fmaf(e, m[k], num);
-          }
-          score = num / den;
-        } else if (args.score_type == MINER_SCORE_MAX) {
-          score = -INFINITY;
-          for (int k = 0; k < K; ++k) score = fmaxf(score, m[k]);
-        } else {
-          score = 0.f;
-          for (int k = 0; k < K; ++k) score += m[k];
-          score /= static_cast<float>(K);
-        }
-        args.out_scores[pc0 + st] = score;
-      }
-      PROF_ADD(6);
-    };
     // raw slot records of the next tile (see RawId): lane l of warp sw owns slot 4 l + sw of every 128-slot half
     uint2 rec_pre[NH];
     uint2 hdr_pre = make_uint2(0u, 0u);
@@ -741,6 +671,7 @@ tscore_kernel(const TScoreArgs args, int n_tiles) {
     };
     int64_t t_cs = 0, t_ce = 0;
     if (n_local > 0) { tile_range<IPT>(args, static_cast<int>(blockIdx.x), t_cs, t_ce); fetch_recs(static_cast<int>(blockIdx.x)); }
+    const bool k_vec4 = (K & 3) == 0;                          // lg rows are then 16-byte aligned
     for (int lt = 0; lt < n_local; ++lt) {
       const int tile = static_cast<int>(blockIdx.x) + lt * static_cast<int>(gridDim.x);
       const int64_t cs = t_cs, ce = t_ce;
@@ -757,44 +688,45 @@ tscore_kernel(const TScoreArgs args, int n_tiles) {
       const int nks = (n_tot + 15) >> 4;
       for (int p = 0; p < npass; ++p, ++u) {
         PROF_ADD(0);
-        tc::named_bar_sync(2, T_SMX);                                          // previous unit's reads of Sm / Sa are done
+        tc::named_bar_sync(2, T_SMX);                                          // previous unit's reads of L are done
         {
-          // logits of the tile's slots, interleaved over the four warps: lg rows are K consecutive floats (model.py:174 hoisted
-          // to the table).  Stored scaled by log2(e): the softmax below runs on ex2.
-          const uint32_t Ku = static_cast<uint32_t>(K);
+          // logits of the tile's slots, one slot per lane (slots interleaved over the four warps): the lg row of a slot is K
+          // consecutive floats (model.py:174 hoisted to the table).  Stored scaled by log2(e): the softmax below runs on ex2.
+          constexpr float LOG2E = 1.4426950408889634f;
 #pragma unroll
           for (int hh = 0; hh < NH; ++hh) {
-            const int base = hh * TM;
-            if (base >= n_tot) break;
-            const uint32_t info = rec_cur[hh].x, meta = rec_cur[hh].y;
-            const uint32_t mult = meta & 0xffffu;
-            const bool kept = mult != 0u && !(info & REC_MASKED);
-            // aux: the bias of a kept slot (model.py:176-177), else the slot's whole logit: -inf for padding, and for a masked record
-            // of multiplicity n  log2(e) 1e-30 + log2 n  (n slots filled with 1e-30, model.py:180, add up to n exp(1e-30))
-            float aux;
-            if (kept) aux = args.bias_mean ? args.bias_mean[(static_cast<int64_t>(tile) * IPT + ((meta >> 24) & 0xfu)) * H + ((meta >> 16) & 0xffu)] : 0.f;
-            else aux = mult == 0u ? -INFINITY : kMaskFill * 1.4426950408889634f + __log2f(static_cast<float>(mult));
-            const uint32_t word = (info & (REC_ID | REC_VALID)) | (kept ? REC_MASKED : 0u);     // bit 30 reused: 1 = kept
-            int cnt = (n_tot - base - sw + 3) >> 2;                            // this warp's slots base + sw + 4 ss < n_tot
-            cnt = cnt > 32 ? 32 : cnt;
+            const int slot = hh * TM + 4 * lane + sw;
+            if (hh * TM >= n_tot) break;
+            if (slot < n_tot) {
+              const uint32_t info = rec_cur[hh].x, meta = rec_cur[hh].y;
+              const uint32_t mult = meta & 0xffffu;
+              float* dst = L + slot * LS;
+              if (mult != 0u && !(info & REC_MASKED)) {
+                // kept slot: lg row (+ the category bias of the slot, model.py:176-177); an id outside the table reads as a zero row
+                const float bias = args.bias_mean ? args.bias_mean[(static_cast<int64_t>(tile) * IPT + ((meta >> 24) & 0xfu)) * H + ((meta >> 16) & 0xffu)] : 0.f;
+                const float* row = args.lg + static_cast<size_t>(info & REC_ID) * K;
+                if (!(info & REC_VALID)) {
+                  for (int k = 0; k < K; ++k) dst[k] = bias * LOG2E;
+                } else if (k_vec4) {
 #pragma unroll
-            for (int kk = 0; kk < KM / 32; ++kk) {                             // 32 codes per pass
-              const int kcol = lane + 32 * kk;
-              const float* lgp = args.lg + kcol;
-              for (int ss0 = 0; ss0 < cnt; ss0 += 16) {
-                float v[16];
+                  for (int h8 = 0; h8 < KM / 32; ++h8) {
+                    float4 x[8];
 #pragma unroll
-                for (int i = 0; i < 16; ++i) {                                 // 16 independent 128-byte row loads in flight
-                  const uint32_t w_s = __shfl_sync(0xffffffffu, word, (ss0 + i) & 31);
-                  v[i] = (ss0 + i < cnt && (w_s >> 30) == 3u && kcol < K) ? lgp[(w_s & REC_ID) * Ku] : 0.f;
+                    for (int i = 0; i < 8; ++i)
+                      if (32 * h8 + 4 * i < K) x[i] = reinterpret_cast<const float4*>(row)[8 * h8 + i];
+#pragma unroll
+                    for (int i = 0; i < 8; ++i)
+                      if (32 * h8 + 4 * i < K)
+                        reinterpret_cast<float4*>(dst)[8 * h8 + i] = make_float4((x[i].x + bias) * LOG2E, (x[i].y + bias) * LOG2E,
+                                                                                 (x[i].z + bias) * LOG2E, (x[i].w + bias) * LOG2E);
+                  }
+                } else {
+                  for (int k = 0; k < K; ++k) dst[k] = (row[k] + bias) * LOG2E;
                 }
-#pragma unroll
-                for (int i = 0; i < 16; ++i) {
-                  const uint32_t w_s = __shfl_sync(0xffffffffu, word, (ss0 + i) & 31);
-                  const float a_s = __shfl_sync(0xffffffffu, aux, (ss0 + i) & 31);
-                  if (ss0 + i < cnt)
-                    L[(base + sw + 4 * (ss0 + i)) * LS + kcol] = (w_s & REC_MASKED) ? (v[i] + a_s) * 1.4426950408889634f : a_s;
-                }
+              } else if (mult != 0u) {
+                // masked record of multiplicity n: n slots filled with 1e-30 (model.py:180) add up to n exp(1e-30) = exp(1e-30 + ln n)
+                const float x = kMaskFill * LOG2E + __log2f(static_cast<float>(mult));
+                for (int k = 0; k < K; ++k) dst[k] = x;
               }
             }
           }
@@ -802,90 +734,230 @@ tscore_kernel(const TScoreArgs args, int n_tiles) {
         tc::named_bar_sync(2, T_SMX);
         PROF_ADD(1);
         // softmax over the history (model.py:181): per 16-lane group, thread t owns code k = 8 group + t/4 and the slots
-        // {2c, 2c+1 : c = t%4 + 4n} of its impression's range [s0, s1); the (hi, lo) rows of the pair leave through 16x128b stores
-        float inv[2];
-        int s0v[2], s1v[2];
-        bool deadv[2];
+        // {2c, 2c+1 : c = t%4 + 4n} of its impression's range [s0, s1); the (hi, lo) rows of the pair leave through 16x128b stores.
+        // Every column the MMAs of this tile read (8 per 16-slot group) is rewritten, zeros outside the impression's own range:
+        // the block "staircase" of A_w moves from tile to tile.
+        const int nparts = (nks * 8 + 31) >> 5;                                // 32-column stores per lane group
+        if (nparts == 1) {
+          // the whole tile is 64 slots or fewer: weights stay in registers across the wait for A_w
+          uint32_t o[2][16];
 #pragma unroll
-        for (int hf = 0; hf < 2; ++hf) {
-          const int g0 = q * 32 + hf * 16;
-          const int li = g0 / LPI;
-          const int k = ((g0 % LPI) / 16) * 8 + (lane >> 2);
-          const int s0 = hdr_start(hd, li), s1 = hdr_end(hd, li);
-          const bool row_ok = k < K && s1 > s0;
-          float* col = L + (row_ok ? k : 0);
-          const int n_lo = s0 >> 3, n_hi = (s1 + 7) >> 3;
-          float mx = -INFINITY;
-          for (int n = n_lo; n < n_hi; ++n) {
-            const int sa = 2 * (c4 + 4 * n);
-            const float a = (sa >= s0 && sa < s1) ? col[sa * LS] : -INFINITY;
-            const float b = (sa + 1 < s1 && sa >= s0) ? col[(sa + 1) * LS] : -INFINITY;
-            mx = fmaxf(mx, fmaxf(a, b));
-          }
-          mx = fmaxf(mx, __shfl_xor_sync(0xffffffffu, mx, 1));
-          mx = fmaxf(mx, __shfl_xor_sync(0xffffffffu, mx, 2));
-          const bool dead = mx == -INFINITY || !row_ok;                        // impression past the end of the batch / unused row
-          float sum = 0.f;
-          for (int n = n_lo; n < n_hi; ++n) {
-            const int sa = 2 * (c4 + 4 * n);
-            if (!dead && sa >= s0 && sa < s1) {
-              const float e = ex2_approx(col[sa * LS] - mx);
-              col[sa * LS] = e;
-              sum += e;
-            }
-            if (!dead && sa >= s0 && sa + 1 < s1) {
-              const float e = ex2_approx(col[(sa + 1) * LS] - mx);
-              col[(sa + 1) * LS] = e;
-              sum += e;
-            }
-          }
-          sum += __shfl_xor_sync(0xffffffffu, sum, 1);
-          sum += __shfl_xor_sync(0xffffffffu, sum, 2);
-          inv[hf] = dead ? 0.f : __fdividef(1.0f, sum);
-          s0v[hf] = s0; s1v[hf] = s1; deadv[hf] = dead;
-        }
-        PROF_ADD(2);
-        if (u > 0) tc::mbar_wait(&bars->w_free, (u - 1) & 1);                  // S1 of the previous unit no longer reads A_w
-        PROF_ADD(3);
-        tc::tcgen05_fence_after();
-        // every column the MMAs of this tile read (8 per 16-slot group) is rewritten, zeros outside the impression's own range:
-        // the block "staircase" of A_w moves from tile to tile
-        const int nparts = (nks * 8 + 31) >> 5;
-#pragma unroll
-        for (int hf = 0; hf < 2; ++hf) {
-          const int g0 = q * 32 + hf * 16;
-          const int k = ((g0 % LPI) / 16) * 8 + (lane >> 2);
-          const float* col = L + (deadv[hf] ? 0 : k);
-          const int s0 = s0v[hf], s1 = s1v[hf];
-          for (int part = 0; part < nparts; ++part) {
-            uint32_t o[16];
+          for (int hf = 0; hf < 2; ++hf) {
+            const int g0 = q * 32 + hf * 16;
+            const int li = g0 / LPI;
+            const int k = ((g0 % LPI) / 16) * 8 + (lane >> 2);
+            const int s0 = hdr_start(hd, li), s1 = hdr_end(hd, li);
+            const bool row_ok = k < K && s1 > s0;
+            const float* col = L + (row_ok ? k : 0);
+            float e[16];
+            float mx = -INFINITY;
 #pragma unroll
             for (int n = 0; n < 8; ++n) {
-              const int sa = 2 * (c4 + 4 * (8 * part + n));
-              const bool in0 = !deadv[hf] && sa >= s0 && sa < s1, in1 = !deadv[hf] && sa >= s0 && sa + 1 < s1;
-              const float w0 = in0 ? col[sa * LS] * inv[hf] : 0.f;               // model.py:181
-              const float w1 = in1 ? col[(sa + 1) * LS] * inv[hf] : 0.f;
-              split_hi_lo(f2_pack(w0, w1), o[2 * n], o[2 * n + 1]);
+              const int sa = 2 * (c4 + 4 * n);
+              e[2 * n] = (row_ok && sa >= s0 && sa < s1) ? col[sa * LS] : -INFINITY;
+              e[2 * n + 1] = (row_ok && sa >= s0 && sa + 1 < s1) ? col[(sa + 1) * LS] : -INFINITY;
+              mx = fmaxf(mx, fmaxf(e[2 * n], e[2 * n + 1]));
             }
-            tc::tmem_st_16x128b_x8(tmem + (static_cast<uint32_t>(g0) << 16) + AW_COL + part * 32, o);
+            mx = fmaxf(mx, __shfl_xor_sync(0xffffffffu, mx, 1));
+            mx = fmaxf(mx, __shfl_xor_sync(0xffffffffu, mx, 2));
+            const bool dead = mx == -INFINITY;                                 // impression past the end of the batch / unused row
+            float sum = 0.f;
+#pragma unroll
+            for (int n = 0; n < 16; ++n) {
+              e[n] = dead ? 0.f : ex2_approx(e[n] - mx);
+              sum += e[n];
+            }
+            sum += __shfl_xor_sync(0xffffffffu, sum, 1);
+            sum += __shfl_xor_sync(0xffffffffu, sum, 2);
+            const float inv = dead ? 0.f : __fdividef(1.0f, sum);
+#pragma unroll
+            for (int n = 0; n < 8; ++n) split_hi_lo(f2_pack(e[2 * n] * inv, e[2 * n + 1] * inv), o[hf][2 * n], o[hf][2 * n + 1]);   // model.py:181
+          }
+          PROF_ADD(2);
+          if (u > 0) tc::mbar_wait(&bars->w_free, (u - 1) & 1);                // S1 of the previous unit no longer reads A_w
+          PROF_ADD(3);
+          tc::tcgen05_fence_after();
+#pragma unroll
+          for (int hf = 0; hf < 2; ++hf) tc::tmem_st_16x128b_x8(tmem + (static_cast<uint32_t>(q * 32 + hf * 16) << 16) + AW_COL, o[hf]);
+        } else {
+          // more than 64 slots: exp2(logit - max) goes back to L in place, the weights are formed 64 slots at a time after the wait
+          float inv[2];
+          int s0v[2], s1v[2];
+          bool deadv[2];
+#pragma unroll
+          for (int hf = 0; hf < 2; ++hf) {
+            const int g0 = q * 32 + hf * 16;
+            const int li = g0 / LPI;
+            const int k = ((g0 % LPI) / 16) * 8 + (lane >> 2);
+            const int s0 = hdr_start(hd, li), s1 = hdr_end(hd, li);
+            const bool row_ok = k < K && s1 > s0;
+            float* col = L + (row_ok ? k : 0);
+            const int n_lo = s0 >> 3, n_hi = (s1 + 7) >> 3;
+            float mx = -INFINITY;
+            for (int n = n_lo; n < n_hi; ++n) {
+              const int sa = 2 * (c4 + 4 * n);
+              const float a = (sa >= s0 && sa < s1) ? col[sa * LS] : -INFINITY;
+              const float b = (sa + 1 < s1 && sa >= s0) ? col[(sa + 1) * LS] : -INFINITY;
+              mx = fmaxf(mx, fmaxf(a, b));
+            }
+            mx = fmaxf(mx, __shfl_xor_sync(0xffffffffu, mx, 1));
+            mx = fmaxf(mx, __shfl_xor_sync(0xffffffffu, mx, 2));
+            const bool dead = mx == -INFINITY || !row_ok;
+            float sum = 0.f;
+            for (int n = n_lo; n < n_hi; ++n) {
+              const int sa = 2 * (c4 + 4 * n);
+              if (!dead && sa >= s0 && sa < s1) {
+                const float e = ex2_approx(col[sa * LS] - mx);
+                col[sa * LS] = e;
+                sum += e;
+              }
+              if (!dead && sa >= s0 && sa + 1 < s1) {
+                const float e = ex2_approx(col[(sa + 1) * LS] - mx);
+                col[(sa + 1) * LS] = e;
+                sum += e;
+              }
+            }
+            sum += __shfl_xor_sync(0xffffffffu, sum, 1);
+            sum += __shfl_xor_sync(0xffffffffu, sum, 2);
+            inv[hf] = dead ? 0.f : __fdividef(1.0f, sum);
+            s0v[hf] = s0; s1v[hf] = s1; deadv[hf] = dead;
+          }
+          PROF_ADD(2);
+          if (u > 0) tc::mbar_wait(&bars->w_free, (u - 1) & 1);
+          PROF_ADD(3);
+          tc::tcgen05_fence_after();
+#pragma unroll
+          for (int hf = 0; hf < 2; ++hf) {
+            const int g0 = q * 32 + hf * 16;
+            const int k = ((g0 % LPI) / 16) * 8 + (lane >> 2);
+            const float* col = L + (deadv[hf] ? 0 : k);
+            const int s0 = s0v[hf], s1 = s1v[hf];
+            for (int part = 0; part < nparts; ++part) {
+              uint32_t o[16];
+#pragma unroll
+              for (int n = 0; n < 8; ++n) {
+                const int sa = 2 * (c4 + 4 * (8 * part + n));
+                const bool in0 = !deadv[hf] && sa >= s0 && sa < s1, in1 = !deadv[hf] && sa >= s0 && sa + 1 < s1;
+                const float w0 = in0 ? col[sa * LS] * inv[hf] : 0.f;               // model.py:181
+                const float w1 = in1 ? col[(sa + 1) * LS] * inv[hf] : 0.f;
+                split_hi_lo(f2_pack(w0, w1), o[2 * n], o[2 * n + 1]);
+              }
+              tc::tmem_st_16x128b_x8(tmem + (static_cast<uint32_t>(g0) << 16) + AW_COL + part * 32, o);
+            }
           }
         }
         tc::tmem_st_wait();
         tc::tcgen05_fence_before();
         tc::mbar_arrive(&bars->w_ready);
         PROF_ADD(4);
-        if (u > 0) score_stage(u - 1);
+      }
+    }
+    if (threadIdx.x == W_SMX0 * 32) PROF_STORE(3);
+  } else {
+    // ------------------------------------------------------------------ score warps: scores of a finished unit (model.py:127-136,213-214).
+    //        Own warps: the MMA issuer waits for D_m / D_a to be drained before the next unit's first S2, so the drain starts the
+    //        moment the last S2 of the unit completes.
+    const int q = warp & 3;
+    const int li_q = (q * 32) / LPI;                           // impression of this quarter's lanes (LPI >= 32)
+    const uint32_t lane_addr = static_cast<uint32_t>(q * 32) << 16;
+    const int st = (warp - W_SCR0) * 32 + lane;                // 0..127
+    const int tl = q * 32 + lane;                              // TMEM lane = (i, k, hl) for the 32-lane reads
+    const int lk = ((tl % LPI) >> 4) * 8 + (tl & 7);
+    const bool lo_part = (tl & 8) != 0;
+    const bool row_ok = lk < K;
+    uint32_t u = 0;
+    int64_t t_cs = 0, t_ce = 0, t_mcs = 0, t_mce = 0;          // next tile: candidate range of the tile and of this quarter's impression
+    auto fetch_range = [&](int tile) {
+      tile_range<IPT>(args, tile, t_cs, t_ce);
+      const int64_t my_imp = static_cast<int64_t>(tile) * IPT + li_q;
+      t_mcs = my_imp < args.B ? cand_off(args, my_imp) : -1;
+      t_mce = my_imp < args.B ? cand_off(args, my_imp + 1) : -1;
+    };
+    if (n_local > 0) fetch_range(static_cast<int>(blockIdx.x));
+    for (int lt = 0; lt < n_local; ++lt) {
+      const int tile = static_cast<int>(blockIdx.x) + lt * static_cast<int>(gridDim.x);
+      const int64_t cs = t_cs, ce = t_ce;
+      const int64_t my_cs = t_mcs < 0 ? ce : t_mcs, my_ce = t_mce < 0 ? ce : t_mce;
+      const int npass = passes_of<NCM>(cs, ce);
+      if (lt + 1 < n_local) fetch_range(tile + static_cast<int>(gridDim.x));   // a tile ahead: off the critical path
+      for (int p = 0; p < npass; ++p, ++u) {
+        const int64_t pc0 = cs + static_cast<int64_t>(p) * NCM;
+        const int nc = static_cast<int>(ce - pc0 < NCM ? ce - pc0 : NCM);
+        // columns of this lane's impression inside the pass (warp-uniform: a warp's 32 lanes belong to one impression)
+        const int64_t r_lo = my_cs - pc0, r_hi = my_ce - pc0;
+        const int c_lo = static_cast<int>(r_lo < 0 ? 0 : (r_lo > nc ? nc : r_lo));
+        int c_hi = static_cast<int>(r_hi < 0 ? 0 : (r_hi > nc ? nc : r_hi));
+        if (c_hi < c_lo) c_hi = c_lo;
+        tc::mbar_wait(&bars->dma_full, u & 1);
+        tc::tcgen05_fence_after();
+        tc::named_bar_sync(1, T_SCR);                                          // the previous unit's score threads are done with Sm / Sa
+        bool released = false;
+        for (int c0 = c_lo & ~15; c0 < c_hi; c0 += 16) {
+          uint32_t vm[16], va[16];
+          tc::tmem_ld_32x16(tmem + lane_addr + DM_COL + c0, vm);
+          tc::tmem_ld_32x16(tmem + lane_addr + DA_COL + c0, va);
+          tc::tmem_ld_wait();
+          if (c0 + 16 >= c_hi) {                                               // last chunk in registers: D_m / D_a are free again
+            tc::tcgen05_fence_before();
+            tc::mbar_arrive(&bars->dma_free);
+            released = true;
+          }
+#pragma unroll
+          for (int c = 0; c < 16; ++c) {
+            const float xm = __uint_as_float(vm[c]), xa = __uint_as_float(va[c]);
+            const float sm_ = xm + __shfl_xor_sync(0xffffffffu, xm, 8);       // A_hi . cand + A_lo . cand
+            const float sa_ = xa + __shfl_xor_sync(0xffffffffu, xa, 8);
+            const int col = c0 + c;
+            if (!lo_part && row_ok && col >= c_lo && col < c_hi) {
+              Sm[col * SS + lk] = sm_;
+              Sa[col * SS + lk] = sa_;
+            }
+          }
+        }
+        if (!released) {
+          tc::tcgen05_fence_before();
+          tc::mbar_arrive(&bars->dma_free);
+        }
+        tc::named_bar_sync(1, T_SCR);
         {
-          const int64_t my_imp = static_cast<int64_t>(tile) * IPT + li_q;
-          f_pc0 = cs + static_cast<int64_t>(p) * NCM;
-          f_nc = static_cast<int>(ce - f_pc0 < NCM ? ce - f_pc0 : NCM);
-          f_cs = my_imp < args.B ? cand_off(args, my_imp) : ce;
-          f_ce = my_imp < args.B ? cand_off(args, my_imp + 1) : ce;
+          // one candidate per group of P threads (P = 4, 2 or 1 by the number of candidates): softmax over K of the attention
+          // logits, weighted sum of the matching scores (model.py:213-214), or max / mean (model.py:128-131)
+          const int P = nc <= 32 ? 4 : (nc <= 64 ? 2 : 1);
+          const int c = st / P, part = st % P;
+          const int ce_ = c < nc ? c : nc - 1;
+          const float* m = Sm + ce_ * SS;
+          const float* a = Sa + ce_ * SS;
+          float score;
+          if (args.score_type == MINER_SCORE_WEIGHTED) {
+            float mx = -INFINITY;
+            for (int k = part; k < K; k += P) mx = fmaxf(mx, a[k]);
+            if (P > 1) mx = fmaxf(mx, __shfl_xor_sync(0xffffffffu, mx, 1));
+            if (P > 2) mx = fmaxf(mx, __shfl_xor_sync(0xffffffffu, mx, 2));
+            float den = 0.f, num = 0.f;
+            for (int k = part; k < K; k += P) {
+              const float e = __expf(a[k] - mx);
+              den += e;
+              num = fmaf(e, m[k], num);
+            }
+            if (P > 1) { den += __shfl_xor_sync(0xffffffffu, den, 1); num += __shfl_xor_sync(0xffffffffu, num, 1); }
+            if (P > 2) { den += __shfl_xor_sync(0xffffffffu, den, 2); num += __shfl_xor_sync(0xffffffffu, num, 2); }
+            score = num / den;
+          } else if (args.score_type == MINER_SCORE_MAX) {
+            score = -INFINITY;
+            for (int k = part; k < K; k += P) score = fmaxf(score, m[k]);
+            if (P > 1) score = fmaxf(score, __shfl_xor_sync(0xffffffffu, score, 1));
+            if (P > 2) score = fmaxf(score, __shfl_xor_sync(0xffffffffu, score, 2));
+          } else {
+            score = 0.f;
+            for (int k = part; k < K; k += P) score += m[k];
+            if (P > 1) score += __shfl_xor_sync(0xffffffffu, score, 1);
+            if (P > 2) score += __shfl_xor_sync(0xffffffffu, score, 2);
+            score /= static_cast<float>(K);
+          }
+          if (c < nc && part == 0) args.out_scores[pc0 + c] = score;
         }
       }
     }
-    if (u > 0) score_stage(u - 1);
-    if (threadIdx.x == W_SMX0 * 32) PROF_STORE(3);
   }
 
   tc::tcgen05_fence_before();
