@@ -195,6 +195,21 @@ int miner_rank_metrics(const float* scores, const int8_t* labels, const int64_t*
                        double* out_partials, double* out_per_impression,
                        void* workspace, size_t workspace_bytes, void* stream);
 
+/* ---- global `auc` over ALL candidates (evaluation.py:53-55: sklearn roc_auc_score on the flattened lists) = the tie-aware
+ *      Mann-Whitney statistic U / (P N), in exact integers and without a comparison sort:
+ *        miner_auc_split   probabilities (same transform as miner_rank_metrics) -> order-preserving uint32 keys, compacted into
+ *                          pos_keys / neg_keys (capacity T each); counts (2 device uint64) = [P, N]
+ *        miner_sort_u32    LSD radix sort (ascending, in place) -- of the positive keys; with several ranks, of the all-gathered
+ *                          positive keys of every rank
+ *        miner_auc_count   out_u2 (device uint64) = sum over the local negatives of 2 #{pos > neg} + #{pos == neg}
+ *      auc = sum_ranks(out_u2) / (2 sum(P) sum(N)).  miner_b200/evaluation.py global_auc drives the three calls (and the NCCL
+ *      all-gather / all-reduce between them). */
+int miner_auc_split(const float* scores, const int8_t* labels, const int64_t* offsets, int64_t B, int64_t T, int transform,
+                    uint32_t* pos_keys, uint32_t* neg_keys, uint64_t* counts, void* stream);
+size_t miner_sort_u32_workspace_bytes(int64_t n);
+int miner_sort_u32(uint32_t* keys, int64_t n, void* workspace, size_t workspace_bytes, void* stream);
+int miner_auc_count(const uint32_t* pos_sorted, int64_t P, const uint32_t* neg_keys, int64_t N, uint64_t* out_u2, void* stream);
+
 /* ---- (a13,a14) losses: Loss.compute (loss.py:27-44) and Loss.compute_eval_loss (loss.py:68-85).
  *      interests (B,K,D); logits (B,C); labels (B,C) fp32 (one-hot for compute, binary for eval).
  *      out (3 floats, device): [total, disagreement, rank_loss]. mode 0 = compute (CE mean), 1 = compute_eval_loss. */

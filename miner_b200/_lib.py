@@ -32,6 +32,7 @@ EXPORTS = [
     'miner_loss_fwd', 'miner_hist_interests_workspace_bytes', 'miner_hist_interests_fwd', 'miner_cand_score_fwd',
     'miner_table_project_workspace_bytes', 'miner_table_project', 'miner_score_table_supported', 'miner_score_table_fwd',
     'miner_score_table_workspace_bytes', 'miner_score_table_tile_geometry',
+    'miner_auc_split', 'miner_sort_u32_workspace_bytes', 'miner_sort_u32', 'miner_auc_count',
     'miner_train_workspace_bytes', 'miner_train_fwd', 'miner_loss_bwd', 'miner_train_bwd',
 ]
 
@@ -103,6 +104,11 @@ def _declare(lib: C.CDLL) -> None:
     lib.miner_score_table_workspace_bytes.argtypes = [i64, i64, i64]
     lib.miner_score_table_workspace_bytes.restype = sz
     lib.miner_score_table_tile_geometry.argtypes = [i64, i64, C.POINTER(i32), C.POINTER(i32)]
+    lib.miner_auc_split.argtypes = [vp, vp, vp, i64, i64, i32, vp, vp, vp, vp]
+    lib.miner_sort_u32_workspace_bytes.argtypes = [i64]
+    lib.miner_sort_u32_workspace_bytes.restype = sz
+    lib.miner_sort_u32.argtypes = [vp, i64, vp, sz, vp]
+    lib.miner_auc_count.argtypes = [vp, i64, vp, i64, vp, vp]
 
 
 def load(build_if_missing: bool = True) -> C.CDLL:

@@ -343,6 +343,27 @@ extern "C" int miner_score_table_fwd(const void* table, const void* tw, const fl
                               D, score_type, out_scores, out_interests, workspace, workspace_bytes, static_cast<cudaStream_t>(stream));
 }
 
+extern "C" int miner_auc_split(const float* scores, const int8_t* labels, const int64_t* offsets, int64_t B, int64_t T, int transform,
+                               uint32_t* pos_keys, uint32_t* neg_keys, uint64_t* counts, void* stream) {
+  MINER_CHECK_ARG(T >= 0 && B >= 0 && transform >= 0 && transform <= 2, "auc_split: bad arguments");
+  MINER_CHECK_ARG(counts && (T == 0 || (scores && labels && pos_keys && neg_keys)), "auc_split: null pointer");
+  MINER_CHECK_ARG(transform != 2 || offsets, "auc_split: the softmax transform needs the impression offsets");
+  return launch_auc_split(scores, labels, offsets, B, T, transform, pos_keys, neg_keys, reinterpret_cast<unsigned long long*>(counts),
+                          static_cast<cudaStream_t>(stream));
+}
+
+extern "C" size_t miner_sort_u32_workspace_bytes(int64_t n) { return sort_u32_ws_bytes(n); }
+
+extern "C" int miner_sort_u32(uint32_t* keys, int64_t n, void* workspace, size_t workspace_bytes, void* stream) {
+  MINER_CHECK_ARG(n >= 0 && (n == 0 || keys), "sort_u32: bad arguments");
+  return launch_sort_u32(keys, n, workspace, workspace_bytes, static_cast<cudaStream_t>(stream));
+}
+
+extern "C" int miner_auc_count(const uint32_t* pos_sorted, int64_t P, const uint32_t* neg_keys, int64_t N, uint64_t* out_u2, void* stream) {
+  MINER_CHECK_ARG(P >= 0 && N >= 0 && out_u2 && (P == 0 || pos_sorted) && (N == 0 || neg_keys), "auc_count: bad arguments");
+  return launch_auc_count(pos_sorted, P, neg_keys, N, reinterpret_cast<unsigned long long*>(out_u2), static_cast<cudaStream_t>(stream));
+}
+
 #if defined(MINER_HIST_PROF) || defined(MINER_TS_PROF)
 // instrumented builds only (scripts/prof_hist.py, scripts/prof_tscore.py): device buffer of 148*5*16 int64 cycle counters.
 // The release library exports nothing outside include/miner_b200.h.

@@ -94,6 +94,13 @@ int launch_target_score(const float* interests, const float* proj /*gelu(I Wt^T)
                         const int64_t* cand_offsets, int64_t B, int64_t C, int64_t K, int64_t D, int score_type,
                         float* out_scores, cudaStream_t stream);
 
+// global AUC building blocks (auc.cu)
+size_t sort_u32_ws_bytes(int64_t n);
+int launch_sort_u32(uint32_t* keys, int64_t n, void* workspace, size_t workspace_bytes, cudaStream_t stream);
+int launch_auc_split(const float* scores, const int8_t* labels, const int64_t* offsets, int64_t B, int64_t T, int transform,
+                     uint32_t* pos_keys, uint32_t* neg_keys, unsigned long long* counts, cudaStream_t stream);
+int launch_auc_count(const uint32_t* pos_sorted, int64_t P, const uint32_t* neg_keys, int64_t N, unsigned long long* out_u2, cudaStream_t stream);
+
 int launch_cast_f32_to_bf16(const float* src, void* dst, int64_t n, cudaStream_t stream);
 
 }  // namespace miner

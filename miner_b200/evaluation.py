@@ -34,23 +34,42 @@ def _parse_metrics(metrics: Sequence[str]):
     return ks
 
 
-def global_auc(probs: Tensor, labels: Tensor) -> float:
-    """``roc_auc_score`` over ALL flattened candidates (reference evaluation.py:53-55): tie-aware Mann-Whitney U from
-    average ranks.  Sorting is library plumbing (torch.sort); the arithmetic is exact in int64/float64."""
-    p = probs.reshape(-1)
-    y = labels.reshape(-1) > 0
-    n_pos = int(y.sum().item())
-    n_neg = p.numel() - n_pos
+def global_auc(scores: Tensor, labels: Tensor, offsets: Optional[Tensor] = None, transform: str = 'sigmoid', group=None,
+               _kernels=None) -> float:
+    """``roc_auc_score`` over ALL flattened candidates (reference evaluation.py:53-55) = the tie-aware Mann-Whitney statistic,
+    exact: probabilities -> order-preserving integer keys (``miner_auc_split``), radix sort of the positive keys
+    (``miner_sort_u32``), every negative binary-searches them (``miner_auc_count``).  With several ranks (``torch.distributed``
+    initialised) the positive keys of all ranks are all-gathered, every rank counts its own negatives against the global
+    positives and ``[2U, N]`` are all-reduced as int64: the value is the single-process one, bit for bit.
+
+    ``scores`` are the raw logits (``transform`` as in ``rank_metrics``: 'sigmoid' SlowEvaluator, 'softmax' FastEvaluator, 'none').
+    ``_kernels`` (tests): ``(split, sort, count)`` stand-ins for the three device calls."""
+    import torch.distributed as dist
+    split, sort, count = _kernels if _kernels is not None else (ops.auc_split, ops.sort_u32, ops.auc_count)
+    pos, neg = split(scores, labels, offsets, transform)
+    multi = dist.is_available() and dist.is_initialized() and dist.get_world_size(group) > 1
+    n_neg = neg.numel()
+    if multi:
+        world = dist.get_world_size(group)
+        sizes = torch.zeros(world, dtype=torch.int64, device=pos.device)
+        sizes[dist.get_rank(group)] = pos.numel()
+        dist.all_reduce(sizes, op=dist.ReduceOp.SUM, group=group)
+        sizes = sizes.tolist()
+        cap = max(max(sizes), 1)
+        mine = torch.zeros(cap, dtype=pos.dtype, device=pos.device)
+        mine[:pos.numel()] = pos
+        gathered = [torch.empty(cap, dtype=pos.dtype, device=pos.device) for _ in range(world)]
+        dist.all_gather(gathered, mine, group=group)
+        pos = torch.cat([g[:n] for g, n in zip(gathered, sizes)])
+    n_pos = pos.numel()
+    u2 = count(sort(pos.contiguous()), neg) if (n_pos and n_neg) else 0
+    if multi:
+        t = torch.tensor([u2, n_neg], dtype=torch.int64, device=pos.device)
+        dist.all_reduce(t, op=dist.ReduceOp.SUM, group=group)
+        u2, n_neg = (int(v) for v in t.tolist())
     if n_pos == 0 or n_neg == 0:
         return float('nan')
-    sp, order = torch.sort(p, stable=True)
-    _, counts = torch.unique_consecutive(sp, return_counts=True)
-    ends = torch.cumsum(counts, 0)                       # 1-based last rank of each tie group
-    starts = ends - counts + 1
-    avg_rank = (starts + ends).to(torch.float64) * 0.5
-    rank_sorted = torch.repeat_interleave(avg_rank, counts)
-    u = rank_sorted[y[order]].sum() - n_pos * (n_pos + 1) / 2.0
-    return float(u.item() / (float(n_pos) * float(n_neg)))
+    return u2 / (2.0 * n_pos * n_neg)
 
 
 class BaseEvaluator:
@@ -79,7 +98,7 @@ class BaseEvaluator:
         out: Dict[str, float] = {}
         for m in metrics:
             if m == 'auc':
-                out['auc'] = global_auc(self._probs(scores_flat, offsets), labels_flat)
+                out['auc'] = global_auc(scores_flat, labels_flat, offsets, self.transform)
             elif m in table:
                 out[m] = table[m]
         if save_result and path is not None:               # evaluation.py:60-61,66-67,73-74,81-82
@@ -94,11 +113,6 @@ class BaseEvaluator:
                         fh.write(str(v))
                         fh.write('\n')
         return out
-
-    def _probs(self, scores_flat: Tensor, offsets: Tensor) -> Tensor:
-        if self.transform == 'sigmoid':
-            return torch.sigmoid(scores_flat)
-        return scores_flat
 
 
 class SlowEvaluator(BaseEvaluator):
@@ -161,7 +175,3 @@ class FastEvaluator(BaseEvaluator):
         offsets[1:] = torch.cumsum(counts, 0)
         labels = torch.tensor([v for t in self._targets for v in t], dtype=torch.int8)
         return logits.reshape(-1), labels.to(dev), offsets.to(dev)
-
-    def _probs(self, scores_flat, offsets):
-        n = offsets.numel() - 1
-        return torch.softmax(scores_flat.view(n, -1), dim=1).reshape(-1)

@@ -487,6 +487,49 @@ def rank_metrics(scores, labels, offsets, transform: str = 'sigmoid', ks: Sequen
     return {n: (float(p[i, 0] / p[i, 1]) if p[i, 1] > 0 else float('nan')) for i, n in enumerate(metric_names(ks))}
 
 
+# ------------------------------------------------------------------------------------------------ global auc (evaluation.py:53-55)
+def auc_split(scores: torch.Tensor, labels: torch.Tensor, offsets: Optional[torch.Tensor], transform: str = 'sigmoid'):
+    """Order-preserving uint32 keys of the candidates' probabilities, positives and negatives compacted apart.
+    Returns ``(pos_keys (P,), neg_keys (N,))`` as int32-typed device tensors (the bits are unsigned keys); one device sync (P, N)."""
+    dev = _need_cuda(scores, labels, offsets)
+    lib = L.load()
+    s = _f32(scores).reshape(-1)
+    y = labels.to(torch.int8).contiguous().reshape(-1)
+    T = s.numel()
+    o = offsets.to(torch.int64).contiguous() if offsets is not None else None
+    B = (o.numel() - 1) if o is not None else 0
+    pos = torch.empty(max(T, 1), dtype=torch.int32, device=dev)
+    neg = torch.empty(max(T, 1), dtype=torch.int32, device=dev)
+    counts = torch.empty(2, dtype=torch.int64, device=dev)
+    with torch.cuda.device(dev):
+        L.check(lib.miner_auc_split(_ptr(s), _ptr(y), _ptr(o), B, T, TRANSFORMS[transform], _ptr(pos), _ptr(neg), _ptr(counts), _stream()))
+    P, N = (int(v) for v in counts.tolist())
+    return pos[:P], neg[:N]
+
+
+def sort_u32(keys: torch.Tensor) -> torch.Tensor:
+    """LSD radix sort (ascending, as unsigned 32-bit keys) in place; returns ``keys``."""
+    dev = _need_cuda(keys)
+    lib = L.load()
+    assert keys.dtype == torch.int32 and keys.is_contiguous()
+    n = keys.numel()
+    ws_bytes = int(lib.miner_sort_u32_workspace_bytes(n))
+    ws = torch.empty(max(ws_bytes, 1), dtype=torch.uint8, device=dev)
+    with torch.cuda.device(dev):
+        L.check(lib.miner_sort_u32(_ptr(keys), n, _ptr(ws), ws.numel(), _stream()))
+    return keys
+
+
+def auc_count(pos_sorted: torch.Tensor, neg_keys: torch.Tensor) -> int:
+    """``sum over negatives of 2 #{pos > neg} + #{pos == neg}`` (= 2 U of the Mann-Whitney statistic), an exact python int."""
+    dev = _need_cuda(pos_sorted, neg_keys)
+    out = torch.empty(1, dtype=torch.int64, device=dev)
+    with torch.cuda.device(dev):
+        L.check(L.load().miner_auc_count(_ptr(pos_sorted.contiguous()), pos_sorted.numel(), _ptr(neg_keys.contiguous()), neg_keys.numel(),
+                                         _ptr(out), _stream()))
+    return int(out.item())
+
+
 # ------------------------------------------------------------------------------------------------ (a13, a14)
 def loss_forward(interests: torch.Tensor, logits: torch.Tensor, labels: torch.Tensor, eval_mode: bool = False) -> torch.Tensor:
     """Returns a (3,) device tensor ``[total, disagreement, rank_loss]`` (reference loss.py:27-44 / 68-85)."""

@@ -122,3 +122,20 @@ def algorithmic_flops_per_impression(his_len: int, cands: float, dim: int, codes
     """SURVEY.md section 8d, reference order, score_type='weighted'."""
     h, c, d, k, dc = his_len, cands, dim, codes, code_dim
     return 2 * h * d * dc + 2 * h * dc * k + 2 * k * h * d + 2 * k * d * d + 4 * c * k * d
+
+
+def deterministic_state(shapes: dict, seed: int = 36) -> dict:
+    """A reproducible ``state_dict`` for a module given its ``{name: shape}``: used to put the SAME weights into the reference's
+    ``FastFormer`` (tests/golden/make_golden.py) and into ``miner_b200.FastFormer`` (the GPU parity test) without storing them.
+    LayerNorm gains ~1, everything else small normals; one generator, keys in sorted order."""
+    g = torch.Generator().manual_seed(seed)
+    out = {}
+    for name in sorted(shapes):
+        shape = tuple(shapes[name])
+        if name.endswith('LayerNorm.weight'):
+            out[name] = 1.0 + 0.1 * torch.randn(shape, generator=g)
+        elif name.endswith('bias'):
+            out[name] = 0.02 * torch.randn(shape, generator=g)
+        else:
+            out[name] = 0.05 * torch.randn(shape, generator=g)
+    return out

@@ -224,6 +224,29 @@ def golden_metrics():
     print('metrics', scores, fscores, ka['ka_mrr'], ka['ka_ndcg5'], tie['eq_mrr'])
 
 
+def golden_fastformer():
+    """BASELINE configs[4]: the reference's FastFormer (src/model/model.py:223-341, hidden size 256) behind the table stub, with
+    deterministic weights (synth.deterministic_state) so the fixture holds only inputs and outputs."""
+    from src.model.model import FastFormer
+    N, D, H, C, B, seed = 300, 256, 50, 5, 6, 36
+    table = synth.make_table(N, D, seed)
+    m = FastFormer(TableStub(table), 'weighted', 0.2).eval()
+    shapes = {k: tuple(v.shape) for k, v in m.state_dict().items()}
+    m.load_state_dict(synth.deterministic_state(shapes, seed))
+    g = torch.Generator().manual_seed(seed + 5)
+    his_ids, his_mask, _ = synth.make_history(B, H, N, g)
+    his_mask[0] = True                                             # one full history
+    his_ids[0] = torch.randint(1, N + 1, (H,), generator=g)
+    cand = torch.randint(1, N + 1, (B, C), generator=g)
+    scores = run_miner(m, his_ids, his_mask, cand)
+    with torch.no_grad():
+        user = m.fast_attn(input_embs=table[his_ids], attention_mask=his_mask)
+    np.savez_compressed(os.path.join(HERE, 'fastformer.npz'), his_ids=his_ids.numpy(), his_mask=his_mask.numpy(), cand=cand.numpy(),
+                        scores=scores.numpy(), user=user.numpy(), keys=np.array(sorted(shapes)),
+                        shapes=np.array([str(shapes[k]) for k in sorted(shapes)]), dims=np.array([N, D, H, C, B, seed]))
+    print('fastformer', scores.shape, float(scores.abs().max()), len(shapes), 'tensors')
+
+
 if __name__ == '__main__':
     torch.manual_seed(36)
     torch.set_num_threads(1)     # single-thread MKL: deterministic summation order in the fixtures
@@ -231,3 +254,4 @@ if __name__ == '__main__':
     golden_model('model_odd', N=50, D=40, H=7, K=5, Dc=9, C=3, B=5, NC=5, Ec=6, seed=11, store_inputs=True)
     golden_model('model_full', N=400, D=768, H=50, K=32, Dc=200, C=20, B=8, NC=20, Ec=100, seed=36, store_inputs=False)
     golden_metrics()
+    golden_fastformer()

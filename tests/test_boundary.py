@@ -204,6 +204,57 @@ def test_two_rank_gradient_averaging_gloo(tmp_path):
     assert 'OK' in outs[0]
 
 
+AUC_WORKER = r'''
+import os, sys, torch, torch.distributed as dist, numpy as np
+sys.path.insert(0, sys.argv[1])
+from miner_b200.evaluation import global_auc
+from miner_b200.parallel import shard_bounds
+from oracle import miner_oracle as O
+rank, world = int(os.environ['RANK']), int(os.environ['WORLD_SIZE'])
+dist.init_process_group('gloo', rank=rank, world_size=world)
+g = np.load(os.path.join(sys.argv[1], 'tests', 'golden', 'metrics.npz'))
+offs = torch.from_numpy(g['offsets'])
+
+# CPU stand-ins for the three device calls (same contracts: uint32 order keys in int32 storage, ascending sort, 2U count)
+def key(p):
+    b = p.astype(np.float32).view(np.uint32)
+    return np.where(b & 0x80000000, ~b, b | 0x80000000).astype(np.uint32)
+def split(scores, labels, offsets, transform):
+    k = key(scores.numpy()); y = labels.numpy()
+    return torch.from_numpy(k[y > 0].view(np.int32).copy()), torch.from_numpy(k[y <= 0].view(np.int32).copy())
+def sort(t):
+    return torch.from_numpy(np.sort(t.numpy().view(np.uint32)).view(np.int32).copy())
+def count(pos, neg):
+    p, n = pos.numpy().view(np.uint32), neg.numpy().view(np.uint32)
+    lb, ub = np.searchsorted(p, n, 'left'), np.searchsorted(p, n, 'right')
+    return int((2 * (len(p) - ub) + (ub - lb)).sum())
+
+s, e = shard_bounds(offs, world, 50)[rank]
+c0, c1 = int(offs[s]), int(offs[e])
+probs, labels = torch.from_numpy(g['probs'].astype(np.float32)), torch.from_numpy(g['labels'].astype(np.int8))
+auc = global_auc(probs[c0:c1], labels[c0:c1], None, 'none', _kernels=(split, sort, count))
+full = O.auc_score(g['labels'], g['probs'].astype(np.float32).astype(np.float64))
+assert abs(auc - full) < 1e-12, (auc, full)
+assert abs(auc - float(g['agg_auc'])) < 1e-7
+if rank == 0:
+    print('OK')
+dist.destroy_process_group()
+'''
+
+
+def test_two_rank_global_auc_gloo(tmp_path):
+    """world_size 2 over gloo: every rank holds a shard of the candidates; all-gather of the positive keys + int64 all-reduce of
+    [2U, N] give the single-process auc (the device calls replaced by numpy stand-ins with the same contracts)."""
+    script = tmp_path / 'auc_worker.py'
+    script.write_text(AUC_WORKER)
+    env = dict(os.environ, MASTER_ADDR='127.0.0.1', MASTER_PORT='29617', WORLD_SIZE='2')
+    procs = [subprocess.Popen([sys.executable, str(script), ROOT], env=dict(env, RANK=str(r)), stdout=subprocess.PIPE,
+                              stderr=subprocess.STDOUT, text=True) for r in range(2)]
+    outs = [p.communicate(timeout=240)[0] for p in procs]
+    assert all(p.returncode == 0 for p in procs), outs
+    assert 'OK' in outs[0]
+
+
 def test_table_level_shape_query_is_host_only():
     """`miner_score_table_supported` is a host-side shape query (no GPU): the table-level kernel covers H <= 256, K <= 64,
     D a multiple of 64; everything else falls back to the reference-order families."""

@@ -533,6 +533,57 @@ def test_slow_and_fast_evaluators():
         assert abs(fs[m] - float(g[f'fast_{m}'])) < 1e-6, (m, fs[m], float(g[f'fast_{m}']))
 
 
+def _u2_numpy(p, y):
+    """2 U of the Mann-Whitney statistic in exact integers (numpy): sum over negatives of 2 #{pos > neg} + #{pos == neg}."""
+    pos = np.sort(p[y > 0])
+    neg = p[y <= 0]
+    lb = np.searchsorted(pos, neg, side='left')
+    ub = np.searchsorted(pos, neg, side='right')
+    return int((2 * (len(pos) - ub) + (ub - lb)).sum()), len(pos), len(neg)
+
+
+@pytest.mark.parametrize('T,levels', [(1, 0), (2, 0), (31, 4), (513, 16), (4097, 0), (200_003, 1000), (1_000_000, 0)])
+def test_global_auc_kernels_exact(T, levels):
+    """Global auc (evaluation.py:53-55) without a comparison sort: split into order-preserving keys, radix sort of the positives,
+    binary-search count.  Exact: 2U, P, N equal the numpy integers; the radix sort equals torch's sort of the same keys; the auc
+    equals the oracle's tie-aware statistic to the last bit of the division.  `levels` > 0 quantises the logits (many ties)."""
+    from miner_b200 import ops
+    from miner_b200.evaluation import global_auc
+    g = torch.Generator().manual_seed(T)
+    s = torch.randn(T, generator=g) * 1.5
+    if levels:
+        s = torch.round(s * levels / 6) * 6 / levels
+    y = (torch.rand(T, generator=g) < 0.12).to(torch.int8)
+    if T >= 2:
+        y[0], y[1] = 1, 0
+    sd, yd = s.to(DEV), y.to(DEV)
+    for transform in ('sigmoid', 'none'):
+        p_ref = (1.0 / (1.0 + torch.exp(-sd))).cpu().numpy() if transform == 'sigmoid' else s.numpy()    # the kernels' own sigmoid bits
+        pos, neg = ops.auc_split(sd, yd, None, transform)
+        u2_ref, P, N = _u2_numpy(p_ref, y.numpy())
+        assert pos.numel() == P and neg.numel() == N
+        srt = ops.sort_u32(pos.clone())
+        as_u = lambda t: (t.to(torch.int64) & 0xffffffff)
+        assert torch.equal(as_u(srt), torch.sort(as_u(pos))[0])
+        u2 = ops.auc_count(srt, neg) if P and N else 0
+        assert u2 == u2_ref
+        auc = global_auc(sd, yd, None, transform)
+        if P and N:
+            assert auc == u2_ref / (2.0 * P * N)
+            assert abs(auc - O.auc_score(y.numpy(), p_ref.astype(np.float64))) < 1e-12
+        else:
+            assert np.isnan(auc)
+    # softmax transform (FastEvaluator): rows of 5
+    if T % 5 == 0 or T < 5:
+        return
+    T5 = T // 5 * 5
+    offs = (torch.arange(T5 // 5 + 1) * 5).to(DEV)
+    auc = global_auc(sd[:T5], yd[:T5], offs, 'softmax')
+    pr = torch.softmax(s[:T5].view(-1, 5), dim=1).reshape(-1).numpy().astype(np.float64)
+    if (y[:T5] > 0).any() and (y[:T5] <= 0).any():
+        assert abs(auc - O.auc_score(y[:T5].numpy(), pr)) < 1e-6        # fp32 softmax arithmetic differs in the last ulp between devices
+
+
 # ------------------------------------------------------------------------------------------------ losses (a13, a14)
 @pytest.mark.parametrize('name', MODELS)
 def test_losses(name):
@@ -746,6 +797,59 @@ def test_sweep_history_and_codes(H, K):
     s = m.score_impressions(eb.his_ids.to(DEV), eb.his_mask.to(DEV), eb.cand_ids.to(DEV), eb.offsets.to(DEV))
     ref = O.miner_forward_csr(table.cpu(), eb.his_ids, eb.his_mask, eb.cand_ids, eb.offsets.numpy(), w.w_proj, w.context_codes, w.w_target)
     assert _nerr(s.cpu(), ref) < 1e-3
+
+
+def test_fastformer_forward_matches_reference_golden():
+    """BASELINE configs[4]: miner_b200.FastFormer.forward -- gather kernel for the candidate / history vectors,
+    PyTorch encoder body, dot-score kernel -- against the scores of the reference's FastFormer (model.py:223-341) on the same
+    deterministic weights; the reference-side call sequence and keywords are the test's own."""
+    import miner_b200 as mb
+    from miner_b200 import synth
+    g = load_golden('fastformer')
+    N, D, H, C, B, seed = (int(v) for v in g['dims'])
+    for dtype, tol in ((torch.float32, 2e-5), (torch.bfloat16, 8e-3)):
+        table = synth.make_table(N, D, seed).to(dtype).to(DEV)
+        m = mb.FastFormer(mb.TableNewsEncoder(table), 'weighted', 0.2).to(DEV).eval()
+        shapes = {k: tuple(v.shape) for k, v in m.state_dict().items() if not k.startswith('news_encoder.')}
+        assert sorted(shapes) == list(g['keys'])
+        m.load_state_dict(synth.deterministic_state(shapes, seed), strict=False)
+        his, mask, cand = (torch.from_numpy(g[k]).to(DEV) for k in ('his_ids', 'his_mask', 'cand'))
+        z, zh = torch.zeros(B, C, 1, dtype=torch.long, device=DEV), torch.zeros(B, H, 1, dtype=torch.long, device=DEV)
+        with torch.no_grad():
+            s = m(title=cand[..., None], title_mask=z, his_title=his[..., None], his_title_mask=zh, his_mask=mask, sapo=z, sapo_mask=z,
+                  his_sapo=zh, his_sapo_mask=zh)
+        assert s.shape == (B, C)
+        err = _nerr(s.cpu(), torch.from_numpy(g['scores']))
+        assert err < tol, (str(dtype), err)
+
+
+def test_build_news_table():
+    """build_news_table: one pass of a news encoder over the news set -> (N + 1, D) table (replaces the per-batch encoding of
+    model.py:96-111); rows land at their news id, the table then drives TableNewsEncoder / the gather kernel bit-exactly."""
+    import miner_b200 as mb
+    N, D, L = 57, 64, 6
+    g = torch.Generator().manual_seed(2)
+    emb = torch.randn(1000, D, generator=g).to(DEV)
+
+    class ToyEncoder(torch.nn.Module):                     # NewsEncoder call contract (news_encoder.py:60-61,108-110)
+        embed_dim = D
+
+        def forward(self, title_encoding, title_attn_mask, sapo_encoding=None, sapo_attn_mask=None):
+            return (emb[title_encoding] * title_attn_mask[..., None]).sum(1)
+
+    titles = torch.randint(0, 1000, (N + 1, L), generator=g).to(DEV)
+    tmask = (torch.rand(N + 1, L, generator=g) < 0.8).float().to(DEV)
+    order = torch.randperm(N + 1, generator=g).to(DEV)
+    batches = [(order[a:a + 16], titles[order[a:a + 16]], tmask[order[a:a + 16]], None, None) for a in range(0, N + 1, 16)]
+    enc = ToyEncoder()
+    table = mb.build_news_table(enc, batches, N, dtype=torch.float32)
+    assert table.shape == (N + 1, D) and torch.equal(table, enc(titles, tmask))
+    t16 = mb.build_news_table(enc, batches, N)
+    assert t16.dtype == torch.bfloat16 and torch.equal(t16, enc(titles, tmask).to(torch.bfloat16))
+    ids = torch.randint(0, N + 1, (9, 4), generator=g).to(DEV)
+    assert torch.equal(mb.TableNewsEncoder(t16)(ids.view(-1, 1)), t16[ids.view(-1)])
+    with pytest.raises(IndexError):
+        mb.build_news_table(enc, [(torch.tensor([N + 1], device=DEV), titles[:1], tmask[:1], None, None)], N)
 
 
 def test_fastformer_style_dot_score():

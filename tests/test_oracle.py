@@ -159,3 +159,32 @@ def test_auc_against_sklearn_when_available():
         y = rng.integers(0, 2, n); y[0], y[1] = 1, 0
         s = np.round(rng.random(n), 1)          # many ties
         assert abs(O.auc_score(y, s) - sk.roc_auc_score(y, s)) < 1e-14
+
+
+def test_fastformer_encoder_body_matches_reference_golden():
+    """BASELINE configs[4]: the Fastformer user-encoder body (PyTorch, written from the equations) against the output of the
+    reference's own FastFormer.fast_attn (tests/golden/fastformer.npz, made by make_golden.py with synth.deterministic_state
+    weights), and the state-dict keys / shapes a reference checkpoint would bring."""
+    import miner_b200 as mb
+    from miner_b200 import synth
+    g = load_golden('fastformer')
+    N, D, H, C, B, seed = (int(v) for v in g['dims'])
+    table = synth.make_table(N, D, seed)
+
+    class Stub(torch.nn.Module):
+        embed_dim = D
+
+    m = mb.FastFormer(Stub(), 'weighted', 0.2).eval()
+    shapes = {k: tuple(v.shape) for k, v in m.state_dict().items()}
+    assert sorted(shapes) == list(g['keys']) and [str(shapes[k]) for k in sorted(shapes)] == list(g['shapes'])
+    m.load_state_dict(synth.deterministic_state(shapes, seed))
+    his_ids, his_mask = torch.from_numpy(g['his_ids']), torch.from_numpy(g['his_mask'])
+    with torch.no_grad():
+        user = m.fast_attn(input_embs=table[his_ids], attention_mask=his_mask)
+    assert np.abs(user.numpy() - g['user']).max() < 2e-5 * np.abs(g['user']).max()
+    scores = torch.matmul(table[torch.from_numpy(g['cand'])], user.unsqueeze(-1)).squeeze(-1)
+    assert np.abs(scores.numpy() - g['scores']).max() < 2e-5 * np.abs(g['scores']).max()
+    with pytest.raises(ValueError):
+        class Wide(torch.nn.Module):
+            embed_dim = 768
+        mb.FastFormer(Wide(), 'weighted', 0.2)
