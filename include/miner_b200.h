@@ -139,7 +139,7 @@ int miner_tc_gemm(const void* a_bf16, const void* a_ids, int id_dtype, int64_t a
 /* The two kernels of the fused tensor-core path on their own (tests / profiling).
  *   miner_hist_interests_fwd: PolyAttention.forward (model.py:159-185) straight from a bf16 table: gathers table[his_ids],
  *      projects on tcgen05, softmax over the history, weighted sum on tcgen05.  Writes the interests split as two bf16 arrays
- *      i_hi + i_lo (B*K, D) and, if out_interests != NULL, as fp32 (B,K,D).  Needs H <= 128, K in {8,16,32}, Dc <= 256, D % 64 == 0.
+ *      i_hi + i_lo (B*K, D) and, if out_interests != NULL, as fp32 (B,K,D).  Needs H <= 128, K in {8,16,32}, Dc <= 208, D % 64 == 0.
  *   miner_cand_score_fwd: matching scores + TargetAwareAttention (model.py:127,200-216, score_type 'weighted') from
  *      i_hi / i_lo and table[cand_ids]; CSR offsets (B+1) or NULL for dense C per row.  out_scores (T) fp32. */
 size_t miner_hist_interests_workspace_bytes(int64_t Dc);

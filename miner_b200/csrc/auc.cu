@@ -18,9 +18,10 @@ namespace {
 
 constexpr int RS_WARPS = 8, RS_SEG = 512;      // keys per warp segment (16 per lane), warps per block
 
-// float -> uint32 whose unsigned order is the float order (-0 < +0 are adjacent but distinct: probabilities never produce -0)
+// float -> uint32 whose unsigned order is the float order; -0 and +0 compare equal as floats, so they share a key
 __device__ __forceinline__ uint32_t order_key(float x) {
-  const uint32_t b = __float_as_uint(x);
+  uint32_t b = __float_as_uint(x);
+  if (b == 0x80000000u) b = 0u;
   return (b & 0x80000000u) ? ~b : (b | 0x80000000u);
 }
 

@@ -53,12 +53,20 @@ class _MinerTrainFn(torch.autograd.Function):
     def forward(ctx, w_proj: Tensor, codes: Tensor, w_target: Tensor, table: Tensor, his_ids: Tensor, his_mask: Tensor, cand_ids: Tensor,
                 math: int):
         interests, scores, saved = ops.train_forward(table, his_ids, his_mask, cand_ids, w_proj, codes, w_target, math)
-        ctx.saved = saved
+        # the big intermediates go through save_for_backward (in-place changes are detected, and saving the OUTPUT `interests` this
+        # way does not tie output -> grad_fn -> ctx -> output into a cycle that only the cyclic GC would free: ~3 GB per step)
+        ctx.save_for_backward(saved.t, saved.w, saved.z, interests)
+        saved.t = saved.w = saved.z = saved.interests = None
+        ctx.meta = saved
         return interests, scores
 
     @staticmethod
     def backward(ctx, d_interests, d_scores):
-        gwp, gc, gwt = ops.train_backward(ctx.saved, d_scores, d_interests)
+        saved = ctx.meta
+        saved.t, saved.w, saved.z, saved.interests = ctx.saved_tensors
+        gwp, gc, gwt = ops.train_backward(saved, d_scores, d_interests)
+        saved.t = saved.w = saved.z = saved.interests = saved.ws = None          # release the step's buffers now, not at GC time
+        ctx.meta = None
         return gwp, gc, gwt, None, None, None, None, None
 
 

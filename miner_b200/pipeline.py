@@ -24,7 +24,9 @@ class HostEvaluator:
             raise L.MinerError('HostEvaluator needs a Miner with a TableNewsEncoder')
         if model.use_category_bias:
             raise NotImplementedError('grouped scoring with category bias: use Miner.forward with the row layout you mean (model.py:176)')
-        self.model, self.wave, self.chunk, self.ks, self.transform = model, int(wave), int(chunk), tuple(ks), transform
+        # waves start on tile boundaries of the table-level kernel (4 impressions at most share a tile): an impression then keeps its
+        # tile partner -- and every bit of its scores -- whatever the wave size
+        self.model, self.wave, self.chunk, self.ks, self.transform = model, max(4, int(wave) // 4 * 4), int(chunk), tuple(ks), transform
         self.table = model.news_encoder.table
         self.dev = self.table.device
         self._math_arg = math
