@@ -347,7 +347,10 @@ tscore_kernel(const TScoreArgs args, int n_tiles) {
   tc::tcgen05_fence_before();
   __syncthreads();
   tc::tcgen05_fence_after();
-  const uint32_t tmem = bars->tmem_base;
+  // the CTA owns all 512 columns of its SM's tensor memory, so the allocation starts at lane 0 / column 0: every TMEM address below
+  // is then a compile-time constant (the MMA-issuing warp is bound by its own instruction stream, not by the tensor pipe)
+  if (bars->tmem_base != 0u) __trap();
+  constexpr uint32_t tmem = 0u;
 
   if (warp < W_G2) {
     // ------------------------------------------------------------------ gathers of the (E, TW) ring: thread = one 16-byte chunk of rows
@@ -486,7 +489,9 @@ tscore_kernel(const TScoreArgs args, int n_tiles) {
     if (bad > 0 && args.oob) atomicAdd(args.oob + 1, bad);   // candidate ids outside the table (their rows read as zero)
   } else if (warp == W_MMA) {
     // ------------------------------------------------------------------ MMA issuer
-    const uint32_t idesc1 = tc::make_idesc_bf16_f32_major(TM, FB, false, true);        // B = gathered tile, MN-major
+    // S1: ONE MMA per 16-slot K-step computes D_I | D_P = A_w . [E_j | TW_j]: B is two 64-feature swizzle atoms wide along N (the E
+    // and TW halves of the stage, E_BYTES apart), read MN-major; the 128 accumulator columns are the I | P halves of the buffer
+    const uint32_t idesc1 = tc::make_idesc_bf16_f32_major(TM, 2 * FB, false, true);
     uint32_t g1 = 0, g2 = 0, u = 0, sg = 0;                      // blocks issued (S1 / S2), units, ring stages consumed
     bool pending = false;
     int pend_j = 0, pend_nc16 = 16;
@@ -542,7 +547,7 @@ tscore_kernel(const TScoreArgs args, int n_tiles) {
         tc::tcgen05_fence_after();
         for (int j = 0; j < KB; ++j) {
           const uint32_t b = g1 & 1;
-          const uint32_t d_i = tmem + IP_COL + b * 128, d_p = d_i + 64;
+          const uint32_t d_i = tmem + IP_COL + b * 128;
 #pragma unroll
           for (int half = 0; half < NH; ++half) {
             const int ng = nks - 8 * half < 8 ? nks - 8 * half : 8;
@@ -554,17 +559,10 @@ tscore_kernel(const TScoreArgs args, int n_tiles) {
             tc::mbar_wait(&bars->full1[s], ph);
             PROF_ADD(2);
             tc::tcgen05_fence_after();
-            const uint64_t e_desc = tc::make_smem_desc_sw128_mn(tc::smem_u32(st1 + s * ST1_BYTES));
-            const uint64_t t_desc = tc::make_smem_desc_sw128_mn(tc::smem_u32(st1 + s * ST1_BYTES + E_BYTES));
+            const uint64_t et_desc = tc::make_smem_desc_sw128_mn_wide(tc::smem_u32(st1 + s * ST1_BYTES), E_BYTES);
             if (tc::elect_one()) {
-#pragma unroll
-              for (int ks = 0; ks < TM / 16; ++ks) {
-                if (ks < ng) {
-                  const uint32_t acc = (half | ks) != 0 ? 1u : 0u;
-                  tc::umma_bf16_ts(d_i, tmem + AW_COL + half * 64 + 8 * ks, e_desc + ks * (2048 >> 4), idesc1, acc);
-                  tc::umma_bf16_ts(d_p, tmem + AW_COL + half * 64 + 8 * ks, t_desc + ks * (2048 >> 4), idesc1, acc);
-                }
-              }
+              for (int ks = 0; ks < ng; ++ks)
+                tc::umma_bf16_ts(d_i, tmem + AW_COL + half * 64 + 8 * ks, et_desc + ks * (2048 >> 4), idesc1, (half | ks) != 0 ? 1u : 0u);
               tc::umma_commit(&bars->empty1[s]);
               if (last_half) {
                 tc::umma_commit(&bars->ip_full[b]);
