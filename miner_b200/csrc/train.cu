@@ -216,6 +216,55 @@ __global__ void __launch_bounds__(TT) target_bwd_kernel(const void* __restrict__
   }
 }
 
+// ---- score_type 'max' / 'mean' (model.py:128-131): scores = max_k / mean_k of m[c,k] = Cd_c . I_k.  One CTA per impression:
+//      dm[c,k] = ds[c] [k == argmax_k m[c,:]]  or  ds[c] / K ;  dI[k] = dI_in[k] + sum_c dm[c,k] Cd_c
+__global__ void __launch_bounds__(TT) target_bwd_simple_kernel(const void* __restrict__ table, int table_dtype, int64_t n_rows,
+                                                               const void* __restrict__ cand_ids, int id_dtype, const float* __restrict__ interests,
+                                                               const float* __restrict__ d_scores, const float* __restrict__ d_interests_in, int C,
+                                                               int K, int D, int score_type, float* __restrict__ d_interests) {
+  extern __shared__ __align__(16) float smem[];
+  float* Cd = smem;                      // [C][D] candidate vectors
+  float* m = Cd + C * D;                 // [C][K] matching scores -> dm
+  const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+  const int64_t b = blockIdx.x;
+  for (int c = 0; c < C; ++c) {
+    const int64_t id = load_id(cand_ids, b * C + c, id_dtype);
+    const bool ok = id >= 0 && id < n_rows;
+    for (int d = tid; d < D; d += TT) Cd[c * D + d] = ok ? table_elem(table, table_dtype, id * D + d) : 0.f;
+  }
+  __syncthreads();
+  const float* Ib = interests + b * static_cast<int64_t>(K) * D;
+  if (score_type == MINER_SCORE_MAX) {
+    for (int i = warp; i < C * K; i += TT / 32) {
+      const int c = i / K, k = i - c * K;
+      float sm_ = 0.f;
+      for (int d = lane; d < D; d += 32) sm_ = fmaf(Cd[c * D + d], Ib[static_cast<int64_t>(k) * D + d], sm_);    // model.py:127
+      sm_ = warp_sum(sm_);
+      if (lane == 0) m[i] = sm_;
+    }
+    __syncthreads();
+    if (tid < C) {
+      const int c = tid;
+      int arg = 0;
+      float best = m[c * K];
+      for (int k = 1; k < K; ++k) if (m[c * K + k] > best) { best = m[c * K + k]; arg = k; }       // first maximum (model.py:129)
+      const float ds = d_scores[b * C + c];
+      for (int k = 0; k < K; ++k) m[c * K + k] = k == arg ? ds : 0.f;
+    }
+  } else {
+    for (int i = tid; i < C * K; i += TT) m[i] = d_scores[b * C + i / K] / static_cast<float>(K);  // model.py:131
+  }
+  __syncthreads();
+  const float* dIin = d_interests_in ? d_interests_in + b * static_cast<int64_t>(K) * D : nullptr;
+  float* dIb = d_interests + b * static_cast<int64_t>(K) * D;
+  for (int i = tid; i < K * D; i += TT) {
+    const int k = i / D, d = i - k * D;
+    float gi = dIin ? dIin[i] : 0.f;
+    for (int c = 0; c < C; ++c) gi = fmaf(m[c * K + k], Cd[c * D + d], gi);
+    dIb[i] = gi;
+  }
+}
+
 // ---- backward through the poly attention (model.py:159-185): CTAs stride over impressions and keep their share of dcodes in
 //      shared memory; dZ1 = dT (1 - T^2) goes to global memory for the dWp contraction
 __global__ void __launch_bounds__(TT) poly_bwd_kernel(const void* __restrict__ table, int table_dtype, int64_t n_rows,
@@ -223,7 +272,7 @@ __global__ void __launch_bounds__(TT) poly_bwd_kernel(const void* __restrict__ t
                                                       const float* __restrict__ codes, const float* __restrict__ T,
                                                       const float* __restrict__ W, const float* __restrict__ dI_a,
                                                       const float* __restrict__ dI_b, int64_t B, int H, int K, int Dc, int D,
-                                                      float* __restrict__ dZ1, float* __restrict__ dcodes_partial) {
+                                                      float* __restrict__ dZ1, float* __restrict__ dcodes_partial, float* __restrict__ d_bias) {
   extern __shared__ __align__(16) float smem[];
   constexpr int DK = 64;                 // feature chunk
   float* codes_s = smem;                 // [K][Dc]
@@ -299,6 +348,13 @@ __global__ void __launch_bounds__(TT) poly_bwd_kernel(const void* __restrict__ t
       }
     }
     __syncthreads();
+    // the category bias adds one scalar per history slot to all K logits of the slot (model.py:176-177): d bias[h] = sum_k dlogits[k,h]
+    if (d_bias)
+      for (int h = tid; h < H; h += TT) {
+        float sb = 0.f;
+        for (int k = 0; k < K; ++k) sb += dw[k * H + h];
+        d_bias[b * H + h] = sb;
+      }
     // dT = dlogits^T codes, dZ1 = dT (1 - T^2)                                          (model.py:171,174)
     for (int i = tid; i < H * Dc; i += TT) {
       const int h = i / Dc, dc = i - h * Dc;
@@ -471,15 +527,20 @@ extern "C" int miner_train_fwd(const void* table, int64_t n_rows, int table_dtyp
                                const void* cand_ids, int id_dtype, const float* w_proj, const float* codes, const float* w_target,
                                int64_t B, int64_t H, int64_t C, int64_t K, int64_t Dc, int64_t D, float* out_interests, float* out_scores,
                                float* save_t, float* save_w, float* save_z, int math, const void* w_proj_bf16, const void* w_target_bf16,
-                               void* workspace, size_t workspace_bytes, void* stream) {
+                               int score_type, const float* bias_mean, void* workspace, size_t workspace_bytes, void* stream) {
   MINER_CHECK_ARG(B >= 0 && H > 0 && C > 0 && K > 0 && Dc > 0 && D > 0 && n_rows > 0, "train_fwd: bad sizes");
+  if (score_type != MINER_SCORE_MAX && score_type != MINER_SCORE_MEAN && score_type != MINER_SCORE_WEIGHTED) {
+    set_error("Invalid method of aggregating matching score");
+    return MINER_ERR_SCORE_TYPE;
+  }
   if (B == 0) return MINER_OK;
-  MINER_CHECK_ARG(table && his_ids && his_mask && cand_ids && w_proj && codes && w_target && out_interests && out_scores && save_t &&
-                      save_w && save_z,
+  const bool weighted = score_type == MINER_SCORE_WEIGHTED;
+  MINER_CHECK_ARG(table && his_ids && his_mask && cand_ids && w_proj && codes && out_interests && out_scores && save_t && save_w &&
+                      (!weighted || (w_target && save_z)),
                   "train_fwd: null pointer");
   MINER_CHECK_ARG(table_dtype == MINER_F32 || table_dtype == MINER_BF16, "train_fwd: table dtype must be fp32 or bf16");
   MINER_CHECK_ARG(id_dtype == MINER_I32 || id_dtype == MINER_I64, "train_fwd: id dtype must be int32 or int64");
-  int rc = check_train_math(math, table_dtype, D, Dc, w_proj_bf16, w_target_bf16);
+  int rc = check_train_math(math, table_dtype, D, Dc, w_proj_bf16, weighted ? w_target_bf16 : w_proj_bf16);
   if (rc) return rc;
   const TrainWs w = train_ws(B, H, K, Dc, D, math);
   if (!workspace || workspace_bytes < w.total) {
@@ -493,20 +554,23 @@ extern "C" int miner_train_fwd(const void* table, int64_t n_rows, int table_dtyp
     // the two projection GEMMs on tcgen05 (bf16 operands, fp32 accumulation), everything else as in the fp32 family
     rc = launch_tc_gemm(table, his_ids, id_dtype, n_rows, w_proj_bf16, save_t, nullptr, B * H, Dc, D, EPI_TANH, st);          // model.py:171
     if (rc) return rc;
-    rc = launch_poly_softmax_wsum(save_t, codes, his_mask, nullptr, nullptr, table, table_dtype, his_ids, id_dtype, n_rows, B, H, K, Dc, D,
+    rc = launch_poly_softmax_wsum(save_t, codes, his_mask, bias_mean, nullptr, table, table_dtype, his_ids, id_dtype, n_rows, B, H, K, Dc, D,
                                   out_interests, save_w, wsb + w.i_bf16, st);                                                  // model.py:174-182
     if (rc) return rc;
-    rc = launch_tc_gemm(wsb + w.i_bf16, nullptr, id_dtype, 0, w_target_bf16, save_z, nullptr, B * K, D, D, EPI_NONE, st);     // model.py:212
+    if (weighted) rc = launch_tc_gemm(wsb + w.i_bf16, nullptr, id_dtype, 0, w_target_bf16, save_z, nullptr, B * K, D, D, EPI_NONE, st);     // model.py:212
     if (rc) return rc;
   } else {
     rc = launch_sgemm_nt(table, table_dtype, his_ids, id_dtype, n_rows, w_proj, save_t, B * H, Dc, D, EPI_TANH, st);          // model.py:171
     if (rc) return rc;
-    rc = launch_poly_softmax_wsum(save_t, codes, his_mask, nullptr, nullptr, table, table_dtype, his_ids, id_dtype, n_rows, B, H, K, Dc, D,
+    rc = launch_poly_softmax_wsum(save_t, codes, his_mask, bias_mean, nullptr, table, table_dtype, his_ids, id_dtype, n_rows, B, H, K, Dc, D,
                                   out_interests, save_w, nullptr, st);                                                          // model.py:174-182
     if (rc) return rc;
-    rc = launch_sgemm_nt(out_interests, MINER_F32, nullptr, id_dtype, 0, w_target, save_z, B * K, D, D, EPI_NONE, st);         // model.py:212
+    if (weighted) rc = launch_sgemm_nt(out_interests, MINER_F32, nullptr, id_dtype, 0, w_target, save_z, B * K, D, D, EPI_NONE, st);         // model.py:212
     if (rc) return rc;
   }
+  if (!weighted)                                                                                                               // model.py:128-131
+    return launch_target_score(out_interests, nullptr, nullptr, nullptr, table, table_dtype, cand_ids, id_dtype, n_rows, nullptr, B, C, K, D,
+                               score_type, out_scores, st);
   const int64_t n = B * K * D;
   gelu_kernel<<<static_cast<int>((n + 1023) / 1024 < 8 * sm_count() ? (n + 1023) / 1024 : 8 * sm_count()), 256, 0, st>>>(save_z, G, n);
   MINER_LAUNCH_OK("gelu");
@@ -535,14 +599,20 @@ extern "C" int miner_train_bwd(const void* table, int64_t n_rows, int table_dtyp
                                const float* save_t, const float* save_w, const float* interests, const float* save_z,
                                const float* d_scores, const float* d_interests, int64_t B, int64_t H, int64_t C, int64_t K, int64_t Dc,
                                int64_t D, float* grad_w_proj, float* grad_codes, float* grad_w_target, int math, const void* w_proj_bf16,
-                               const void* w_target_bf16, void* workspace, size_t workspace_bytes, void* stream) {
+                               const void* w_target_bf16, int score_type, float* d_bias_mean, void* workspace, size_t workspace_bytes,
+                               void* stream) {
   (void)w_proj;
   MINER_CHECK_ARG(B > 0 && H > 0 && C > 0 && K > 0 && Dc > 0 && D > 0 && n_rows > 0, "train_bwd: bad sizes");
-  MINER_CHECK_ARG(table && his_ids && his_mask && cand_ids && codes && w_target && save_t && save_w && interests && save_z && d_scores &&
-                      grad_w_proj && grad_codes && grad_w_target,
+  if (score_type != MINER_SCORE_MAX && score_type != MINER_SCORE_MEAN && score_type != MINER_SCORE_WEIGHTED) {
+    set_error("Invalid method of aggregating matching score");
+    return MINER_ERR_SCORE_TYPE;
+  }
+  const bool weighted = score_type == MINER_SCORE_WEIGHTED;
+  MINER_CHECK_ARG(table && his_ids && his_mask && cand_ids && codes && save_t && save_w && interests && d_scores && grad_w_proj && grad_codes &&
+                      (!weighted || (w_target && save_z && grad_w_target)),
                   "train_bwd: null pointer");
   {
-    const int rc0 = check_train_math(math, table_dtype, D, Dc, w_proj_bf16, w_target_bf16);
+    const int rc0 = check_train_math(math, table_dtype, D, Dc, w_proj_bf16, weighted ? w_target_bf16 : w_proj_bf16);
     if (rc0) return rc0;
   }
   const bool tensor = math == MINER_MATH_TENSOR;
@@ -561,8 +631,18 @@ extern "C" int miner_train_bwd(const void* table, int64_t n_rows, int table_dtyp
   float* pWp = reinterpret_cast<float*>(ws + w.part_wp);
   float* pWt = reinterpret_cast<float*>(ws + w.part_wt);
   float* pCodes = reinterpret_cast<float*>(ws + w.part_codes);
-  // 1. target-aware attention: dI (direct paths), dZ
-  {
+  // 1. target-aware attention: dI (direct paths), dZ   -- or, for 'max' / 'mean', dI alone
+  if (!weighted) {
+    const size_t smem = sizeof(float) * (static_cast<size_t>(C) * D + static_cast<size_t>(C) * K);
+    if (smem > 200 * 1024 || C > TT) {
+      set_error("train_bwd: C=%lld D=%lld needs %zu bytes of shared memory", (long long)C, (long long)D, smem);
+      return MINER_ERR_UNSUPPORTED;
+    }
+    MINER_CUDA_OK(cudaFuncSetAttribute(target_bwd_simple_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, static_cast<int>(smem)));
+    target_bwd_simple_kernel<<<static_cast<unsigned>(B), TT, smem, st>>>(table, table_dtype, n_rows, cand_ids, id_dtype, interests, d_scores,
+                                                                        d_interests, (int)C, (int)K, (int)D, score_type, dI);
+    MINER_LAUNCH_OK("target_bwd_simple");
+  } else {
     const size_t smem = sizeof(float) * (static_cast<size_t>(C) * D + 4 * C * K);
     if (smem > 200 * 1024 || C > TT) {
       set_error("train_bwd: C=%lld D=%lld needs %zu bytes of shared memory", (long long)C, (long long)D, smem);
@@ -574,7 +654,9 @@ extern "C" int miner_train_bwd(const void* table, int64_t n_rows, int table_dtyp
     MINER_LAUNCH_OK("target_bwd");
   }
   // 2. Z = I Wt^T:  dI2 = dZ Wt  (as dZ (Wt^T)^T with the NT GEMM),  dWt = dZ^T I
-  if (tensor) {
+  if (!weighted) {
+    dI2 = nullptr;
+  } else if (tensor) {
     dim3 tb(32, 8);
     const int64_t R = B * K;
     __nv_bfloat16* dz16 = reinterpret_cast<__nv_bfloat16*>(ws + w.dz_bf16);
@@ -617,7 +699,7 @@ extern "C" int miner_train_bwd(const void* table, int64_t n_rows, int table_dtyp
     }
     MINER_CUDA_OK(cudaFuncSetAttribute(poly_bwd_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, static_cast<int>(smem)));
     poly_bwd_kernel<<<w.g_poly, TT, smem, st>>>(table, table_dtype, n_rows, his_ids, id_dtype, his_mask, codes, save_t, save_w, dI, dI2, B,
-                                                (int)H, (int)K, (int)Dc, (int)D, dZ1, pCodes);
+                                                (int)H, (int)K, (int)Dc, (int)D, dZ1, pCodes, d_bias_mean);
     MINER_LAUNCH_OK("poly_bwd");
     sum_partials_kernel<<<static_cast<int>((K * Dc + 255) / 256), 256, 0, st>>>(pCodes, w.g_poly, K * Dc, grad_codes);
     MINER_LAUNCH_OK("sum_partials(dcodes)");

@@ -1108,7 +1108,7 @@ def test_rank_count_invariance_single_gpu():
 @pytest.mark.skipif(torch.cuda.device_count() < 2, reason='needs two GPUs')
 def test_strong_scaling_rank_invariance_torchrun(tmp_path):
     """bench.py --scaling strong at 1 and at 2 ranks (torchrun, NCCL): one global batch, the six metrics agree to 1e-12."""
-    import json, subprocess, sys as _sys
+    import json, os, subprocess, sys as _sys
     root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
     common = ['bench.py', '--scaling', 'strong', '--impressions', '20000', '--steps', '1', '--warmup', '3', '--no-cpu-baseline',
               '--no-reference-order', '--no-breakdown', '--no-extras']
