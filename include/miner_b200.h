@@ -219,13 +219,20 @@ int miner_loss_fwd(const float* interests, const float* logits, const float* lab
                    float* out, void* workspace, size_t workspace_bytes, void* stream);
 
 /* ---- Train variant: Miner.forward with the intermediates its backward needs, the backward of
- *      Loss.compute (loss.py:27-44) and the backward of Miner.forward (model.py:61-138, score_type 'weighted', category bias
- *      off) down to the three weight matrices.  fp32, reference operation order, deterministic reductions.  Dense layout:
- *      cand_ids (B,C).  The news table is a frozen buffer: no gradient flows into its rows.
- *      miner_train_fwd writes interests (B,K,D), scores (B,C) and saves T = tanh(E Wp^T) (B*H,Dc), the softmax weights
- *      (B,K,H) and Z = I Wt^T (B*K,D).  miner_loss_bwd: d loss / d interests and d loss / d logits, scaled by *grad_out
- *      (device float, NULL = 1).  miner_train_bwd: grad_w_proj (Dc,D), grad_codes (K,Dc), grad_w_target (D,D) from d_scores
- *      (B,C) and d_interests (B,K,D, nullable).  The same workspace size serves fwd and bwd.
+ *      Loss.compute (loss.py:27-44) and the backward of Miner.forward (model.py:61-138) down to the weight matrices, for every
+ *      score_type (model.py:127-136) and with or without the category-bias scalar of the poly attention (model.py:176-177).
+ *      fp32, reference operation order, deterministic reductions.  Dense layout: cand_ids (B,C).  The news table is a frozen buffer
+ *      here (no gradient flows into its rows).
+ *      miner_train_fwd writes interests (B,K,D), scores (B,C) and saves T = tanh(E Wp^T) (B*H,Dc), the softmax weights (B,K,H) and,
+ *      for 'weighted', Z = I Wt^T (B*K,D).  bias_mean (B,H) or NULL is added to every code's logit of a history slot.
+ *      miner_loss_bwd: d loss / d interests and d loss / d logits, scaled by *grad_out (device float, NULL = 1).
+ *      miner_train_bwd: grad_w_proj (Dc,D), grad_codes (K,Dc), grad_w_target (D,D; 'weighted' only, else NULL) from d_scores (B,C)
+ *      and d_interests (B,K,D, nullable); d_bias_mean (B,H) or NULL receives d loss / d bias_mean (the category embedding's
+ *      gradient continues from there).  grad_table (n_rows, D) fp32 or NULL: the gradient of the table ROWS (history rows through
+ *      I = w E and tanh(E Wp^T), candidate rows through the matching / attention dots) is ADDED into it with atomics -- zero it
+ *      first -- so that the table can be a trainable parameter or the dense output of an upstream news encoder (the reference
+ *      trains its encoder, trainer.py:146-169); it needs its own scratch of miner_train_table_grad_workspace_bytes.
+ *      The same workspace size serves fwd and bwd.
  *      math = MINER_MATH_FP32, or MINER_MATH_TENSOR: the five projection-sized GEMMs of the step (E Wp^T, I Wt^T, dZ Wt,
  *      dZ^T I, dZ1^T E) on tcgen05 with bf16 operands and fp32 accumulation (bf16 table, D % 64 == 0, bf16 weight copies). */
 size_t miner_train_workspace_bytes(int64_t B, int64_t H, int64_t K, int64_t Dc, int64_t D, int math);
@@ -233,7 +240,7 @@ int miner_train_fwd(const void* table, int64_t n_rows, int table_dtype, const vo
                     const void* cand_ids, int id_dtype, const float* w_proj, const float* codes, const float* w_target,
                     int64_t B, int64_t H, int64_t C, int64_t K, int64_t Dc, int64_t D, float* out_interests, float* out_scores,
                     float* save_t, float* save_w, float* save_z,
-                    int math, const void* w_proj_bf16, const void* w_target_bf16,
+                    int math, const void* w_proj_bf16, const void* w_target_bf16, int score_type, const float* bias_mean,
                     void* workspace, size_t workspace_bytes, void* stream);
 int miner_loss_bwd(const float* interests, const float* logits, const float* labels, const float* grad_out,
                    int64_t B, int64_t C, int64_t K, int64_t D, float* d_interests, float* d_logits, void* stream);
@@ -243,8 +250,10 @@ int miner_train_bwd(const void* table, int64_t n_rows, int table_dtype, const vo
                     const float* d_scores, const float* d_interests,
                     int64_t B, int64_t H, int64_t C, int64_t K, int64_t Dc, int64_t D,
                     float* grad_w_proj, float* grad_codes, float* grad_w_target,
-                    int math, const void* w_proj_bf16, const void* w_target_bf16,
+                    int math, const void* w_proj_bf16, const void* w_target_bf16, int score_type, float* d_bias_mean,
+                    float* grad_table, void* table_grad_workspace, size_t table_grad_workspace_bytes,
                     void* workspace, size_t workspace_bytes, void* stream);
+size_t miner_train_table_grad_workspace_bytes(int64_t B, int64_t H, int64_t Dc, int64_t D);
 
 #ifdef __cplusplus
 }

@@ -33,7 +33,7 @@ EXPORTS = [
     'miner_table_project_workspace_bytes', 'miner_table_project', 'miner_score_table_supported', 'miner_score_table_fwd',
     'miner_score_table_workspace_bytes', 'miner_score_table_tile_geometry',
     'miner_auc_split', 'miner_sort_u32_workspace_bytes', 'miner_sort_u32', 'miner_auc_count',
-    'miner_train_workspace_bytes', 'miner_train_fwd', 'miner_loss_bwd', 'miner_train_bwd',
+    'miner_train_workspace_bytes', 'miner_train_fwd', 'miner_loss_bwd', 'miner_train_bwd', 'miner_train_table_grad_workspace_bytes',
 ]
 
 
@@ -96,10 +96,12 @@ def _declare(lib: C.CDLL) -> None:
     lib.miner_train_workspace_bytes.argtypes = [i64, i64, i64, i64, i64, i32]
     lib.miner_train_workspace_bytes.restype = sz
     lib.miner_train_fwd.argtypes = [vp, i64, i32, vp, vp, vp, i32, vp, vp, vp, i64, i64, i64, i64, i64, i64, vp, vp, vp, vp, vp, i32, vp, vp,
-                                    vp, sz, vp]
+                                    i32, vp, vp, sz, vp]
     lib.miner_loss_bwd.argtypes = [vp, vp, vp, vp, i64, i64, i64, i64, vp, vp, vp]
     lib.miner_train_bwd.argtypes = [vp, i64, i32, vp, vp, vp, i32, vp, vp, vp, vp, vp, vp, vp, vp, vp, i64, i64, i64, i64, i64, i64, vp, vp, vp,
-                                    i32, vp, vp, vp, sz, vp]
+                                    i32, vp, vp, i32, vp, vp, vp, sz, vp, sz, vp]
+    lib.miner_train_table_grad_workspace_bytes.argtypes = [i64, i64, i64, i64]
+    lib.miner_train_table_grad_workspace_bytes.restype = sz
     lib.miner_score_table_fwd.argtypes = [vp, vp, vp, i64, vp, vp, vp, vp, i32, vp, i64, i64, i64, i64, i64, i32, vp, vp, vp, sz, vp]
     lib.miner_score_table_workspace_bytes.argtypes = [i64, i64, i64]
     lib.miner_score_table_workspace_bytes.restype = sz

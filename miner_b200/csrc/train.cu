@@ -139,7 +139,7 @@ __global__ void __launch_bounds__(TT) target_bwd_kernel(const void* __restrict__
                                                         const void* __restrict__ cand_ids, int id_dtype, const float* __restrict__ interests,
                                                         const float* __restrict__ Z, const float* __restrict__ d_scores,
                                                         const float* __restrict__ d_interests_in, int C, int K, int D,
-                                                        float* __restrict__ d_interests, float* __restrict__ dZ) {
+                                                        float* __restrict__ d_interests, float* __restrict__ dZ, float* __restrict__ grad_table) {
   extern __shared__ __align__(16) float smem[];
   float* Cd = smem;                      // [C][D] candidate vectors
   float* m = Cd + C * D;                 // [C][K] matching scores
@@ -214,6 +214,18 @@ __global__ void __launch_bounds__(TT) target_bwd_kernel(const void* __restrict__
     dIb[i] = gi;
     dZb[i] = gg * gelu_erf_grad(Zb[i]);
   }
+  if (grad_table) {
+    // gradient of the candidate rows: m = Cd I^T and a = Cd gelu(Z)^T are both linear in Cd (model.py:127,213)
+    for (int i = tid; i < C * D; i += TT) {
+      const int c = i / D, d = i - c * D;
+      const int64_t id = load_id(cand_ids, b * C + c, id_dtype);
+      if (id < 0 || id >= n_rows) continue;
+      float gc = 0.f;
+      for (int k = 0; k < K; ++k)
+        gc = fmaf(dm[c * K + k], Ib[static_cast<int64_t>(k) * D + d], fmaf(da[c * K + k], gelu_erf(Zb[static_cast<int64_t>(k) * D + d]), gc));
+      atomicAdd(grad_table + id * D + d, gc);
+    }
+  }
 }
 
 // ---- score_type 'max' / 'mean' (model.py:128-131): scores = max_k / mean_k of m[c,k] = Cd_c . I_k.  One CTA per impression:
@@ -221,7 +233,8 @@ __global__ void __launch_bounds__(TT) target_bwd_kernel(const void* __restrict__
 __global__ void __launch_bounds__(TT) target_bwd_simple_kernel(const void* __restrict__ table, int table_dtype, int64_t n_rows,
                                                                const void* __restrict__ cand_ids, int id_dtype, const float* __restrict__ interests,
                                                                const float* __restrict__ d_scores, const float* __restrict__ d_interests_in, int C,
-                                                               int K, int D, int score_type, float* __restrict__ d_interests) {
+                                                               int K, int D, int score_type, float* __restrict__ d_interests,
+                                                               float* __restrict__ grad_table) {
   extern __shared__ __align__(16) float smem[];
   float* Cd = smem;                      // [C][D] candidate vectors
   float* m = Cd + C * D;                 // [C][K] matching scores -> dm
@@ -262,6 +275,16 @@ __global__ void __launch_bounds__(TT) target_bwd_simple_kernel(const void* __res
     float gi = dIin ? dIin[i] : 0.f;
     for (int c = 0; c < C; ++c) gi = fmaf(m[c * K + k], Cd[c * D + d], gi);
     dIb[i] = gi;
+  }
+  if (grad_table) {
+    for (int i = tid; i < C * D; i += TT) {
+      const int c = i / D, d = i - c * D;
+      const int64_t id = load_id(cand_ids, b * C + c, id_dtype);
+      if (id < 0 || id >= n_rows) continue;
+      float gc = 0.f;
+      for (int k = 0; k < K; ++k) gc = fmaf(m[c * K + k], Ib[static_cast<int64_t>(k) * D + d], gc);
+      atomicAdd(grad_table + id * D + d, gc);
+    }
   }
 }
 
@@ -380,6 +403,39 @@ __global__ void __launch_bounds__(TT) poly_bwd_kernel(const void* __restrict__ t
     __syncthreads();
   }
   for (int i = tid; i < K * Dc; i += TT) dcodes_partial[static_cast<int64_t>(blockIdx.x) * K * Dc + i] = dcodes_s[i];
+}
+
+// ---- gradient of the history rows of the table (the table as a trainable parameter / the dense output of an upstream encoder):
+//      I = w E and T = tanh(E Wp^T) are the two places a history row enters (model.py:171,182), so
+//      dE[h] = sum_k w[k,h] dI[k] + dZ1[h] Wp   (dE2 = dZ1 Wp comes from a GEMM); rows are scattered with atomics (a news id can
+//      occur in many impressions).  Masked slots keep their softmax weight (the 1e-30 fill), so they get their gradient too.
+__global__ void __launch_bounds__(TT) hist_table_grad_kernel(const void* __restrict__ his_ids, int id_dtype, int64_t n_rows,
+                                                             const float* __restrict__ W, const float* __restrict__ dI_a,
+                                                             const float* __restrict__ dI_b, const float* __restrict__ dE2, int H, int K, int D,
+                                                             float* __restrict__ grad_table) {
+  extern __shared__ __align__(16) float smem[];
+  float* w = smem;                          // [K][H]
+  int64_t* ids_s = reinterpret_cast<int64_t*>(w + ((K * H + 1) & ~1));
+  const int tid = threadIdx.x;
+  const int64_t b = blockIdx.x;
+  for (int i = tid; i < K * H; i += TT) w[i] = W[b * K * H + i];
+  for (int h = tid; h < H; h += TT) {
+    const int64_t id = load_id(his_ids, b * H + h, id_dtype);
+    ids_s[h] = (id >= 0 && id < n_rows) ? id : -1;
+  }
+  __syncthreads();
+  for (int d = tid; d < D; d += TT) {
+    for (int h = 0; h < H; ++h) {
+      const int64_t id = ids_s[h];
+      if (id < 0) continue;
+      float g = dE2[(b * H + h) * D + d];
+      for (int k = 0; k < K; ++k) {
+        const int64_t o = (b * K + k) * D + d;
+        g = fmaf(w[k * H + h], dI_a[o] + (dI_b ? dI_b[o] : 0.f), g);
+      }
+      atomicAdd(grad_table + id * D + d, g);
+    }
+  }
 }
 
 // ---- out_partial[s][m][n] = sum over the rows r of split s of A[r][m] * Bm[r][n]   (A^T B over a row range);  Bm rows are
@@ -523,6 +579,11 @@ extern "C" size_t miner_train_workspace_bytes(int64_t B, int64_t H, int64_t K, i
   return train_ws(B, H, K, Dc, D, math).total;
 }
 
+extern "C" size_t miner_train_table_grad_workspace_bytes(int64_t B, int64_t H, int64_t Dc, int64_t D) {
+  if (B <= 0) return 256;
+  return align_up(sizeof(float) * static_cast<size_t>(D) * Dc, 256) + align_up(sizeof(float) * static_cast<size_t>(B) * H * D, 256);
+}
+
 extern "C" int miner_train_fwd(const void* table, int64_t n_rows, int table_dtype, const void* his_ids, const uint8_t* his_mask,
                                const void* cand_ids, int id_dtype, const float* w_proj, const float* codes, const float* w_target,
                                int64_t B, int64_t H, int64_t C, int64_t K, int64_t Dc, int64_t D, float* out_interests, float* out_scores,
@@ -599,9 +660,8 @@ extern "C" int miner_train_bwd(const void* table, int64_t n_rows, int table_dtyp
                                const float* save_t, const float* save_w, const float* interests, const float* save_z,
                                const float* d_scores, const float* d_interests, int64_t B, int64_t H, int64_t C, int64_t K, int64_t Dc,
                                int64_t D, float* grad_w_proj, float* grad_codes, float* grad_w_target, int math, const void* w_proj_bf16,
-                               const void* w_target_bf16, int score_type, float* d_bias_mean, void* workspace, size_t workspace_bytes,
-                               void* stream) {
-  (void)w_proj;
+                               const void* w_target_bf16, int score_type, float* d_bias_mean, float* grad_table, void* table_grad_ws,
+                               size_t table_grad_ws_bytes, void* workspace, size_t workspace_bytes, void* stream) {
   MINER_CHECK_ARG(B > 0 && H > 0 && C > 0 && K > 0 && Dc > 0 && D > 0 && n_rows > 0, "train_bwd: bad sizes");
   if (score_type != MINER_SCORE_MAX && score_type != MINER_SCORE_MEAN && score_type != MINER_SCORE_WEIGHTED) {
     set_error("Invalid method of aggregating matching score");
@@ -619,6 +679,10 @@ extern "C" int miner_train_bwd(const void* table, int64_t n_rows, int table_dtyp
   const TrainWs w = train_ws(B, H, K, Dc, D, math);
   if (!workspace || workspace_bytes < w.total) {
     set_error("train_bwd: workspace too small (%zu bytes needed)", w.total);
+    return MINER_ERR_WORKSPACE;
+  }
+  if (grad_table && (!w_proj || !table_grad_ws || table_grad_ws_bytes < miner_train_table_grad_workspace_bytes(B, H, Dc, D))) {
+    set_error("train_bwd: the table gradient needs w_proj and %zu bytes of its own workspace", miner_train_table_grad_workspace_bytes(B, H, Dc, D));
     return MINER_ERR_WORKSPACE;
   }
   auto st = static_cast<cudaStream_t>(stream);
@@ -640,7 +704,7 @@ extern "C" int miner_train_bwd(const void* table, int64_t n_rows, int table_dtyp
     }
     MINER_CUDA_OK(cudaFuncSetAttribute(target_bwd_simple_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, static_cast<int>(smem)));
     target_bwd_simple_kernel<<<static_cast<unsigned>(B), TT, smem, st>>>(table, table_dtype, n_rows, cand_ids, id_dtype, interests, d_scores,
-                                                                        d_interests, (int)C, (int)K, (int)D, score_type, dI);
+                                                                        d_interests, (int)C, (int)K, (int)D, score_type, dI, grad_table);
     MINER_LAUNCH_OK("target_bwd_simple");
   } else {
     const size_t smem = sizeof(float) * (static_cast<size_t>(C) * D + 4 * C * K);
@@ -650,7 +714,7 @@ extern "C" int miner_train_bwd(const void* table, int64_t n_rows, int table_dtyp
     }
     MINER_CUDA_OK(cudaFuncSetAttribute(target_bwd_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, static_cast<int>(smem)));
     target_bwd_kernel<<<static_cast<unsigned>(B), TT, smem, st>>>(table, table_dtype, n_rows, cand_ids, id_dtype, interests, save_z, d_scores,
-                                                                 d_interests, (int)C, (int)K, (int)D, dI, dZ);
+                                                                 d_interests, (int)C, (int)K, (int)D, dI, dZ, grad_table);
     MINER_LAUNCH_OK("target_bwd");
   }
   // 2. Z = I Wt^T:  dI2 = dZ Wt  (as dZ (Wt^T)^T with the NT GEMM),  dWt = dZ^T I
@@ -703,6 +767,22 @@ extern "C" int miner_train_bwd(const void* table, int64_t n_rows, int table_dtyp
     MINER_LAUNCH_OK("poly_bwd");
     sum_partials_kernel<<<static_cast<int>((K * Dc + 255) / 256), 256, 0, st>>>(pCodes, w.g_poly, K * Dc, grad_codes);
     MINER_LAUNCH_OK("sum_partials(dcodes)");
+  }
+  // 3b. gradient of the history rows of the table: dE = w^T dI + dZ1 Wp, scattered by news id
+  if (grad_table) {
+    char* tg = static_cast<char*>(table_grad_ws);
+    float* WpT = reinterpret_cast<float*>(tg);                                                       // (D, Dc)
+    float* dE2 = reinterpret_cast<float*>(tg + align_up(sizeof(float) * D * Dc, 256));               // (B H, D)
+    dim3 tb(32, 8), tgd(static_cast<unsigned>((D + 31) / 32), static_cast<unsigned>((Dc + 31) / 32));
+    transpose_kernel<<<tgd, tb, 0, st>>>(w_proj, WpT, (int)Dc, (int)D);
+    MINER_LAUNCH_OK("transpose(Wp)");
+    int rc = launch_sgemm_nt(dZ1, MINER_F32, nullptr, id_dtype, 0, WpT, dE2, B * H, D, Dc, EPI_NONE, st);
+    if (rc) return rc;
+    const size_t smem = sizeof(float) * ((static_cast<size_t>(K) * H + 1) & ~static_cast<size_t>(1)) + sizeof(int64_t) * H;
+    MINER_CUDA_OK(cudaFuncSetAttribute(hist_table_grad_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, static_cast<int>(smem)));
+    hist_table_grad_kernel<<<static_cast<unsigned>(B), TT, smem, st>>>(his_ids, id_dtype, n_rows, save_w, dI, dI2, dE2, (int)H, (int)K, (int)D,
+                                                                      grad_table);
+    MINER_LAUNCH_OK("hist_table_grad");
   }
   // 4. Z1 = E Wp^T:  dWp = dZ1^T E  (E gathered from the table)
   if (tensor) {

@@ -18,8 +18,9 @@ State-dict keys match the reference (``poly_attn.linear.weight``, ``poly_attn.co
 
 All arithmetic runs in the sm_100a kernels of libminer_b200.so through ``miner_b200.ops``; there is no
 PyTorch fallback -- CPU tensors raise.  The train variant has real backward kernels for the
-table-based forward with ``score_type='weighted'`` and no category bias (``miner_train_fwd`` / ``miner_train_bwd``); every other
-forward under autograd still works, and calling ``.backward()`` through it raises NotImplementedError.
+table-based forward (``miner_train_fwd`` / ``miner_train_bwd``: every ``score_type``, with or without the category bias, optional
+sparse gradient of the table rows); the op-level modules on dense tensors (``PolyAttention`` / ``TargetAwareAttention`` behind a
+generic encoder) still run forward under autograd and raise NotImplementedError on ``.backward()``.
 """
 from __future__ import annotations
 
@@ -42,17 +43,17 @@ class _NoBackward(torch.autograd.Function):
 
     @staticmethod
     def backward(ctx, *grads):
-        raise NotImplementedError('miner_b200: backward kernels exist for the table-based forward with score_type="weighted" and no '
-                                  'category bias (SURVEY.md section 8 f1); this path has none')
+        raise NotImplementedError('miner_b200: the backward kernels belong to Miner.forward (any encoder, any score_type, with or without '
+                                  'the category bias); the op-level modules called on their own have none')
 
 
 class _MinerTrainFn(torch.autograd.Function):
     """Train variant of the table-based forward: ``miner_train_fwd`` / ``miner_train_bwd``."""
 
     @staticmethod
-    def forward(ctx, w_proj: Tensor, codes: Tensor, w_target: Tensor, table: Tensor, his_ids: Tensor, his_mask: Tensor, cand_ids: Tensor,
-                math: int):
-        interests, scores, saved = ops.train_forward(table, his_ids, his_mask, cand_ids, w_proj, codes, w_target, math)
+    def forward(ctx, w_proj: Tensor, codes: Tensor, w_target: Optional[Tensor], bias_mean: Optional[Tensor], table: Tensor,
+                his_ids: Tensor, his_mask: Tensor, cand_ids: Tensor, math: int, score_type: str):
+        interests, scores, saved = ops.train_forward(table, his_ids, his_mask, cand_ids, w_proj, codes, w_target, math, score_type, bias_mean)
         # the big intermediates go through save_for_backward (in-place changes are detected, and saving the OUTPUT `interests` this
         # way does not tie output -> grad_fn -> ctx -> output into a cycle that only the cyclic GC would free: ~3 GB per step)
         ctx.save_for_backward(saved.t, saved.w, saved.z, interests)
@@ -64,10 +65,13 @@ class _MinerTrainFn(torch.autograd.Function):
     def backward(ctx, d_interests, d_scores):
         saved = ctx.meta
         saved.t, saved.w, saved.z, saved.interests = ctx.saved_tensors
-        gwp, gc, gwt = ops.train_backward(saved, d_scores, d_interests)
+        want_table = ctx.needs_input_grad[4]
+        gwp, gc, gwt, dbias, gtab = ops.train_backward(saved, d_scores, d_interests, want_table_grad=want_table)
         saved.t = saved.w = saved.z = saved.interests = saved.ws = None          # release the step's buffers now, not at GC time
         ctx.meta = None
-        return gwp, gc, gwt, None, None, None, None, None
+        if gtab is not None and gtab.dtype != saved.table.dtype:
+            gtab = gtab.to(saved.table.dtype)
+        return gwp, gc, gwt, dbias, gtab, None, None, None, None, None
 
 
 def _attach(out: Tensor, *params: Tensor) -> Tensor:
@@ -84,9 +88,13 @@ class TableNewsEncoder(nn.Module):
     ``table`` is (N, D) float32 or bfloat16 on the GPU; row 0 is the pad news.
     """
 
-    def __init__(self, table: Tensor):
+    def __init__(self, table: Tensor, trainable: bool = False):
         super().__init__()
-        self.register_buffer('table', table.detach().contiguous())
+        if trainable:
+            # the table as a parameter: the train variant returns the gradient of its rows (sparse scatter-add, miner_train_bwd)
+            self.table = nn.Parameter(table.detach().contiguous().clone())
+        else:
+            self.register_buffer('table', table.detach().contiguous())
 
     @property
     def embed_dim(self) -> int:
@@ -231,9 +239,16 @@ class Miner(nn.Module):
         self._table_proj = None
 
     def _bias_mean(self, his_category: Tensor, category: Tensor) -> Tensor:
-        if self.training and self.category_dropout.p > 0:
-            raise NotImplementedError('miner_b200: category dropout in train mode belongs to the train variant (section 8 f1)')
-        mean, _ = ops.category_bias(self.category_embedding.weight, his_category, category)      # model.py:113-120,176
+        """``category_bias.mean(dim=2)`` (model.py:113-120,176).  Inference: the ``miner_category_bias`` kernel.  Under autograd the
+        (B,H,Ec) x (B,Ec,C) cosine with its train-mode dropout is the reference's own handful of torch ops on tiny tensors, so the
+        category embedding gets its gradient through torch autograd; the scoring kernels take ``bias_mean`` and return its gradient."""
+        if torch.is_grad_enabled() and (self.category_embedding.weight.requires_grad or self.training):
+            he = self.category_dropout(self.category_embedding(his_category))              # model.py:113-114
+            ce = self.category_dropout(self.category_embedding(category))                  # model.py:115-116
+            he = torch.div(he, torch.linalg.norm(he, dim=2, keepdim=True))                 # utils.py:21-23
+            ce = torch.div(ce, torch.linalg.norm(ce, dim=2, keepdim=True))
+            return torch.matmul(he, ce.permute(0, 2, 1)).mean(dim=2)                       # model.py:176
+        mean, _ = ops.category_bias(self.category_embedding.weight, his_category, category)
         return mean
 
     def forward(self, title: Tensor, title_mask: Tensor, his_title: Tensor, his_title_mask: Tensor,
@@ -258,13 +273,13 @@ class Miner(nn.Module):
             w = self._weights(with_bf16=(math == L.MATH_TENSOR))
             cand_ids = title.reshape(batch_size, num_candidates, -1)[..., 0]
             his_ids = his_title.reshape(batch_size, his_length, -1)[..., 0]
-            if (torch.is_grad_enabled() and self.score_type == 'weighted' and not self.use_category_bias
-                    and any(p.requires_grad for p in self.parameters())):
+            if torch.is_grad_enabled() and any(p.requires_grad for p in self.parameters()):
                 # train variant (reference trainer.py:246-261): forward that keeps its intermediates + real backward kernels
-                return _MinerTrainFn.apply(self.poly_attn.linear.weight, self.poly_attn.context_codes,
-                                           self.target_aware_attn.linear.weight, table, his_ids, his_mask, cand_ids,
+                wt = self.target_aware_attn.linear.weight if self.score_type == 'weighted' else None
+                return _MinerTrainFn.apply(self.poly_attn.linear.weight, self.poly_attn.context_codes, wt, bias_mean, table, his_ids,
+                                           his_mask, cand_ids,
                                            L.MATH_TENSOR if (self.train_math == 'tensor' and table.dtype == torch.bfloat16
-                                                             and table.shape[1] % 64 == 0) else L.MATH_FP32)
+                                                             and table.shape[1] % 64 == 0) else L.MATH_FP32, self.score_type)
             if self.table_level and table.dtype == torch.bfloat16 and ops.score_table_supported(his_length, self.poly_attn.context_codes.shape[0],
                                                                                                table.shape[1]):
                 interests, scores = ops.score_table(self.table_projections(), his_ids, his_mask, cand_ids, self.score_type,
@@ -288,6 +303,18 @@ class Miner(nn.Module):
             his_sapo_mask = his_sapo_mask.view(batch_size * his_length, -1)
             history_repr = self.news_encoder(title_encoding=his_title, title_attn_mask=his_title_mask,
                                              sapo_encoding=his_sapo, sapo_attn_mask=his_sapo_mask).view(batch_size, his_length, -1)
+            if torch.is_grad_enabled() and (history_repr.requires_grad or any(p.requires_grad for p in self.parameters())):
+                # train variant behind ANY differentiable encoder: its dense outputs are the "table" (rows = the B*H history vectors
+                # followed by the B*C candidate vectors), the ids are just row numbers, and the table-row gradient of the backward
+                # kernels is d loss / d encoder output -- autograd carries it on into the encoder (reference trainer.py:146-169)
+                D = history_repr.shape[-1]
+                dev = history_repr.device
+                virt = torch.cat([history_repr.reshape(-1, D), candidate_repr.reshape(-1, D)], dim=0).float()
+                hid = torch.arange(batch_size * his_length, device=dev).view(batch_size, his_length)
+                cid = (batch_size * his_length + torch.arange(batch_size * num_candidates, device=dev)).view(batch_size, num_candidates)
+                wt = self.target_aware_attn.linear.weight if self.score_type == 'weighted' else None
+                return _MinerTrainFn.apply(self.poly_attn.linear.weight, self.poly_attn.context_codes, wt, bias_mean, virt, hid, his_mask, cid,
+                                           L.MATH_FP32, self.score_type)
             interests = ops.poly_attention(history_repr, his_mask, self.poly_attn.linear.weight, self.poly_attn.context_codes,
                                            bias_mean)
             wt = self.target_aware_attn.linear.weight if self.score_type == 'weighted' else None

@@ -556,14 +556,20 @@ class TrainSaved:
 
 
 def train_forward(table: torch.Tensor, his_ids: torch.Tensor, his_mask: torch.Tensor, cand_ids: torch.Tensor,
-                  w_proj: torch.Tensor, codes: torch.Tensor, w_target: torch.Tensor, math: int = L.MATH_FP32):
-    """Miner.forward (reference model.py:61-138, 'weighted', no category bias) keeping what the backward needs.
+                  w_proj: torch.Tensor, codes: torch.Tensor, w_target: Optional[torch.Tensor], math: int = L.MATH_FP32,
+                  score_type: str = 'weighted', bias_mean: Optional[torch.Tensor] = None):
+    """Miner.forward (reference model.py:61-138) keeping what the backward needs; any ``score_type``, optional category-bias
+    scalar ``bias_mean`` (B,H) (model.py:176-177).
 
     Dense layout, ``cand_ids`` (B,C).  Returns ``(interests (B,K,D), scores (B,C), saved)``.  ``math=MATH_TENSOR`` runs the
     projection-sized GEMMs of the step on tcgen05 with bf16 operands (bf16 table, D % 64 == 0).
     """
-    dev = _need_cuda(table, his_ids, his_mask, cand_ids, w_proj, codes, w_target)
+    dev = _need_cuda(table, his_ids, his_mask, cand_ids, w_proj, codes, w_target, bias_mean)
     lib = L.load()
+    st = L.SCORE_TYPES.get(score_type, -1)
+    if st < 0:
+        raise ValueError('Invalid method of aggregating matching score')
+    weighted = st == L.SCORE_WEIGHTED
     table = table.detach().contiguous()
     B, H = his_ids.shape
     Cn = cand_ids.shape[1]
@@ -574,39 +580,51 @@ def train_forward(table: torch.Tensor, his_ids: torch.Tensor, his_mask: torch.Te
     if it != it2:
         cid, it2 = _ids(cand_ids.to(his_ids.dtype))
     m = _mask_u8(his_mask)
-    wp, cd, wt = _f32(w_proj), _f32(codes), _f32(w_target)
+    wp, cd = _f32(w_proj), _f32(codes)
+    wt = _f32(w_target) if weighted else None
+    bm = _f32(bias_mean) if bias_mean is not None else None
     f = dict(dtype=torch.float32, device=dev)
     interests, scores = torch.empty(B, K, D, **f), torch.empty(B, Cn, **f)
-    t, w, z = torch.empty(B * H, Dc, **f), torch.empty(B, K, H, **f), torch.empty(B * K, D, **f)
+    t, w = torch.empty(B * H, Dc, **f), torch.empty(B, K, H, **f)
+    z = torch.empty(B * K, D, **f) if weighted else None
     wp16 = cast_bf16(wp) if math == L.MATH_TENSOR else None
-    wt16 = cast_bf16(wt) if math == L.MATH_TENSOR else None
+    wt16 = cast_bf16(wt) if (math == L.MATH_TENSOR and weighted) else None
     ws_bytes = lib.miner_train_workspace_bytes(B, H, K, Dc, D, math)
     ws = torch.empty(max(ws_bytes, 1), dtype=torch.uint8, device=dev)
     with torch.cuda.device(dev):
         L.check(lib.miner_train_fwd(_ptr(table), table.shape[0], _table_dtype(table), _ptr(hid), _ptr(m), _ptr(cid), it, _ptr(wp), _ptr(cd),
                                     _ptr(wt), B, H, Cn, K, Dc, D, _ptr(interests), _ptr(scores), _ptr(t), _ptr(w), _ptr(z), math,
-                                    _ptr(wp16), _ptr(wt16), _ptr(ws), ws.numel(), _stream()))
+                                    _ptr(wp16), _ptr(wt16), st, _ptr(bm), _ptr(ws), ws.numel(), _stream()))
     saved = TrainSaved(table=table, his_ids=hid, his_mask=m, cand_ids=cid, id_dtype=it, w_proj=wp, codes=cd, w_target=wt, t=t, w=w, z=z,
-                       interests=interests, ws=ws, dims=(B, H, Cn, K, Dc, D), math=math, w_proj_bf16=wp16, w_target_bf16=wt16)
+                       interests=interests, ws=ws, dims=(B, H, Cn, K, Dc, D), math=math, w_proj_bf16=wp16, w_target_bf16=wt16,
+                       score_type=st, has_bias=bm is not None)
     return interests, scores, saved
 
 
-def train_backward(saved: TrainSaved, d_scores: Optional[torch.Tensor], d_interests: Optional[torch.Tensor]):
-    """Gradients of the three weight matrices: ``(grad_w_proj (Dc,D), grad_codes (K,Dc), grad_w_target (D,D))``."""
+def train_backward(saved: TrainSaved, d_scores: Optional[torch.Tensor], d_interests: Optional[torch.Tensor], want_table_grad: bool = False):
+    """Gradients ``(grad_w_proj (Dc,D), grad_codes (K,Dc), grad_w_target (D,D) or None, d_bias_mean (B,H) or None,
+    grad_table (N,D) fp32 or None)``."""
     lib = L.load()
     B, H, Cn, K, Dc, D = saved.dims
     dev = saved.table.device
     f = dict(dtype=torch.float32, device=dev)
+    weighted = saved.score_type == L.SCORE_WEIGHTED
     ds = _f32(d_scores) if d_scores is not None else torch.zeros(B, Cn, **f)
     di = _f32(d_interests) if d_interests is not None else None
-    gwp, gc, gwt = torch.empty(Dc, D, **f), torch.empty(K, Dc, **f), torch.empty(D, D, **f)
+    gwp, gc = torch.empty(Dc, D, **f), torch.empty(K, Dc, **f)
+    gwt = torch.empty(D, D, **f) if weighted else None
+    dbias = torch.empty(B, H, **f) if saved.has_bias else None
+    gtab = torch.zeros(saved.table.shape[0], D, **f) if want_table_grad else None
+    tg_bytes = int(lib.miner_train_table_grad_workspace_bytes(B, H, Dc, D)) if want_table_grad else 0
+    tg_ws = torch.empty(tg_bytes, dtype=torch.uint8, device=dev) if want_table_grad else None
     with torch.cuda.device(dev):
         L.check(lib.miner_train_bwd(_ptr(saved.table), saved.table.shape[0], _table_dtype(saved.table), _ptr(saved.his_ids),
                                     _ptr(saved.his_mask), _ptr(saved.cand_ids), saved.id_dtype, _ptr(saved.w_proj), _ptr(saved.codes),
                                     _ptr(saved.w_target), _ptr(saved.t), _ptr(saved.w), _ptr(saved.interests), _ptr(saved.z), _ptr(ds),
                                     _ptr(di), B, H, Cn, K, Dc, D, _ptr(gwp), _ptr(gc), _ptr(gwt), saved.math, _ptr(saved.w_proj_bf16),
-                                    _ptr(saved.w_target_bf16), _ptr(saved.ws), saved.ws.numel(), _stream()))
-    return gwp, gc, gwt
+                                    _ptr(saved.w_target_bf16), saved.score_type, _ptr(dbias), _ptr(gtab), _ptr(tg_ws), tg_bytes, _ptr(saved.ws),
+                                    saved.ws.numel(), _stream()))
+    return gwp, gc, gwt, dbias, gtab
 
 
 def loss_backward(interests: torch.Tensor, logits: torch.Tensor, labels: torch.Tensor, grad_out: Optional[torch.Tensor] = None):

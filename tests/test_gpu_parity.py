@@ -278,14 +278,18 @@ def _forward_with_grad(m, x):
 
 
 def test_backward_fails_loudly():
-    """Paths without backward kernels ('max' / 'mean' aggregation, category bias) raise instead of returning wrong gradients."""
+    """The op-level modules called on their own (dense tensors, outside Miner.forward) have no backward kernels: they raise instead
+    of returning wrong gradients.  Miner.forward itself is differentiable on every branch (test_train_gradients_every_branch)."""
+    import miner_b200 as mb
     g = load_golden('model_small')
     x = golden_model_inputs(g)
-    m = build_miner(x, 'max').train()
-    I, S = _forward_with_grad(m, x)
-    assert S.requires_grad
+    D, (K, Dc) = x['table'].shape[1], x['codes'].shape
+    pa = mb.PolyAttention(D, K, Dc).to(DEV)
+    emb = x['table'].to(DEV)[x['his_ids'].to(DEV)].float().requires_grad_(True)
+    out = pa(emb, x['his_mask'].to(DEV))
+    assert out.requires_grad
     with pytest.raises(NotImplementedError):
-        S.sum().backward()
+        out.sum().backward()
 
 
 @pytest.mark.parametrize('name', MODELS)
@@ -1068,6 +1072,93 @@ def test_miner_forward_table_level_matches_reference(name):
     B, C = x['cand'].shape
     s_csr = m.score_impressions(x['his_ids'].to(DEV), x['his_mask'].to(DEV), x['cand'].reshape(-1).to(DEV), (torch.arange(B + 1) * C).to(DEV))
     assert torch.equal(s_csr.view(B, C), S.detach())
+
+
+# ------------------------------------------------------------------------------------------------ train variant: every branch
+@pytest.mark.parametrize('score_type', ['weighted', 'max', 'mean'])
+@pytest.mark.parametrize('use_bias', [False, True])
+def test_train_gradients_every_branch(score_type, use_bias):
+    """SURVEY section 8 f1 edges: backward for score_type 'max' / 'mean' (model.py:128-131), for the category-bias branch
+    (model.py:113-120,176: the category embedding gets its gradient) and the gradient of the table ROWS (the table as a
+    trainable parameter), against autograd through the oracle (= the reference's own operation order).  Dropout p = 0 so that
+    both sides see the same bias; fp32, tolerance 1e-3 normwise (measured ~1e-6)."""
+    import torch.nn as nn
+    import miner_b200 as mb
+    from miner_b200 import synth
+    B, H, N, D, K, Dc, NC, Ec = 12, 12, 60, 64, 8, 24, 7, 10
+    table = synth.make_table(N, D, 3)
+    w = synth.make_weights(D, K, Dc, 3, NC, Ec)
+    his, mask, hcat, cand, ccat, labels = synth.make_train_batch(B, H, N, 4, 3, NC)
+    kw = dict(num_category=NC, category_embed_dim=Ec, category_pad_token_id=0) if use_bias else {}
+    m = mb.Miner(mb.TableNewsEncoder(table.to(DEV), trainable=True), use_bias, K, Dc, score_type, 0.0, **kw).to(DEV).train()
+    with torch.no_grad():
+        m.poly_attn.linear.weight.copy_(w.w_proj); m.poly_attn.context_codes.copy_(w.context_codes)
+        if score_type == 'weighted':
+            m.target_aware_attn.linear.weight.copy_(w.w_target)
+        if use_bias:
+            m.category_embedding.weight.copy_(w.cat_emb)
+    z, zh = torch.zeros(B, 5, 1, dtype=torch.long, device=DEV), torch.zeros(B, H, 1, dtype=torch.long, device=DEV)
+    I, S = m(cand.to(DEV)[..., None], z, his.to(DEV)[..., None], zh, mask.to(DEV), z, z, zh, zh,
+             category=ccat.to(DEV) if use_bias else None, his_category=hcat.to(DEV) if use_bias else None)
+    loss = mb.Loss(nn.CrossEntropyLoss(reduction='mean')).compute(I, S, labels.to(DEV))
+    loss.backward()
+    # oracle autograd
+    tp = table.clone().requires_grad_(True)
+    ps = [t.clone().requires_grad_(True) for t in (w.w_proj, w.context_codes, w.w_target)]
+    ce = w.cat_emb.clone().requires_grad_(True) if use_bias else None
+    Io, So = O.miner_forward(tp, his, mask, cand, ps[0], ps[1], ps[2] if score_type == 'weighted' else None, score_type,
+                             ce, hcat if use_bias else None, ccat if use_bias else None)
+    lo = O.loss_compute(Io, So, labels.float())
+    lo.backward()
+    assert abs(loss.item() - lo.item()) < 1e-5 * max(1.0, abs(lo.item()))
+    pairs = [(m.poly_attn.linear.weight.grad, ps[0].grad), (m.poly_attn.context_codes.grad, ps[1].grad), (m.news_encoder.table.grad, tp.grad)]
+    if score_type == 'weighted':
+        pairs.append((m.target_aware_attn.linear.weight.grad, ps[2].grad))
+    if use_bias:
+        pairs.append((m.category_embedding.weight.grad[1:], ce.grad[1:]))       # row 0 = padding_idx: no gradient
+    for got, ref in pairs:
+        assert got is not None and torch.isfinite(got).all()
+        assert _nerr(got.cpu(), ref) < 1e-3, (score_type, use_bias, _nerr(got.cpu(), ref))
+
+
+def test_train_through_a_generic_encoder():
+    """Miner.forward behind a differentiable news encoder that is NOT a table (the reference trains its RoBERTa encoder,
+    trainer.py:146-169): the encoder's dense outputs take the table's place in the train kernels and d loss / d outputs flows on
+    into the encoder by autograd."""
+    import torch.nn as nn
+    import miner_b200 as mb
+    from miner_b200 import synth
+    B, H, N, D, K, Dc = 10, 9, 40, 64, 8, 24
+    table = synth.make_table(N, D, 5)
+    w = synth.make_weights(D, K, Dc, 5)
+    his, mask, _, cand, _, labels = synth.make_train_batch(B, H, N, 4, 5)
+
+    class Enc(nn.Module):                                   # NewsEncoder call contract; a linear map of looked-up rows
+        embed_dim = D
+
+        def __init__(self):
+            super().__init__()
+            self.emb = nn.Parameter(table.clone())
+            self.mix = nn.Parameter(torch.eye(D) + 0.01 * torch.randn(D, D, generator=torch.Generator().manual_seed(1)))
+
+        def forward(self, title_encoding, title_attn_mask, sapo_encoding=None, sapo_attn_mask=None):
+            return self.emb[title_encoding[:, 0]] @ self.mix
+
+    enc = Enc().to(DEV)
+    m = mb.Miner(enc, False, K, Dc, 'weighted', 0.0).to(DEV).train()
+    with torch.no_grad():
+        m.poly_attn.linear.weight.copy_(w.w_proj); m.poly_attn.context_codes.copy_(w.context_codes); m.target_aware_attn.linear.weight.copy_(w.w_target)
+    z, zh = torch.zeros(B, 5, 1, dtype=torch.long, device=DEV), torch.zeros(B, H, 1, dtype=torch.long, device=DEV)
+    I, S = m(cand.to(DEV)[..., None], z, his.to(DEV)[..., None], zh, mask.to(DEV), z, z, zh, zh)
+    mb.Loss(nn.CrossEntropyLoss(reduction='mean')).compute(I, S, labels.to(DEV)).backward()
+    emb = table.clone().requires_grad_(True)
+    mix = enc.mix.detach().cpu().clone().requires_grad_(True)
+    ps = [t.clone().requires_grad_(True) for t in (w.w_proj, w.context_codes, w.w_target)]
+    Io, So = O.miner_forward(emb @ mix, his, mask, cand, ps[0], ps[1], ps[2], 'weighted')
+    O.loss_compute(Io, So, labels.float()).backward()
+    for got, ref in ((enc.emb.grad, emb.grad), (enc.mix.grad, mix.grad), (m.poly_attn.linear.weight.grad, ps[0].grad),
+                     (m.target_aware_attn.linear.weight.grad, ps[2].grad)):
+        assert _nerr(got.cpu(), ref) < 1e-3
 
 
 # ------------------------------------------------------------------------------------------------ rank-count invariance
