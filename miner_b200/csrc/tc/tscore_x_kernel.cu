@@ -37,7 +37,10 @@ constexpr int KM = 32;                       // context codes covered (K <= 32)
 constexpr int SL = 112;                      // slot capacity of a tile: IPT * ((H + 1) & ~1) <= 112, i.e. at most 7 16-slot K-steps
 constexpr int NKS_MAX = SL / 16;
 constexpr int NCM = 80;                      // candidate columns per pass
-constexpr int S1 = 4, S2 = 5;                // ring depths: (E, TW) blocks / candidate blocks
+#ifndef MINER_TSX_S2
+#define MINER_TSX_S2 5
+#endif
+constexpr int S1 = 4, S2 = MINER_TSX_S2;     // ring depths: (E, TW) blocks / candidate blocks
 constexpr int E_BYTES = SL * FB * 2;         // 14 KB
 constexpr int ST1_BYTES = 2 * E_BYTES;       // E | TW
 constexpr int C_BYTES = NCM * FB * 2;        // 10 KB
@@ -60,8 +63,15 @@ static_assert(G1_STEP == 16, "a gather thread's row jj is 16-row group jj: one K
 constexpr int W_G2 = T_G1 / 32, W_MMA = W_G2 + T_G2 / 32, W_EPI0 = W_MMA + 1, W_SMX0 = W_EPI0 + T_EPI / 32, W_SCR0 = W_SMX0 + T_SMX / 32;
 constexpr int W_SX = W_SCR0 + T_SCR / 32;      // the SX issuer: its MMA chain shares no accumulator with S1 / S2, so it runs in its own warp
 constexpr int T_THREADS = (W_SX + 1) * 32;
-constexpr uint32_t AW_COL = 0, DP_COL = 128, DX_COL = 256, DA_COL = DX_COL + NCM;   // A_w x 2 | D_P x 2 | D_X | D_a x 2
-static_assert(DA_COL + 2 * NCM <= 512 && DX_COL + NCM - 1 + CC <= 512, "tensor memory map");
+#ifndef MINER_TSX_NDP
+#define MINER_TSX_NDP 2
+#endif
+constexpr int NDP = MINER_TSX_NDP;           // D_P buffers; S2 of a block is issued LAG = NDP - 1 blocks after its S1, so the epilogue warps
+constexpr int LAG = NDP - 1;                 // always have a finished S1 waiting for them
+constexpr int NDA = NDP == 2 ? 2 : 1;        // D_a buffers (what fits)
+constexpr uint32_t AW_COL = 0, DP_COL = 128, DX_COL = DP_COL + 64 * NDP, DA_COL = DX_COL + NCM;   // A_w x 2 | D_P x NDP | D_X | D_a x NDA
+static_assert(DA_COL + NDA * NCM <= 512 && DX_COL + NCM - 1 + CC <= 512, "tensor memory map");
+static_assert(S2 >= LAG + 2, "a candidate stage is held from SX of its block to S2 of its block");
 
 // ablation switches for A/B timing runs (results are wrong by construction): -DMINER_TSX_ABL=<bits>
 //   1 score warps without their arithmetic   2 softmax warps store zeros   4 epilogue without the gelu   8 no SX MMAs   16 no S2 MMAs
@@ -73,7 +83,7 @@ constexpr int ABL = MINER_TSX_ABL;
 
 struct XBarriers {
   uint64_t full1[S1], empty1[S1], full2[S2], empty2[S2];
-  uint64_t w_ready[2], w_free[2], ip_full[2], a_ready[2], x_full, x_free, dma_full[2], dma_free[2];
+  uint64_t w_ready[2], w_free[2], ip_full[NDP], a_ready[NDP], x_full, x_free, dma_full[NDA], dma_free[NDA];
   uint32_t tmem_base;
 };
 
@@ -130,9 +140,9 @@ tscore_x_kernel(const TScoreArgs args, int n_tiles) {
     for (int s = 0; s < S2; ++s) { tc::mbar_init(&bars->full2[s], T_G2); tc::mbar_init(&bars->empty2[s], 2); }
     for (int b = 0; b < 2; ++b) {
       tc::mbar_init(&bars->w_ready[b], T_SMX); tc::mbar_init(&bars->w_free[b], T_SCR + 1);
-      tc::mbar_init(&bars->ip_full[b], 1); tc::mbar_init(&bars->a_ready[b], T_EPI);
-      tc::mbar_init(&bars->dma_full[b], 1); tc::mbar_init(&bars->dma_free[b], T_SCR);
     }
+    for (int b = 0; b < NDP; ++b) { tc::mbar_init(&bars->ip_full[b], 1); tc::mbar_init(&bars->a_ready[b], T_EPI); }
+    for (int b = 0; b < NDA; ++b) { tc::mbar_init(&bars->dma_full[b], 1); tc::mbar_init(&bars->dma_free[b], T_SCR); }
     tc::mbar_init(&bars->x_full, 1);
     tc::mbar_init(&bars->x_free, T_SCR);
     tc::fence_barrier_init();
@@ -266,18 +276,24 @@ tscore_x_kernel(const TScoreArgs args, int n_tiles) {
   } else if (warp == W_MMA) {
     // ------------------------------------------------------------------ MMA issuer
     const uint32_t idesc1 = tc::make_idesc_bf16_f32_major(TM, FB, false, true);   // S1: N = 64 features, B (the TW half of the stage) MN-major
-    uint32_t g1 = 0, g2 = 0, u = 0;                              // blocks issued (S1 + SX / S2), units
-    bool pending = false;
-    int pend_j = 0, pend_nc16 = 16;
-    uint32_t pend_u = 0;
+    uint32_t g1 = 0, g2 = 0, u = 0;                              // blocks issued (S1 / S2), units
+    // blocks whose S1 is issued and whose S2 is still to come (at most LAG): block index in its unit | nc16 << 8 | unit << 16
+    uint32_t pq[LAG] = {0u};
+    int npend = 0;
     PROF_DECL;
-    auto stage2 = [&]() {                                        // S2 of block g2
-      const uint32_t b = g2 & 1;
+    auto stage2 = [&]() {                                        // S2 of block g2 = the oldest pending block
+      const uint32_t pend = pq[0];
+#pragma unroll
+      for (int i = 0; i + 1 < LAG; ++i) pq[i] = pq[i + 1];
+      --npend;
+      const int pend_j = static_cast<int>(pend & 0xffu), pend_nc16 = static_cast<int>((pend >> 8) & 0xffu);
+      const uint32_t pend_u = pend >> 16;
+      const uint32_t b = g2 % NDP;
       PROF_ADD(0);
-      tc::mbar_wait(&bars->a_ready[b], (g2 >> 1) & 1);
+      tc::mbar_wait(&bars->a_ready[b], (g2 / NDP) & 1);
       PROF_ADD(4);
-      const uint32_t db = pend_u & 1;                            // D_a buffer of the unit
-      if (pend_j == 0) tc::mbar_wait(&bars->dma_free[db], ((pend_u >> 1) & 1) ^ 1);   // the attention logits of unit u - 2 are out of it
+      const uint32_t db = NDA == 2 ? (pend_u & 1) : 0;           // D_a buffer of the unit
+      if (pend_j == 0) tc::mbar_wait(&bars->dma_free[db], (((NDA == 2 ? pend_u >> 1 : pend_u) & 1) ^ 1));   // the previous user's attention logits are out of it
       PROF_ADD(6);
       tc::tcgen05_fence_after();
       const uint32_t s = g2 % S2;
@@ -315,7 +331,7 @@ tscore_x_kernel(const TScoreArgs args, int n_tiles) {
         tc::tcgen05_fence_after();
         const uint32_t aw = tmem + AW_COL + 64 * wb;
         for (int j = 0; j < KB; ++j) {
-          const uint32_t b = g1 & 1;
+          const uint32_t b = g1 % NDP;
           const uint32_t d_p = tmem + DP_COL + b * 64;
           const uint32_t s = g1 % S1, ph = (g1 / S1) & 1;
           PROF_ADD(0);
@@ -325,7 +341,13 @@ tscore_x_kernel(const TScoreArgs args, int n_tiles) {
           const uint32_t st_addr = tc::smem_u32(st1 + s * ST1_BYTES);
           const uint64_t tw_desc = tc::make_smem_desc_sw128_mn(st_addr + E_BYTES);
           if (tc::elect_one()) {
+#ifdef MINER_TSX_S1_UNROLL
+#pragma unroll
+            for (int ks = 0; ks < NKS_MAX; ++ks)
+              if (ks < nks) tc::umma_bf16_ts(d_p, aw + 8 * ks, tw_desc + ks * (2048 >> 4), idesc1, ks != 0 ? 1u : 0u);
+#else
             for (int ks = 0; ks < nks; ++ks) tc::umma_bf16_ts(d_p, aw + 8 * ks, tw_desc + ks * (2048 >> 4), idesc1, ks != 0 ? 1u : 0u);
+#endif
             tc::umma_commit(&bars->ip_full[b]);
             tc::umma_commit(&bars->empty1[s]);
             if (j == KB - 1) tc::umma_commit(&bars->w_free[wb]);   // (the score warps read A_w too: they arrive on it themselves)
@@ -334,12 +356,17 @@ tscore_x_kernel(const TScoreArgs args, int n_tiles) {
           PROF_ADD(3);
           ++g1;
           PROF_ADD(9);
-          if (pending) stage2();
-          pending = true; pend_j = j; pend_nc16 = nc16; pend_u = u;
+          if (npend == LAG) stage2();
+          pq[LAG - 1] = static_cast<uint32_t>(j) | (static_cast<uint32_t>(nc16) << 8) | (u << 16);
+          if (npend < LAG - 1) {                                 // (start-up only: keep the queue packed at its front)
+#pragma unroll
+            for (int i = 0; i + 1 < LAG; ++i) if (i == npend) pq[i] = pq[LAG - 1];
+          }
+          ++npend;
         }
       }
     }
-    if (pending) stage2();
+    while (npend > 0) stage2();
     if (lane == 0) PROF_STORE(0);
   } else if (warp < W_SMX0) {
     // ------------------------------------------------------------------ epilogue warps: P -> G = gelu(P) as bf16 hi | lo, in place
@@ -356,9 +383,9 @@ tscore_x_kernel(const TScoreArgs args, int n_tiles) {
       if (lt + 1 < n_local) fetch_info(args, tile0 + (lt + 1) * tstep, nx);
       const int nblk = npass * KB;
       for (int jb = 0; jb < nblk; ++jb, ++g) {
-        const uint32_t b = g & 1;
+        const uint32_t b = g % NDP;
         PROF_ADD(0);
-        tc::mbar_wait(&bars->ip_full[b], (g >> 1) & 1);
+        tc::mbar_wait(&bars->ip_full[b], (g / NDP) & 1);
         PROF_ADD(1);
         tc::tcgen05_fence_after();
         const uint32_t acc = tmem + grp_addr + DP_COL + b * 64;
@@ -621,7 +648,8 @@ tscore_x_kernel(const TScoreArgs args, int n_tiles) {
         const int cut = static_cast<int>(m0 < 0 ? 0 : (m0 > nc ? nc : m0));
         const int nmax = cut > nc - cut ? cut : nc - cut;
         const int rounds = (nmax + CC - 1) / CC;
-        const uint32_t db = u & 1;                             // A_w / D_a buffer of the unit
+        const uint32_t db = u & 1;                             // A_w buffer of the unit
+        const uint32_t dab = NDA == 2 ? (u & 1) : 0;           // its D_a buffer
         PROF_ADD(0);
         tc::mbar_wait(&bars->x_full, u & 1);                   // every S1 / SX of the unit is complete
         PROF_ADD(1);
@@ -721,18 +749,18 @@ tscore_x_kernel(const TScoreArgs args, int n_tiles) {
         // attention logits a[c, k] out of D_a (lanes (i, k, hl), columns = candidates), transposed through shared memory
         const int c_lo = li_q == 0 ? 0 : cut, c_hi = li_q == 0 ? cut : nc;
         PROF_ADD(0);
-        tc::mbar_wait(&bars->dma_full[db], (u >> 1) & 1);
+        tc::mbar_wait(&bars->dma_full[dab], (NDA == 2 ? u >> 1 : u) & 1);
         PROF_ADD(5);
         tc::tcgen05_fence_after();
         tc::named_bar_sync(1, T_SCR);                          // Xs is dead, Sa (same bytes) may be written; Sm is complete
         bool released = false;
         for (int c0 = c_lo & ~15; c0 < c_hi; c0 += 16) {
           uint32_t va[16];
-          tc::tmem_ld_32x16(tmem + lane_addr + DA_COL + NCM * db + c0, va);
+          tc::tmem_ld_32x16(tmem + lane_addr + DA_COL + NCM * dab + c0, va);
           tc::tmem_ld_wait();
           if (c0 + 16 >= c_hi) {                               // last chunk in registers: this D_a buffer is free again
             tc::tcgen05_fence_before();
-            tc::mbar_arrive(&bars->dma_free[db]);
+            tc::mbar_arrive(&bars->dma_free[dab]);
             released = true;
           }
 #pragma unroll
@@ -745,7 +773,7 @@ tscore_x_kernel(const TScoreArgs args, int n_tiles) {
         }
         if (!released) {
           tc::tcgen05_fence_before();
-          tc::mbar_arrive(&bars->dma_free[db]);
+          tc::mbar_arrive(&bars->dma_free[dab]);
         }
         PROF_ADD(10);
         tc::named_bar_sync(1, T_SCR);

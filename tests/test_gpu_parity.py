@@ -936,10 +936,15 @@ def test_table_level_scores(B, H, D, K, Dc, mean_c, max_c, score_type):
             ref[offs[i]:offs[i + 1]] = O.aggregate_scores(Iref[i:i + 1], cr, score_type, wt)[0]
         assert _nerr(I.cpu(), Iref) < 3e-5
         assert _nerr(s.cpu(), ref) < 3e-4
-    # int32 ids and the no-interests call give the same bits
+    # the scores-only call (the X-formulation kernel where the shape allows, tscore_x_kernel.cu) meets the same bound, and int32 ids
+    # give the same bits as int64 ids
     _, s32 = ops.score_table(tp, eb.his_ids.int().to(DEV), eb.his_mask.to(DEV), eb.cand_ids.int().to(DEV), score_type,
                              cand_offsets=eb.offsets.to(DEV), bias_mean=bias.to(DEV))
-    assert torch.equal(s32, s)
+    _, s64 = ops.score_table(tp, eb.his_ids.to(DEV), eb.his_mask.to(DEV), eb.cand_ids.to(DEV), score_type,
+                             cand_offsets=eb.offsets.to(DEV), bias_mean=bias.to(DEV))
+    assert torch.equal(s32, s64)
+    assert _nerr(s32.cpu(), ref) < 3e-4
+    assert _nerr(s32.cpu(), s.cpu()) < 2e-5
 
 
 def test_table_level_dense_layout_and_invariance():
@@ -1068,10 +1073,11 @@ def test_miner_forward_table_level_matches_reference(name):
     print(f'{name}: table-level normwise score error {err:.2e}')
     ref_I = O.miner_forward(x['table'].to(torch.bfloat16), x['his_ids'], x['his_mask'], x['cand'], x['w_proj'], x['codes'], x['w_target'])[0]
     close_norm(I.cpu().numpy(), ref_I.numpy(), 1e-3)
-    # and grouped scoring picks the table-level mode by default, same bits as the explicit call
+    # and grouped scoring picks the table-level mode by default (scores only: the X-formulation kernel where the shape allows)
     B, C = x['cand'].shape
     s_csr = m.score_impressions(x['his_ids'].to(DEV), x['his_mask'].to(DEV), x['cand'].reshape(-1).to(DEV), (torch.arange(B + 1) * C).to(DEV))
-    assert torch.equal(s_csr.view(B, C), S.detach())
+    close_norm(s_csr.view(B, C).cpu().numpy(), g['scores_weighted_bf16table'], 1e-3)
+    close_norm(s_csr.view(B, C).cpu().numpy(), S.detach().cpu().numpy(), 2e-5)
 
 
 # ------------------------------------------------------------------------------------------------ train variant: every branch
