@@ -188,7 +188,8 @@ tscore_kernel(const TScoreArgs args, int n_tiles) {
   constexpr int IP_COL = 64 * NH, DM_COL = IP_COL + 256, DA_COL = DM_COL + NCM;
   static_assert(LPI >= 32, "a warp's 32 TMEM lanes belong to one impression");
   extern __shared__ uint8_t smem_raw[];
-  uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~static_cast<uintptr_t>(1023));
+  // aligned by OFFSET (not by integer arithmetic on the pointer) so that the compiler keeps the shared address space: LDS / STS, not generic LD / ST
+  uint8_t* smem = smem_raw + ((1024u - (tc::smem_u32(smem_raw) & 1023u)) & 1023u);
   uint8_t* st1 = smem;                                         // [S1][E 16 KB | TW 16 KB]
   uint8_t* st2 = st1 + S1 * ST1_BYTES;                         // [S2][12 KB] candidate rows
   // scratch: the logits L of the unit the softmax warps prepare, and the score transposes Sm / Sa of the unit the score warps finish
@@ -573,6 +574,7 @@ tscore_kernel(const TScoreArgs args, int n_tiles) {
                 const float bias = args.bias_mean ? args.bias_mean[(static_cast<int64_t>(tile) * IPT + ((meta >> 24) & 0xfu)) * H + ((meta >> 16) & 0xffu)] : 0.f;
                 const float* row = args.lg + static_cast<size_t>(info & REC_ID) * K;
                 if (!(info & REC_VALID)) {
+#pragma unroll 1
                   for (int k = 0; k < K; ++k) dst[k] = bias * LOG2E;
                 } else if (k_vec4) {
 #pragma unroll
@@ -588,11 +590,13 @@ tscore_kernel(const TScoreArgs args, int n_tiles) {
                                                                                  (x[i].z + bias) * LOG2E, (x[i].w + bias) * LOG2E);
                   }
                 } else {
+#pragma unroll 1
                   for (int k = 0; k < K; ++k) dst[k] = (row[k] + bias) * LOG2E;
                 }
               } else if (mult != 0u) {
                 // masked record of multiplicity n: n slots filled with 1e-30 (model.py:180) add up to n exp(1e-30) = exp(1e-30 + ln n)
                 const float x = kMaskFill * LOG2E + __log2f(static_cast<float>(mult));
+#pragma unroll 1
                 for (int k = 0; k < K; ++k) dst[k] = x;
               }
             }
