@@ -452,8 +452,8 @@ def main():
     if rank == 0 and not args.no_breakdown:
         if math == _lib.MATH_TABLE:
             stages = [('table_project: tc_gemm tanh(table Wp^T) + table_logits + tc_gemm table Wt^T (once per step, N rows)', 'proj'),
-                      ('tpack_kernel + tscore_kernel: pack the histories into tiles, then gather table/tw/cand rows + softmax_H + interests + gelu + '
-                       'matching/attention MMAs + softmax_K + score (tcgen05)', 'score')]
+                      ('tpack_kernel + tscore_x_kernel: pack the histories into tiles, then gather table/tw/cand rows + softmax_H + P = w tw + gelu + '
+                       'X = E cand^T / attention MMAs + m = w X + softmax_K + score (tcgen05)', 'score')]
         elif math == _lib.MATH_TENSOR:
             # fused tcgen05 path: two kernels per wave of `chunk` impressions
             stages = [('hist_kernel: gather + tanh(E Wp^T) + logits/softmax + weighted sum (tcgen05)', 1),

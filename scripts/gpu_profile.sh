@@ -7,7 +7,7 @@ $CMD > gpurun_out/prof_plain.log 2>&1 &&
 ncu --metrics gpu__time_duration.sum --clock-control none -c 400 --csv --log-file gpurun_out/launches.csv $CMD > gpurun_out/ncu_launches.log 2>&1
 echo "launch list exit $?"
 $CMD > gpurun_out/prof_plain2.log 2>&1 &&
-ncu --set full --clock-control none --import-source on -k regex:"${PROF_KERNELS:-tscore_kernel|tpack_kernel|rank_metrics_kernel|tc_gemm_kernel|table_logits_kernel}" -s ${PROF_SKIP:-12} -c ${PROF_COUNT:-5} -o gpurun_out/prof -f $CMD > gpurun_out/ncu_full.log 2>&1
+ncu --set full --clock-control none --import-source on -k regex:"${PROF_KERNELS:-tscore_x_kernel|tscore_kernel|tpack_kernel|rank_metrics_kernel|tc_gemm_kernel|table_logits_kernel}" -s ${PROF_SKIP:-12} -c ${PROF_COUNT:-5} -o gpurun_out/prof -f $CMD > gpurun_out/ncu_full.log 2>&1
 echo "full capture exit $?"
 tail -3 gpurun_out/ncu_full.log
 ls -la gpurun_out | tail -8

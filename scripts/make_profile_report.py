@@ -16,7 +16,7 @@ subprocess.run([sys.executable, os.path.join(ROOT, 'scripts', 'ncu_summary.py'),
                stdout=subprocess.DEVNULL, check=True)
 lib = os.path.join(ROOT, 'miner_b200', 'libminer_b200.so')
 with open(out, 'a') as f:
-    for kre, stem in (('tscore_kernel', 'tscore_kernel'), ('hist_kernel2', 'hist_kernel2'), ('cand_kernel', 'cand_kernel')):
+    for kre, stem in (('tscore_x_kernel', 'tscore_x_kernel'), ('tscore_kernel', 'tscore_kernel'), ('hist_kernel2', 'hist_kernel2'), ('cand_kernel', 'cand_kernel')):
         r = subprocess.run([sys.executable, os.path.join(ROOT, 'scripts', 'ncu_hot.py'), rep, kre, lib, stem, '14'], capture_output=True, text=True)
         if r.returncode == 0 and r.stdout.strip():
             f.write(f'\n== hot source lines, warp-stall samples ({kre}) ==\n' + r.stdout)
@@ -29,7 +29,7 @@ old = json.load(open(tpath)) if os.path.exists(tpath) else {}
 traffic = {}
 for row in rows[2:]:
     name = row[hdr.index('Kernel Name')]
-    key = 'tscore_kernel' if 'tscore_kernel' in name else 'hist_kernel' if 'hist_kernel' in name else 'cand_kernel' if 'cand_kernel' in name else None
+    key = 'tscore_kernel' if ('tscore_kernel' in name or 'tscore_x_kernel' in name) else 'hist_kernel' if 'hist_kernel' in name else 'cand_kernel' if 'cand_kernel' in name else None
     if not key:
         continue
     tot = 0.0
