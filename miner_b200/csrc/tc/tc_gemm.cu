@@ -51,8 +51,8 @@ __device__ __forceinline__ float apply_epilogue(float v, int epi) {
 
 __global__ void __launch_bounds__(THREADS, 1)
 tc_gemm_kernel(const __grid_constant__ CUtensorMap tmap_b, const uint16_t* __restrict__ A, const void* __restrict__ a_ids,
-               int id_dtype, int64_t a_rows_in_table, float* __restrict__ C, __nv_bfloat16* __restrict__ Cb, int64_t M, int N,
-               int K, int epi, int m_tiles, int n_tiles) {
+               int id_dtype, int64_t a_rows_in_table, float* __restrict__ Cfull, __nv_bfloat16* __restrict__ Cb, int64_t M, int N,
+               int K, int epi, int m_tiles, int n_tiles, int k_splits) {
   extern __shared__ uint8_t smem_raw[];
   uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~static_cast<uintptr_t>(1023));
   uint8_t* a_tiles = smem;
@@ -61,8 +61,17 @@ tc_gemm_kernel(const __grid_constant__ CUtensorMap tmap_b, const uint16_t* __res
 
   const int warp = threadIdx.x >> 5;
   const int lane = threadIdx.x & 31;
-  const int num_kb = K / GK;
-  const int total_tiles = m_tiles * n_tiles;
+  // split-K (k_splits > 1, weight-gradient GEMMs: few output tiles, very long K): work item = (tile, split); split s accumulates
+  // its k-blocks into its own fp32 partial C + s M N, summed by the caller in split order
+  const int kb_all = K / GK;
+  const int kb_per = (kb_all + k_splits - 1) / k_splits;
+  const int total_tiles = m_tiles * n_tiles * k_splits;
+  auto kb_range = [&](int item, int& kb0, int& nkb) {
+    const int sp = item % k_splits;
+    kb0 = sp * kb_per;
+    nkb = kb_all - kb0 < kb_per ? kb_all - kb0 : kb_per;
+    if (nkb < 0) nkb = 0;
+  };
 
   if (threadIdx.x == 0) {
     for (int s = 0; s < STAGES; ++s) {
@@ -89,7 +98,10 @@ tc_gemm_kernel(const __grid_constant__ CUtensorMap tmap_b, const uint16_t* __res
     // ------------------------------------------------------------------ A producers (gather fused)
     const int chunk = lane & 7;                 // 16-byte chunk of the 128-byte k-block row
     uint32_t issued = 0, signalled = 0;
-    for (int tile = blockIdx.x; tile < total_tiles; tile += gridDim.x) {
+    for (int item = blockIdx.x; item < total_tiles; item += gridDim.x) {
+      const int tile = item / k_splits;
+      int kb0, num_kb;
+      kb_range(item, kb0, num_kb);
       const int64_t m0 = static_cast<int64_t>(tile / n_tiles) * GM;
       const uint16_t* src[8];
       uint32_t nbytes[8];
@@ -104,7 +116,7 @@ tc_gemm_kernel(const __grid_constant__ CUtensorMap tmap_b, const uint16_t* __res
           row = load_id(a_ids, m, id_dtype);
           if (row < 0 || row >= a_rows_in_table) { ok = false; row = 0; }
         }
-        src[j] = A + row * K + chunk * 8;
+        src[j] = A + row * K + chunk * 8 + static_cast<int64_t>(kb0) * GK;
         nbytes[j] = ok ? 16u : 0u;
         dst_off[j] = static_cast<uint32_t>((r >> 3) * 1024 + (r & 7) * 128 + ((chunk ^ (r & 7)) << 4));
       }
@@ -134,13 +146,16 @@ tc_gemm_kernel(const __grid_constant__ CUtensorMap tmap_b, const uint16_t* __res
     // ------------------------------------------------------------------ B producer (TMA)
     if (lane == 0) {
       uint32_t it = 0;
-      for (int tile = blockIdx.x; tile < total_tiles; tile += gridDim.x) {
+      for (int item = blockIdx.x; item < total_tiles; item += gridDim.x) {
+        const int tile = item / k_splits;
+        int kb0, num_kb;
+        kb_range(item, kb0, num_kb);
         const int n0 = (tile % n_tiles) * GN;
         for (int kb = 0; kb < num_kb; ++kb, ++it) {
           const uint32_t s = it % STAGES, ph = (it / STAGES) & 1;
           tc::mbar_wait(&bars->empty[s], ph ^ 1);
           tc::mbar_arrive_expect_tx(&bars->full[s], B_BYTES);
-          tc::tma_load_2d(&tmap_b, &bars->full[s], tc::smem_u32(b_tiles + s * B_BYTES), kb * GK, n0);
+          tc::tma_load_2d(&tmap_b, &bars->full[s], tc::smem_u32(b_tiles + s * B_BYTES), (kb0 + kb) * GK, n0);
         }
       }
     }
@@ -148,7 +163,10 @@ tc_gemm_kernel(const __grid_constant__ CUtensorMap tmap_b, const uint16_t* __res
     // ------------------------------------------------------------------ MMA issuer
     if (lane == 0) {
       uint32_t it = 0, acc_it = 0;
-      for (int tile = blockIdx.x; tile < total_tiles; tile += gridDim.x, ++acc_it) {
+      for (int item = blockIdx.x; item < total_tiles; item += gridDim.x, ++acc_it) {
+        const int tile = item / k_splits;
+        int kb0, num_kb;
+        kb_range(item, kb0, num_kb);
         const int n0 = (tile % n_tiles) * GN;
         int n_eff = N - n0 < GN ? N - n0 : GN;
         n_eff = (n_eff + 15) & ~15;
@@ -175,7 +193,9 @@ tc_gemm_kernel(const __grid_constant__ CUtensorMap tmap_b, const uint16_t* __res
     // ------------------------------------------------------------------ epilogue (warps 6..9)
     const int q = warp & 3;                     // TMEM lane quarter this warp may access
     uint32_t acc_it = 0;
-    for (int tile = blockIdx.x; tile < total_tiles; tile += gridDim.x, ++acc_it) {
+    for (int item = blockIdx.x; item < total_tiles; item += gridDim.x, ++acc_it) {
+      const int tile = item / k_splits;
+      float* C = Cfull ? Cfull + static_cast<int64_t>(item % k_splits) * M * N : nullptr;
       const int64_t m0 = static_cast<int64_t>(tile / n_tiles) * GM;
       const int n0 = (tile % n_tiles) * GN;
       const uint32_t as = acc_it & 1, aph = (acc_it >> 1) & 1;
@@ -252,7 +272,28 @@ bool tc_gemm_supported(int64_t K, int64_t N) { return K >= GK && K % GK == 0 && 
 
 int launch_tc_gemm(const void* A, const void* a_ids, int id_dtype, int64_t a_rows_in_table, const void* B, float* C, void* c_bf16,
                    int64_t M, int64_t N, int64_t K, int epilogue, cudaStream_t stream) {
+  return launch_tc_gemm_splitk(A, a_ids, id_dtype, a_rows_in_table, B, C, c_bf16, M, N, K, epilogue, 1, stream);
+}
+
+int tc_gemm_splits(int64_t M, int64_t N, int64_t K) {
+  const int64_t tiles = ((M + GM - 1) / GM) * ((N + GN - 1) / GN);
+  int64_t s = sm_count() / (tiles > 0 ? tiles : 1);
+  const int64_t kb = K / GK;
+  if (s > kb / 8) s = kb / 8;                  // at least 8 k-blocks per split
+  if (s < 1) s = 1;
+  const int64_t per = (kb + s - 1) / s;
+  s = (kb + per - 1) / per;                    // no empty split
+  return static_cast<int>(s);
+}
+
+int launch_tc_gemm_splitk(const void* A, const void* a_ids, int id_dtype, int64_t a_rows_in_table, const void* B, float* C, void* c_bf16,
+                          int64_t M, int64_t N, int64_t K, int epilogue, int k_splits, cudaStream_t stream) {
   if (M == 0) return MINER_OK;
+  MINER_CHECK_ARG(k_splits >= 1 && (k_splits == 1 || (C && !c_bf16 && epilogue == EPI_NONE)), "tc_gemm: split-K needs fp32 partials and no epilogue");
+  if (k_splits > 1) {
+    const int64_t kb = K / GK, per = (kb + k_splits - 1) / k_splits;
+    MINER_CHECK_ARG((kb + per - 1) / per == k_splits, "tc_gemm: a split without k-blocks (use tc_gemm_splits)");
+  }
   MINER_CHECK_ARG(A && B && (C || c_bf16), "tc_gemm: null pointer");
   if (!tc_gemm_supported(K, N)) {
     set_error("tc_gemm: unsupported shape N=%lld K=%lld (need K %% 64 == 0, N >= 16)", (long long)N, (long long)K);
@@ -280,12 +321,12 @@ int launch_tc_gemm(const void* A, const void* a_ids, int id_dtype, int64_t a_row
   }
   const int m_tiles = static_cast<int>((M + GM - 1) / GM);
   const int n_tiles = static_cast<int>((N + GN - 1) / GN);
-  const int64_t total = static_cast<int64_t>(m_tiles) * n_tiles;
+  const int64_t total = static_cast<int64_t>(m_tiles) * n_tiles * k_splits;
   const int grid = static_cast<int>(total < sm_count() ? total : sm_count());
   MINER_CUDA_OK(cudaFuncSetAttribute(tc_gemm_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, SMEM_BYTES));
   tc_gemm_kernel<<<grid, THREADS, SMEM_BYTES, stream>>>(tmap, static_cast<const uint16_t*>(A), a_ids, id_dtype, a_rows_in_table, C,
                                                         static_cast<__nv_bfloat16*>(c_bf16), M, static_cast<int>(N),
-                                                        static_cast<int>(K), epilogue, m_tiles, n_tiles);
+                                                        static_cast<int>(K), epilogue, m_tiles, n_tiles, k_splits);
   MINER_LAUNCH_OK("tc_gemm");
   return MINER_OK;
 }

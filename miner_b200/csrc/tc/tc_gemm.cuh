@@ -14,4 +14,11 @@ bool tc_gemm_supported(int64_t K, int64_t N);
 int launch_tc_gemm(const void* A, const void* a_ids, int id_dtype, int64_t a_rows_in_table, const void* B, float* C,
                    void* c_bf16, int64_t M, int64_t N, int64_t K, int epilogue, cudaStream_t stream);
 
+// split-K form for GEMMs with few output tiles and a very long reduction (the weight gradients of the train variant): split s writes
+// its fp32 partial to C + s M N (C must hold k_splits M N floats); the caller sums them in split order.  tc_gemm_splits picks a
+// split count that fills the SMs and leaves no split empty.
+int tc_gemm_splits(int64_t M, int64_t N, int64_t K);
+int launch_tc_gemm_splitk(const void* A, const void* a_ids, int id_dtype, int64_t a_rows_in_table, const void* B, float* C,
+                          void* c_bf16, int64_t M, int64_t N, int64_t K, int epilogue, int k_splits, cudaStream_t stream);
+
 }  // namespace miner

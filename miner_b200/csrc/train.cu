@@ -539,12 +539,16 @@ TrainWs train_ws(int64_t B, int64_t H, int64_t K, int64_t Dc, int64_t D, int mat
   w.s_wp = atb_splits(B * H, static_cast<int>(((Dc + 63) / 64) * ((D + 63) / 64)));
   w.s_wt = atb_splits(B * K, static_cast<int>(((D + 63) / 64) * ((D + 63) / 64)));
   w.g_poly = static_cast<int>(B < 4 * sm_count() ? B : 4 * sm_count());
-  w.part_wp = take(math == MINER_MATH_TENSOR ? 0 : f * w.s_wp * Dc * D);
-  w.part_wt = take(math == MINER_MATH_TENSOR ? 0 : f * w.s_wt * D * D);
-  w.part_codes = take(f * w.g_poly * K * Dc);
-  w.di2 = w.g;
   w.bk_pad = (B * K + 63) / 64 * 64;
   w.bh_pad = (B * H + 63) / 64 * 64;
+  if (math == MINER_MATH_TENSOR) {     // split-K partials of the two weight-gradient GEMMs (tc_gemm)
+    w.s_wp = tc_gemm_splits(Dc, D, w.bh_pad);
+    w.s_wt = tc_gemm_splits(D, D, w.bk_pad);
+  }
+  w.part_wp = take(f * w.s_wp * Dc * D);
+  w.part_wt = take(f * w.s_wt * D * D);
+  w.part_codes = take(f * w.g_poly * K * Dc);
+  w.di2 = w.g;
   if (math == MINER_MATH_TENSOR) {
     w.i_bf16 = take(2 * static_cast<size_t>(B) * K * D);
     w.dz_bf16 = w.i_bf16;              // forward / backward never need both
@@ -738,8 +742,12 @@ extern "C" int miner_train_bwd(const void* table, int64_t n_rows, int table_dtyp
     MINER_LAUNCH_OK("transpose_cast(dZ)");
     transpose_cast_kernel<<<tg, tb, 0, st>>>(interests, it, R, (int)D, w.bk_pad);
     MINER_LAUNCH_OK("transpose_cast(I)");
-    rc = launch_tc_gemm(dzt, nullptr, id_dtype, 0, it, grad_w_target, nullptr, D, D, w.bk_pad, EPI_NONE, st);      // dWt[o,i] = sum_r dZ[r,o] I[r,i]
+    rc = launch_tc_gemm_splitk(dzt, nullptr, id_dtype, 0, it, w.s_wt > 1 ? pWt : grad_w_target, nullptr, D, D, w.bk_pad, EPI_NONE, w.s_wt, st);   // dWt[o,i] = sum_r dZ[r,o] I[r,i]
     if (rc) return rc;
+    if (w.s_wt > 1) {
+      sum_partials_kernel<<<static_cast<int>((D * D + 255) / 256), 256, 0, st>>>(pWt, w.s_wt, D * D, grad_w_target);
+      MINER_LAUNCH_OK("sum_partials(dWt)");
+    }
   } else {
     dim3 tb(32, 8), tg(static_cast<unsigned>((D + 31) / 32), static_cast<unsigned>((D + 31) / 32));
     transpose_kernel<<<tg, tb, 0, st>>>(w_target, WtT, (int)D, (int)D);
@@ -796,8 +804,12 @@ extern "C" int miner_train_bwd(const void* table, int64_t n_rows, int table_dtyp
     gather_transpose_kernel<<<dim3(static_cast<unsigned>((w.bh_pad + 31) / 32), static_cast<unsigned>((D + 31) / 32)), tb, 0, st>>>(
         static_cast<const uint16_t*>(table), n_rows, his_ids, id_dtype, R, (int)D, w.bh_pad, et);
     MINER_LAUNCH_OK("gather_transpose(E)");
-    const int rc = launch_tc_gemm(dz1t, nullptr, id_dtype, 0, et, grad_w_proj, nullptr, Dc, D, w.bh_pad, EPI_NONE, st);     // dWp[c,d] = sum_r dZ1[r,c] E[r,d]
+    const int rc = launch_tc_gemm_splitk(dz1t, nullptr, id_dtype, 0, et, w.s_wp > 1 ? pWp : grad_w_proj, nullptr, Dc, D, w.bh_pad, EPI_NONE, w.s_wp, st);   // dWp[c,d] = sum_r dZ1[r,c] E[r,d]
     if (rc) return rc;
+    if (w.s_wp > 1) {
+      sum_partials_kernel<<<static_cast<int>((Dc * D + 255) / 256), 256, 0, st>>>(pWp, w.s_wp, Dc * D, grad_w_proj);
+      MINER_LAUNCH_OK("sum_partials(dWp)");
+    }
   } else {
     const int64_t R = B * H;
     const int64_t rps = ((R + w.s_wp - 1) / w.s_wp + 15) / 16 * 16;
