@@ -2,7 +2,7 @@
 //   Loss.compute           (reference src/loss.py:27-44):  mean_{b,k,l}( cos(I_k, I_l), diagonal zeroed ) + CE_mean(logits, argmax(labels))
 //   Loss.compute_eval_loss (src/loss.py:68-85):            same disagreement + ( -sum logsigmoid(logits) * labels )
 // One CTA per impression: the K interest vectors are L2-normalised into shared memory (utils.py:21-23 order: divide
-// first, then dot), then one thread per (k,l) pair accumulates the cosine; the row's cross-entropy / logsigmoid term
+// first, then dot), the off-diagonal cosines are summed as |sum_k u_k|^2 - sum_k |u_k|^2; the row's cross-entropy / logsigmoid term
 // is computed by warp 0.  Per-impression partials are reduced by a single block in a fixed order (deterministic).
 #include "common.cuh"
 
@@ -27,15 +27,13 @@ __global__ void __launch_bounds__(LT) loss_rows_kernel(const float* __restrict__
     for (int d = lane; d < D; d += 32) In[k * DP + d] = Ib[static_cast<int64_t>(k) * D + d] / nrm;
   }
   __syncthreads();
+  // sum over the off-diagonal pairs (zero_diagonal=True, utils.py:24-27):  sum_{k != l} u_k . u_l = |sum_k u_k|^2 - sum_k |u_k|^2
+  // -- O(K D) instead of the K^2 D of the pairwise form; the diagonal terms are the COMPUTED |u_k|^2, not 1
   float local = 0.f;
-  for (int p = tid; p < K * K; p += LT) {
-    const int l = p / K, k = p - l * K;          // lanes walk k: conflict-free with the +1 padding, row l is a broadcast
-    if (k == l) continue;                        // zero_diagonal=True (utils.py:24-27)
-    const float* x = In + k * DP;
-    const float* y = In + l * DP;
-    float s = 0.f;
-    for (int d = 0; d < D; ++d) s = fmaf(x[d], y[d], s);
-    local += s;
+  for (int d = tid; d < D; d += LT) {
+    float s = 0.f, q = 0.f;
+    for (int k = 0; k < K; ++k) { const float u = In[k * DP + d]; s += u; q = fmaf(u, u, q); }
+    local += s * s - q;
   }
   local = warp_sum(local);
   if (lane == 0) wsum[warp] = local;
