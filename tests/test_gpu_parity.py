@@ -1026,6 +1026,66 @@ def test_table_level_mask_patterns(B, H, D, K, Dc):
             ref[offs[i]:offs[i + 1]] = O.aggregate_scores(Iref[i:i + 1], cr, 'weighted', wt)[0]
         assert _nerr(I.cpu(), Iref) < 3e-5
         assert _nerr(s.cpu(), ref) < 3e-4
+        _, sx = ops.score_table(tp, his.to(DEV), mask.to(DEV), eb.cand_ids.to(DEV), 'weighted', cand_offsets=eb.offsets.to(DEV),
+                                bias_mean=None if bm is None else bm.to(DEV), check_bounds=True)         # scores only: tscore_x_kernel where the shape allows
+        assert _nerr(sx.cpu(), ref) < 3e-4
+
+
+@pytest.mark.parametrize('H,K,D,Dc,score_type', [(50, 32, 256, 48, 'weighted'), (56, 30, 128, 40, 'weighted'), (50, 8, 128, 24, 'weighted'),
+                                                 (41, 17, 192, 40, 'max'), (50, 32, 128, 40, 'mean')])
+def test_table_level_x_kernel_edges(H, K, D, Dc, score_type):
+    """The scores-only table-level call on the shapes tscore_x_kernel.cu covers (two impressions per tile, K <= 32, H <= 56), at its
+    edges: an odd number of impressions (a last tile with one impression), K not a multiple of 4 (the lg rows then are not copied by
+    cp.async), tiles of 1, 2, 33, 64, 81 and 200 candidates (one / two contraction rounds per impression, several 80-column passes
+    per tile), histories that fill all 56 slots, a fully masked history next to a full one, int32 ids, and ids outside the table
+    (counted, read as zero rows).  Scores against the oracle in the reference's operation order, 3e-4 normwise."""
+    from miner_b200 import ops, synth
+    N, B = 700, 37
+    table = synth.make_table(N, D, 5, torch.bfloat16)
+    w = synth.make_weights(D, K, Dc, 5)
+    g = torch.Generator().manual_seed(23)
+    counts = torch.tensor([1, 2, 33, 64, 81, 200, 31, 32, 17, 48, 79, 80, 3] + [int(c) for c in torch.randint(1, 60, (B - 13,), generator=g)])
+    offsets = torch.zeros(B + 1, dtype=torch.int64)
+    offsets[1:] = torch.cumsum(counts, 0)
+    cand = torch.randint(1, N + 1, (int(offsets[-1]),), generator=g)
+    his = torch.randint(1, N + 1, (B, H), generator=g)
+    length = torch.randint(1, H + 1, (B,), generator=g)
+    length[0], length[1], length[2] = H, H, 1                  # a tile whose two histories fill every slot
+    mask = torch.arange(H)[None, :] >= (H - length)[:, None]
+    mask[3] = False                                            # fully masked
+    his = his * mask
+    sw = ops.ScoreWeights(w.w_proj.to(DEV), w.context_codes.to(DEV), w.w_target.to(DEV), True)
+    tp = ops.table_project(table.to(DEV), sw, weighted=True)
+    wp, wt = w.w_proj.to(torch.bfloat16).float(), w.w_target.to(torch.bfloat16).float()
+    offs = offsets.numpy()
+
+    def reference(his_, cand_):
+        Iref = O.poly_attention(table.float()[his_], mask, wp, w.context_codes)
+        ref = torch.empty(int(offs[-1]))
+        for i in range(B):
+            cr = table.float()[cand_[offs[i]:offs[i + 1]]][None]
+            ref[offs[i]:offs[i + 1]] = O.aggregate_scores(Iref[i:i + 1], cr, score_type, wt)[0]
+        return ref
+    ref = reference(his, cand)
+    _, s = ops.score_table(tp, his.to(DEV), mask.to(DEV), cand.to(DEV), score_type, cand_offsets=offsets.to(DEV), check_bounds=True)
+    assert _nerr(s.cpu(), ref) < 3e-4
+    _, s32 = ops.score_table(tp, his.int().to(DEV), mask.to(DEV), cand.int().to(DEV), score_type, cand_offsets=offsets.to(DEV))
+    assert torch.equal(s32, s)
+    # ids outside the table: counted in the workspace, scored as zero rows (the evaluators turn the counters into an IndexError)
+    his_bad, cand_bad = his.clone(), cand.clone()
+    his_bad[5, H - 1], cand_bad[7], cand_bad[int(offsets[5]) + 150] = N + 5, -3, N + 1
+    ws = ops.score_table_workspace(B, H, K, DEV)
+    _, sb = ops.score_table(tp, his_bad.to(DEV), mask.to(DEV), cand_bad.to(DEV), score_type, cand_offsets=offsets.to(DEV), workspace=ws)
+    assert ops.oob_counts(ws).tolist() == [1, 2]
+    with pytest.raises(IndexError):
+        ops.check_oob(ws)
+    tz = torch.cat([table.float(), torch.zeros(1, D)])          # row N + 1 of this copy is the zero row a bad id reads
+    Iz = O.poly_attention(tz[torch.where((his_bad < 0) | (his_bad > N), torch.full_like(his_bad, N + 1), his_bad)], mask, wp, w.context_codes)
+    cz = torch.where((cand_bad < 0) | (cand_bad > N), torch.full_like(cand_bad, N + 1), cand_bad)
+    refz = torch.empty(int(offs[-1]))
+    for i in range(B):
+        refz[offs[i]:offs[i + 1]] = O.aggregate_scores(Iz[i:i + 1], tz[cz[offs[i]:offs[i + 1]]][None], score_type, wt)[0]
+    assert _nerr(sb.cpu(), refz) < 3e-4
 
 
 @pytest.mark.parametrize('scale_t,scale_w', [(1.0, 20.0), (1.0, 60.0), (2.0, 20.0)])
