@@ -16,13 +16,13 @@
 // TMEM map (496 of 512 columns): A_w 2 x 64 | D_P 2 x 64 (the first 32 columns of a buffer become packed G hi|lo) | D_X 80 | D_a 2 x 80.
 // TMEM lanes of A_w / D_P / D_a are (impression i, code k, part hl) exactly as in tscore_kernel.cu; D_X has lane = history slot.
 //   warps 0-3   gather table[id] (E) and tw[id] rows of the tile's slots per 64-feature block (4-stage ring of 28 KB)
-//   warps 4-5   gather the tile's candidate rows (5-stage ring of 10 KB)
-//   warp 6      MMA issuer, per block j:  S1(j): D_P[b] = A_w . TW_j  (TS form, B read MN-major);
-//                                         SX(j): D_X += E_j . cand_j^T (SS form, both operands K-major as gathered);
-//                                         S2(j-1): D_a += A_G[b'] . cand_(j-1)^T (TS form)
-//   warps 7-14  epilogue of D_P per block (pair sum, gelu, bf16 hi/lo split, in place)
-//   warps 15-18 softmax over the history (model.py:174-181) from the lg rows (cp.async) -> A_w[u & 1]
-//   warps 19-22 per finished unit: A_w -> W and D_X -> Xs in shared memory, m = W X on the CUDA cores (4 codes x 4 candidates per
+//   warp 4      S1 / S2 issuer, per block j:  S1(j): D_P[b] = A_w . TW_j (TS form, B = the TW half of the stage read MN-major);
+//                                             S2(j - 1): D_a[u & 1] += A_G[b'] . cand_(j-1)^T (TS form)
+//   warp 5      SX issuer:                    D_X += E_j . cand_j^T (SS form, both operands K-major as gathered)
+//   warps 6-7   gather the tile's candidate rows (5-stage ring of 10 KB)
+//   warps 8-15  epilogue of D_P per block (pair sum, gelu, bf16 hi/lo split, in place)
+//   warps 16-19 softmax over the history (model.py:174-181) from the lg rows (cp.async) -> A_w[u & 1]
+//   warps 20-23 per finished unit: A_w -> W and D_X -> Xs in shared memory, m = W X on the CUDA cores (4 codes x 4 candidates per
 //               thread), drain D_a[u & 1], softmax over K, scores
 #include "tscore_common.cuh"
 
@@ -56,13 +56,18 @@ static_assert(SMEM <= 232448, "shared memory budget");
 static_assert(E_BYTES % 1024 == 0 && C_BYTES % 1024 == 0, "swizzle atoms are 1 KB");
 
 constexpr int T_EPI = 256, T_SMX = 128, T_SCR = 128;
-constexpr int T_G1 = 128, T_G2 = 64;
-constexpr int G1_ROWS = NKS_MAX, G2_ROWS = NCM * 8 / T_G2;
+#ifndef MINER_TSX_TG1
+#define MINER_TSX_TG1 128
+#endif
+constexpr int T_G1 = MINER_TSX_TG1, T_G2 = 64;
 constexpr int G1_STEP = T_G1 / 8, G2_STEP = T_G2 / 8;
-static_assert(G1_STEP == 16, "a gather thread's row jj is 16-row group jj: one K-step of S1");
-constexpr int W_G2 = T_G1 / 32, W_MMA = W_G2 + T_G2 / 32, W_EPI0 = W_MMA + 1, W_SMX0 = W_EPI0 + T_EPI / 32, W_SCR0 = W_SMX0 + T_SMX / 32;
-constexpr int W_SX = W_SCR0 + T_SCR / 32;      // the SX issuer: its MMA chain shares no accumulator with S1 / S2, so it runs in its own warp
-constexpr int T_THREADS = (W_SX + 1) * 32;
+constexpr int G1_ROWS = SL / G1_STEP, G2_ROWS = NCM * 8 / T_G2;
+static_assert(G1_STEP == 16 || G1_STEP == 8, "a gather thread's row jj lies in 16-row group jj * G1_STEP / 16: one K-step of S1");
+// warp roles (a warp's scheduler and its TMEM lane quarter are warp % 4: the epilogue / softmax / score groups are multiples of four
+// warps, one per quarter).  Two gather warps for the (E, TW) ring instead of four were measured slower (36.1 vs 38.4 M impressions/s).
+constexpr int W_G1 = 0, W_MMA = W_G1 + T_G1 / 32, W_SX = W_MMA + 1, W_G2 = W_SX + 1, W_EPI0 = W_G2 + T_G2 / 32, W_SMX0 = W_EPI0 + T_EPI / 32,
+              W_SCR0 = W_SMX0 + T_SMX / 32;
+constexpr int T_THREADS = (W_SCR0 + T_SCR / 32) * 32;
 #ifndef MINER_TSX_NDP
 #define MINER_TSX_NDP 2
 #endif
@@ -171,7 +176,7 @@ tscore_x_kernel(const TScoreArgs args, int n_tiles) {
   if (bars->tmem_base != 0u) __trap();                         // the CTA owns the SM's tensor memory: every address below is a constant
   constexpr uint32_t tmem = 0u;
 
-  if (warp < W_G2) {
+  if (warp < W_MMA) {
     // ------------------------------------------------------------------ gathers of the (E, TW) ring: thread = one 16-byte chunk of rows
     //        r0 + 16 jj, i.e. one row of every 16-slot group (K-step) of the tile
     const int t = threadIdx.x;
@@ -213,7 +218,7 @@ tscore_x_kernel(const TScoreArgs args, int n_tiles) {
           const uint32_t jb = static_cast<uint32_t>(j) * (FB * 2);
 #pragma unroll
           for (int jj = 0; jj < G1_ROWS; ++jj) {
-            if (jj < nks) {
+            if (jj * G1_STEP < nks * 16) {
               const uint32_t o = eoff[jj] + jb, sz = (((emask >> jj) & 1u) && !(ABL & 32)) ? 16u : 0u;
               tc::cp_async_16(base + jj * (G1_STEP * 128), table_b + o, sz);
               tc::cp_async_16(base + E_BYTES + jj * (G1_STEP * 128), tw_b + o, sz);
@@ -226,10 +231,10 @@ tscore_x_kernel(const TScoreArgs args, int n_tiles) {
     }
     tc::cp_async_wait_all();
     if (threadIdx.x == 0) PROF_STORE(2);
-  } else if (warp < W_MMA) {
+  } else if (warp >= W_G2 && warp < W_EPI0) {
     // ------------------------------------------------------------------ gathers of the candidate ring: thread = one 16-byte chunk of
     //        rows r0 + 8 jj; the candidate ids of the next unit are fetched one unit ahead and kept raw
-    const int t = threadIdx.x - T_G1;
+    const int t = threadIdx.x - W_G2 * 32;
     const int chunk = t & 7, r0 = t >> 3;
     const uint32_t row_bytes = static_cast<uint32_t>(D) * 2;
     const char* table_b = reinterpret_cast<const char*>(args.table);
@@ -385,7 +390,7 @@ tscore_x_kernel(const TScoreArgs args, int n_tiles) {
     }
     while (npend > 0) stage2();
     if (lane == 0) PROF_STORE(0);
-  } else if (warp < W_SMX0) {
+  } else if (warp >= W_EPI0 && warp < W_SMX0) {
     // ------------------------------------------------------------------ epilogue warps: P -> G = gelu(P) as bf16 hi | lo, in place
     const int ew = warp - W_EPI0;
     const int q = warp & 3;                                    // TMEM lane quarter
@@ -428,7 +433,7 @@ tscore_x_kernel(const TScoreArgs args, int n_tiles) {
       }
     }
     if (ew == 0 && lane == 0) PROF_STORE(1);
-  } else if (warp < W_SCR0) {
+  } else if (warp >= W_SMX0 && warp < W_SCR0) {
     // ------------------------------------------------------------------ softmax warps: lg rows of the tile's slots (cp.async, issued
     //        as soon as the previous unit's logits have been read) -> softmax over the history -> A_w[u & 1] in tensor memory
     const int sw = warp - W_SMX0;
