@@ -300,9 +300,10 @@ __global__ void __launch_bounds__(TT) poly_bwd_kernel(const void* __restrict__ t
   constexpr int DK = 64;                 // feature chunk
   float* codes_s = smem;                 // [K][Dc]
   float* dcodes_s = codes_s + K * Dc;    // [K][Dc]
-  float* dIc = dcodes_s + K * Dc;        // [K][DK+1]
-  float* Ec = dIc + K * (DK + 1);        // [H][DK+1]
-  float* dw = Ec + H * (DK + 1);         // [K][H]  dw -> dlogits
+  constexpr int DS = DK + 12;            // row stride of the chunk tiles: 16-byte aligned rows; rows two apart (a warp's slot tiles) are 24 banks apart: conflict-free LDS.128
+  float* dIc = smem + ((2 * K * Dc + 3) & ~3);   // [K][DS], 16-byte aligned
+  float* Ec = dIc + K * DS;              // [H][DS]
+  float* dw = Ec + H * DS;               // [K][H]  dw -> dlogits
   int* ids_s = reinterpret_cast<int*>(dw + K * H);   // [H] table row of each history slot, -1 = zero row
   const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
   for (int i = tid; i < K * Dc; i += TT) { codes_s[i] = codes[i]; dcodes_s[i] = 0.f; }
@@ -321,34 +322,34 @@ __global__ void __launch_bounds__(TT) poly_bwd_kernel(const void* __restrict__ t
       for (int i = tid; i < K * DK; i += TT) {
         const int k = i / DK, d = i - k * DK;
         const int64_t o = (b * K + k) * D + d0 + d;
-        dIc[k * (DK + 1) + d] = d < dn ? dI_a[o] + (dI_b ? dI_b[o] : 0.f) : 0.f;
+        dIc[k * DS + d] = d < dn ? dI_a[o] + (dI_b ? dI_b[o] : 0.f) : 0.f;
       }
       for (int i = tid; i < H * DK; i += TT) {
         const int h = i / DK, d = i - h * DK;
         const int id = ids_s[h];
-        Ec[h * (DK + 1) + d] = (d < dn && id >= 0) ? table_elem(table, table_dtype, static_cast<int64_t>(id) * D + d0 + d) : 0.f;
+        Ec[h * DS + d] = (d < dn && id >= 0) ? table_elem(table, table_dtype, static_cast<int64_t>(id) * D + d0 + d) : 0.f;
       }
       __syncthreads();
-      // 4 (codes) x 2 (slots) register tiles: 6 shared-memory loads per 8 FMAs
+      // 4 (codes) x 2 (slots) register tiles, four features per step: 6 LDS.128 per 32 FMAs
       const int th_n = (H + 1) / 2, tk_n = (K + 3) / 4;
       for (int t = tid; t < th_n * tk_n; t += TT) {
         const int tk = t / th_n, th = t - tk * th_n;
         const int k0 = tk * 4, h0 = th * 2;
-        const float* x[4];
-        const float* y[2];
+        const float4* x[4];
+        const float4* y[2];
 #pragma unroll
-        for (int i = 0; i < 4; ++i) x[i] = dIc + (k0 + i < K ? k0 + i : K - 1) * (DK + 1);
+        for (int i = 0; i < 4; ++i) x[i] = reinterpret_cast<const float4*>(dIc + (k0 + i < K ? k0 + i : K - 1) * DS);
 #pragma unroll
-        for (int j = 0; j < 2; ++j) y[j] = Ec + (h0 + j < H ? h0 + j : H - 1) * (DK + 1);
+        for (int j = 0; j < 2; ++j) y[j] = reinterpret_cast<const float4*>(Ec + (h0 + j < H ? h0 + j : H - 1) * DS);
         float acc[4][2] = {{0.f, 0.f}, {0.f, 0.f}, {0.f, 0.f}, {0.f, 0.f}};
-#pragma unroll 8
-        for (int d = 0; d < DK; ++d) {
-          const float y0 = y[0][d], y1 = y[1][d];
+#pragma unroll 4
+        for (int d = 0; d < DK / 4; ++d) {
+          const float4 y0 = y[0][d], y1 = y[1][d];
 #pragma unroll
           for (int i = 0; i < 4; ++i) {
-            const float xv = x[i][d];
-            acc[i][0] = fmaf(xv, y0, acc[i][0]);
-            acc[i][1] = fmaf(xv, y1, acc[i][1]);
+            const float4 xv = x[i][d];
+            acc[i][0] = fmaf(xv.x, y0.x, fmaf(xv.y, y0.y, fmaf(xv.z, y0.z, fmaf(xv.w, y0.w, acc[i][0]))));
+            acc[i][1] = fmaf(xv.x, y1.x, fmaf(xv.y, y1.y, fmaf(xv.z, y1.z, fmaf(xv.w, y1.w, acc[i][1]))));
           }
         }
 #pragma unroll
@@ -764,7 +765,7 @@ extern "C" int miner_train_bwd(const void* table, int64_t n_rows, int table_dtyp
   }
   // 3. poly attention: dZ1, dcodes
   {
-    const size_t smem = sizeof(float) * (2 * static_cast<size_t>(K) * Dc + K * 65 + H * 65 + K * H) + sizeof(int) * H;
+    const size_t smem = sizeof(float) * (2 * static_cast<size_t>(K) * Dc + K * 76 + H * 76 + K * H + 4) + sizeof(int) * H;
     if (smem > 220 * 1024) {
       set_error("train_bwd: H=%lld K=%lld Dc=%lld need %zu bytes of shared memory", (long long)H, (long long)K, (long long)Dc, smem);
       return MINER_ERR_UNSUPPORTED;
