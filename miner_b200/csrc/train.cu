@@ -380,26 +380,82 @@ __global__ void __launch_bounds__(TT) poly_bwd_kernel(const void* __restrict__ t
         d_bias[b * H + h] = sb;
       }
     // dT = dlogits^T codes, dZ1 = dT (1 - T^2)                                          (model.py:171,174)
-    for (int i = tid; i < H * Dc; i += TT) {
-      const int h = i / Dc, dc = i - h * Dc;
-      float s = 0.f;
-      for (int k = 0; k < K; ++k) s = fmaf(dw[k * H + h], codes_s[k * Dc + dc], s);
-      const float t = T[(b * H + h) * Dc + dc];
-      dZ1[(b * H + h) * Dc + dc] = s * (1.0f - t * t);
+    if ((Dc & 3) == 0) {
+      // 2 (slots) x 4 (code dimensions) register tiles: 3 shared-memory loads per 8 FMAs
+      const int tc_n = Dc / 4, th2_n = (H + 1) / 2;
+      for (int t = tid; t < th2_n * tc_n; t += TT) {
+        const int th = t / tc_n, c0 = (t - th * tc_n) * 4;
+        const int h0 = th * 2, h1 = h0 + 1 < H ? h0 + 1 : h0;
+        float a0[4] = {0.f, 0.f, 0.f, 0.f}, a1[4] = {0.f, 0.f, 0.f, 0.f};
+#pragma unroll 4
+        for (int k = 0; k < K; ++k) {
+          const float4 cv = *reinterpret_cast<const float4*>(codes_s + k * Dc + c0);
+          const float w0 = dw[k * H + h0], w1 = dw[k * H + h1];
+          a0[0] = fmaf(w0, cv.x, a0[0]); a0[1] = fmaf(w0, cv.y, a0[1]); a0[2] = fmaf(w0, cv.z, a0[2]); a0[3] = fmaf(w0, cv.w, a0[3]);
+          a1[0] = fmaf(w1, cv.x, a1[0]); a1[1] = fmaf(w1, cv.y, a1[1]); a1[2] = fmaf(w1, cv.z, a1[2]); a1[3] = fmaf(w1, cv.w, a1[3]);
+        }
+        const int64_t o0 = (b * H + h0) * Dc + c0;
+        const float4 t0 = *reinterpret_cast<const float4*>(T + o0);
+        *reinterpret_cast<float4*>(dZ1 + o0) = make_float4(a0[0] * (1.0f - t0.x * t0.x), a0[1] * (1.0f - t0.y * t0.y), a0[2] * (1.0f - t0.z * t0.z),
+                                                            a0[3] * (1.0f - t0.w * t0.w));
+        if (h0 + 1 < H) {
+          const int64_t o1 = o0 + Dc;
+          const float4 t1 = *reinterpret_cast<const float4*>(T + o1);
+          *reinterpret_cast<float4*>(dZ1 + o1) = make_float4(a1[0] * (1.0f - t1.x * t1.x), a1[1] * (1.0f - t1.y * t1.y), a1[2] * (1.0f - t1.z * t1.z),
+                                                              a1[3] * (1.0f - t1.w * t1.w));
+        }
+      }
+    } else {
+      for (int i = tid; i < H * Dc; i += TT) {
+        const int h = i / Dc, dc = i - h * Dc;
+        float s = 0.f;
+        for (int k = 0; k < K; ++k) s = fmaf(dw[k * H + h], codes_s[k * Dc + dc], s);
+        const float t = T[(b * H + h) * Dc + dc];
+        dZ1[(b * H + h) * Dc + dc] = s * (1.0f - t * t);
+      }
     }
     // dcodes += dlogits T                                                              (model.py:174)
-    for (int i = tid; i < ((K + 3) / 4) * Dc; i += TT) {                               // 4 codes per thread: one T load feeds 4 FMAs
-      const int k4 = i / Dc, dc = i - k4 * Dc;
-      const int k0 = k4 * 4;
-      float s[4] = {0.f, 0.f, 0.f, 0.f};
-      for (int h = 0; h < H; ++h) {
-        const float tv = T[(b * H + h) * Dc + dc];
+    if ((Dc & 3) == 0) {
+      // 4 (codes) x 4 (code dimensions) register tiles: one 16-byte T load + 4 shared-memory loads per 16 FMAs
+      const int tc_n = Dc / 4;
+      for (int i = tid; i < ((K + 3) / 4) * tc_n; i += TT) {
+        const int k4 = i / tc_n, c0 = (i - k4 * tc_n) * 4;
+        const int k0 = k4 * 4;
+        const float* wr[4];
 #pragma unroll
-        for (int j = 0; j < 4; ++j) s[j] = fmaf(dw[(k0 + j < K ? k0 + j : K - 1) * H + h], tv, s[j]);
+        for (int j = 0; j < 4; ++j) wr[j] = dw + (k0 + j < K ? k0 + j : K - 1) * H;
+        float s[4][4] = {};
+        const float* tp = T + b * H * Dc + c0;
+#pragma unroll 2
+        for (int h = 0; h < H; ++h) {
+          const float4 tv = *reinterpret_cast<const float4*>(tp + static_cast<int64_t>(h) * Dc);
+#pragma unroll
+          for (int j = 0; j < 4; ++j) {
+            const float wv = wr[j][h];
+            s[j][0] = fmaf(wv, tv.x, s[j][0]); s[j][1] = fmaf(wv, tv.y, s[j][1]); s[j][2] = fmaf(wv, tv.z, s[j][2]); s[j][3] = fmaf(wv, tv.w, s[j][3]);
+          }
+        }
+#pragma unroll
+        for (int j = 0; j < 4; ++j)
+          if (k0 + j < K) {
+            float* dc4 = dcodes_s + (k0 + j) * Dc + c0;
+            dc4[0] += s[j][0]; dc4[1] += s[j][1]; dc4[2] += s[j][2]; dc4[3] += s[j][3];
+          }
       }
+    } else {
+      for (int i = tid; i < ((K + 3) / 4) * Dc; i += TT) {                             // 4 codes per thread: one T load feeds 4 FMAs
+        const int k4 = i / Dc, dc = i - k4 * Dc;
+        const int k0 = k4 * 4;
+        float s[4] = {0.f, 0.f, 0.f, 0.f};
+        for (int h = 0; h < H; ++h) {
+          const float tv = T[(b * H + h) * Dc + dc];
 #pragma unroll
-      for (int j = 0; j < 4; ++j)
-        if (k0 + j < K) dcodes_s[(k0 + j) * Dc + dc] += s[j];
+          for (int j = 0; j < 4; ++j) s[j] = fmaf(dw[(k0 + j < K ? k0 + j : K - 1) * H + h], tv, s[j]);
+        }
+#pragma unroll
+        for (int j = 0; j < 4; ++j)
+          if (k0 + j < K) dcodes_s[(k0 + j) * Dc + dc] += s[j];
+      }
     }
     __syncthreads();
   }
