@@ -134,6 +134,101 @@ __global__ void __launch_bounds__(TT) loss_bwd_kernel(const float* __restrict__ 
   }
 }
 
+// The same backward with the interest rows held in REGISTERS (D = 128 NV, K <= 32): 16 warps, two rows per warp, each lane owns NV
+// float4 of a row; the norms and the dots with the column sum are warp reductions, the column sum of the normalised rows goes through
+// one [16][D] shared-memory stage.  Memory-bound (reads I once, writes dI once) instead of three passes over a 98 KB shared-memory copy.
+constexpr int LBW = 16;                  // warps per CTA
+template <int NV>
+__global__ void __launch_bounds__(LBW * 32) loss_bwd_rows_kernel(const float* __restrict__ interests, const float* __restrict__ logits,
+                                                                 const float* __restrict__ labels, const float* __restrict__ grad_out, int64_t B,
+                                                                 int C, int K, float* __restrict__ d_interests, float* __restrict__ d_logits) {
+  constexpr int D = 128 * NV;
+  extern __shared__ __align__(16) float smem[];
+  float (*part)[D] = reinterpret_cast<float (*)[D]>(smem);     // [LBW][D] per-warp sums of its normalised rows
+  float* Usum = smem + LBW * D;                                // [D]
+  const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+  const int64_t b = blockIdx.x;
+  const float g = grad_out ? grad_out[0] : 1.0f;
+  float4 u[2][NV];
+  float nrm[2];
+  float4 ps[NV];
+#pragma unroll
+  for (int j = 0; j < NV; ++j) ps[j] = make_float4(0.f, 0.f, 0.f, 0.f);
+#pragma unroll
+  for (int r = 0; r < 2; ++r) {
+    const int k = warp + LBW * r;
+    nrm[r] = 1.f;
+    if (k < K) {
+      const float4* row = reinterpret_cast<const float4*>(interests + (b * K + k) * D);
+      float ss = 0.f;
+#pragma unroll
+      for (int j = 0; j < NV; ++j) {
+        const float4 v = row[lane + 32 * j];
+        u[r][j] = v;
+        ss = fmaf(v.x, v.x, fmaf(v.y, v.y, fmaf(v.z, v.z, fmaf(v.w, v.w, ss))));
+      }
+      const float n = sqrtf(warp_sum(ss));
+      nrm[r] = n;
+#pragma unroll
+      for (int j = 0; j < NV; ++j) {
+        float4 v = u[r][j];
+        v.x /= n; v.y /= n; v.z /= n; v.w /= n;                    // utils.py:21-23: divide first
+        u[r][j] = v;
+        ps[j].x += v.x; ps[j].y += v.y; ps[j].z += v.z; ps[j].w += v.w;
+      }
+    }
+  }
+#pragma unroll
+  for (int j = 0; j < NV; ++j) reinterpret_cast<float4*>(part[warp])[lane + 32 * j] = ps[j];
+  __syncthreads();
+  for (int d = tid; d < D; d += LBW * 32) {
+    float s = 0.f;
+#pragma unroll
+    for (int w = 0; w < LBW; ++w) s += part[w][d];
+    Usum[d] = s;
+  }
+  __syncthreads();
+  const float scale = g * 2.0f / (static_cast<float>(B) * K * K);
+#pragma unroll
+  for (int r = 0; r < 2; ++r) {
+    const int k = warp + LBW * r;
+    if (k < K) {
+      float dot = 0.f;
+      float4 us[NV];
+#pragma unroll
+      for (int j = 0; j < NV; ++j) {
+        us[j] = reinterpret_cast<const float4*>(Usum)[lane + 32 * j];
+        const float4 v = u[r][j];
+        dot = fmaf(v.x, us[j].x, fmaf(v.y, us[j].y, fmaf(v.z, us[j].z, fmaf(v.w, us[j].w, dot))));
+      }
+      dot = warp_sum(dot);
+      // S_k = Usum - u_k ;  u_k . S_k = u_k . Usum - |u_k|^2 with |u_k|^2 = 1
+      const float c1 = dot - 1.0f, inv = scale / nrm[r];
+      float4* out = reinterpret_cast<float4*>(d_interests + (b * K + k) * D);
+#pragma unroll
+      for (int j = 0; j < NV; ++j) {
+        const float4 v = u[r][j];
+        out[lane + 32 * j] = make_float4(((us[j].x - v.x) - c1 * v.x) * inv, ((us[j].y - v.y) - c1 * v.y) * inv, ((us[j].z - v.z) - c1 * v.z) * inv,
+                                         ((us[j].w - v.w) - c1 * v.w) * inv);
+      }
+    }
+  }
+  if (warp == 0) {
+    const float* lg = logits + b * C;
+    const float* lb = labels + b * C;
+    float best = -INFINITY; int arg = 0;
+    for (int c = 0; c < C; ++c) { const float v = lb[c]; if (v > best) { best = v; arg = c; } }     // argmax, first maximum
+    float mx = -INFINITY;
+    for (int c = lane; c < C; c += 32) mx = fmaxf(mx, lg[c]);
+    mx = warp_max(mx);
+    float se = 0.f;
+    for (int c = lane; c < C; c += 32) se += expf(lg[c] - mx);
+    se = warp_sum(se);
+    for (int c = lane; c < C; c += 32)
+      d_logits[b * C + c] = g * (expf(lg[c] - mx) / se - (c == arg ? 1.0f : 0.0f)) / static_cast<float>(B);
+  }
+}
+
 // ---- backward through the target-aware attention of one impression (model.py:127,200-216): one CTA per impression
 __global__ void __launch_bounds__(TT) target_bwd_kernel(const void* __restrict__ table, int table_dtype, int64_t n_rows,
                                                         const void* __restrict__ cand_ids, int id_dtype, const float* __restrict__ interests,
@@ -704,6 +799,21 @@ extern "C" int miner_loss_bwd(const float* interests, const float* logits, const
                               int64_t C, int64_t K, int64_t D, float* d_interests, float* d_logits, void* stream) {
   MINER_CHECK_ARG(B > 0 && C > 0 && K > 0 && D > 0, "loss_bwd: bad sizes");
   MINER_CHECK_ARG(interests && logits && labels && d_interests && d_logits, "loss_bwd: null pointer");
+  if (K <= 2 * LBW && D % 128 == 0 && D <= 768 && (reinterpret_cast<uintptr_t>(interests) | reinterpret_cast<uintptr_t>(d_interests)) % 16 == 0) {
+    auto st = static_cast<cudaStream_t>(stream);
+    switch (D / 128) {      // rows in registers (see loss_bwd_rows_kernel)
+#define MINER_LB(NVV)                                                                                                                          \
+  case NVV:                                                                                                                                    \
+    MINER_CUDA_OK(cudaFuncSetAttribute(loss_bwd_rows_kernel<NVV>, cudaFuncAttributeMaxDynamicSharedMemorySize, (LBW + 1) * 128 * NVV * 4));    \
+    loss_bwd_rows_kernel<NVV><<<static_cast<unsigned>(B), LBW * 32, (LBW + 1) * 128 * NVV * 4, st>>>(interests, logits, labels, grad_out, B,   \
+                                                                                                     (int)C, (int)K, d_interests, d_logits);     \
+    break
+      MINER_LB(1); MINER_LB(2); MINER_LB(3); MINER_LB(4); MINER_LB(5); MINER_LB(6);
+#undef MINER_LB
+    }
+    MINER_LAUNCH_OK("loss_bwd_rows");
+    return MINER_OK;
+  }
   const size_t smem = sizeof(float) * (static_cast<size_t>(K) * (D + 1) + D + 2 * K);
   if (smem > 220 * 1024) {
     set_error("loss_bwd: K=%lld D=%lld needs %zu bytes of shared memory", (long long)K, (long long)D, smem);
