@@ -18,6 +18,10 @@
 namespace miner {
 
 constexpr int MT = 256;            // threads per block (8 warps)
+#ifndef MINER_RM_MINB
+#define MINER_RM_MINB 3
+#endif
+constexpr int RM_MINB = MINER_RM_MINB;   // resident blocks per SM the kernel is compiled for (register cap) and launched with
 constexpr int MCAP = 1024;         // candidates per impression staged in shared memory per warp
 constexpr int MAXK = 8;            // cut-offs
 constexpr int LOG2_TAB = 256;      // ranks below this take log2 from a shared-memory table
@@ -32,7 +36,7 @@ __device__ __forceinline__ float transform_score(float s, int transform, float m
 }
 
 template <int NK>
-__global__ void __launch_bounds__(MT, 2) rank_metrics_kernel(const float* __restrict__ scores, const int8_t* __restrict__ labels,
+__global__ void __launch_bounds__(MT, RM_MINB) rank_metrics_kernel(const float* __restrict__ scores, const int8_t* __restrict__ labels,
                                                           const int64_t* __restrict__ offsets, int64_t B, int transform,
                                                           MetricKs ks, double* __restrict__ block_partials,
                                                           double* __restrict__ per_impression) {
@@ -171,7 +175,7 @@ __global__ void rank_metrics_finalize(const double* __restrict__ block_partials,
 
 static int metrics_grid(int64_t B) {
   int64_t blocks = (B + MT / 32 - 1) / (MT / 32);
-  const int64_t cap = static_cast<int64_t>(sm_count()) * 4;
+  const int64_t cap = static_cast<int64_t>(sm_count()) * 2 * RM_MINB;
   if (blocks > cap) blocks = cap;
   if (blocks < 1) blocks = 1;
   return static_cast<int>(blocks);
