@@ -40,18 +40,34 @@ class HostEvaluator:
             self._pws = torch.empty(max(n, 1), dtype=torch.uint8, device=self.dev)
         return self._pws
 
-    def _stage(self, host: Dict[str, torch.Tensor], a: int, b: int):
-        """Issue the H2D copies of impressions [a, b) on the copy stream; returns device tensors + the event to wait on."""
-        offs = host['offsets']
-        c0, c1 = int(offs[a]), int(offs[b])
+    def _buffers(self, host: Dict[str, torch.Tensor], bounds, cb):
+        """Two persistent sets of device buffers for the waves (kept across calls while they are large enough): no allocator traffic and
+        no cross-stream recycling inside the timed path.  A set is rewritten by the copy stream only after the kernels that read it."""
+        n_imp = max(b - a for a, b in zip(bounds[:-1], bounds[1:]))
+        n_cand = max(max(b - a for a, b in zip(cb[:-1], cb[1:])), 1)
+        H = host['his_ids'].shape[1]
+        key = (H, host['his_ids'].dtype, host['his_mask'].dtype, host['cand_ids'].dtype, host['labels'].dtype)
+        cur = getattr(self, '_bufs', None)
+        if cur is None or cur['key'] != key or cur['n_imp'] < n_imp or cur['n_cand'] < n_cand:
+            mk = lambda shape, dt: torch.empty(shape, dtype=dt, device=self.dev)
+            sets = [{'his_ids': mk((n_imp, H), key[1]), 'his_mask': mk((n_imp, H), key[2]), 'cand_ids': mk((n_cand,), key[3]),
+                     'labels': mk((n_cand,), key[4]), 'offsets': mk((n_imp + 1,), torch.int64), 'scores': mk((n_cand,), torch.float32),
+                     'free': None} for _ in range(2)]
+            cur = self._bufs = {'key': key, 'n_imp': n_imp, 'n_cand': n_cand, 'sets': sets}
+        return cur['sets']
+
+    def _stage(self, host: Dict[str, torch.Tensor], buf, a: int, b: int, c0: int, c1: int):
+        """Issue the H2D copies of impressions [a, b) into one buffer set on the copy stream; returns views of it + the event to wait on."""
         with torch.cuda.stream(self.copy_stream):
-            d = {'his_ids': host['his_ids'][a:b].to(self.dev, non_blocking=True),
-                 'his_mask': host['his_mask'][a:b].to(self.dev, non_blocking=True),
-                 'cand_ids': host['cand_ids'][c0:c1].to(self.dev, non_blocking=True),
-                 'labels': host['labels'][c0:c1].to(self.dev, non_blocking=True),
-                 'offsets': offs[a:b + 1].to(self.dev, non_blocking=True)}
+            if buf['free'] is not None:
+                self.copy_stream.wait_event(buf['free'])          # the kernels of the wave that used this set last are done
+            d = {}
+            for k, lo, hi in (('his_ids', a, b), ('his_mask', a, b), ('cand_ids', c0, c1), ('labels', c0, c1), ('offsets', a, b + 1)):
+                d[k] = buf[k][:hi - lo]
+                d[k].copy_(host[k][lo:hi], non_blocking=True)
             ev = torch.cuda.Event()
             ev.record(self.copy_stream)
+        d['scores'] = buf['scores'][:c1 - c0]
         d['c0'] = c0
         return d, ev
 
@@ -72,28 +88,32 @@ class HostEvaluator:
         total = None
         scores_all = torch.empty(int(host['offsets'][-1]), dtype=torch.float32, device=self.dev) if want_scores else None
         bounds = list(range(0, B, self.wave)) + [B]
-        nxt = self._stage(host, bounds[0], bounds[1]) if B > 0 else None
-        for i in range(len(bounds) - 1):
+        n_waves = len(bounds) - 1
+        cb = [int(host['offsets'][b]) for b in bounds]
+        sets = self._buffers(host, bounds, cb) if n_waves > 0 else None
+        stage = lambda i: self._stage(host, sets[i & 1], bounds[i], bounds[i + 1], cb[i], cb[i + 1])
+        nxt = stage(0) if n_waves > 0 else None
+        for i in range(n_waves):
             d, ev = nxt
-            nxt = self._stage(host, bounds[i + 1], bounds[i + 2]) if i + 2 < len(bounds) else None
+            nxt = stage(i + 1) if i + 1 < n_waves else None
             compute.wait_event(ev)
-            offs = d['offsets'] - d['c0']
+            offs = d['offsets'].sub_(d['c0'])
             if self.math == L.MATH_TABLE:
                 nb = d['his_ids'].shape[0]
                 if getattr(self, '_tws', None) is None or self._tws.numel() < L.load().miner_score_table_workspace_bytes(nb, Hh, Kk):
                     self._tws = ops.score_table_workspace(max(nb, self.wave), Hh, Kk, self.dev)
                 _, s = ops.score_table(self._proj, d['his_ids'], d['his_mask'], d['cand_ids'], self.model.score_type, cand_offsets=offs,
-                                       workspace=self._tws)
+                                       out_scores=d['scores'], workspace=self._tws)
             else:
                 _, s = ops.score(self.table, d['his_ids'], d['his_mask'], d['cand_ids'], w, self.model.score_type, cand_offsets=offs,
-                                 math=self.math, chunk=self.chunk)
+                                 math=self.math, chunk=self.chunk, out_scores=d['scores'])
             p, _ = ops.rank_metrics_raw(s, d['labels'], offs, self.transform, self.ks)
             total = p if total is None else total + p
             if want_scores:
                 scores_all[d['c0']:d['c0'] + s.numel()] = s
-            for t in d.values():                      # the copy stream must not recycle these buffers before the kernels are done
-                if isinstance(t, torch.Tensor):
-                    t.record_stream(compute)
+            free = torch.cuda.Event()
+            free.record(compute)
+            sets[i & 1]['free'] = free
         if total is None:
             total = torch.zeros(2 * (2 + 2 * len(self.ks)), dtype=torch.float64, device=self.dev)
         if self.check_bounds and getattr(self, '_tws', None) is not None:

@@ -514,6 +514,45 @@ def test_rank_metrics_ties_nan_and_long_impressions():
         assert abs(agg[n] - np.nanmean(ref[n])) < 1e-12
 
 
+def test_rank_metrics_ragged_lengths_all_kernel_paths():
+    """Impressions of 1..1100 candidates in one call: one lane per impression (<= 64), the whole warp from shared memory (65..1024 inside
+    a group that fits the staging capacity), the whole warp from global memory (a group past the capacity); ties (scores rounded to two
+    digits), graded labels, impressions without positives / without negatives, B not a multiple of 32; sigmoid and no transform, and
+    the softmax transform (warp-per-impression kernel) against the same oracle."""
+    from miner_b200 import ops
+    rng = np.random.default_rng(11)
+    lens = np.concatenate([rng.integers(1, 65, 70), [65, 64, 200, 1, 2], rng.integers(1, 40, 37), [1100, 3, 5], rng.integers(1, 30, 50),
+                           [64] * 33, rng.integers(60, 70, 12)])
+    offs = np.concatenate([[0], np.cumsum(lens)])
+    T = int(offs[-1])
+    y = (rng.random(T) < 0.12).astype(np.int64) * rng.integers(1, 4, T)          # graded labels 0..3
+    y[offs[3]:offs[4]] = 0                                                          # no positives
+    y[offs[5]:offs[6]] = 1                                                          # no negatives
+    raw = np.round(rng.normal(0, 1.5, T), 1).astype(np.float32)                     # many exact ties
+    dev = lambda a, dt=None: torch.from_numpy(a).to(DEV) if dt is None else torch.from_numpy(a).to(dt).to(DEV)
+    names = ops.metric_names((1, 5, 10))
+    for transform in ('none', 'sigmoid', 'softmax'):
+        if transform == 'none':
+            p = raw
+        elif transform == 'sigmoid':
+            p = torch.sigmoid(torch.from_numpy(raw)).numpy()
+        else:
+            p = np.concatenate([torch.softmax(torch.from_numpy(raw[a:b]), 0).numpy() for a, b in zip(offs[:-1], offs[1:])])
+        ref = O.per_impression_metrics(y, p.astype(np.float64), offs, ks=(1, 5, 10))
+        partials, per = ops.rank_metrics_raw(dev(raw), dev(y, torch.int8), dev(offs), transform, (1, 5, 10), per_impression=True)
+        per = per.cpu().numpy()
+        for i, n in enumerate(names):
+            if transform == 'none':          # given probabilities: pure comparisons, float64 arithmetic
+                np.testing.assert_allclose(per[:, i], ref[n], rtol=1e-12, atol=0, equal_nan=True, err_msg=f'{transform} {n}')
+            else:                            # the transform's last bit may make or break a tie of two different raw scores
+                same = np.isclose(per[:, i], ref[n], rtol=1e-12, atol=0, equal_nan=True)
+                assert same.mean() > 0.97, (transform, n, same.mean())
+        pp = partials.cpu().numpy().reshape(-1, 2)
+        for i, n in enumerate(names):
+            col = per[:, i]
+            assert pp[i, 1] == np.sum(~np.isnan(col)) and abs(pp[i, 0] - np.nansum(col)) < 1e-9 * max(1.0, abs(np.nansum(col)))
+
+
 def test_slow_and_fast_evaluators():
     from types import SimpleNamespace
     import miner_b200 as mb
