@@ -366,10 +366,20 @@ def main():
     proj_ws = torch.empty(max(_lib.load().miner_table_project_workspace_bytes(table.shape[0], DC), 1), dtype=torch.uint8, device=dev)
     tws = ops.score_table_workspace(B, H, K, dev) if math == _lib.MATH_TABLE else None   # packed tiles: rebuilt by every call
 
+    stage_marks = None                            # while a list: device_step appends one CUDA event per stage boundary (table mode)
+
+    def mark():
+        if stage_marks is not None:
+            e = torch.cuda.Event(enable_timing=True)
+            e.record()
+            stage_marks.append(e)
+
     def score_step(d, m, out=None, ws=None):
         out = scores_buf if out is None else out
         if m == _lib.MATH_TABLE:
+            mark()
             ops.table_project(table, sw, out=proj, workspace=proj_ws)       # part of the step: nothing is carried over between steps
+            mark()
             ops.score_table(proj, d['his_ids'], d['his_mask'], d['cand_ids'], 'weighted', cand_offsets=d['offsets'], out_scores=out,
                             workspace=tws if ws is None else ws)
         else:
@@ -378,7 +388,9 @@ def main():
 
     def device_step(d, m=None):
         score_step(d, math if m is None else m)
+        mark()
         partials, _ = ops.rank_metrics_raw(scores_buf, d['labels'], d['offsets'], 'sigmoid', KS)
+        mark()
         parallel.allreduce_partials(partials)
         return partials
 
@@ -416,8 +428,15 @@ def main():
     if rank == 0:
         sampler.start()
     l0 = ops.launch_count()
+    stage_marks = [] if math == _lib.MATH_TABLE else None
     ms_dev, partials = timed(lambda: device_step(resident), args.steps)
     launches = ops.launch_count() - l0
+    # stage times INSIDE the timed region (four events per step on the launching stream): under the board's power cap the steps of a
+    # long run are slower than a kernel timed alone after an idle gap, so these -- not the stand-alone times -- go into the roofline
+    in_loop = None
+    if stage_marks:
+        ev, stage_marks = stage_marks, None
+        in_loop = [sum(ev[4 * i + j].elapsed_time(ev[4 * i + j + 1]) for i in range(args.steps)) / args.steps for j in range(3)]
     metrics_out = parallel.finalize_metrics(partials, names)
     if math == _lib.MATH_TABLE:
         ops.check_oob(tws)                       # an id outside the table would have raised here (the reference: IndexError)
@@ -475,6 +494,11 @@ def main():
             kernels.append({'kernel': name, 'ms_per_step': one(fn), 'launches_per_step': 3 if mask == 'proj' else (2 if mask == 'score' else nchunks)})
         kernels.append({'kernel': 'rank_metrics (+finalize)', 'launches_per_step': 2,
                         'ms_per_step': one(lambda: ops.rank_metrics_raw(scores_buf, resident['labels'], resident['offsets'], 'sigmoid', KS))})
+        if in_loop is not None:
+            for k, ms_in in zip(kernels, in_loop):
+                k['ms_alone'] = k['ms_per_step']                      # one call after an idle gap (burst clocks)
+                k['ms_per_step'] = ms_in                              # CUDA events inside the timed steps (sustained, power-capped clocks)
+                k['timing'] = 'ms_per_step: CUDA events around the stage inside the timed steps; ms_alone: one call after an idle gap'
         tot = sum(k['ms_per_step'] for k in kernels)
         for k in kernels:
             k['share'] = k['ms_per_step'] / tot
@@ -519,6 +543,11 @@ def main():
                         'algorithmic_bytes_per_impression': byts[mask],
                         'algorithmic_bytes_note': 'SURVEY 8(d): (H + C) D s gathered rows + (H + C) 8 ids + H mask + 5 C scores/labels, every one of '
                                                   'the H = 50 history slots counted'}
+            if 'ms_alone' in kernels[top]:
+                roofline['ms_per_launch_alone'] = kernels[top]['ms_alone'] / nchunks
+                roofline['frac_alone'] = roofline['frac'] * kernels[top]['ms_per_step'] / kernels[top]['ms_alone']
+                roofline['timing_note'] = ('ms_per_launch / achieved / frac: the kernel pair timed by CUDA events inside the timed steps (the board '
+                                           'runs at its power cap there, SM clock ~1800 of 1965 MHz); *_alone: one launch after an idle gap')
             if math == _lib.MATH_TABLE:
                 # what the kernel really gathers: per history slot a table row and a tw row, but the masked padding slots of an
                 # impression are ONE slot (same row, same softmax term); + lg rows, compact slot records, candidates
