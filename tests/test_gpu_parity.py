@@ -825,6 +825,11 @@ def test_host_evaluator_pipeline():
         p, s = ev.evaluate(host, want_scores=True)
         assert torch.equal(s, s_ref)
         assert torch.allclose(p, p_ref, rtol=1e-12, atol=0)
+        p2, _ = ev.evaluate(host)                  # the second call reuses the two device buffer sets of the first
+        assert torch.equal(p2, p)
+        assert ev._wave_bounds(B)[-1] == B and all(b % 4 == 0 for b in ev._wave_bounds(B)[:-1])
+    ev = mb.HostEvaluator(m, wave=400, first_wave=400, wave_growth=1.0, max_wave=400)        # equal waves
+    assert len(ev._wave_bounds(B)) == 5 and torch.equal(ev.evaluate(host, want_scores=True)[1], s_ref)
     p0, _ = mb.HostEvaluator(m).evaluate({k: v[:0] if k != 'offsets' else v[:1] for k, v in host.items()})
     assert float(p0.abs().sum()) == 0.0
 
