@@ -92,6 +92,10 @@ class HostEvaluator:
         Returns (partials (2*M,) float64 on the device: [sum, count] per metric of ops.metric_names(ks), scores (T,) or None)."""
         B = host['his_ids'].shape[0]
         Hh, Kk = host['his_ids'].shape[1], self.model.poly_attn.context_codes.shape[0]
+        compute = torch.cuda.current_stream(self.dev)
+        # the wave buffers are allocated on (and may be recycled from blocks last used on) the compute stream: the copy stream must not
+        # write into them ahead of the work already queued there
+        self.copy_stream.wait_stream(compute)
         if self._math_arg is None:
             self.math = ops.default_eval_math(self.table, host['his_ids'].shape[1], self.model.poly_attn.context_codes.shape[0])
         w = self.model._weights(with_bf16=(self.math != L.MATH_FP32))
@@ -99,7 +103,6 @@ class HostEvaluator:
             # the table-level projections belong to the call: they are recomputed here, not carried over between calls
             self._proj = ops.table_project(self.table, w, weighted=self.model.score_type == 'weighted', out=getattr(self, '_proj', None),
                                            workspace=self._proj_ws())
-        compute = torch.cuda.current_stream(self.dev)
         total = None
         scores_all = torch.empty(int(host['offsets'][-1]), dtype=torch.float32, device=self.dev) if want_scores else None
         bounds = self._wave_bounds(B)

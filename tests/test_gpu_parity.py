@@ -834,6 +834,56 @@ def test_host_evaluator_pipeline():
     assert float(p0.abs().sum()) == 0.0
 
 
+def test_poisoned_allocator_no_uninitialized_reads_no_stream_races():
+    """Every free block of the caching allocator is filled with a byte pattern before each run, then the scoring step and the
+    HostEvaluator pipeline (copy stream + compute stream) run on freshly allocated buffers WITHOUT synchronising in between: a kernel
+    that reads memory it did not write, or a copy that runs ahead of work queued on the other stream, changes the outputs."""
+    import miner_b200 as mb
+    from miner_b200 import synth, ops
+    from miner_b200 import _lib
+    B, H, N, D, K, Dc = 20000, 50, 30000, 768, 32, 200          # (scripts/stress_poison.py is the long form of this test)
+    table = synth.make_table(N, D, 36, torch.bfloat16).to(DEV)
+    w = synth.make_weights(D, K, Dc, 36)
+    eb = synth.make_eval_batch(B, H, N, 36)
+    m = mb.Miner(mb.TableNewsEncoder(table), False, K, Dc, 'weighted', 0.2).to(DEV).eval()
+    with torch.no_grad():
+        m.poly_attn.linear.weight.copy_(w.w_proj)
+        m.poly_attn.context_codes.copy_(w.context_codes)
+        m.target_aware_attn.linear.weight.copy_(w.w_target)
+    d = {k: getattr(eb, k).to(DEV) for k in ('his_ids', 'his_mask', 'cand_ids', 'labels', 'offsets')}
+    host = {k: getattr(eb, k).pin_memory() for k in ('his_ids', 'his_mask', 'cand_ids', 'labels', 'offsets')}
+
+    def poison(byte):
+        torch.cuda.synchronize()
+        torch.cuda.empty_cache()
+        blocks = [torch.full((256 << 20,), byte, dtype=torch.uint8, device=DEV) for _ in range(6)]
+        small = [torch.full((1 << 16,), byte, dtype=torch.uint8, device=DEV) for _ in range(64)]
+        torch.cuda.synchronize()
+        del blocks, small
+
+    ref = None
+    for byte in (0x00, 0xFF, 0x7F, 0x80, 0xFF):
+        poison(byte)
+        m.invalidate()
+        proj = ops.table_project(table, m._weights(with_bf16=True))
+        _, scores = ops.score_table(proj, d['his_ids'], d['his_mask'], d['cand_ids'], 'weighted', cand_offsets=d['offsets'])
+        part, per = ops.rank_metrics_raw(scores, d['labels'], d['offsets'], 'sigmoid', (5, 10), per_impression=True)
+        ev = mb.HostEvaluator(m, wave=4096, chunk=1024)
+        p_e2e, s_e2e = ev.evaluate(host, want_scores=True)
+        s_ro = m.score_impressions(d['his_ids'], d['his_mask'], d['cand_ids'], d['offsets'], math=_lib.MATH_TENSOR)
+        p_e2e2, _ = ev.evaluate(host)
+        cur = {'lg': proj.lg, 'tw': proj.tw, 'scores': scores, 'partials': part, 'per': per, 'e2e_scores': s_e2e, 'e2e_partials': p_e2e,
+               'reference_order_scores': s_ro, 'e2e_partials_again': p_e2e2}
+        torch.cuda.synchronize()
+        if ref is None:
+            ref = {k: v.clone() for k, v in cur.items()}
+            assert torch.equal(s_e2e, scores)
+            continue
+        for k, v in cur.items():
+            same = (v == ref[k]) | (torch.isnan(v.float()) & torch.isnan(ref[k].float()))
+            assert bool(same.all()), (hex(byte), k, int((~same).sum()))
+
+
 # ------------------------------------------------------------------------------------------------ sweep (BASELINE config 4) and Fastformer-style scoring (config 5)
 @pytest.mark.parametrize('H', [50, 100, 200])
 @pytest.mark.parametrize('K', [8, 16, 32, 64])
