@@ -3,9 +3,12 @@
 // compute_mrr_score / compute_dcg_score / compute_ndcg_score / is_hit (evaluation.py:177-249) plus sklearn's
 // roc_auc_score per impression (group_auc, evaluation.py:56-59).
 //
-// CSR layout: impression b owns candidates offsets[b] .. offsets[b+1].  One warp per impression (grid-stride, the
-// grid a multiple of the SM count).  The warp stages the transformed scores in shared memory, then each lane derives
-// the rank of its candidates by counting -- pure comparisons, so the ranking is bit-exact given the scores:
+// CSR layout: impression b owns candidates offsets[b] .. offsets[b+1].  Two kernels share the arithmetic (ImpressionTally):
+//   rank_metrics_lane_kernel  (transforms none / sigmoid) a warp stages the candidates of 32 consecutive impressions, one lane ranks
+//                             each of them; longer impressions fall back to the whole warp
+//   rank_metrics_kernel       (softmax transform) one warp per impression, grid-stride
+// The transformed scores are staged in shared memory, then the rank of a candidate is derived by counting -- pure comparisons, so
+// the ranking is bit-exact given the scores:
 //     gt  = #{j : p_j >  p_i}
 //     rank_np = gt + #{j > i : p_j == p_i}   position under np.argsort(p)[::-1] (evaluation.py:188,208) with the tie rule
 //                                            "stable ascending sort, reversed" (oracle/miner_oracle.py)
