@@ -46,7 +46,9 @@ stop = True; t.join()
 ts = [ev[i].elapsed_time(ev[i + 1]) for i in range(calls)]
 win = max(calls // 4, 1)
 means = [sum(ts[i:i + win]) / len(ts[i:i + win]) for i in range(0, calls, win)]
+half = samples[len(samples) // 2:]
 pw = sorted(s[0] for s in samples); ck = sorted(s[1] for s in samples)
-print('first %.2f  windows %s  last-half mean %.3f ms  | power median %.0f max %.0f W, sm clock median %d min %d MHz (%d samples)' % (
+print('first %.2f  windows %s  last-half mean %.3f ms  | power median %.0f max %.0f W, sm clock median %d min %d MHz (%d samples); '
+      'second half of the run: mean %.0f W, mean clock %.0f MHz' % (
     ts[0], ' '.join('%.2f' % m for m in means), sum(ts[calls // 2:]) / len(ts[calls // 2:]), pw[len(pw) // 2], pw[-1], ck[len(ck) // 2], ck[0],
-    len(samples)))
+    len(samples), sum(s[0] for s in half) / len(half), sum(s[1] for s in half) / len(half)))
