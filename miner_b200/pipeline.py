@@ -1,9 +1,11 @@
 """Host-to-metrics evaluation pipeline: the call a user makes to score a block of impressions that lives in (pinned)
 host memory and get the ranking metrics back.
 
-Waves of `wave` impressions are copied host->device on a copy stream while the previous wave is being scored
-(table-level tscore_kernel, or hist_kernel -> cand_kernel in reference order, then rank_metrics) on the compute stream; the per-wave [sum, count] metric partials add up
-(exactly what ranks all-reduce, parallel.allreduce_partials).  Everything on the device runs in the sm_100a kernels of
+Waves of impressions are copied host->device on a copy stream, into one of two persistent sets of device buffers, while the
+previous wave is being scored (table-level tpack + scoring kernel, or hist_kernel -> cand_kernel in reference order, then
+rank_metrics) on the compute stream; the per-wave [sum, count] metric partials add up (exactly what ranks all-reduce,
+parallel.allreduce_partials).  The first wave is small (its copy is the only one nothing hides), later waves double up to
+4 x `wave`.  Everything on the device runs in the sm_100a kernels of
 libminer_b200.so; this file is stream / buffer plumbing only.
 """
 from __future__ import annotations
