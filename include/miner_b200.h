@@ -136,6 +136,12 @@ int miner_cast_f32_to_bf16(const float* src, void* dst, int64_t n, void* stream)
 int miner_tc_gemm(const void* a_bf16, const void* a_ids, int id_dtype, int64_t a_rows_in_table, const void* b_bf16,
                   float* c, void* c_bf16, int64_t M, int64_t N, int64_t K, int epilogue, void* stream);
 
+/* The weight-gradient GEMM of the train variant on its own (trainer.py:246-261: d loss / d nn.Linear.weight = dY^T X):
+ *      c[s][M,N] fp32 = sum over the rows of split s of a[r,:]^T b[r,:], a (R,M) and b (R,N) bf16 row-major, read MN-major by
+ *      tcgen05 (no transposed copies); c holds k_splits partials, summed by the caller in split order.
+ *      Needs M % 8 == 0, N % 8 == 0, N >= 16. */
+int miner_tc_gemm_tn(const void* a_bf16, const void* b_bf16, float* c, int64_t R, int64_t M, int64_t N, int k_splits, void* stream);
+
 /* The two kernels of the fused tensor-core path on their own (tests / profiling).
  *   miner_hist_interests_fwd: PolyAttention.forward (model.py:159-185) straight from a bf16 table: gathers table[his_ids],
  *      projects on tcgen05, softmax over the history, weighted sum on tcgen05.  Writes the interests split as two bf16 arrays

@@ -28,7 +28,7 @@ EXPORTS = [
     'miner_abi_version', 'miner_last_error', 'miner_device_info', 'miner_launch_count', 'miner_gather', 'miner_category_bias',
     'miner_poly_attn_workspace_bytes', 'miner_poly_attn_fwd', 'miner_target_score_workspace_bytes',
     'miner_target_score_fwd', 'miner_score_workspace_bytes', 'miner_score_fwd', 'miner_cast_f32_to_bf16',
-    'miner_tc_gemm', 'miner_rank_metrics_workspace_bytes', 'miner_rank_metrics', 'miner_loss_workspace_bytes',
+    'miner_tc_gemm', 'miner_tc_gemm_tn', 'miner_rank_metrics_workspace_bytes', 'miner_rank_metrics', 'miner_loss_workspace_bytes',
     'miner_loss_fwd', 'miner_hist_interests_workspace_bytes', 'miner_hist_interests_fwd', 'miner_cand_score_fwd',
     'miner_table_project_workspace_bytes', 'miner_table_project', 'miner_score_table_supported', 'miner_score_table_fwd',
     'miner_score_table_workspace_bytes', 'miner_score_table_tile_geometry',
@@ -79,6 +79,7 @@ def _declare(lib: C.CDLL) -> None:
     lib.miner_score_fwd.argtypes = [C.POINTER(ScoreParams), i64, vp, sz, vp]
     lib.miner_cast_f32_to_bf16.argtypes = [vp, vp, i64, vp]
     lib.miner_tc_gemm.argtypes = [vp, vp, i32, i64, vp, vp, vp, i64, i64, i64, i32, vp]
+    lib.miner_tc_gemm_tn.argtypes = [vp, vp, vp, i64, i64, i64, i32, vp]
     lib.miner_rank_metrics_workspace_bytes.argtypes = [i64, i32]
     lib.miner_rank_metrics_workspace_bytes.restype = sz
     lib.miner_rank_metrics.argtypes = [vp, vp, vp, i64, i32, C.POINTER(i32), i32, vp, vp, vp, sz, vp]

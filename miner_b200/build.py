@@ -13,7 +13,7 @@ PKG = os.path.dirname(os.path.abspath(__file__))
 CSRC = os.path.join(PKG, 'csrc')
 OBJ = os.path.join(PKG, 'build')
 LIB = os.path.join(PKG, 'libminer_b200.so')
-SOURCES = ['api.cu', 'gather.cu', 'sgemm.cu', 'poly.cu', 'target.cu', 'bias.cu', 'metrics.cu', 'auc.cu', 'loss.cu', 'train.cu', 'tc/tc_gemm.cu', 'tc/tmap.cu', 'tc/hist_kernel2.cu', 'tc/cand_kernel.cu', 'tc/table_project.cu', 'tc/tscore_kernel.cu', 'tc/tscore_x_kernel.cu']
+SOURCES = ['api.cu', 'gather.cu', 'sgemm.cu', 'poly.cu', 'target.cu', 'bias.cu', 'metrics.cu', 'auc.cu', 'loss.cu', 'train.cu', 'tc/tc_gemm.cu', 'tc/tc_gemm_tn.cu', 'tc/tmap.cu', 'tc/hist_kernel2.cu', 'tc/cand_kernel.cu', 'tc/table_project.cu', 'tc/tscore_kernel.cu', 'tc/tscore_x_kernel.cu']
 NVCC_FLAGS = ['-gencode', 'arch=compute_100a,code=sm_100a', '-O3', '-lineinfo', '-std=c++17', '-Xcompiler', '-fPIC',
               '-Xptxas', '-v', '--expt-relaxed-constexpr']
 

@@ -21,4 +21,10 @@ int tc_gemm_splits(int64_t M, int64_t N, int64_t K);
 int launch_tc_gemm_splitk(const void* A, const void* a_ids, int id_dtype, int64_t a_rows_in_table, const void* B, float* C,
                           void* c_bf16, int64_t M, int64_t N, int64_t K, int epilogue, int k_splits, cudaStream_t stream);
 
+// C[M,N] = A^T B over the rows: A (R,M) and B (R,N) bf16 row-major, read MN-major by the tensor cores (tc_gemm_tn.cu; the weight-gradient
+// GEMMs of the train variant, no transposed operand copies).  Split-K over the rows as above: C holds k_splits partials of M N floats
+// (k_splits from tc_gemm_splits(M, N, R rounded up to 64)).  Needs M % 8 == 0, N % 8 == 0, N >= 16.
+bool tc_gemm_tn_supported(int64_t R, int64_t M, int64_t N);
+int launch_tc_gemm_tn_splitk(const void* A, const void* B, float* C, int64_t R, int64_t M, int64_t N, int k_splits, cudaStream_t stream);
+
 }  // namespace miner

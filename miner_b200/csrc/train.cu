@@ -904,13 +904,22 @@ extern "C" int miner_train_bwd(const void* table, int64_t n_rows, int table_dtyp
     MINER_LAUNCH_OK("transpose_cast(Wt)");
     rc = launch_tc_gemm(dz16, nullptr, id_dtype, 0, wtt16, dI2, nullptr, R, D, D, EPI_NONE, st);
     if (rc) return rc;
-    const dim3 tg(static_cast<unsigned>((w.bk_pad + 31) / 32), static_cast<unsigned>((D + 31) / 32));
-    transpose_cast_kernel<<<tg, tb, 0, st>>>(dZ, dzt, R, (int)D, w.bk_pad);
-    MINER_LAUNCH_OK("transpose_cast(dZ)");
-    transpose_cast_kernel<<<tg, tb, 0, st>>>(interests, it, R, (int)D, w.bk_pad);
-    MINER_LAUNCH_OK("transpose_cast(I)");
-    rc = launch_tc_gemm_splitk(dzt, nullptr, id_dtype, 0, it, w.s_wt > 1 ? pWt : grad_w_target, nullptr, D, D, w.bk_pad, EPI_NONE, w.s_wt, st);   // dWt[o,i] = sum_r dZ[r,o] I[r,i]
-    if (rc) return rc;
+    if (tc_gemm_tn_supported(R, D, D)) {
+      // dWt[o,i] = sum_r dZ[r,o] I[r,i]: both operands row-major as they are (dz16 from above, a bf16 copy of the interests), read
+      // MN-major by the tensor cores -- no transposed copies
+      rc = launch_cast_f32_to_bf16(interests, it, R * D, st);
+      if (rc) return rc;
+      rc = launch_tc_gemm_tn_splitk(dz16, it, w.s_wt > 1 ? pWt : grad_w_target, R, D, D, w.s_wt, st);
+      if (rc) return rc;
+    } else {
+      const dim3 tg(static_cast<unsigned>((w.bk_pad + 31) / 32), static_cast<unsigned>((D + 31) / 32));
+      transpose_cast_kernel<<<tg, tb, 0, st>>>(dZ, dzt, R, (int)D, w.bk_pad);
+      MINER_LAUNCH_OK("transpose_cast(dZ)");
+      transpose_cast_kernel<<<tg, tb, 0, st>>>(interests, it, R, (int)D, w.bk_pad);
+      MINER_LAUNCH_OK("transpose_cast(I)");
+      rc = launch_tc_gemm_splitk(dzt, nullptr, id_dtype, 0, it, w.s_wt > 1 ? pWt : grad_w_target, nullptr, D, D, w.bk_pad, EPI_NONE, w.s_wt, st);   // dWt[o,i] = sum_r dZ[r,o] I[r,i]
+      if (rc) return rc;
+    }
     if (w.s_wt > 1) {
       sum_partials_kernel<<<static_cast<int>((D * D + 255) / 256), 256, 0, st>>>(pWt, w.s_wt, D * D, grad_w_target);
       MINER_LAUNCH_OK("sum_partials(dWt)");
@@ -965,14 +974,25 @@ extern "C" int miner_train_bwd(const void* table, int64_t n_rows, int table_dtyp
     const int64_t R = B * H;
     __nv_bfloat16* dz1t = reinterpret_cast<__nv_bfloat16*>(ws + w.dz1t);
     uint16_t* et = reinterpret_cast<uint16_t*>(ws + w.et);
-    transpose_cast_kernel<<<dim3(static_cast<unsigned>((w.bh_pad + 31) / 32), static_cast<unsigned>((Dc + 31) / 32)), tb, 0, st>>>(dZ1, dz1t, R, (int)Dc,
-                                                                                                                              w.bh_pad);
-    MINER_LAUNCH_OK("transpose_cast(dZ1)");
-    gather_transpose_kernel<<<dim3(static_cast<unsigned>((w.bh_pad + 31) / 32), static_cast<unsigned>((D + 31) / 32)), tb, 0, st>>>(
-        static_cast<const uint16_t*>(table), n_rows, his_ids, id_dtype, R, (int)D, w.bh_pad, et);
-    MINER_LAUNCH_OK("gather_transpose(E)");
-    const int rc = launch_tc_gemm_splitk(dz1t, nullptr, id_dtype, 0, et, w.s_wp > 1 ? pWp : grad_w_proj, nullptr, Dc, D, w.bh_pad, EPI_NONE, w.s_wp, st);   // dWp[c,d] = sum_r dZ1[r,c] E[r,d]
-    if (rc) return rc;
+    int rc = MINER_OK;
+    if (tc_gemm_tn_supported(R, Dc, D)) {
+      // dWp[c,d] = sum_r dZ1[r,c] E[r,d]: dZ1 as bf16 and the gathered history rows, both row-major, read MN-major (invalid ids: zero rows)
+      rc = launch_cast_f32_to_bf16(dZ1, dz1t, R * Dc, st);
+      if (rc) return rc;
+      rc = launch_gather(table, n_rows, D, MINER_BF16, his_ids, R, id_dtype, et, nullptr, st);
+      if (rc) return rc;
+      rc = launch_tc_gemm_tn_splitk(dz1t, et, w.s_wp > 1 ? pWp : grad_w_proj, R, Dc, D, w.s_wp, st);
+      if (rc) return rc;
+    } else {
+      transpose_cast_kernel<<<dim3(static_cast<unsigned>((w.bh_pad + 31) / 32), static_cast<unsigned>((Dc + 31) / 32)), tb, 0, st>>>(dZ1, dz1t, R, (int)Dc,
+                                                                                                                                w.bh_pad);
+      MINER_LAUNCH_OK("transpose_cast(dZ1)");
+      gather_transpose_kernel<<<dim3(static_cast<unsigned>((w.bh_pad + 31) / 32), static_cast<unsigned>((D + 31) / 32)), tb, 0, st>>>(
+          static_cast<const uint16_t*>(table), n_rows, his_ids, id_dtype, R, (int)D, w.bh_pad, et);
+      MINER_LAUNCH_OK("gather_transpose(E)");
+      rc = launch_tc_gemm_splitk(dz1t, nullptr, id_dtype, 0, et, w.s_wp > 1 ? pWp : grad_w_proj, nullptr, Dc, D, w.bh_pad, EPI_NONE, w.s_wp, st);   // dWp[c,d] = sum_r dZ1[r,c] E[r,d]
+      if (rc) return rc;
+    }
     if (w.s_wp > 1) {
       sum_partials_kernel<<<static_cast<int>((Dc * D + 255) / 256), 256, 0, st>>>(pWp, w.s_wp, Dc * D, grad_w_proj);
       MINER_LAUNCH_OK("sum_partials(dWp)");

@@ -450,6 +450,20 @@ def tc_gemm(a_bf16: torch.Tensor, b_bf16: torch.Tensor, epilogue: int = 0, a_ids
     return (c, cb) if want_bf16 else c
 
 
+def tc_gemm_tn(a_bf16: torch.Tensor, b_bf16: torch.Tensor, k_splits: int = 1) -> torch.Tensor:
+    """The tcgen05 weight-gradient GEMM on its own: ``A^T B`` over the rows of ``A (R,M)`` and ``B (R,N)`` (both row-major bf16, read
+    MN-major); returns the ``(k_splits, M, N)`` fp32 partials (tests / profiling)."""
+    dev = _need_cuda(a_bf16, b_bf16)
+    assert a_bf16.dtype == torch.bfloat16 and b_bf16.dtype == torch.bfloat16 and a_bf16.shape[0] == b_bf16.shape[0]
+    a, b = a_bf16.contiguous(), b_bf16.contiguous()
+    R, M = a.shape
+    N = b.shape[1]
+    c = torch.empty(k_splits, M, N, dtype=torch.float32, device=dev)
+    with torch.cuda.device(dev):
+        L.check(L.load().miner_tc_gemm_tn(_ptr(a), _ptr(b), _ptr(c), R, M, N, k_splits, _stream()))
+    return c
+
+
 # ------------------------------------------------------------------------------------------------ (a7..a12)
 TRANSFORMS = {'none': 0, 'sigmoid': 1, 'softmax': 2}
 

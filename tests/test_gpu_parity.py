@@ -464,6 +464,27 @@ def test_tc_gemm_gathered_rows():
     close_norm(c.cpu().numpy(), torch.tanh(a @ w.float().T).numpy(), 2e-5)
 
 
+@pytest.mark.parametrize('R,M,N,splits', [(4096, 768, 768, 1), (4099, 200, 768, 3), (131072, 768, 768, 8), (777, 8, 16, 2), (64, 136, 264, 1),
+                                          (300, 64, 320, 7)])
+def test_tc_gemm_tn_weight_gradient_gemm(R, M, N, splits):
+    """C = A^T B over the rows with both operands row-major (MN-major for tcgen05): ragged R (TMA zero fill), M / N that are not
+    multiples of the 128 x 256 tile, split-K partials (a split may be empty), against an fp32 matmul of the same bf16 values."""
+    from miner_b200 import ops
+    g = torch.Generator().manual_seed(R + M + N)
+    a = (torch.randn(R, M, generator=g) * 0.5).to(torch.bfloat16)
+    b = (torch.randn(R, N, generator=g) * 0.5).to(torch.bfloat16)
+    c = ops.tc_gemm_tn(a.to(DEV), b.to(DEV), splits)
+    assert c.shape == (splits, M, N)
+    ref = a.to(DEV).float().T @ b.to(DEV).float()
+    close_norm(c.sum(0).cpu().numpy(), ref.cpu().numpy(), 2e-5)
+    if splits > 1:                                                   # every partial is the sum over its own block of rows
+        per = ((R + 63) // 64 + splits - 1) // splits * 64
+        for s_ in range(splits):
+            blk = slice(min(R, s_ * per), min(R, (s_ + 1) * per))
+            part = a[blk].to(DEV).float().T @ b[blk].to(DEV).float()
+            assert float((c[s_] - part).abs().max()) <= 2e-5 * float(ref.abs().max()), s_
+
+
 # ------------------------------------------------------------------------------------------------ ranking metrics (a7..a12)
 def test_rank_metrics_match_reference_per_impression():
     from miner_b200 import ops
