@@ -29,7 +29,7 @@ __global__ void __launch_bounds__(PT) poly_softmax_wsum_kernel(
     const float* __restrict__ proj, const float* __restrict__ codes, const uint8_t* __restrict__ mask,
     const float* __restrict__ bias_mean, const float* __restrict__ emb, const void* __restrict__ table, int table_dtype,
     const void* __restrict__ his_ids, int id_dtype, int64_t n_rows, int H, int K, int Dc, int D,
-    float* __restrict__ out_interests, float* __restrict__ out_weights, __nv_bfloat16* __restrict__ out_interests_bf16) {
+    float* __restrict__ out_interests, float* __restrict__ out_weights, __nv_bfloat16* __restrict__ out_interests_bf16, int stage_rows) {
   extern __shared__ __align__(16) float smem[];
   const int HP = H + 1;                          // padded row of the logits / weights tile
   const int KP = (K + 3) & ~3;                   // weights^T rows padded to float4
@@ -45,6 +45,21 @@ __global__ void __launch_bounds__(PT) poly_softmax_wsum_kernel(
   if (his_ids && tid < H) {
     const int64_t id = load_id(his_ids, b * H + tid, id_dtype);
     row_of[tid] = (id >= 0 && id < n_rows) ? id : -1;             // out-of-range id: zero row (gather semantics)
+  }
+  // (staged path, see the weighted sum) the impression's H table rows start their way into shared memory now
+  const bool staged = stage_rows != 0;
+  uint4* Es = reinterpret_cast<uint4*>(WT + ((H * KP + 3) & ~3));   // [H][D / 8] bf16 rows
+  if (staged) {
+    __syncthreads();                                               // row_of
+    const int NVs = D >> 3;
+    for (int i = tid; i < H * NVs; i += PT) {
+      const int h = i / NVs, vv = i % NVs;
+      const int64_t row = row_of[h];
+      const uint4* src = reinterpret_cast<const uint4*>(static_cast<const char*>(table) + (row >= 0 ? row : 0) * (static_cast<int64_t>(D) * 2)) + vv;
+      const uint32_t dst = static_cast<uint32_t>(__cvta_generic_to_shared(Es + i));
+      asm volatile("cp.async.cg.shared.global [%0], [%1], 16, %2;" ::"r"(dst), "l"(src), "r"(row >= 0 ? 16u : 0u) : "memory");
+    }
+    asm volatile("cp.async.commit_group;" ::: "memory");
   }
 
   // ---- logits tile: register-tiled (TH x TK) mini-GEMM over Dc chunks ----
@@ -137,6 +152,65 @@ __global__ void __launch_bounds__(PT) poly_softmax_wsum_kernel(
   // ---- interests[k,d] = sum_h w[k,h] E[h,d]   (model.py:182) ----
   const float* embb = emb ? emb + b * static_cast<int64_t>(H) * D : nullptr;
   const int64_t row_bytes = static_cast<int64_t>(D) * (table_dtype == MINER_F32 ? 4 : 2);
+  // bf16 table rows staged in shared memory (cp.async issued at the top of the kernel, so the gather runs under the logits and the
+  // softmax): thread = (8-feature vector v, code slice ks) keeps 8 codes x 8 features; a history row costs one LDS.128 of the row and
+  // two of the weights per 64 FMAs.  The sum over the history runs in slot order, as in the generic path below.
+  if (staged) {
+    asm volatile("cp.async.wait_all;" ::: "memory");
+    __syncthreads();
+    constexpr int KC = 8;
+    const int NV = D >> 3;
+    const int KS = PT / NV < 8 ? PT / NV : 8;                    // code slices that work side by side
+    const int v = tid % NV, ks = tid / NV;
+    if (ks >= KS) return;                                          // (no block-wide barrier below)
+    for (int kg = ks * KC; kg < K; kg += KS * KC) {
+      float acc[KC][8];
+#pragma unroll
+      for (int k = 0; k < KC; ++k)
+#pragma unroll
+        for (int j = 0; j < 8; ++j) acc[k][j] = 0.f;
+#pragma unroll 2
+      for (int h = 0; h < H; ++h) {
+        const uint4 raw = Es[static_cast<size_t>(h) * NV + v];
+        float e[8];
+        e[0] = __uint_as_float(raw.x << 16), e[1] = __uint_as_float(raw.x & 0xffff0000u);
+        e[2] = __uint_as_float(raw.y << 16), e[3] = __uint_as_float(raw.y & 0xffff0000u);
+        e[4] = __uint_as_float(raw.z << 16), e[5] = __uint_as_float(raw.z & 0xffff0000u);
+        e[6] = __uint_as_float(raw.w << 16), e[7] = __uint_as_float(raw.w & 0xffff0000u);
+        const float4* wrow = reinterpret_cast<const float4*>(WT + h * KP + kg);
+#pragma unroll
+        for (int k4 = 0; k4 < KC / 4; ++k4) {
+          if (kg + k4 * 4 < K) {
+            const float4 w = wrow[k4];
+#pragma unroll
+            for (int j = 0; j < 8; ++j) {
+              acc[k4 * 4 + 0][j] = fmaf(w.x, e[j], acc[k4 * 4 + 0][j]);
+              acc[k4 * 4 + 1][j] = fmaf(w.y, e[j], acc[k4 * 4 + 1][j]);
+              acc[k4 * 4 + 2][j] = fmaf(w.z, e[j], acc[k4 * 4 + 2][j]);
+              acc[k4 * 4 + 3][j] = fmaf(w.w, e[j], acc[k4 * 4 + 3][j]);
+            }
+          }
+        }
+      }
+#pragma unroll
+      for (int k = 0; k < KC; ++k) {
+        if (kg + k < K) {
+          const int64_t o = (b * K + kg + k) * static_cast<int64_t>(D) + 8 * v;
+          if (out_interests) {
+            *reinterpret_cast<float4*>(out_interests + o) = make_float4(acc[k][0], acc[k][1], acc[k][2], acc[k][3]);
+            *reinterpret_cast<float4*>(out_interests + o + 4) = make_float4(acc[k][4], acc[k][5], acc[k][6], acc[k][7]);
+          }
+          if (out_interests_bf16) {
+            __nv_bfloat162 p0 = __floats2bfloat162_rn(acc[k][0], acc[k][1]), p1 = __floats2bfloat162_rn(acc[k][2], acc[k][3]);
+            __nv_bfloat162 p2 = __floats2bfloat162_rn(acc[k][4], acc[k][5]), p3 = __floats2bfloat162_rn(acc[k][6], acc[k][7]);
+            *reinterpret_cast<uint4*>(out_interests_bf16 + o) = make_uint4(*reinterpret_cast<uint32_t*>(&p0), *reinterpret_cast<uint32_t*>(&p1),
+                                                                           *reinterpret_cast<uint32_t*>(&p2), *reinterpret_cast<uint32_t*>(&p3));
+          }
+        }
+      }
+    }
+    return;
+  }
   for (int kg = 0; kg < K; kg += KG) {
     float w_acc[KG][DJ];
 #pragma unroll
@@ -200,7 +274,14 @@ int launch_poly_softmax_wsum(const float* proj, const float* codes, const uint8_
     set_error("poly attention: unsupported shape H=%lld K=%lld D=%lld (need H<=256, K<=64, D<=1024)", (long long)H, (long long)K, (long long)D);
     return MINER_ERR_UNSUPPORTED;
   }
-  const size_t smem = poly_smem_bytes(static_cast<int>(H), static_cast<int>(K));
+  size_t smem = poly_smem_bytes(static_cast<int>(H), static_cast<int>(K));
+  // bf16 rows of one impression staged in shared memory when they fit beside the logit tiles (two blocks per SM up to ~100 KB each)
+  const size_t stage_bytes = static_cast<size_t>(H) * D * 2;
+  const int stage_rows = (!emb && table && table_dtype == MINER_BF16 && D % 8 == 0 && D / 8 <= PT && smem + stage_bytes <= 110 * 1024 &&
+                          reinterpret_cast<uintptr_t>(table) % 16 == 0 && (!out_interests || reinterpret_cast<uintptr_t>(out_interests) % 16 == 0) &&
+                          (!out_interests_bf16 || reinterpret_cast<uintptr_t>(out_interests_bf16) % 16 == 0))
+                             ? 1 : 0;
+  if (stage_rows) smem += stage_bytes;
   const int dj = static_cast<int>((D + PT - 1) / PT);
   auto bf = static_cast<__nv_bfloat16*>(out_interests_bf16);
 #define MINER_POLY(DJ)                                                                                                   \
@@ -208,7 +289,7 @@ int launch_poly_softmax_wsum(const float* proj, const float* codes, const uint8_
     MINER_CUDA_OK(cudaFuncSetAttribute(poly_softmax_wsum_kernel<DJ>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem)); \
     poly_softmax_wsum_kernel<DJ><<<static_cast<unsigned>(B), PT, smem, stream>>>(                                        \
         proj, codes, mask, bias_mean, emb, table, table_dtype, his_ids, id_dtype, n_rows, (int)H, (int)K, (int)Dc, (int)D,       \
-        out_interests, out_weights, bf);                                                                                 \
+        out_interests, out_weights, bf, stage_rows);                                                                     \
   } while (0)
   switch (dj) {
     case 1: MINER_POLY(1); break;
