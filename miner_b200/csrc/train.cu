@@ -243,28 +243,66 @@ __global__ void __launch_bounds__(TT) target_bwd_kernel(const void* __restrict__
   float* da = dm + C * K;                // [C][K]
   const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
   const int64_t b = blockIdx.x;
-  for (int c = 0; c < C; ++c) {
-    const int64_t id = load_id(cand_ids, b * C + c, id_dtype);
-    const bool ok = id >= 0 && id < n_rows;
-    for (int d = tid; d < D; d += TT) Cd[c * D + d] = ok ? table_elem(table, table_dtype, id * D + d) : 0.f;
+  if (table_dtype == MINER_BF16 && (D & 7) == 0 && (reinterpret_cast<uintptr_t>(table) & 15) == 0) {
+    const int nv = D >> 3;                                  // 16-byte loads: eight bf16 features of a candidate row per request
+    for (int i = tid; i < C * nv; i += TT) {
+      const int c = i / nv, v = i - c * nv;
+      const int64_t id = load_id(cand_ids, b * C + c, id_dtype);
+      uint4 raw = make_uint4(0u, 0u, 0u, 0u);
+      if (id >= 0 && id < n_rows) raw = __ldg(reinterpret_cast<const uint4*>(static_cast<const uint16_t*>(table) + id * D) + v);
+      float4* dst = reinterpret_cast<float4*>(Cd + c * D + 8 * v);
+      dst[0] = make_float4(__uint_as_float(raw.x << 16), __uint_as_float(raw.x & 0xffff0000u), __uint_as_float(raw.y << 16),
+                           __uint_as_float(raw.y & 0xffff0000u));
+      dst[1] = make_float4(__uint_as_float(raw.z << 16), __uint_as_float(raw.z & 0xffff0000u), __uint_as_float(raw.w << 16),
+                           __uint_as_float(raw.w & 0xffff0000u));
+    }
+  } else {
+    for (int c = 0; c < C; ++c) {
+      const int64_t id = load_id(cand_ids, b * C + c, id_dtype);
+      const bool ok = id >= 0 && id < n_rows;
+      for (int d = tid; d < D; d += TT) Cd[c * D + d] = ok ? table_elem(table, table_dtype, id * D + d) : 0.f;
+    }
   }
   __syncthreads();
   const float* Ib = interests + b * static_cast<int64_t>(K) * D;
   const float* Zb = Z + b * static_cast<int64_t>(K) * D;
   constexpr int CB = 8;                                     // candidates per sweep over an interest row: gelu(Z) is evaluated once per sweep
+  const float* dIin = d_interests_in ? d_interests_in + b * static_cast<int64_t>(K) * D : nullptr;
+  float* dIb = d_interests + b * static_cast<int64_t>(K) * D;
+  float* dZb = dZ + b * static_cast<int64_t>(K) * D;
+  // four features per request (16-byte global loads, LDS.128 of the candidate rows) when the rows allow it
+  const bool vec4 = (D & 3) == 0 && ((reinterpret_cast<uintptr_t>(interests) | reinterpret_cast<uintptr_t>(Z) | reinterpret_cast<uintptr_t>(d_interests) |
+                                      reinterpret_cast<uintptr_t>(dZ) | reinterpret_cast<uintptr_t>(d_interests_in)) & 15) == 0;
   for (int k = warp; k < K; k += TT / 32) {
     for (int c0 = 0; c0 < C; c0 += CB) {
       float sm_[CB], sa_[CB];
 #pragma unroll
       for (int j = 0; j < CB; ++j) sm_[j] = sa_[j] = 0.f;
-      for (int d = lane; d < D; d += 32) {
-        const float iv = Ib[static_cast<int64_t>(k) * D + d];
-        const float gv = gelu_erf(Zb[static_cast<int64_t>(k) * D + d]);                // model.py:212
+      if (vec4) {
+        const float4* I4 = reinterpret_cast<const float4*>(Ib + static_cast<int64_t>(k) * D);
+        const float4* Z4 = reinterpret_cast<const float4*>(Zb + static_cast<int64_t>(k) * D);
+        for (int d4 = lane; d4 < (D >> 2); d4 += 32) {
+          const float4 iv = I4[d4], zv = Z4[d4];
+          const float4 gv = make_float4(gelu_erf(zv.x), gelu_erf(zv.y), gelu_erf(zv.z), gelu_erf(zv.w));   // model.py:212
 #pragma unroll
-        for (int j = 0; j < CB; ++j) {
-          const float cd = c0 + j < C ? Cd[(c0 + j) * D + d] : 0.f;
-          sm_[j] = fmaf(cd, iv, sm_[j]);                                               // model.py:127
-          sa_[j] = fmaf(cd, gv, sa_[j]);                                               // model.py:213
+          for (int j = 0; j < CB; ++j) {
+            if (c0 + j < C) {
+              const float4 cd = *reinterpret_cast<const float4*>(Cd + (c0 + j) * D + 4 * d4);
+              sm_[j] = fmaf(cd.x, iv.x, fmaf(cd.y, iv.y, fmaf(cd.z, iv.z, fmaf(cd.w, iv.w, sm_[j]))));     // model.py:127
+              sa_[j] = fmaf(cd.x, gv.x, fmaf(cd.y, gv.y, fmaf(cd.z, gv.z, fmaf(cd.w, gv.w, sa_[j]))));     // model.py:213
+            }
+          }
+        }
+      } else {
+        for (int d = lane; d < D; d += 32) {
+          const float iv = Ib[static_cast<int64_t>(k) * D + d];
+          const float gv = gelu_erf(Zb[static_cast<int64_t>(k) * D + d]);                // model.py:212
+#pragma unroll
+          for (int j = 0; j < CB; ++j) {
+            const float cd = c0 + j < C ? Cd[(c0 + j) * D + d] : 0.f;
+            sm_[j] = fmaf(cd, iv, sm_[j]);                                               // model.py:127
+            sa_[j] = fmaf(cd, gv, sa_[j]);                                               // model.py:213
+          }
         }
       }
 #pragma unroll
@@ -295,19 +333,35 @@ __global__ void __launch_bounds__(TT) target_bwd_kernel(const void* __restrict__
     }
   }
   __syncthreads();
-  const float* dIin = d_interests_in ? d_interests_in + b * static_cast<int64_t>(K) * D : nullptr;
-  float* dIb = d_interests + b * static_cast<int64_t>(K) * D;
-  float* dZb = dZ + b * static_cast<int64_t>(K) * D;
-  for (int i = tid; i < K * D; i += TT) {
-    const int k = i / D, d = i - k * D;
-    float gi = dIin ? dIin[i] : 0.f, gg = 0.f;
-    for (int c = 0; c < C; ++c) {
-      const float cd = Cd[c * D + d];
-      gi = fmaf(dm[c * K + k], cd, gi);
-      gg = fmaf(da[c * K + k], cd, gg);
+  if (vec4) {
+    const int nv = D >> 2;
+    for (int i = tid; i < K * nv; i += TT) {
+      const int k = i / nv, d = 4 * (i - k * nv);
+      float4 gi = dIin ? *reinterpret_cast<const float4*>(dIin + static_cast<int64_t>(k) * D + d) : make_float4(0.f, 0.f, 0.f, 0.f);
+      float4 gg = make_float4(0.f, 0.f, 0.f, 0.f);
+      for (int c = 0; c < C; ++c) {
+        const float4 cd = *reinterpret_cast<const float4*>(Cd + c * D + d);
+        const float wm = dm[c * K + k], wa = da[c * K + k];
+        gi.x = fmaf(wm, cd.x, gi.x), gi.y = fmaf(wm, cd.y, gi.y), gi.z = fmaf(wm, cd.z, gi.z), gi.w = fmaf(wm, cd.w, gi.w);
+        gg.x = fmaf(wa, cd.x, gg.x), gg.y = fmaf(wa, cd.y, gg.y), gg.z = fmaf(wa, cd.z, gg.z), gg.w = fmaf(wa, cd.w, gg.w);
+      }
+      const float4 zv = *reinterpret_cast<const float4*>(Zb + static_cast<int64_t>(k) * D + d);
+      *reinterpret_cast<float4*>(dIb + static_cast<int64_t>(k) * D + d) = gi;
+      *reinterpret_cast<float4*>(dZb + static_cast<int64_t>(k) * D + d) =
+          make_float4(gg.x * gelu_erf_grad(zv.x), gg.y * gelu_erf_grad(zv.y), gg.z * gelu_erf_grad(zv.z), gg.w * gelu_erf_grad(zv.w));
     }
-    dIb[i] = gi;
-    dZb[i] = gg * gelu_erf_grad(Zb[i]);
+  } else {
+    for (int i = tid; i < K * D; i += TT) {
+      const int k = i / D, d = i - k * D;
+      float gi = dIin ? dIin[i] : 0.f, gg = 0.f;
+      for (int c = 0; c < C; ++c) {
+        const float cd = Cd[c * D + d];
+        gi = fmaf(dm[c * K + k], cd, gi);
+        gg = fmaf(da[c * K + k], cd, gg);
+      }
+      dIb[i] = gi;
+      dZb[i] = gg * gelu_erf_grad(Zb[i]);
+    }
   }
   if (grad_table) {
     // gradient of the candidate rows: m = Cd I^T and a = Cd gelu(Z)^T are both linear in Cd (model.py:127,213)
@@ -404,6 +458,8 @@ __global__ void __launch_bounds__(TT) poly_bwd_kernel(const void* __restrict__ t
   for (int i = tid; i < K * Dc; i += TT) { codes_s[i] = codes[i]; dcodes_s[i] = 0.f; }
   __syncthreads();
   const int npairs = K * H;
+  const bool vec_fill = table_dtype == MINER_BF16 && (D & 7) == 0 && (reinterpret_cast<uintptr_t>(table) & 15) == 0 &&
+                        (reinterpret_cast<uintptr_t>(dI_a) & 15) == 0 && (!dI_b || (reinterpret_cast<uintptr_t>(dI_b) & 15) == 0);
   for (int64_t b = blockIdx.x; b < B; b += gridDim.x) {
     for (int h = tid; h < H; h += TT) {
       const int64_t id = load_id(his_ids, b * H + h, id_dtype);
@@ -414,15 +470,40 @@ __global__ void __launch_bounds__(TT) poly_bwd_kernel(const void* __restrict__ t
     // dw[k,h] = sum_d dI[k,d] E[h,d]                                                   (model.py:182)
     for (int d0 = 0; d0 < D; d0 += DK) {
       const int dn = D - d0 < DK ? D - d0 : DK;
-      for (int i = tid; i < K * DK; i += TT) {
-        const int k = i / DK, d = i - k * DK;
-        const int64_t o = (b * K + k) * D + d0 + d;
-        dIc[k * DS + d] = d < dn ? dI_a[o] + (dI_b ? dI_b[o] : 0.f) : 0.f;
-      }
-      for (int i = tid; i < H * DK; i += TT) {
-        const int h = i / DK, d = i - h * DK;
-        const int id = ids_s[h];
-        Ec[h * DS + d] = (d < dn && id >= 0) ? table_elem(table, table_dtype, static_cast<int64_t>(id) * D + d0 + d) : 0.f;
+      if (vec_fill && dn == DK) {
+        // 16-byte loads: four gradient values, eight bf16 features of a table row per request
+        for (int i = tid; i < K * (DK / 4); i += TT) {
+          const int k = i / (DK / 4), d4 = i - k * (DK / 4);
+          const int64_t o = (b * K + k) * D + d0 + 4 * d4;
+          float4 g = *reinterpret_cast<const float4*>(dI_a + o);
+          if (dI_b) {
+            const float4 g2 = *reinterpret_cast<const float4*>(dI_b + o);
+            g.x += g2.x, g.y += g2.y, g.z += g2.z, g.w += g2.w;
+          }
+          *reinterpret_cast<float4*>(dIc + k * DS + 4 * d4) = g;
+        }
+        for (int i = tid; i < H * (DK / 8); i += TT) {
+          const int h = i / (DK / 8), c = i - h * (DK / 8);
+          const int id = ids_s[h];
+          uint4 raw = make_uint4(0u, 0u, 0u, 0u);
+          if (id >= 0) raw = __ldg(reinterpret_cast<const uint4*>(static_cast<const uint16_t*>(table) + static_cast<int64_t>(id) * D + d0) + c);
+          float4* dst = reinterpret_cast<float4*>(Ec + h * DS + 8 * c);
+          dst[0] = make_float4(__uint_as_float(raw.x << 16), __uint_as_float(raw.x & 0xffff0000u), __uint_as_float(raw.y << 16),
+                               __uint_as_float(raw.y & 0xffff0000u));
+          dst[1] = make_float4(__uint_as_float(raw.z << 16), __uint_as_float(raw.z & 0xffff0000u), __uint_as_float(raw.w << 16),
+                               __uint_as_float(raw.w & 0xffff0000u));
+        }
+      } else {
+        for (int i = tid; i < K * DK; i += TT) {
+          const int k = i / DK, d = i - k * DK;
+          const int64_t o = (b * K + k) * D + d0 + d;
+          dIc[k * DS + d] = d < dn ? dI_a[o] + (dI_b ? dI_b[o] : 0.f) : 0.f;
+        }
+        for (int i = tid; i < H * DK; i += TT) {
+          const int h = i / DK, d = i - h * DK;
+          const int id = ids_s[h];
+          Ec[h * DS + d] = (d < dn && id >= 0) ? table_elem(table, table_dtype, static_cast<int64_t>(id) * D + d0 + d) : 0.f;
+        }
       }
       __syncthreads();
       // 4 (codes) x 2 (slots) register tiles, four features per step: 6 LDS.128 per 32 FMAs
