@@ -18,6 +18,10 @@ namespace miner {
 namespace {
 
 constexpr int TT = 256;
+#ifndef MINER_POLY_BWD_DK
+#define MINER_POLY_BWD_DK 128
+#endif
+constexpr int POLY_BWD_DK = MINER_POLY_BWD_DK;   // feature chunk of poly_bwd's dw contraction
 
 __device__ __forceinline__ float table_elem(const void* table, int dtype, int64_t idx) {
   return dtype == MINER_F32 ? reinterpret_cast<const float*>(table)[idx]
@@ -446,7 +450,7 @@ __global__ void __launch_bounds__(TT) poly_bwd_kernel(const void* __restrict__ t
                                                       const float* __restrict__ dI_b, int64_t B, int H, int K, int Dc, int D,
                                                       float* __restrict__ dZ1, float* __restrict__ dcodes_partial, float* __restrict__ d_bias) {
   extern __shared__ __align__(16) float smem[];
-  constexpr int DK = 64;                 // feature chunk
+  constexpr int DK = POLY_BWD_DK;        // feature chunk (128: half as many fill / barrier rounds per impression as 64, still two blocks per SM)
   float* codes_s = smem;                 // [K][Dc]
   float* dcodes_s = codes_s + K * Dc;    // [K][Dc]
   constexpr int DS = DK + 12;            // row stride of the chunk tiles: 16-byte aligned rows; rows two apart (a warp's slot tiles) are 24 banks apart: conflict-free LDS.128
@@ -1021,7 +1025,7 @@ extern "C" int miner_train_bwd(const void* table, int64_t n_rows, int table_dtyp
   }
   // 3. poly attention: dZ1, dcodes
   {
-    const size_t smem = sizeof(float) * (2 * static_cast<size_t>(K) * Dc + K * 76 + H * 76 + K * H + 4) + sizeof(int) * H;
+    const size_t smem = sizeof(float) * (2 * static_cast<size_t>(K) * Dc + K * (POLY_BWD_DK + 12) + H * (POLY_BWD_DK + 12) + K * H + 4) + sizeof(int) * H;
     if (smem > 220 * 1024) {
       set_error("train_bwd: H=%lld K=%lld Dc=%lld need %zu bytes of shared memory", (long long)H, (long long)K, (long long)Dc, smem);
       return MINER_ERR_UNSUPPORTED;
