@@ -92,7 +92,7 @@ int launch_target_score(const float* interests, const float* proj /*gelu(I Wt^T)
                         const float* matching /*(T,K) caller-supplied matching scores or null*/, const float* cand,
                         const void* table, int table_dtype, const void* cand_ids, int id_dtype, int64_t n_rows,
                         const int64_t* cand_offsets, int64_t B, int64_t C, int64_t K, int64_t D, int score_type,
-                        float* out_scores, cudaStream_t stream);
+                        float* out_scores, cudaStream_t stream, bool proj_is_preactivation = false);
 
 // global AUC building blocks (auc.cu)
 size_t sort_u32_ws_bytes(int64_t n);

@@ -63,6 +63,8 @@ __global__ void __launch_bounds__(PT) poly_softmax_wsum_kernel(
   }
 
   // ---- logits tile: register-tiled (TH x TK) mini-GEMM over Dc chunks ----
+  static_assert(TH == 2 && TK == 4, "the logits tile is read as one float2 and one float4");
+  const bool h_even = (H & 1) == 0;
   const int tiles_h = (H + TH - 1) / TH, tiles_k = (K + TK - 1) / TK;
   const int n_tiles = tiles_h * tiles_k;
   float acc[MAXT][TH][TK];
@@ -90,11 +92,17 @@ __global__ void __launch_bounds__(PT) poly_softmax_wsum_kernel(
         const int h0 = (tile / tiles_k) * TH, k0 = (tile % tiles_k) * TK;
 #pragma unroll 8
         for (int c = 0; c < DCB; ++c) {
+          // (rows are padded: entries past H / K belong to accumulators that are never stored)
           float a[TH], bb[TK];
+          if (h_even) {
+            const float2 av = *reinterpret_cast<const float2*>(As + c * (H + 4) + h0);
+            a[0] = av.x, a[1] = av.y;
+          } else {
 #pragma unroll
-          for (int i = 0; i < TH; ++i) a[i] = (h0 + i < H) ? As[c * (H + 4) + h0 + i] : 0.f;
-#pragma unroll
-          for (int j = 0; j < TK; ++j) bb[j] = (k0 + j < K) ? Bs[c * (KP + 4) + k0 + j] : 0.f;
+            for (int i = 0; i < TH; ++i) a[i] = (h0 + i < H) ? As[c * (H + 4) + h0 + i] : 0.f;
+          }
+          const float4 bv = *reinterpret_cast<const float4*>(Bs + c * (KP + 4) + k0);
+          bb[0] = bv.x, bb[1] = bv.y, bb[2] = bv.z, bb[3] = bv.w;
 #pragma unroll
           for (int i = 0; i < TH; ++i)
 #pragma unroll

@@ -19,7 +19,7 @@ template <int DPL>
 __global__ void __launch_bounds__(TT) target_score_kernel(
     const float* __restrict__ interests, const float* __restrict__ proj, const float* __restrict__ matching,
     const float* __restrict__ cand, const void* __restrict__ table, int table_dtype, const void* __restrict__ cand_ids, int id_dtype, int64_t n_rows,
-    const int64_t* __restrict__ cand_offsets, int64_t C, int K, int D, int score_type, float* __restrict__ out_scores) {
+    const int64_t* __restrict__ cand_offsets, int64_t C, int K, int D, int score_type, float* __restrict__ out_scores, int proj_preact) {
   extern __shared__ __align__(16) float smem[];
   float* cand_s = smem;                       // [CC][D]
   float* m_s = cand_s + CC * D;               // [CC][K+1]
@@ -56,6 +56,7 @@ __global__ void __launch_bounds__(TT) target_score_kernel(
         const int d = lane + j * 32;
         iv[j] = d < D ? Ib[static_cast<int64_t>(k) * D + d] : 0.f;
         pv[j] = (weighted && d < D) ? Pb[static_cast<int64_t>(k) * D + d] : 0.f;
+        if (proj_preact) pv[j] = gelu_erf(pv[j]);         // `proj` is I Wt^T itself (train forward keeps it for the backward): gelu here, model.py:212
       }
       for (int c = 0; c < nc; ++c) {
         float m = 0.f, a = 0.f;
@@ -109,7 +110,7 @@ __global__ void __launch_bounds__(TT) target_score_kernel(
 int launch_target_score(const float* interests, const float* proj, const float* matching, const float* cand, const void* table,
                         int table_dtype,
                         const void* cand_ids, int id_dtype, int64_t n_rows, const int64_t* cand_offsets, int64_t B, int64_t C,
-                        int64_t K, int64_t D, int score_type, float* out_scores, cudaStream_t stream) {
+                        int64_t K, int64_t D, int score_type, float* out_scores, cudaStream_t stream, bool proj_is_preactivation) {
   if (B == 0) return MINER_OK;
   if (score_type != MINER_SCORE_MAX && score_type != MINER_SCORE_MEAN && score_type != MINER_SCORE_WEIGHTED) {
     set_error("Invalid method of aggregating matching score");
@@ -126,7 +127,7 @@ int launch_target_score(const float* interests, const float* proj, const float* 
     MINER_CUDA_OK(cudaFuncSetAttribute(target_score_kernel<DPL>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem)); \
     target_score_kernel<DPL><<<static_cast<unsigned>(B), TT, smem, stream>>>(                                            \
         interests, proj, matching, cand, table, table_dtype, cand_ids, id_dtype, n_rows, cand_offsets, C, (int)K, (int)D,          \
-        score_type, out_scores);                                                                                         \
+        score_type, out_scores, proj_is_preactivation ? 1 : 0);                                                          \
   } while (0)
   if (D <= 256) MINER_TGT(8);
   else if (D <= 512) MINER_TGT(16);

@@ -32,11 +32,6 @@ __device__ __forceinline__ float gelu_erf_grad(float z) {
   return 0.5f * (1.0f + erff(z * 0.70710678118654752440f)) + z * 0.3989422804014327f * expf(-0.5f * z * z);
 }
 
-__global__ void gelu_kernel(const float* __restrict__ z, float* __restrict__ g, int64_t n) {
-  for (int64_t i = static_cast<int64_t>(blockIdx.x) * blockDim.x + threadIdx.x; i < n; i += static_cast<int64_t>(gridDim.x) * blockDim.x)
-    g[i] = gelu_erf(z[i]);
-}
-
 __global__ void transpose_kernel(const float* __restrict__ src, float* __restrict__ dst, int rows, int cols) {
   __shared__ float tile[32][33];
   const int c0 = blockIdx.x * 32, r0 = blockIdx.y * 32;
@@ -873,11 +868,10 @@ extern "C" int miner_train_fwd(const void* table, int64_t n_rows, int table_dtyp
   if (!weighted)                                                                                                               // model.py:128-131
     return launch_target_score(out_interests, nullptr, nullptr, nullptr, table, table_dtype, cand_ids, id_dtype, n_rows, nullptr, B, C, K, D,
                                score_type, out_scores, st);
-  const int64_t n = B * K * D;
-  gelu_kernel<<<static_cast<int>((n + 1023) / 1024 < 8 * sm_count() ? (n + 1023) / 1024 : 8 * sm_count()), 256, 0, st>>>(save_z, G, n);
-  MINER_LAUNCH_OK("gelu");
-  return launch_target_score(out_interests, G, nullptr, nullptr, table, table_dtype, cand_ids, id_dtype, n_rows, nullptr, B, C, K, D,
-                             MINER_SCORE_WEIGHTED, out_scores, st);                                                           // model.py:127,213-214
+  // gelu(Z) is applied inside the scoring kernel (Z itself is what the backward needs): no gelu(Z) array is written
+  (void)G;
+  return launch_target_score(out_interests, save_z, nullptr, nullptr, table, table_dtype, cand_ids, id_dtype, n_rows, nullptr, B, C, K, D,
+                             MINER_SCORE_WEIGHTED, out_scores, st, true);                                                           // model.py:127,213-214
 }
 
 extern "C" int miner_loss_bwd(const float* interests, const float* logits, const float* labels, const float* grad_out, int64_t B,
