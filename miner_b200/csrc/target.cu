@@ -34,7 +34,21 @@ __global__ void __launch_bounds__(TT) target_score_kernel(
 
   for (int64_t c0 = c_begin; c0 < c_end; c0 += CC) {
     const int nc = static_cast<int>(c_end - c0 < CC ? c_end - c0 : CC);
-    // stage the chunk's candidate vectors (fp32 in smem)
+    // stage the chunk's candidate vectors (fp32 in smem); bf16 table rows with 16-byte loads, eight features per request
+    if (!cand && table_dtype == MINER_BF16 && (D & 7) == 0 && (reinterpret_cast<uintptr_t>(table) & 15) == 0) {
+      const int nv = D >> 3;
+      for (int i = tid; i < nc * nv; i += TT) {
+        const int c = i / nv, v = i - c * nv;
+        const int64_t id = load_id(cand_ids, c0 + c, id_dtype);
+        uint4 raw = make_uint4(0u, 0u, 0u, 0u);
+        if (id >= 0 && id < n_rows) raw = __ldg(reinterpret_cast<const uint4*>(static_cast<const uint16_t*>(table) + id * D) + v);
+        float4* dst = reinterpret_cast<float4*>(cand_s + c * D + 8 * v);
+        dst[0] = make_float4(__uint_as_float(raw.x << 16), __uint_as_float(raw.x & 0xffff0000u), __uint_as_float(raw.y << 16),
+                             __uint_as_float(raw.y & 0xffff0000u));
+        dst[1] = make_float4(__uint_as_float(raw.z << 16), __uint_as_float(raw.z & 0xffff0000u), __uint_as_float(raw.w << 16),
+                             __uint_as_float(raw.w & 0xffff0000u));
+      }
+    } else
     for (int i = tid; i < nc * D; i += TT) {
       const int c = i / D, d = i - c * D;
       float v;
