@@ -322,6 +322,10 @@ def main():
     from miner_b200 import ops, synth, parallel, _lib
 
     assert torch.cuda.is_available(), 'bench.py needs a CUDA device (there is no CPU fallback in the product path)'
+    # one process per GPU: run on (and pin host buffers into) the GPU's own NUMA node; undone before the CPU baseline leg
+    prev_affinity = parallel.bind_to_gpu_cpus(local_rank) if os.environ.get('MINER_BENCH_AFFINITY', '1') != '0' else None
+    affinity_note = (f'process bound to the {len(os.sched_getaffinity(0))} CPUs NVML lists as local to its GPU' if prev_affinity is not None
+                     else 'process CPU affinity unchanged')
     torch.cuda.set_device(local_rank)
     dev = torch.device('cuda', local_rank)
     if world > 1:
@@ -562,6 +566,9 @@ def main():
     # ---- CPU baseline + parity on the same sample (rank 0, N=1 only)
     cpu_baseline, parity = None, None
     if rank == 0 and world == 1 and not args.no_cpu_baseline:
+        if prev_affinity is not None:
+            os.sched_setaffinity(0, prev_affinity)            # the CPU arm gets every core the process was given
+            prev_affinity = None
         torch.set_num_threads(cores)
         n = args.cpu_sample
         inputs = cpu_inputs(n)
@@ -666,7 +673,7 @@ def main():
                        'math': args.math + (' (both nn.Linear layers applied once per table row INSIDE every step, then tpack + one fused scoring kernel)' if math == _lib.MATH_TABLE else ' (reference operation order)'),
                        'impressions_per_gpu_per_step': B, 'candidates_per_gpu_per_step': T, 'chunk_impressions': chunk,
                        'l2': 'inputs per step (>600 MB ids + 154 MB table + 154 MB projected table + workspace) exceed the 126 MB L2; no explicit flush',
-                       'parallelism': f'dp{world} (impressions sharded, table+weights replicated)'},
+                       'parallelism': f'dp{world} (impressions sharded, table+weights replicated)', 'host': affinity_note},
             'e2e': {'value': e2e_v, 'unit': 'impressions/s', 'ms_per_step': ms_e2e, 'h2d_bytes_per_step': h2d_bytes,
                     'd2h_bytes_per_step': 2 * len(names) * 8 + 8},
             'gpu_launches': int(launches),

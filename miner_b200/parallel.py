@@ -103,3 +103,26 @@ class FlatGradients:
 def finalize_metrics(partials: torch.Tensor, names: Sequence[str]) -> Dict[str, float]:
     p = partials.detach().to('cpu', torch.float64).view(-1, 2)
     return {n: (float(p[i, 0] / p[i, 1]) if p[i, 1] > 0 else float('nan')) for i, n in enumerate(names)}
+
+
+def bind_to_gpu_cpus(gpu_index: int):
+    """Restrict this process to the CPUs NVML reports as local to ``gpu_index`` (its NUMA node), intersected with the CPUs the process
+    may already use.  One process per GPU streams pinned host buffers to its GPU: allocated after this call they are first touched --
+    and therefore placed -- on the GPU's own memory node instead of wherever the launcher started the process.  Returns the previous
+    affinity set (pass it to ``os.sched_setaffinity(0, ...)`` to undo) or ``None`` when nothing was changed."""
+    import os
+    try:
+        import pynvml
+        pynvml.nvmlInit()
+        h = pynvml.nvmlDeviceGetHandleByIndex(gpu_index)
+        words = (max(os.cpu_count() or 1, 1) + 63) // 64
+        mask = pynvml.nvmlDeviceGetCpuAffinity(h, words)
+        local = {64 * i + b for i, w in enumerate(mask) for b in range(64) if (int(w) >> b) & 1}
+        allowed = os.sched_getaffinity(0)
+        target = local & allowed
+        if not target or target == allowed:
+            return None
+        os.sched_setaffinity(0, target)
+        return allowed
+    except Exception:
+        return None
