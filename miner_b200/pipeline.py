@@ -18,6 +18,18 @@ from . import ops
 from . import _lib as L
 
 
+def wave_bounds(B: int, first_wave: int, wave_growth: float, max_wave: int):
+    """Impression boundaries ``[0, b1, ..., B]`` of the waves: the first has ``first_wave`` impressions, each later one ``wave_growth``
+    times the previous up to ``max_wave``; every boundary but the last is a multiple of 4 (tile boundaries of the table-level kernel)."""
+    first_wave = max(4, int(first_wave) // 4 * 4)
+    max_wave = max(first_wave, int(max_wave) // 4 * 4)
+    bounds, w = [0], first_wave
+    while bounds[-1] < B:
+        bounds.append(min(B, bounds[-1] + w))
+        w = min(max_wave, max(4, int(w * max(1.0, float(wave_growth))) // 4 * 4))
+    return bounds
+
+
 class HostEvaluator:
     def __init__(self, model, wave: int = 65536, chunk: int = 32768, ks: Sequence[int] = (5, 10), transform: str = 'sigmoid',
                  math: Optional[int] = None, check_bounds: bool = True, first_wave: Optional[int] = None, wave_growth: float = 2.0,
@@ -45,11 +57,7 @@ class HostEvaluator:
         self.max_wave = max(self.first_wave, int(max_wave if max_wave is not None else 4 * self.wave) // 4 * 4)
 
     def _wave_bounds(self, B: int):
-        bounds, w = [0], self.first_wave
-        while bounds[-1] < B:
-            bounds.append(min(B, bounds[-1] + w))
-            w = min(self.max_wave, max(4, int(w * self.wave_growth) // 4 * 4))
-        return bounds
+        return wave_bounds(B, self.first_wave, self.wave_growth, self.max_wave)
 
     def _proj_ws(self) -> torch.Tensor:
         n = L.load().miner_table_project_workspace_bytes(self.table.shape[0], self.model.poly_attn.context_codes.shape[1])

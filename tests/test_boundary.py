@@ -286,3 +286,27 @@ def test_default_math_selection_is_host_logic():
     class _Shape:                                                                     # a 3M-row table (4.6 GB) without allocating it
         dtype, shape = torch.bfloat16, (3_000_000, 768)
     assert ops.default_eval_math(_Shape, 50, 32) == _lib.MATH_TENSOR                  # beyond the kernel's 32-bit row offsets: reference order
+
+
+def test_host_evaluator_wave_schedule_is_host_logic():
+    """The wave schedule of the host pipeline (small first wave, doubling up to a cap) covers every impression exactly once and cuts on
+    multiples of 4 impressions (tile boundaries of the table-level kernel), for any batch size."""
+    from miner_b200.pipeline import wave_bounds
+    assert wave_bounds(0, 16384, 2.0, 262144) == [0]
+    b = wave_bounds(1_000_000, 16384, 2.0, 262144)
+    assert b[0] == 0 and b[-1] == 1_000_000 and b[1] == 16384 and b[2] == 16384 + 32768
+    sizes = [y - x for x, y in zip(b[:-1], b[1:])]
+    assert max(sizes) == 262144 and len(sizes) == 7
+    for B, first, growth, cap in ((1501, 128, 2.0, 2048), (333, 83, 1.5, 400), (7, 4, 1.0, 4), (100, 1000, 3.0, 10)):
+        b = wave_bounds(B, first, growth, cap)
+        assert b[0] == 0 and b[-1] == B and all(y > x for x, y in zip(b[:-1], b[1:]))
+        assert all(x % 4 == 0 for x in b[:-1])
+    assert wave_bounds(4096, 1024, 1.0, 1024) == [0, 1024, 2048, 3072, 4096]          # equal waves
+
+
+def test_bind_to_gpu_cpus_without_nvml_changes_nothing():
+    import os
+    from miner_b200 import parallel
+    before = os.sched_getaffinity(0)
+    assert parallel.bind_to_gpu_cpus(0) is None or os.sched_getaffinity(0) <= before
+    os.sched_setaffinity(0, before)
