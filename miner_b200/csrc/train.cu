@@ -763,7 +763,7 @@ TrainWs train_ws(int64_t B, int64_t H, int64_t K, int64_t Dc, int64_t D, int mat
   size_t off = 0;
   auto take = [&](size_t bytes) { size_t o = off; off += align_up(bytes, 256); return o; };
   const size_t f = sizeof(float);
-  w.g = take(f * B * K * D);           // gelu(Z) in the forward; dI (Wt path) in the backward
+  w.g = take(f * B * K * D);           // dI (Wt path) in the backward (the forward applies gelu(Z) inside the scoring kernel)
   w.di = take(f * B * K * D);
   w.dz = take(f * B * K * D);
   w.dz1 = take(f * B * H * Dc);
@@ -846,7 +846,6 @@ extern "C" int miner_train_fwd(const void* table, int64_t n_rows, int table_dtyp
   }
   auto st = static_cast<cudaStream_t>(stream);
   char* wsb = static_cast<char*>(workspace);
-  float* G = reinterpret_cast<float*>(wsb + w.g);
   if (math == MINER_MATH_TENSOR) {
     // the two projection GEMMs on tcgen05 (bf16 operands, fp32 accumulation), everything else as in the fp32 family
     rc = launch_tc_gemm(table, his_ids, id_dtype, n_rows, w_proj_bf16, save_t, nullptr, B * H, Dc, D, EPI_TANH, st);          // model.py:171
@@ -869,7 +868,6 @@ extern "C" int miner_train_fwd(const void* table, int64_t n_rows, int table_dtyp
     return launch_target_score(out_interests, nullptr, nullptr, nullptr, table, table_dtype, cand_ids, id_dtype, n_rows, nullptr, B, C, K, D,
                                score_type, out_scores, st);
   // gelu(Z) is applied inside the scoring kernel (Z itself is what the backward needs): no gelu(Z) array is written
-  (void)G;
   return launch_target_score(out_interests, save_z, nullptr, nullptr, table, table_dtype, cand_ids, id_dtype, n_rows, nullptr, B, C, K, D,
                              MINER_SCORE_WEIGHTED, out_scores, st, true);                                                           // model.py:127,213-214
 }
